@@ -1,0 +1,21 @@
+"""clip_ebc_b200 -- B200-native (sm_100a) implementation of the CLIP-EBC inference hot path.
+
+Drop-in for the reference's ``get_model()/model(x)`` (models/__init__.py:10-29, models/clip/model.py:191-217) and
+``sliding_window_predict`` (utils/eval_utils.py:26-96) for the CLIP ViT-B/16 + VPT backbone. All arithmetic runs in
+hand-written CUDA kernels behind the C-ABI of ``include/clipebc_b200.h``; there is no CPU or PyTorch fallback.
+"""
+from ._lib import LIB_PATH, load  # noqa: F401
+
+__all__ = ["get_model", "sliding_window_predict", "CLIP_EBC", "load", "LIB_PATH"]
+
+
+def __getattr__(name):  # lazy: importing the package must not require torch.cuda
+    if name in ("get_model", "CLIP_EBC"):
+        from . import model
+
+        return getattr(model, name)
+    if name == "sliding_window_predict":
+        from .eval_utils import sliding_window_predict
+
+        return sliding_window_predict
+    raise AttributeError(name)

@@ -1,0 +1,603 @@
+// C-ABI of the CLIP-EBC hot path (include/clipebc_b200.h): model object (reference state_dict in, packed device
+// weights out), the two reference-facing entry points (model(x), sliding_window_predict) and single-kernel test hooks.
+// Host orchestration only -- every arithmetic step runs in the sm_100a kernels of this directory.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clipebc_b200.h"
+#include "kernels.h"
+
+namespace cebc {
+
+static std::atomic<int64_t> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return CLIPEBC_ECUDA;
+}
+#define CUDA_TRY(expr)                                         \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return fail_cuda(_e, #expr);        \
+  } while (0)
+// kernel launchers return nullptr or a message
+#define K_TRY(expr)                                                        \
+  do {                                                                     \
+    const char* _m = (expr);                                               \
+    if (_m != nullptr) return fail(CLIPEBC_ECUDA, std::string(_m));        \
+  } while (0)
+
+constexpr int kWidth = 768, kLayers = 12, kHeads = 12, kPatch = 16, kEmbed = 512, kHidden = 3072;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct RawTensor {
+  DevBuf buf;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct LayerPack {
+  DevBuf w_qkv, w_out, w_fc, w_proj;  // bf16
+  DevBuf const_kv;                    // bf16 [num_vpt, 2304] (deep VPT)
+  const float *b_qkv, *b_out, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+}  // namespace
+}  // namespace cebc
+
+using namespace cebc;
+
+struct clipebc_model {
+  clipebc_config cfg;
+  std::map<std::string, RawTensor> raw;
+  bool packed = false;
+  // packed
+  LayerPack layer[kLayers];
+  DevBuf w_patch;           // bf16 [768, 768]
+  DevBuf w_c1, w_c2;        // bf16 [768, 9*768]
+  DevBuf b_c1, b_c2;        // f32 [768]
+  DevBuf w_p3;              // bf16 [512, 3*768] = hi|hi|lo
+  DevBuf tmat;              // f32 [N, 512]
+  DevBuf pack_tmp_f32, pack_tmp_bf16;
+  std::map<int, DevBuf> pos_cache;  // key hp * 4096 + wp -> f32 [1 + hp*wp, 768]
+  // workspace
+  DevBuf ws_patch_rows, ws_patch_embed, ws_X, ws_Xn, ws_QKV, ws_AO, ws_Hid, ws_Y, ws_Ub, ws_Uf, ws_D1, ws_D2, ws_F,
+      ws_preds, ws_idx;
+};
+
+namespace {
+
+const float* raw_ptr(clipebc_model* m, const std::string& name) { return m->raw.at(name).buf.as<float>(); }
+
+bool check_shape(clipebc_model* m, const std::string& name, std::initializer_list<int64_t> want, std::string* err) {
+  auto it = m->raw.find(name);
+  if (it == m->raw.end()) { *err = "missing tensor '" + name + "'"; return false; }
+  const auto& s = it->second.shape;
+  std::vector<int64_t> w(want);
+  if (s != w) {
+    std::string got = "[", exp = "[";
+    for (auto v : s) got += std::to_string(v) + ",";
+    for (auto v : w) exp += std::to_string(v) + ",";
+    *err = "tensor '" + name + "' has shape " + got + "] expected " + exp + "]";
+    return false;
+  }
+  return true;
+}
+
+std::string blk(int l, const char* tail) {
+  return "image_encoder.transformer.resblocks." + std::to_string(l) + "." + tail;
+}
+
+int to_bf16(cudaStream_t s, const float* src, int64_t n, DevBuf* dst) {
+  CUDA_TRY(dst->reserve(static_cast<size_t>(n) * 2));
+  K_TRY(f32_to_bf16(s, src, dst->as<__nv_bfloat16>(), n));
+  return CLIPEBC_OK;
+}
+
+// PyTorch upsample_bicubic2d (align_corners=False, A=-0.75) of the patch part of the positional embedding
+// (reference: _clip/image_encoder.py:183-198). Runs once per (hp, wp) on the host.
+void cubic_coeffs(float t, float w[4]) {
+  const float A = -0.75f;
+  auto c1 = [&](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };
+  auto c2 = [&](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };
+  w[0] = c2(t + 1.f); w[1] = c1(t); w[2] = c1(1.f - t); w[3] = c2(2.f - t);
+}
+
+int get_pos(clipebc_model* m, int hp, int wp, cudaStream_t stream, const float** out) {
+  const int g0 = m->cfg.input_size / kPatch;
+  if (hp == g0 && wp == g0) { *out = raw_ptr(m, "image_encoder.positional_embedding"); return CLIPEBC_OK; }
+  const int key = hp * 4096 + wp;
+  auto it = m->pos_cache.find(key);
+  if (it != m->pos_cache.end()) { *out = it->second.as<float>(); return CLIPEBC_OK; }
+  std::vector<float> src(static_cast<size_t>(1 + g0 * g0) * kWidth);
+  CUDA_TRY(cudaMemcpy(src.data(), raw_ptr(m, "image_encoder.positional_embedding"), src.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<float> dst(static_cast<size_t>(1 + hp * wp) * kWidth);
+  std::memcpy(dst.data(), src.data(), kWidth * 4);
+  const float sy = static_cast<float>(g0) / hp, sx = static_cast<float>(g0) / wp;
+  for (int oy = 0; oy < hp; ++oy) {
+    const float fy = (oy + 0.5f) * sy - 0.5f;
+    const int iy = static_cast<int>(std::floor(fy));
+    float wy[4]; cubic_coeffs(fy - iy, wy);
+    for (int ox = 0; ox < wp; ++ox) {
+      const float fx = (ox + 0.5f) * sx - 0.5f;
+      const int ix = static_cast<int>(std::floor(fx));
+      float wx[4]; cubic_coeffs(fx - ix, wx);
+      float* o = &dst[static_cast<size_t>(1 + oy * wp + ox) * kWidth];
+      for (int c = 0; c < kWidth; ++c) o[c] = 0.f;
+      for (int a = 0; a < 4; ++a) {
+        const int yy = std::min(std::max(iy - 1 + a, 0), g0 - 1);
+        for (int b = 0; b < 4; ++b) {
+          const int xx = std::min(std::max(ix - 1 + b, 0), g0 - 1);
+          const float wgt = wy[a] * wx[b];
+          const float* s = &src[static_cast<size_t>(1 + yy * g0 + xx) * kWidth];
+          for (int c = 0; c < kWidth; ++c) o[c] += wgt * s[c];
+        }
+      }
+    }
+  }
+  DevBuf& buf = m->pos_cache[key];
+  CUDA_TRY(buf.reserve(dst.size() * 4));
+  CUDA_TRY(cudaMemcpyAsync(buf.p, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  *out = buf.as<float>();
+  return CLIPEBC_OK;
+}
+
+GemmParams plain(int M, int N, int K, void* out, int ldo, const float* bias, const float* resid = nullptr, int ldr = 0) {
+  GemmParams p = gemm_params_plain(M, N, K);
+  p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
+  return p;
+}
+
+// The ViT blocks + decoder + head for `nw` windows whose patch embeddings are already in m->ws_patch_embed.
+int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int src_pitch, int nw, int hp, int wp,
+                const float* pos, float* exp_out, float* logits_out) {
+  const clipebc_config& c = m->cfg;
+  const bool deep = c.deep_vpt != 0;
+  const int n_prompt_live = deep ? 0 : c.num_vpt;
+  const int n_const = deep ? c.num_vpt : 0;
+  const int npatch = hp * wp;
+  const int T = 1 + n_prompt_live + npatch;
+  const int M = nw * T;
+  const int gh = hp * kPatch / c.reduction, gw = wp * kPatch / c.reduction;
+  const int Hp = gh + 2, Wp = gw + 2;
+  const int Mp = nw * Hp * Wp;
+
+  CUDA_TRY(m->ws_X.reserve(static_cast<size_t>(M) * kWidth * 4));
+  CUDA_TRY(m->ws_Xn.reserve(static_cast<size_t>(M) * kWidth * 2));
+  CUDA_TRY(m->ws_QKV.reserve(static_cast<size_t>(M) * 3 * kWidth * 2));
+  CUDA_TRY(m->ws_AO.reserve(static_cast<size_t>(M) * kWidth * 2));
+  CUDA_TRY(m->ws_Hid.reserve(static_cast<size_t>(M) * kHidden * 2));
+  CUDA_TRY(m->ws_Y.reserve(static_cast<size_t>(nw) * npatch * kWidth * 4));
+  CUDA_TRY(m->ws_Ub.reserve(static_cast<size_t>(Mp) * kWidth * 2));
+  CUDA_TRY(m->ws_Uf.reserve(static_cast<size_t>(Mp) * kWidth * 4));
+  CUDA_TRY(m->ws_D1.reserve(static_cast<size_t>(Mp) * kWidth * 2));
+  CUDA_TRY(m->ws_D2.reserve(static_cast<size_t>(Mp) * 2 * kWidth * 2));
+  CUDA_TRY(m->ws_F.reserve(static_cast<size_t>(Mp) * kEmbed * 4));
+
+  float* X = m->ws_X.as<float>();
+  __nv_bfloat16* Xn = m->ws_Xn.as<__nv_bfloat16>();
+  __nv_bfloat16* QKV = m->ws_QKV.as<__nv_bfloat16>();
+  __nv_bfloat16* AO = m->ws_AO.as<__nv_bfloat16>();
+  __nv_bfloat16* Hid = m->ws_Hid.as<__nv_bfloat16>();
+
+  K_TRY(assemble_tokens(s, m->ws_patch_embed.as<float>(), win_base_dev, src_pitch,
+                        raw_ptr(m, "image_encoder.class_embedding"), pos, raw_ptr(m, "image_encoder.ln_pre.weight"),
+                        raw_ptr(m, "image_encoder.ln_pre.bias"), deep ? nullptr : raw_ptr(m, "vpt_0"), n_prompt_live, nw,
+                        hp, wp, X));
+
+  for (int l = 0; l < kLayers; ++l) {
+    const LayerPack& L = m->layer[l];
+    K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, 1, M, 1, 1, 0));
+    K_TRY(gemm_bf16_tn(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
+                       plain(M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
+    K_TRY(attention_h64(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO));
+    K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
+                       plain(M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
+    K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, 1, M, 1, 1, 0));
+    K_TRY(gemm_bf16_tn(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
+                       plain(M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
+    K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
+                       plain(M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
+  }
+
+  // ln_post on the patch rows only (cls / prompt rows are dropped, model.py:185-188), fp32 out
+  float* Y = m->ws_Y.as<float>();
+  K_TRY(layernorm768(s, X, raw_ptr(m, "image_encoder.ln_post.weight"), raw_ptr(m, "image_encoder.ln_post.bias"), Y, 0,
+                     static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch));
+  __nv_bfloat16* Ub = m->ws_Ub.as<__nv_bfloat16>();
+  float* Uf = m->ws_Uf.as<float>();
+  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf));
+
+  // decoder BasicBlock as two implicit GEMMs over the zero-bordered grid: 9 taps = 9 row-shifted K-segments
+  GemmParams pc = gemm_params_plain(Mp, kWidth, 9 * kWidth);
+  pc.n_seg = 9; pc.seg_kblocks = kWidth / 64;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      pc.seg_row_shift[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
+      pc.seg_col_start[ky * 3 + kx] = 0;
+    }
+  __nv_bfloat16* D1 = m->ws_D1.as<__nv_bfloat16>();
+  __nv_bfloat16* D2 = m->ws_D2.as<__nv_bfloat16>();
+  GemmParams p1 = pc;
+  p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp;
+  K_TRY(gemm_bf16_tn(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
+  GemmParams p2 = pc;
+  p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
+  K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth, m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
+
+  // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
+  GemmParams pp = gemm_params_plain(Mp, kEmbed, 3 * kWidth);
+  pp.n_seg = 3; pp.seg_kblocks = kWidth / 64;
+  pp.seg_col_start[0] = 0; pp.seg_col_start[1] = kWidth; pp.seg_col_start[2] = 0;
+  float* F = m->ws_F.as<float>();
+  pp.out = F; pp.ldo = kEmbed; pp.bias = raw_ptr(m, "projection.bias");
+  K_TRY(gemm_bf16_tn(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
+
+  K_TRY(ebc_head(s, F, m->tmat.as<float>(), raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
+  return CLIPEBC_OK;
+}
+
+int default_chunk(const clipebc_model* m) { return m->cfg.window_chunk > 0 ? m->cfg.window_chunk : 96; }
+
+int check_window_geometry(clipebc_model* m, int h, int w) {
+  if (h <= 0 || w <= 0 || h % kPatch != 0 || w % kPatch != 0)
+    return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of 16");
+  if ((h % m->cfg.reduction) != 0 || (w % m->cfg.reduction) != 0)
+    return fail(CLIPEBC_EINVAL, "window height/width must be multiples of the reduction");
+  const int T = 1 + m->cfg.num_vpt + (h / kPatch) * (w / kPatch);
+  if (T > 256) return fail(CLIPEBC_EINVAL, "window too large: 1 + num_vpt + patches must be <= 256 tokens");
+  return CLIPEBC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* clipebc_last_error(void) { return g_err.c_str(); }
+int clipebc_abi_version(void) { return CLIPEBC_ABI_VERSION; }
+int64_t clipebc_launch_count(void) { return g_launches.load(); }
+
+int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
+  if (!cfg || !out) return fail(CLIPEBC_EINVAL, "null argument");
+  if (cfg->reduction != 8 && cfg->reduction != 16 && cfg->reduction != 32)
+    return fail(CLIPEBC_EINVAL, "reduction must be 8, 16 or 32");
+  if (cfg->input_size <= 0 || cfg->input_size % kPatch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of 16");
+  if (cfg->num_vpt < 0 || cfg->num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
+  if (cfg->num_bins < 1 || cfg->num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
+  clipebc_model* m = new clipebc_model();
+  m->cfg = *cfg;
+  *out = m;
+  return CLIPEBC_OK;
+}
+
+void clipebc_model_destroy(clipebc_model* m) { delete m; }
+
+int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!m || !name || !data || ndim < 0 || (ndim > 0 && !shape)) return fail(CLIPEBC_EINVAL, "null argument");
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail(CLIPEBC_EINVAL, std::string("empty tensor '") + name + "'");
+    numel *= shape[i];
+  }
+  RawTensor& t = m->raw[name];
+  t.shape.assign(shape, shape + ndim);
+  t.numel = numel;
+  CUDA_TRY(t.buf.reserve(static_cast<size_t>(numel) * 4));
+  CUDA_TRY(cudaMemcpy(t.buf.p, data, static_cast<size_t>(numel) * 4, cudaMemcpyDefault));
+  m->packed = false;
+  return CLIPEBC_OK;
+}
+
+int clipebc_model_pack(clipebc_model* m, void* stream_) {
+  if (!m) return fail(CLIPEBC_EINVAL, "null model");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const clipebc_config& c = m->cfg;
+  const int g0 = c.input_size / kPatch;
+  std::string err;
+  const int n_vpt_layers = c.deep_vpt ? kLayers : 1;
+  bool ok = true;
+  if (c.num_vpt > 0)
+    for (int l = 0; l < n_vpt_layers && ok; ++l) ok = check_shape(m, "vpt_" + std::to_string(l), {c.num_vpt, kWidth}, &err);
+  ok = ok && check_shape(m, "logit_scale", {}, &err) &&
+       check_shape(m, "image_encoder.class_embedding", {kWidth}, &err) &&
+       check_shape(m, "image_encoder.positional_embedding", {1 + g0 * g0, kWidth}, &err) &&
+       check_shape(m, "image_encoder.conv1.weight", {kWidth, 3, kPatch, kPatch}, &err) &&
+       check_shape(m, "image_encoder.ln_pre.weight", {kWidth}, &err) && check_shape(m, "image_encoder.ln_pre.bias", {kWidth}, &err) &&
+       check_shape(m, "image_encoder.ln_post.weight", {kWidth}, &err) && check_shape(m, "image_encoder.ln_post.bias", {kWidth}, &err);
+  for (int l = 0; l < kLayers && ok; ++l) {
+    ok = check_shape(m, blk(l, "attn.in_proj_weight"), {3 * kWidth, kWidth}, &err) &&
+         check_shape(m, blk(l, "attn.in_proj_bias"), {3 * kWidth}, &err) &&
+         check_shape(m, blk(l, "attn.out_proj.weight"), {kWidth, kWidth}, &err) &&
+         check_shape(m, blk(l, "attn.out_proj.bias"), {kWidth}, &err) &&
+         check_shape(m, blk(l, "ln_1.weight"), {kWidth}, &err) && check_shape(m, blk(l, "ln_1.bias"), {kWidth}, &err) &&
+         check_shape(m, blk(l, "ln_2.weight"), {kWidth}, &err) && check_shape(m, blk(l, "ln_2.bias"), {kWidth}, &err) &&
+         check_shape(m, blk(l, "mlp.c_fc.weight"), {kHidden, kWidth}, &err) && check_shape(m, blk(l, "mlp.c_fc.bias"), {kHidden}, &err) &&
+         check_shape(m, blk(l, "mlp.c_proj.weight"), {kWidth, kHidden}, &err) && check_shape(m, blk(l, "mlp.c_proj.bias"), {kWidth}, &err);
+  }
+  for (int k = 1; k <= 2 && ok; ++k) {
+    const std::string cv = "image_decoder.0.conv" + std::to_string(k) + ".weight", bn = "image_decoder.0.bn" + std::to_string(k);
+    ok = check_shape(m, cv, {kWidth, kWidth, 3, 3}, &err) && check_shape(m, bn + ".weight", {kWidth}, &err) &&
+         check_shape(m, bn + ".bias", {kWidth}, &err) && check_shape(m, bn + ".running_mean", {kWidth}, &err) &&
+         check_shape(m, bn + ".running_var", {kWidth}, &err);
+  }
+  ok = ok && check_shape(m, "projection.weight", {kEmbed, kWidth, 1, 1}, &err) && check_shape(m, "projection.bias", {kEmbed}, &err) &&
+       check_shape(m, "text_features", {c.num_bins, kEmbed}, &err) && check_shape(m, "anchor_points", {c.num_bins}, &err);
+  if (!ok) return fail(CLIPEBC_ESTATE, "pack: " + err);
+
+  int rc;
+  if ((rc = to_bf16(s, raw_ptr(m, "image_encoder.conv1.weight"), static_cast<int64_t>(kWidth) * kWidth, &m->w_patch))) return rc;
+  for (int l = 0; l < kLayers; ++l) {
+    LayerPack& L = m->layer[l];
+    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * kWidth * kWidth, &L.w_qkv))) return rc;
+    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "attn.out_proj.weight")), static_cast<int64_t>(kWidth) * kWidth, &L.w_out))) return rc;
+    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), static_cast<int64_t>(kHidden) * kWidth, &L.w_fc))) return rc;
+    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "mlp.c_proj.weight")), static_cast<int64_t>(kWidth) * kHidden, &L.w_proj))) return rc;
+    L.b_qkv = raw_ptr(m, blk(l, "attn.in_proj_bias"));
+    L.b_out = raw_ptr(m, blk(l, "attn.out_proj.bias"));
+    L.b_fc = raw_ptr(m, blk(l, "mlp.c_fc.bias"));
+    L.b_proj = raw_ptr(m, blk(l, "mlp.c_proj.bias"));
+    L.ln1_g = raw_ptr(m, blk(l, "ln_1.weight")); L.ln1_b = raw_ptr(m, blk(l, "ln_1.bias"));
+    L.ln2_g = raw_ptr(m, blk(l, "ln_2.weight")); L.ln2_b = raw_ptr(m, blk(l, "ln_2.bias"));
+    if (c.deep_vpt && c.num_vpt > 0) {
+      // constant prompt K/V of layer l: in_proj(LN1_l(vpt_l)) -- same kernels as the live path
+      CUDA_TRY(m->pack_tmp_bf16.reserve(static_cast<size_t>(c.num_vpt) * kWidth * 2));
+      CUDA_TRY(L.const_kv.reserve(static_cast<size_t>(c.num_vpt) * 3 * kWidth * 2));
+      K_TRY(layernorm768(s, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_bf16.p, 1, c.num_vpt, 1, 1, 0));
+      K_TRY(gemm_bf16_tn(s, EPI_BIAS_BF16, m->pack_tmp_bf16.as<__nv_bfloat16>(), c.num_vpt, kWidth, kWidth,
+                         L.w_qkv.as<__nv_bfloat16>(), kWidth,
+                         plain(c.num_vpt, 3 * kWidth, kWidth, L.const_kv.p, 3 * kWidth, L.b_qkv), 0));
+    }
+  }
+  for (int k = 1; k <= 2; ++k) {
+    const std::string cv = "image_decoder.0.conv" + std::to_string(k) + ".weight", bn = "image_decoder.0.bn" + std::to_string(k);
+    DevBuf& W = (k == 1) ? m->w_c1 : m->w_c2;
+    DevBuf& B = (k == 1) ? m->b_c1 : m->b_c2;
+    CUDA_TRY(W.reserve(static_cast<size_t>(kWidth) * 9 * kWidth * 2));
+    CUDA_TRY(B.reserve(kWidth * 4));
+    K_TRY(fold_conv3x3_bn(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".bias"), raw_ptr(m, bn + ".running_mean"),
+                          raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth, kWidth, W.as<__nv_bfloat16>(), B.as<float>()));
+  }
+  CUDA_TRY(m->w_p3.reserve(static_cast<size_t>(kEmbed) * 3 * kWidth * 2));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), kEmbed, kWidth, m->w_p3.as<__nv_bfloat16>()));
+  CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * kEmbed * 4));
+  K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, kEmbed, m->tmat.as<float>()));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  m->pos_cache.clear();
+  m->packed = true;
+  return CLIPEBC_OK;
+}
+
+int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, int w, float* exp_out_dev,
+                            float* logits_out_dev, void* stream_) {
+  if (!m || !x_dev || !exp_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
+  if (B <= 0) return fail(CLIPEBC_EINVAL, "batch must be positive");
+  int rc;
+  if ((rc = check_window_geometry(m, h, w))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int hp = h / kPatch, wp = w / kPatch, npatch = hp * wp;
+  const int gh = h / m->cfg.reduction, gw = w / m->cfg.reduction;
+  const float* pos;
+  if ((rc = get_pos(m, hp, wp, s, &pos))) return rc;
+
+  const int64_t rows = static_cast<int64_t>(B) * npatch;
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * kWidth * 2));
+  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
+  K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
+                     kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+  // window b reads patch rows [b * npatch, (b+1) * npatch)
+  std::vector<int> base(B);
+  for (int b = 0; b < B; ++b) base[b] = b * npatch;
+  CUDA_TRY(m->ws_idx.reserve(static_cast<size_t>(B) * 4));
+  CUDA_TRY(cudaMemcpyAsync(m->ws_idx.p, base.data(), static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // `base` is pageable host memory
+
+  const int chunk = default_chunk(m);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nw = std::min(chunk, B - b0);
+    float* lo = logits_out_dev ? logits_out_dev + static_cast<int64_t>(b0) * m->cfg.num_bins * gh * gw : nullptr;
+    if ((rc = run_windows(m, s, m->ws_idx.as<int>() + b0, wp, nw, hp, wp, pos,
+                          exp_out_dev + static_cast<int64_t>(b0) * gh * gw, lo)))
+      return rc;
+  }
+  return CLIPEBC_OK;
+}
+
+int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_rows, int* n_cols, int* row_origins,
+                           int* col_origins) {
+  if (!n_rows || !n_cols) return fail(CLIPEBC_EINVAL, "null argument");
+  if (wh <= 0 || ww <= 0 || sh <= 0 || sw <= 0) return fail(CLIPEBC_EINVAL, "window size and stride must be positive");
+  if (sh > wh || sw > ww) return fail(CLIPEBC_EINVAL, "stride must not exceed the window size");
+  if (H < wh || W < ww) return fail(CLIPEBC_EINVAL, "image smaller than the window");
+  // int(np.ceil((H - h) / s) + 1)   (utils/eval_utils.py:54-55)
+  const int nr = (H - wh + sh - 1) / sh + 1, nc = (W - ww + sw - 1) / sw + 1;
+  *n_rows = nr; *n_cols = nc;
+  if (row_origins)
+    for (int i = 0; i < nr; ++i) { int x0 = i * sh; if (x0 + wh > H) x0 = H - wh; row_origins[i] = x0; }
+  if (col_origins)
+    for (int j = 0; j < nc; ++j) { int y0 = j * sw; if (y0 + ww > W) y0 = W - ww; col_origins[j] = y0; }
+  return CLIPEBC_OK;
+}
+
+int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int H, int W, int wh, int ww, int sh,
+                                   int sw, float* density_out_dev, float* count_out_dev, void* stream_) {
+  if (!m || !image_dev || !density_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
+  int rc, nr = 0, nc = 0;
+  if ((rc = clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, nullptr, nullptr))) return rc;
+  if ((rc = check_window_geometry(m, wh, ww))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int r = m->cfg.reduction;
+  std::vector<int> ro(nr), co(nc);
+  clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, ro.data(), co.data());
+  const int n_win = nr * nc;
+  const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
+  const int gh = wh / r, gw = ww / r;
+  const float* pos;
+  if ((rc = get_pos(m, hp, wp, s, &pos))) return rc;
+
+  bool on_grid = true;
+  for (int v : ro) on_grid = on_grid && (v % kPatch == 0);
+  for (int v : co) on_grid = on_grid && (v % kPatch == 0);
+
+  // host-side index tables: [0, n_win) win_base | [n_win, 3 n_win) origins (y, x) | row cells | col cells
+  std::vector<int> tab(static_cast<size_t>(3) * n_win + nr + nc);
+  int src_pitch;
+  int64_t rows;
+  if (on_grid) {
+    // one patch grid per image, shared by all overlapping windows (the unfold never materialises windows)
+    const int GH = H / kPatch, GW = W / kPatch;
+    rows = static_cast<int64_t>(GH) * GW;
+    src_pitch = GW;
+    for (int i = 0; i < nr; ++i)
+      for (int j = 0; j < nc; ++j) tab[i * nc + j] = (ro[i] / kPatch) * GW + co[j] / kPatch;
+  } else {
+    rows = static_cast<int64_t>(n_win) * npatch;
+    src_pitch = wp;
+    for (int k = 0; k < n_win; ++k) tab[k] = k * npatch;
+  }
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j) {
+      tab[n_win + 2 * (i * nc + j)] = ro[i];
+      tab[n_win + 2 * (i * nc + j) + 1] = co[j];
+    }
+  for (int i = 0; i < nr; ++i) tab[3 * n_win + i] = ro[i] / r;       // x_start // reduction (eval_utils.py:90)
+  for (int j = 0; j < nc; ++j) tab[3 * n_win + nr + j] = co[j] / r;
+  CUDA_TRY(m->ws_idx.reserve(tab.size() * 4));
+  CUDA_TRY(cudaMemcpyAsync(m->ws_idx.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const int* d_base = m->ws_idx.as<int>();
+  const int* d_orig = d_base + n_win;
+  const int* d_rc = d_base + 3 * n_win;
+  const int* d_cc = d_rc + nr;
+
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * kWidth * 2));
+  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
+  if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.as<__nv_bfloat16>()));
+  else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
+                     kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+
+  CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
+  float* preds = m->ws_preds.as<float>();
+  const int chunk = default_chunk(m);
+  for (int b0 = 0; b0 < n_win; b0 += chunk) {
+    const int nw = std::min(chunk, n_win - b0);
+    if ((rc = run_windows(m, s, d_base + b0, src_pitch, nw, hp, wp, pos, preds + static_cast<int64_t>(b0) * gh * gw, nullptr)))
+      return rc;
+  }
+  K_TRY(fold_average(s, preds, d_rc, d_cc, nr, nc, gh, gw, H / r, W / r, density_out_dev, count_out_dev));
+  return CLIPEBC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single kernels
+int clipebc_f32_to_bf16(const float* in_dev, void* out, int64_t n, void* stream) {
+  K_TRY(f32_to_bf16(static_cast<cudaStream_t>(stream), in_dev, static_cast<__nv_bfloat16*>(out), n));
+  return CLIPEBC_OK;
+}
+
+int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* W, int64_t ldw,
+                      int M, int N, int K, int n_seg, const int* seg_row_shift, const int* seg_col_start, void* out,
+                      int ldo, const float* bias, const float* resid, int ldr, int mask_hp, int mask_wp, int block_n,
+                      void* stream) {
+  if (!A || !W || !out) return fail(CLIPEBC_EINVAL, "null argument");
+  if (n_seg < 1 || n_seg > kMaxGemmSegs) return fail(CLIPEBC_EINVAL, "n_seg must be in 1..9");
+  if (K <= 0 || K % (64 * n_seg) != 0) return fail(CLIPEBC_EINVAL, "K must be a positive multiple of 64 * n_seg");
+  GemmParams p = gemm_params_plain(M, N, K);
+  p.n_seg = n_seg;
+  p.seg_kblocks = K / 64 / n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    p.seg_row_shift[i] = seg_row_shift ? seg_row_shift[i] : 0;
+    p.seg_col_start[i] = seg_col_start ? seg_col_start[i] : 0;
+  }
+  p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp;
+  const char* e = gemm_bf16_tn(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
+                               lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);
+  if (e) return fail(std::strncmp(e, "gemm:", 5) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
+  return CLIPEBC_OK;
+}
+
+int clipebc_layernorm768(const float* in, const float* g, const float* b, void* out, int out_is_bf16, int64_t n_rows_out,
+                         int rows_out_per_group, int rows_in_per_group, int in_row_offset, void* stream) {
+  K_TRY(layernorm768(static_cast<cudaStream_t>(stream), in, g, b, out, out_is_bf16, n_rows_out, rows_out_per_group,
+                     rows_in_per_group, in_row_offset));
+  return CLIPEBC_OK;
+}
+
+int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_win, int t_live, void* out, void* stream) {
+  K_TRY(attention_h64(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
+                      static_cast<const __nv_bfloat16*>(const_kv), n_const, n_win, t_live, static_cast<__nv_bfloat16*>(out)));
+  return CLIPEBC_OK;
+}
+
+int clipebc_patchify16(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, void* out, void* stream) {
+  K_TRY(patchify16(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, static_cast<__nv_bfloat16*>(out)));
+  return CLIPEBC_OK;
+}
+
+int clipebc_resample_to_padded(const float* Y, int n_win, int hp, int wp, int gh, int gw, void* Ub, float* Uf, void* stream) {
+  K_TRY(resample_to_padded(static_cast<cudaStream_t>(stream), Y, n_win, hp, wp, gh, gw, static_cast<__nv_bfloat16*>(Ub), Uf));
+  return CLIPEBC_OK;
+}
+
+int clipebc_ebc_head(const float* F, const float* tmat, const float* anchors, int n_bins, int n_win, int gh, int gw,
+                     float* exp_out, float* logits_out, void* stream) {
+  K_TRY(ebc_head(static_cast<cudaStream_t>(stream), F, tmat, anchors, n_bins, n_win, gh, gw, exp_out, logits_out));
+  return CLIPEBC_OK;
+}
+
+int clipebc_fold_average(const float* preds, const int* row_cells_host, const int* col_cells_host, int n_rows, int n_cols,
+                         int gh, int gw, int Ho, int Wo, float* density, float* count, void* stream_) {
+  if (!preds || !row_cells_host || !col_cells_host || !density) return fail(CLIPEBC_EINVAL, "null argument");
+  if (n_rows <= 0 || n_cols <= 0) return fail(CLIPEBC_EINVAL, "fold: no windows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, static_cast<size_t>(n_rows + n_cols) * 4));
+  cudaError_t e = cudaMemcpyAsync(d, row_cells_host, static_cast<size_t>(n_rows) * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + n_rows, col_cells_host, static_cast<size_t>(n_cols) * 4, cudaMemcpyHostToDevice, s);
+  const char* msg = nullptr;
+  if (e == cudaSuccess) msg = fold_average(s, preds, d, d + n_rows, n_rows, n_cols, gh, gw, Ho, Wo, density, count);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail_cuda(e, "fold upload");
+  if (msg) return fail(CLIPEBC_ECUDA, msg);
+  if (e2 != cudaSuccess) return fail_cuda(e2, "fold sync");
+  return CLIPEBC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// HBM-bound kernels of the CLIP-EBC hot path: LayerNorm, window unfold / patchify, token assembly (cls + pos + ln_pre
+// + VPT splice), bilinear resample onto the zero-bordered decoder grid, and the pack-time weight transforms.
+// All are one-warp-per-row (768 channels = 6 x 128-bit per lane) or one-thread-per-vector kernels with coalesced,
+// vectorised global accesses and warp-shuffle reductions.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cebc {
+
+namespace {
+
+constexpr int kD = 768;
+constexpr int kVecPerLane = kD / 4 / 32;  // 6 float4 per lane
+
+struct Row768 {
+  float4 v[kVecPerLane];
+};
+
+__device__ __forceinline__ Row768 load_row(const float* p, int lane) {
+  Row768 r;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) r.v[i] = p4[i * 32 + lane];
+  return r;
+}
+__device__ __forceinline__ Row768 load_row_ldg(const float* p, int lane) {
+  Row768 r;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) r.v[i] = __ldg(p4 + i * 32 + lane);
+  return r;
+}
+__device__ __forceinline__ void add_row(Row768& a, const Row768& b) {
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    a.v[i].x += b.v[i].x; a.v[i].y += b.v[i].y; a.v[i].z += b.v[i].z; a.v[i].w += b.v[i].w;
+  }
+}
+// nn.LayerNorm(768, eps=1e-5) on one row held by a warp (reference: blocks.py:8-14); two-pass statistics in fp32.
+__device__ __forceinline__ void layernorm_row(Row768& r, const float* gamma, const float* beta, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+    r.v[i].x = (r.v[i].x - mean) * rstd * g.x + b.x;
+    r.v[i].y = (r.v[i].y - mean) * rstd * g.y + b.y;
+    r.v[i].z = (r.v[i].z - mean) * rstd * g.z + b.z;
+    r.v[i].w = (r.v[i].w - mean) * rstd * g.w + b.w;
+  }
+}
+__device__ __forceinline__ void store_row_f32(float* p, const Row768& r, int lane) {
+  float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) p4[i * 32 + lane] = r.v[i];
+}
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* p, const Row768& r, int lane) {
+  uint2* p2 = reinterpret_cast<uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i)
+    p2[i * 32 + lane] = make_uint2(pack_bf16x2(r.v[i].x, r.v[i].y), pack_bf16x2(r.v[i].z, r.v[i].w));
+}
+
+// ------------------------------------------------------------------ LayerNorm ----------------------------------
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, void* __restrict__ out,
+                                                           int64_t n_rows_out, int rows_out_per_group,
+                                                           int rows_in_per_group, int in_row_offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows_out;
+       r += warps_total) {
+    const int64_t g = r / rows_out_per_group;
+    const int64_t in_row = g * rows_in_per_group + in_row_offset + (r - g * rows_out_per_group);
+    Row768 x = load_row(in + in_row * kD, lane);
+    layernorm_row(x, gamma, beta, lane);
+    if constexpr (OUT_BF16)
+      store_row_bf16(static_cast<__nv_bfloat16*>(out) + r * kD, x, lane);
+    else
+      store_row_f32(static_cast<float*>(out) + r * kD, x, lane);
+  }
+}
+
+// ------------------------------------------------------------------ patchify -----------------------------------
+// One thread per 4 horizontally adjacent pixels; consecutive threads walk along an image row (coalesced 16B reads),
+// each writes 4 bf16 (8 B) into its patch row; 4 consecutive threads fill one 32 B sector.
+__global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict__ image, int n_img, int H, int W,
+                                                         int y0, int x0, int gh, int gw,
+                                                         __nv_bfloat16* __restrict__ out) {
+  const int64_t quads_per_row = static_cast<int64_t>(gw) * 4;            // 4 quads per patch row of 16 px
+  const int64_t per_img = static_cast<int64_t>(3) * gh * 16 * quads_per_row;
+  const int64_t total = per_img * n_img;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t t = idx;
+    const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
+    const int yy = static_cast<int>(t % (gh * 16)); t /= (gh * 16);
+    const int c = static_cast<int>(t % 3);
+    const int img = static_cast<int>(t / 3);
+    const int gx = qx >> 2, px4 = qx & 3;
+    const int gy = yy >> 4, py = yy & 15;
+    const float* src = image + ((static_cast<int64_t>(img) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * 4;
+    float4 v;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      v = *reinterpret_cast<const float4*>(src);
+    } else {
+      v = make_float4(src[0], src[1], src[2], src[3]);
+    }
+    const int64_t patch = (static_cast<int64_t>(img) * gh + gy) * gw + gx;
+    uint2* dst = reinterpret_cast<uint2*>(out + patch * kD + c * 256 + py * 16 + px4 * 4);
+    *dst = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __restrict__ image, int H, int W,
+                                                                 const int* __restrict__ origins_yx, int n_win, int hp,
+                                                                 int wp, __nv_bfloat16* __restrict__ out) {
+  const int64_t quads_per_row = static_cast<int64_t>(wp) * 4;
+  const int64_t per_win = static_cast<int64_t>(3) * hp * 16 * quads_per_row;
+  const int64_t total = per_win * n_win;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t t = idx;
+    const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
+    const int yy = static_cast<int>(t % (hp * 16)); t /= (hp * 16);
+    const int c = static_cast<int>(t % 3);
+    const int win = static_cast<int>(t / 3);
+    const int oy = origins_yx[2 * win], ox = origins_yx[2 * win + 1];
+    const int gx = qx >> 2, px4 = qx & 3;
+    const int gy = yy >> 4, py = yy & 15;
+    const float* src = image + (static_cast<int64_t>(c) * H + (oy + yy)) * W + ox + qx * 4;
+    const float4 v = make_float4(src[0], src[1], src[2], src[3]);
+    const int64_t patch = (static_cast<int64_t>(win) * hp + gy) * wp + gx;
+    uint2* dst = reinterpret_cast<uint2*>(out + patch * kD + c * 256 + py * 16 + px4 * 4);
+    *dst = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------ token assembly -----------------------------
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch_embed,
+                                                              const int* __restrict__ win_base, int src_pitch,
+                                                              const float* __restrict__ class_emb,
+                                                              const float* __restrict__ pos,
+                                                              const float* __restrict__ ln_g,
+                                                              const float* __restrict__ ln_b,
+                                                              const float* __restrict__ vpt0, int n_prompt, int n_win,
+                                                              int hp, int wp, float* __restrict__ X) {
+  const int lane = threadIdx.x & 31;
+  const int t_live = 1 + n_prompt + hp * wp;
+  const int64_t n_rows = static_cast<int64_t>(n_win) * t_live;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
+       r += warps_total) {
+    const int win = static_cast<int>(r / t_live);
+    const int t = static_cast<int>(r - static_cast<int64_t>(win) * t_live);
+    Row768 x;
+    if (t == 0) {
+      x = load_row_ldg(class_emb, lane);
+      add_row(x, load_row_ldg(pos, lane));
+      layernorm_row(x, ln_g, ln_b, lane);
+    } else if (t <= n_prompt) {
+      x = load_row_ldg(vpt0 + static_cast<int64_t>(t - 1) * kD, lane);  // prompts join after ln_pre (model.py:161-168)
+    } else {
+      const int pidx = t - 1 - n_prompt;
+      const int py = pidx / wp, px = pidx - py * wp;
+      const int64_t src = static_cast<int64_t>(win_base[win]) + static_cast<int64_t>(py) * src_pitch + px;
+      x = load_row(patch_embed + src * kD, lane);
+      add_row(x, load_row_ldg(pos + static_cast<int64_t>(1 + pidx) * kD, lane));
+      layernorm_row(x, ln_g, ln_b, lane);
+    }
+    store_row_f32(X + r * kD, x, lane);
+  }
+}
+
+// ------------------------------------------------------------------ resample -----------------------------------
+// PyTorch upsample_bilinear2d, align_corners=False, scale_factor given: src = (dst + 0.5) / scale - 0.5, clamped at 0.
+__device__ __forceinline__ void bilinear_src(int dst, float inv_scale, int in_size, int& i0, int& i1, float& lam) {
+  float s = (dst + 0.5f) * inv_scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = static_cast<int>(s);
+  i0 = i0 > in_size - 1 ? in_size - 1 : i0;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  lam = s - static_cast<float>(i0);
+}
+
+__global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __restrict__ Y, int n_win, int hp, int wp,
+                                                                 int gh, int gw, __nv_bfloat16* __restrict__ U_bf16,
+                                                                 float* __restrict__ U_f32) {
+  const int lane = threadIdx.x & 31;
+  const int Hp = gh + 2, Wp = gw + 2;
+  const int64_t n_rows = static_cast<int64_t>(n_win) * Hp * Wp;
+  const float inv_sy = static_cast<float>(hp) / static_cast<float>(gh);
+  const float inv_sx = static_cast<float>(wp) / static_cast<float>(gw);
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
+       r += warps_total) {
+    const int win = static_cast<int>(r / (Hp * Wp));
+    const int q = static_cast<int>(r - static_cast<int64_t>(win) * Hp * Wp);
+    const int py = q / Wp, px = q - py * Wp;
+    Row768 o;
+    if (py == 0 || py == Hp - 1 || px == 0 || px == Wp - 1) {
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) o.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (gh == hp && gw == wp) {
+      o = load_row(Y + (static_cast<int64_t>(win) * hp * wp + static_cast<int64_t>(py - 1) * wp + (px - 1)) * kD, lane);
+    } else {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(py - 1, inv_sy, hp, y0, y1, ly);
+      bilinear_src(px - 1, inv_sx, wp, x0, x1, lx);
+      const float* base = Y + static_cast<int64_t>(win) * hp * wp * kD;
+      const Row768 a = load_row(base + (static_cast<int64_t>(y0) * wp + x0) * kD, lane);
+      const Row768 b = load_row(base + (static_cast<int64_t>(y0) * wp + x1) * kD, lane);
+      const Row768 c = load_row(base + (static_cast<int64_t>(y1) * wp + x0) * kD, lane);
+      const Row768 d = load_row(base + (static_cast<int64_t>(y1) * wp + x1) * kD, lane);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) {
+        o.v[i].x = w00 * a.v[i].x + w01 * b.v[i].x + w10 * c.v[i].x + w11 * d.v[i].x;
+        o.v[i].y = w00 * a.v[i].y + w01 * b.v[i].y + w10 * c.v[i].y + w11 * d.v[i].y;
+        o.v[i].z = w00 * a.v[i].z + w01 * b.v[i].z + w10 * c.v[i].z + w11 * d.v[i].z;
+        o.v[i].w = w00 * a.v[i].w + w01 * b.v[i].w + w10 * c.v[i].w + w11 * d.v[i].w;
+      }
+    }
+    store_row_bf16(U_bf16 + r * kD, o, lane);
+    store_row_f32(U_f32 + r * kD, o, lane);
+  }
+}
+
+// ------------------------------------------------------------------ pack-time ----------------------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// BN(eval) folds exactly into the bias-free conv: W' = W * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)
+// (reference: models/utils.py:290-303 with nn.BatchNorm2d in eval mode).
+__global__ void fold_conv3x3_bn_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                       const float* __restrict__ var, float eps, int O, int I,
+                                       __nv_bfloat16* __restrict__ Wp, float* __restrict__ bias) {
+  const int64_t total = static_cast<int64_t>(O) * I * 9;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // idx enumerates the destination [O][tap][I]
+    const int i = static_cast<int>(idx % I);
+    const int tap = static_cast<int>((idx / I) % 9);
+    const int o = static_cast<int>(idx / (static_cast<int64_t>(I) * 9));
+    const float s = gamma[o] / sqrtf(var[o] + eps);
+    Wp[idx] = __float2bfloat16_rn(W[(static_cast<int64_t>(o) * I + i) * 9 + tap] * s);
+    if (i == 0 && tap == 0) bias[o] = beta[o] - mean[o] * s;
+  }
+}
+
+__global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(O) * I;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % I);
+    const int64_t o = idx / I;
+    const float w = W[idx];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    __nv_bfloat16* row = out + o * 3 * I;
+    row[i] = hi;
+    row[I + i] = hi;
+    row[2 * I + i] = lo;
+  }
+}
+
+// F.normalize(text, p=2, dim=-1) (eps 1e-12) scaled by exp(logit_scale)  (model.py:204,207-208); one warp per bin
+__global__ void pack_text_kernel(const float* __restrict__ text, const float* __restrict__ logit_scale, int n, int d,
+                                 float* __restrict__ tmat) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) { const float v = text[static_cast<int64_t>(row) * d + i]; s += v * v; }
+  s = warp_sum(s);
+  const float scale = expf(logit_scale[0]) / fmaxf(sqrtf(s), 1e-12f);
+  for (int i = lane; i < d; i += 32) tmat[static_cast<int64_t>(row) * d + i] = text[static_cast<int64_t>(row) * d + i] * scale;
+}
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+inline const char* last_err() {
+  note_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
+                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int in_row_offset) {
+  if (n_rows_out <= 0) return nullptr;
+  if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
+  const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
+  if (out_is_bf16)
+    layernorm768_kernel<true><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
+                                                          rows_in_per_group, in_row_offset);
+  else
+    layernorm768_kernel<false><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
+                                                           rows_in_per_group, in_row_offset);
+  return last_err();
+}
+
+const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
+                       __nv_bfloat16* out) {
+  if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
+  if (y0 < 0 || x0 < 0 || y0 + gh * 16 > H || x0 + gw * 16 > W) return "patchify: grid exceeds image";
+  const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * 16 * gw * 4;
+  patchify16_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, n_img, H, W, y0, x0, gh, gw,
+                                                                                     out);
+  return last_err();
+}
+
+const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
+                               int n_win, int hp, int wp, __nv_bfloat16* out) {
+  if (n_win <= 0) return "patchify: no windows";
+  const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * 16 * wp * 4;
+  patchify16_windows_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, H, W, origins_yx_dev,
+                                                                                             n_win, hp, wp, out);
+  return last_err();
+}
+
+const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
+                            const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X) {
+  if (n_win <= 0) return "assemble_tokens: no windows";
+  if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
+  const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
+  assemble_tokens_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(
+      patch_embed, win_base_dev, src_pitch, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
+  return last_err();
+}
+
+const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
+                               __nv_bfloat16* U_bf16, float* U_f32) {
+  if (n_win <= 0) return "resample: no windows";
+  const int64_t rows = static_cast<int64_t>(n_win) * (gh + 2) * (gw + 2);
+  resample_to_padded_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(Y, n_win, hp, wp, gh, gw, U_bf16,
+                                                                                         U_f32);
+  return last_err();
+}
+
+const char* f32_to_bf16(cudaStream_t stream, const float* in, __nv_bfloat16* out, int64_t n) {
+  if (n <= 0) return nullptr;
+  f32_to_bf16_kernel<<<grid_for(n, 256, 4096), 256, 0, stream>>>(in, out, n);
+  return last_err();
+}
+
+const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
+                            const float* var, float eps, int O, int I, __nv_bfloat16* Wp, float* bias) {
+  fold_conv3x3_bn_kernel<<<grid_for(static_cast<int64_t>(O) * I * 9, 256, 4096), 256, 0, stream>>>(W, gamma, beta, mean,
+                                                                                                   var, eps, O, I, Wp, bias);
+  return last_err();
+}
+
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, __nv_bfloat16* out) {
+  split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(W, O, I, out);
+  return last_err();
+}
+
+const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat) {
+  if (n <= 0) return "pack_text: no bins";
+  pack_text_kernel<<<(n + 3) / 4, 128, 0, stream>>>(text, logit_scale, n, d, tmat);
+  return last_err();
+}
+
+}  // namespace cebc

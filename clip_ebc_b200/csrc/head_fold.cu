@@ -1,0 +1,139 @@
+// EBC head (L2-normalise -> cosine logits against the fixed bin text embeddings -> softmax -> anchor expectation) and
+// the overlapping-window fold/average as an atomic-free gather, plus the per-image count reduction.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cebc {
+
+namespace {
+
+constexpr int kE = 512;  // CLIP embed dim of ViT-B/16
+
+// One warp per interior cell of the padded decoder grid. Reference: models/clip/model.py:200-212
+//   f^ = f / max(||f||, 1e-12);  logits = (exp(logit_scale) * f^) @ t^T;  probs = softmax;  exp = sum probs * anchor
+// tmat already holds exp(logit_scale) * t^ (pack_text).
+__global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__ F, const float* __restrict__ tmat,
+                                                       const float* __restrict__ anchors, int n_bins, int n_win, int gh,
+                                                       int gw, float* __restrict__ exp_out,
+                                                       float* __restrict__ logits_out) {
+  const int lane = threadIdx.x & 31;
+  const int Hp = gh + 2, Wp = gw + 2;
+  const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t cell = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < n_cells;
+       cell += warps_total) {
+    const int win = static_cast<int>(cell / (gh * gw));
+    const int q = static_cast<int>(cell - static_cast<int64_t>(win) * gh * gw);
+    const int y = q / gw, x = q - y * gw;
+    const int64_t row = (static_cast<int64_t>(win) * Hp + (y + 1)) * Wp + (x + 1);
+    const float4* f4 = reinterpret_cast<const float4*>(F + row * kE);
+    float4 f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = f4[i * 32 + lane];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ss += (f[i].x * f[i].x + f[i].y * f[i].y) + (f[i].z * f[i].z + f[i].w * f[i].w);
+    ss = warp_sum(ss);
+    const float inv_norm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+
+    float my_logit = -INFINITY;
+    for (int b = 0; b < n_bins; ++b) {
+      const float4* t4 = reinterpret_cast<const float4*>(tmat + static_cast<int64_t>(b) * kE);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(t4 + i * 32 + lane);
+        d += (f[i].x * t.x + f[i].y * t.y) + (f[i].z * t.z + f[i].w * t.w);
+      }
+      d = warp_sum(d) * inv_norm;
+      if (lane == b) my_logit = d;
+    }
+    const float mx = warp_max(my_logit);
+    const float e = (lane < n_bins) ? __expf(my_logit - mx) : 0.f;
+    const float den = warp_sum(e);
+    const float num = warp_sum(lane < n_bins ? e * __ldg(anchors + lane) : 0.f);
+    if (lane == 0) exp_out[cell] = num / den;
+    if (logits_out != nullptr && lane < n_bins)
+      logits_out[((static_cast<int64_t>(win) * n_bins + lane) * gh + y) * gw + x] = my_logit;
+  }
+}
+
+// One thread per output cell; windows covering the cell are visited in ascending window index (row-major i, j), which
+// reproduces the fp32 summation order of the reference loop (utils/eval_utils.py:79-95) bit for bit. No atomics.
+__global__ void __launch_bounds__(256) fold_average_kernel(const float* __restrict__ preds,
+                                                           const int* __restrict__ row_cells,
+                                                           const int* __restrict__ col_cells, int n_rows, int n_cols,
+                                                           int gh, int gw, int Ho, int Wo, float* __restrict__ density) {
+  const int64_t total = static_cast<int64_t>(Ho) * Wo;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int oy = static_cast<int>(idx / Wo), ox = static_cast<int>(idx - static_cast<int64_t>(oy) * Wo);
+    float sum = 0.f, cnt = 0.f;
+    for (int i = 0; i < n_rows; ++i) {
+      const int dy = oy - __ldg(row_cells + i);
+      if (dy < 0 || dy >= gh) continue;
+      for (int j = 0; j < n_cols; ++j) {
+        const int dx = ox - __ldg(col_cells + j);
+        if (dx < 0 || dx >= gw) continue;
+        sum += preds[(static_cast<int64_t>(i) * n_cols + j) * gh * gw + dy * gw + dx];
+        cnt += 1.0f;
+      }
+    }
+    density[idx] = sum / cnt;  // cnt == 0 -> NaN, as numpy's 0/0 in the reference
+  }
+}
+
+// Deterministic single-block sum (fixed association order, independent of grid size / GPU count).
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float sh[1024];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+inline const char* last_err() {
+  note_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
+                     int n_win, int gh, int gw, float* exp_out, float* logits_out) {
+  if (n_bins < 1 || n_bins > 32) return "ebc_head: 1..32 bins supported";
+  if (n_win <= 0) return "ebc_head: no windows";
+  const int64_t cells = static_cast<int64_t>(n_win) * gh * gw;
+  int64_t blocks = (cells + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  ebc_head_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(F, tmat, anchors, n_bins, n_win, gh, gw, exp_out,
+                                                                logits_out);
+  return last_err();
+}
+
+const char* fold_average(cudaStream_t stream, const float* preds, const int* row_cells_dev, const int* col_cells_dev,
+                         int n_rows, int n_cols, int gh, int gw, int Ho, int Wo, float* density, float* count_out) {
+  if (n_rows <= 0 || n_cols <= 0 || Ho <= 0 || Wo <= 0) return "fold: empty problem";
+  const int64_t total = static_cast<int64_t>(Ho) * Wo;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  fold_average_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(preds, row_cells_dev, col_cells_dev, n_rows, n_cols,
+                                                                    gh, gw, Ho, Wo, density);
+  const char* e = last_err();
+  if (e) return e;
+  if (count_out != nullptr) {
+    sum_kernel<<<1, 1024, 0, stream>>>(density, total, count_out);
+    return last_err();
+  }
+  return nullptr;
+}
+
+}  // namespace cebc

@@ -1,0 +1,111 @@
+// Internal (C++) launcher contracts for the sm_100a kernels of the CLIP-EBC hot path.
+// The public C-ABI lives in include/clipebc_b200.h; api.cu maps one onto the other.
+// Launchers return nullptr on success or a static error string (no exceptions, no torch types).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace cebc {
+
+// ------------------------------------------------------------------ GEMM ---------------------------------------
+enum GemmEpilogue : int {
+  EPI_F32 = 0,                  // out f32 = acc (+ bias if given)
+  EPI_BIAS_F32 = 1,             // out f32 = acc + bias
+  EPI_BIAS_BF16 = 2,            // out bf16 = acc + bias
+  EPI_BIAS_GELU_BF16 = 3,       // out bf16 = quickgelu(acc + bias)
+  EPI_BIAS_RESID_F32 = 4,       // out f32 = acc + bias + resid   (out may alias resid)
+  EPI_BIAS_RELU_MASK_BF16 = 5,  // out bf16 = border ? 0 : relu(acc + bias)          (decoder conv1 on the padded grid)
+  EPI_BIAS_RESID_RELU_SPLIT = 6 // t = relu(acc + bias + resid); out[:, n] = hi(t), out[:, N + n] = lo(t)  (bf16 pair)
+};
+
+constexpr int kMaxGemmSegs = 9;
+
+struct GemmParams {
+  int M, N, K;                        // K = n_seg * seg_kblocks * 64
+  int n_seg, seg_kblocks;             // A-operand K-segments
+  int seg_row_shift[kMaxGemmSegs];    // A row offset of each segment (may be negative: TMA zero-fills OOB rows)
+  int seg_col_start[kMaxGemmSegs];    // A column start of each segment
+  void* out;                          // f32 or bf16, see epilogue
+  int ldo;                            // elements
+  const float* bias;                  // [N]
+  const float* resid;                 // f32 [M, ldr]
+  int ldr;
+  int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
+};
+
+inline GemmParams gemm_params_plain(int M, int N, int K) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.n_seg = 1; p.seg_kblocks = K / 64;
+  return p;
+}
+
+// D[M,N] = A[M,K] * W[N,K]^T. A: bf16 [a_rows, a_cols] pitch lda; W: bf16 [N, K] pitch ldw. block_n: 0 = auto.
+const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
+                         int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
+int device_num_sms();
+// every kernel launch of this library is counted (clipebc_launch_count in the C-ABI)
+void note_launch(int n = 1);
+
+// ------------------------------------------------------------------ LayerNorm ----------------------------------
+// out[r] = LN(in[map(r)]) * gamma + beta, eps 1e-5, fp32 statistics (two-pass, in registers). D = 768 only.
+// Row map: in_row = (r / rows_out_per_group) * rows_in_per_group + in_row_offset + r % rows_out_per_group.
+const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
+                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int in_row_offset);
+
+// ------------------------------------------------------------------ stem ---------------------------------------
+// image f32 [n_img, 3, H, W] -> patch rows bf16 [n_img * gh * gw, 768], k = c*256 + py*16 + px, on the grid whose
+// (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches).
+const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
+                       __nv_bfloat16* out);
+// per-window patchify when window origins are not on the 16-pixel grid: out rows [n_win * hp * wp, 768]
+const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
+                               int n_win, int hp, int wp, __nv_bfloat16* out);
+
+// Assemble the residual stream X f32 [n_win * t_live, 768]:
+//   row 0            : LN_pre(class_emb + pos[0])
+//   rows 1..n_prompt : vpt0 rows (shallow VPT only; n_prompt = 0 for deep)            (model.py:161-168)
+//   remaining rows   : LN_pre(patch_embed[src_row(win, p)] + pos[1 + p])              (model.py:147-157)
+// src_row = win_base[win] + (p / wp) * src_pitch + p % wp  (gather from a shared per-image patch grid or per-window rows)
+const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
+                            const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X);
+
+// ------------------------------------------------------------------ attention ----------------------------------
+// qkv bf16 [n_win * t_live, 3*768] (q | k | v, head h at columns 64h..64h+63 of each third); const_kv bf16
+// [n_const, 3*768] rows appended as extra keys/values for every window (deep-VPT prompt tokens); out bf16
+// [n_win * t_live, 768]. softmax(q k^T / 8) v per (window, head), no mask. t_live + n_const <= 256.
+const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                          int n_win, int t_live, __nv_bfloat16* out);
+
+// ------------------------------------------------------------------ decoder / head -----------------------------
+// Y f32 [n_win * hp * wp, 768] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
+// zero-bordered NHWC grids U_bf16 / U_f32 [n_win, gh + 2, gw + 2, 768]  (model.py:195-196).
+const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
+                               __nv_bfloat16* U_bf16, float* U_f32);
+
+// F f32 [n_win * (gh+2) * (gw+2), 512] projected features on the padded grid -> EBC head on interior cells:
+// normalise, logits against tmat f32 [n_bins, 512] (= logit_scale * normalised text features), softmax, expectation
+// over anchors. exp_out f32 [n_win, 1, gh, gw]; logits_out (nullable) f32 [n_win, n_bins, gh, gw]. (model.py:200-212)
+const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
+                     int n_win, int gh, int gw, float* exp_out, float* logits_out);
+
+// ------------------------------------------------------------------ fold ---------------------------------------
+// preds f32 [n_rows * n_cols, 1, gh, gw] -> density f32 [Ho, Wo]: average of overlapping windows, summed in ascending
+// window order (bit-exact vs the numpy loop of eval_utils.py:79-95); optional per-image sum (count).
+const char* fold_average(cudaStream_t stream, const float* preds, const int* row_cells_dev, const int* col_cells_dev,
+                         int n_rows, int n_cols, int gh, int gw, int Ho, int Wo, float* density, float* count_out);
+
+// ------------------------------------------------------------------ pack-time helpers --------------------------
+const char* f32_to_bf16(cudaStream_t stream, const float* in, __nv_bfloat16* out, int64_t n);
+// W f32 [O, I, 3, 3] + BN(gamma, beta, mean, var, eps) -> Wp bf16 [O, 9*I] (tap-major K: k = (ky*3+kx)*I + i), bias f32 [O]
+const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
+                            const float* var, float eps, int O, int I, __nv_bfloat16* Wp, float* bias);
+// W f32 [O, I] -> bf16 [O, 3*I] = [hi | hi | lo]
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, __nv_bfloat16* out);
+// text f32 [n, d] -> tmat = exp(logit_scale) * text / max(||text||, 1e-12)
+const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat);
+
+}  // namespace cebc

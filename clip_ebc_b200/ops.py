@@ -1,0 +1,138 @@
+"""Thin tensor-level wrappers over the single-kernel C-ABI entry points (tests, profiling, bench).
+
+torch is used for device memory and streams only; all arithmetic happens in ``libclipebc_b200.so``.
+Every wrapper requires CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+EPI_F32, EPI_BIAS_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_RELU_MASK_BF16, \
+    EPI_BIAS_RESID_RELU_SPLIT = range(7)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("clip_ebc_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("clip_ebc_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def window_origins(H: int, W: int, window: Tuple[int, int], stride: Tuple[int, int]):
+    """Host-only integer part of sliding_window_predict (reference utils/eval_utils.py:54-66)."""
+    import ctypes as C
+
+    lib = _lib.load()
+    nr, nc = C.c_int(0), C.c_int(0)
+    _lib.check(lib.clipebc_window_origins(H, W, window[0], window[1], stride[0], stride[1], C.byref(nr), C.byref(nc),
+                                          None, None), "window_origins")
+    ro, co = (C.c_int * nr.value)(), (C.c_int * nc.value)()
+    _lib.check(lib.clipebc_window_origins(H, W, window[0], window[1], stride[0], stride[1], C.byref(nr), C.byref(nc),
+                                          ro, co), "window_origins")
+    return list(ro), list(co)
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().clipebc_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "f32_to_bf16")
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
+         resid: Optional[torch.Tensor] = None, M: Optional[int] = None, K: Optional[int] = None,
+         seg_row_shift: Optional[Sequence[int]] = None, seg_col_start: Optional[Sequence[int]] = None,
+         mask_hw: Tuple[int, int] = (0, 0), block_n: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D = A[M,K] @ W[N,K]^T with a fused epilogue. a, w: bf16 2-D contiguous."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    N = w.shape[0]
+    K = w.shape[1] if K is None else K
+    M = a.shape[0] if M is None else M
+    n_seg = 1 if seg_row_shift is None and seg_col_start is None else len(seg_row_shift or seg_col_start)
+    rs = _lib.int_array(seg_row_shift or [0] * n_seg)
+    cs = _lib.int_array(seg_col_start or [0] * n_seg)
+    if out is None:
+        if epi in (EPI_F32, EPI_BIAS_F32, EPI_BIAS_RESID_F32):
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        elif epi == EPI_BIAS_RESID_RELU_SPLIT:
+            out = torch.empty((M, 2 * N), dtype=torch.bfloat16, device=a.device)
+        else:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.load().clipebc_gemm_bf16(
+        epi, _ptr(a), a.shape[0], a.shape[1], a.stride(0), _ptr(w), w.stride(0), M, N, K, n_seg, rs, cs, _ptr(out),
+        out.stride(0), _ptr(bias), _ptr(resid), resid.stride(0) if resid is not None else 0, mask_hw[0], mask_hw[1],
+        block_n, _stream()), "gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_bf16: bool = True,
+              n_rows_out: Optional[int] = None, rows_out_per_group: int = 1, rows_in_per_group: int = 1,
+              in_row_offset: int = 0) -> torch.Tensor:
+    assert x.dtype == torch.float32 and x.shape[-1] == 768
+    n = x.numel() // 768 if n_rows_out is None else n_rows_out
+    out = torch.empty((n, 768), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    _lib.check(_lib.load().clipebc_layernorm768(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), int(out_bf16), n,
+                                                rows_out_per_group, rows_in_per_group, in_row_offset, _stream()),
+               "layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (n_win * t_live, 2304)
+    n_const = 0 if const_kv is None else const_kv.shape[0]
+    out = torch.empty((n_win * t_live, 768), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().clipebc_attention(_ptr(qkv), _ptr(const_kv), n_const, n_win, t_live, _ptr(out), _stream()),
+               "attention")
+    return out
+
+
+def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = None,
+             gw: Optional[int] = None) -> torch.Tensor:
+    n, c, H, W = image.shape
+    assert c == 3 and image.dtype == torch.float32
+    gh = (H - y0) // 16 if gh is None else gh
+    gw = (W - x0) // 16 if gw is None else gw
+    out = torch.empty((n * gh * gw, 768), dtype=torch.bfloat16, device=image.device)
+    _lib.check(_lib.load().clipebc_patchify16(_ptr(image), n, H, W, y0, x0, gh, gw, _ptr(out), _stream()), "patchify")
+    return out
+
+
+def resample_to_padded(Y: torch.Tensor, n_win: int, hp: int, wp: int, gh: int, gw: int):
+    ub = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=torch.bfloat16, device=Y.device)
+    uf = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=torch.float32, device=Y.device)
+    _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, _ptr(ub), _ptr(uf), _stream()),
+               "resample")
+    return ub, uf
+
+
+def ebc_head(F: torch.Tensor, tmat: torch.Tensor, anchors: torch.Tensor, n_win: int, gh: int, gw: int,
+             want_logits: bool = False):
+    n_bins = tmat.shape[0]
+    exp = torch.empty((n_win, 1, gh, gw), dtype=torch.float32, device=F.device)
+    logits = torch.empty((n_win, n_bins, gh, gw), dtype=torch.float32, device=F.device) if want_logits else None
+    _lib.check(_lib.load().clipebc_ebc_head(_ptr(F), _ptr(tmat), _ptr(anchors), n_bins, n_win, gh, gw, _ptr(exp),
+                                            _ptr(logits), _stream()), "ebc_head")
+    return (exp, logits) if want_logits else exp
+
+
+def fold_average(preds: torch.Tensor, row_cells: Sequence[int], col_cells: Sequence[int], Ho: int, Wo: int,
+                 want_count: bool = False):
+    """preds f32 [n_rows*n_cols, 1, gh, gw] (device) -> density [Ho, Wo] (device), optional count [1]."""
+    gh, gw = preds.shape[-2:]
+    assert preds.shape[0] == len(row_cells) * len(col_cells)
+    dens = torch.empty((Ho, Wo), dtype=torch.float32, device=preds.device)
+    cnt = torch.empty((1,), dtype=torch.float32, device=preds.device) if want_count else None
+    _lib.check(_lib.load().clipebc_fold_average(_ptr(preds), _lib.int_array(row_cells), _lib.int_array(col_cells),
+                                                len(row_cells), len(col_cells), gh, gw, Ho, Wo, _ptr(dens), _ptr(cnt),
+                                                _stream()), "fold")
+    return (dens, cnt) if want_count else dens

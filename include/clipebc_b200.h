@@ -1,0 +1,109 @@
+/*
+ * clipebc_b200 -- C-ABI of the B200-native (sm_100a) CLIP-EBC inference hot path.
+ *
+ * Drop-in boundary for the two reference entry points (the reference has no FFI layer of its own; both are Python
+ * callables, see INTEGRATION.md for the ctypes binding a maintainer would add):
+ *
+ *   get_model(...)/model(x)            /root/reference/models/__init__.py:10-29, models/clip/model.py:191-217
+ *   sliding_window_predict(...)        /root/reference/utils/eval_utils.py:26-96
+ *
+ * Conventions
+ *   - every function returns 0 on success, a CLIPEBC_E* code otherwise; clipebc_last_error() gives the message of the
+ *     last failure on the calling thread (reference convention: Python AssertionError / RuntimeError; the Python host
+ *     side in clip_ebc_b200/ keeps the reference's asserts and maps non-zero codes to RuntimeError).
+ *   - plain pointers and sizes only. "dev" pointers are CUDA device pointers on the current device, "host" pointers
+ *     are ordinary host memory; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - all work is enqueued on `stream`; inputs are borrowed and never written; outputs are caller-allocated.
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry point fails with CLIPEBC_ECUDA.
+ */
+#ifndef CLIPEBC_B200_H_
+#define CLIPEBC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIPEBC_OK 0
+#define CLIPEBC_EINVAL 1   /* bad argument / shape / unsupported configuration */
+#define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
+#define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
+
+#define CLIPEBC_ABI_VERSION 1
+
+typedef struct clipebc_model clipebc_model;
+
+/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16") -- models/clip/model.py:31-45, _clip_ebc :220-270.
+ * Only width 768 / 12 heads / patch 16 / embed 512 (ViT-B/16) is implemented. */
+typedef struct clipebc_config {
+  int input_size;   /* side of the square the positional embedding was built for (224)        */
+  int reduction;    /* 8, 16 or 32 (model.reduction; encoder reduction is 16)                  */
+  int num_vpt;      /* visual prompt tokens per layer (32)                                    */
+  int deep_vpt;     /* 1: per-layer prompts vpt_0..vpt_11, 0: shallow (vpt_0 only, propagated) */
+  int num_bins;     /* N = len(bins) = len(anchor_points), 1..32                              */
+  int window_chunk; /* windows per internal pass (0 = library default)                         */
+} clipebc_config;
+
+const char* clipebc_last_error(void);
+int clipebc_abi_version(void);
+/* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
+int64_t clipebc_launch_count(void);
+
+/* ---- model lifetime: mirrors get_model() + load_state_dict() + .eval() ---------------------------------------- */
+int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out);
+void clipebc_model_destroy(clipebc_model* m);
+/* Upload one fp32 tensor under its reference state_dict key (models/clip/model.py state_dict):
+ *   vpt_{l}, logit_scale, image_encoder.{class_embedding,positional_embedding,conv1.weight,ln_pre.*,ln_post.*,
+ *   transformer.resblocks.{l}.{attn.in_proj_weight,attn.in_proj_bias,attn.out_proj.*,ln_1.*,ln_2.*,mlp.c_fc.*,
+ *   mlp.c_proj.*}}, image_decoder.0.{conv1.weight,bn1.*,conv2.weight,bn2.*}, projection.{weight,bias}
+ * plus the two plain attributes of the reference module: text_features [N,512] and anchor_points [N].
+ * `data` may be a host or a device pointer (copied, caller keeps ownership). Invalidates a previous pack. */
+int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Build the device-resident packed form: bf16 GEMM layouts, BatchNorm folded into the decoder convs, hi/lo split of
+ * the projection, exp(logit_scale) * normalised text matrix, constant prompt K/V rows (deep VPT). */
+int clipebc_model_pack(clipebc_model* m, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------------------------------- */
+/* model(x) in eval mode: x_dev f32 [B,3,h,w] -> exp_out_dev f32 [B,1,h/r,w/r]; logits_out_dev (nullable) f32
+ * [B,N,h/r,w/r] is the train-mode first output (models/clip/model.py:214-217). */
+int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, int w, float* exp_out_dev,
+                            float* logits_out_dev, void* stream);
+/* sliding_window_predict(model, image[1,3,H,W], (wh,ww), (sh,sw)) -> density_out_dev f32 [H/r, W/r] (the [1,1,.,.]
+ * tensor of the reference, on the device) and, if count_out_dev != NULL, its sum (eval.py:35, test_nwpu.py:100). */
+int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int H, int W, int wh, int ww, int sh,
+                                   int sw, float* density_out_dev, float* count_out_dev, void* stream);
+
+/* ---- integer part of sliding_window_predict, host only (utils/eval_utils.py:54-66) ----------------------------- */
+/* Writes n_rows/n_cols and, when the arrays are non-NULL (capacity >= n_rows / n_cols), the clamped window origins. */
+int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_rows, int* n_cols, int* row_origins,
+                           int* col_origins);
+
+/* ---- single kernels (unit/parity tests and profiling; all pointers are device pointers) ------------------------ */
+int clipebc_f32_to_bf16(const float* in_dev, void* out_bf16_dev, int64_t n, void* stream);
+/* epi: 0 f32, 1 bias f32, 2 bias bf16, 3 bias+quickgelu bf16, 4 bias+resid f32, 5 bias+relu+border-mask bf16,
+ *      6 bias+resid+relu hi/lo split bf16. See clip_ebc_b200/csrc/kernels.h for the contract. */
+int clipebc_gemm_bf16(int epi, const void* A_bf16_dev, int64_t a_rows, int64_t a_cols, int64_t lda,
+                      const void* W_bf16_dev, int64_t ldw, int M, int N, int K, int n_seg, const int* seg_row_shift,
+                      const int* seg_col_start, void* out_dev, int ldo, const float* bias_dev, const float* resid_dev,
+                      int ldr, int mask_hp, int mask_wp, int block_n, void* stream);
+int clipebc_layernorm768(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int in_row_offset, void* stream);
+int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
+                      void* out_bf16_dev, void* stream);
+int clipebc_patchify16(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw,
+                       void* out_bf16_dev, void* stream);
+int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, void* U_bf16_dev,
+                               float* U_f32_dev, void* stream);
+int clipebc_ebc_head(const float* F_dev, const float* tmat_dev, const float* anchors_dev, int n_bins, int n_win, int gh,
+                     int gw, float* exp_out_dev, float* logits_out_dev, void* stream);
+/* preds_dev f32 [n_rows*n_cols, gh, gw]; row_cells/col_cells: HOST arrays of window origins // reduction. */
+int clipebc_fold_average(const float* preds_dev, const int* row_cells_host, const int* col_cells_host, int n_rows,
+                         int n_cols, int gh, int gw, int Ho, int Wo, float* density_out_dev, float* count_out_dev,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPEBC_B200_H_ */

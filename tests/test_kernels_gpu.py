@@ -1,0 +1,223 @@
+"""Single-kernel parity tests (B200 only): each sm_100a kernel, called through the C-ABI, against a plain PyTorch
+fp32 statement of the same op on the same seeded inputs. Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from clip_ebc_b200 import ops as _ops
+
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (300, 768, 768), (1000, 2304, 768),
+                                   (777, 768, 3072), (32, 2304, 768), (12608, 768, 768)])
+def test_gemm_plain_f32(ops, M, N, K, block_n):
+    a, w = _bf(_rand((M, K), 1)), _bf(_rand((N, K), 2, 0.05))
+    out = ops.gemm(a, w, ops.EPI_F32, block_n=block_n)
+    ref = a.float() @ w.float().t()
+    # bf16 inputs are exact in both; only fp32 accumulation order differs -> 1e-5 relative to the output scale
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_bias_bf16_and_gelu(ops):
+    M, N, K = 1234, 3072, 768
+    a, w, b = _bf(_rand((M, K), 3)), _bf(_rand((N, K), 4, 0.04)), _rand((N,), 5)
+    ref = a.float() @ w.float().t() + b
+    out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b)
+    assert out.dtype == torch.bfloat16
+    assert _rel(out, ref) < 6e-3  # one bf16 rounding of the output (2^-8)
+    out = ops.gemm(a, w, ops.EPI_BIAS_GELU_BF16, bias=b)
+    refg = ref * torch.sigmoid(1.702 * ref)
+    assert _rel(out, refg) < 6e-3
+
+
+def test_gemm_bias_resid_inplace(ops):
+    M, N, K = 2000, 768, 3072
+    a, w, b = _bf(_rand((M, K), 6)), _bf(_rand((N, K), 7, 0.02)), _rand((N,), 8)
+    x = _rand((M, N), 9)
+    ref = x + a.float() @ w.float().t() + b
+    out = ops.gemm(a, w, ops.EPI_BIAS_RESID_F32, bias=b, resid=x, out=x)  # in place on the residual stream
+    assert out.data_ptr() == x.data_ptr()
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_conv_segments_match_conv2d(ops):
+    """3x3 conv over the zero-bordered NHWC grid as 9 row-shifted K-segments == F.conv2d(padding=1)."""
+    B, g, Cc = 3, 14, 768
+    Hp = Wp = g + 2
+    x = _bf(_rand((B, Cc, g, g), 10))
+    wt = _bf(_rand((Cc, Cc, 3, 3), 11, 0.02))
+    bias = _rand((Cc,), 12)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), padding=1) + bias.view(1, -1, 1, 1))
+    xp = torch.zeros((B, Hp, Wp, Cc), dtype=torch.bfloat16, device="cuda")
+    xp[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1)
+    wk = wt.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).contiguous()  # [O, (ky, kx, I)]
+    shifts = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+    out = ops.gemm(xp.view(-1, Cc), wk, ops.EPI_BIAS_RELU_MASK_BF16, bias=bias, K=9 * Cc, seg_row_shift=shifts,
+                   seg_col_start=[0] * 9, mask_hw=(Hp, Wp))
+    out = out.view(B, Hp, Wp, Cc)
+    # border rows must be exactly zero so the result can feed the next conv
+    border = out.clone()
+    border[:, 1:-1, 1:-1, :] = 0
+    assert border.abs().max().item() == 0.0
+    got = out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+    assert _rel(got, ref) < 6e-3  # bf16 output rounding
+
+
+def test_gemm_resid_relu_split_and_split_projection(ops):
+    """conv2-style epilogue writes hi|lo; the [hi|lo|hi] x [Whi|Whi|Wlo] GEMM reproduces an fp32 linear to ~1e-5."""
+    M, Cc, E = 900, 768, 512
+    a, w, b = _bf(_rand((M, Cc), 13)), _bf(_rand((Cc, Cc), 14, 0.03)), _rand((Cc,), 15)
+    u = _rand((M, Cc), 16)
+    t_ref = F.relu(a.float() @ w.float().t() + b + u)
+    split = ops.gemm(a, w, ops.EPI_BIAS_RESID_RELU_SPLIT, bias=b, resid=u)
+    hi, lo = split[:, :Cc].float(), split[:, Cc:].float()
+    assert _rel(hi + lo, t_ref) < 3e-5  # hi + lo carries ~16 mantissa bits
+    wp = _rand((E, Cc), 17, 0.05)
+    bp = _rand((E,), 18)
+    w_hi = wp.to(torch.bfloat16)
+    w_lo = (wp - w_hi.float()).to(torch.bfloat16)
+    w3 = torch.cat([w_hi, w_hi, w_lo], dim=1).contiguous()
+    out = ops.gemm(split, w3, ops.EPI_BIAS_F32, bias=bp, K=3 * Cc, seg_row_shift=[0, 0, 0],
+                   seg_col_start=[0, Cc, 0])
+    ref = (hi + lo).double() @ wp.double().t() + bp.double()
+    assert _rel(out, ref.float()) < 5e-5
+
+
+def test_gemm_rejects_bad_shapes(ops):
+    a, w = _bf(_rand((64, 100), 1)), _bf(_rand((256, 100), 2))
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, ops.EPI_F32)  # K not a multiple of 64
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+def test_layernorm(ops):
+    x = _rand((1000, 768), 20, 3.0) + 0.5
+    g, b = _rand((768,), 21) * 0.1 + 1.0, _rand((768,), 22) * 0.1
+    ref = F.layer_norm(x, (768,), g, b, 1e-5)
+    out = ops.layernorm(x, g, b, out_bf16=False)
+    assert (out - ref).abs().max().item() < 2e-5
+    outb = ops.layernorm(x, g, b, out_bf16=True)
+    assert torch.equal(outb, out.to(torch.bfloat16))
+    # row map: take the last 196 rows of every group of 229 (ln_post on the patch rows)
+    x = _rand((3 * 229, 768), 23)
+    out = ops.layernorm(x, g, b, out_bf16=False, n_rows_out=3 * 196, rows_out_per_group=196, rows_in_per_group=229,
+                        in_row_offset=33)
+    ref = F.layer_norm(x.view(3, 229, 768)[:, 33:], (768,), g, b, 1e-5).reshape(-1, 768)
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("n_win,t_live,n_const", [(2, 197, 32), (3, 229, 0), (1, 50, 0), (2, 17, 5), (1, 256, 0)])
+def test_attention(ops, n_win, t_live, n_const):
+    qkv = _bf(_rand((n_win * t_live, 2304), 30))
+    ckv = _bf(_rand((n_const, 2304), 31)) if n_const else None
+    out = ops.attention(qkv, n_win, t_live, ckv).float().view(n_win, t_live, 12, 64)
+    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
+    if n_const:
+        ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
+        k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
+        v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    # P is rounded to bf16 before P@V and the output is bf16: 2^-8 relative
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+# ----------------------------------------------------------------------------------------------- stem / decoder
+def test_patchify_matches_unfold(ops):
+    img = _rand((2, 3, 64, 96), 40)
+    out = ops.patchify(img).float().view(2, 4 * 6, 768)
+    ref = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2)  # [n, L, c*256 + py*16 + px]
+    assert torch.equal(out, ref.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("g", [28, 14, 7])
+def test_resample_matches_interpolate(ops, g):
+    n = 2
+    Y = _rand((n * 196, 768), 41)
+    ub, uf = ops.resample_to_padded(Y, n, 14, 14, g, g)
+    x = Y.view(n, 14, 14, 768).permute(0, 3, 1, 2)
+    ref = x if g == 14 else F.interpolate(x, scale_factor=g / 14, mode="bilinear")
+    uf = uf.view(n, g + 2, g + 2, 768)
+    assert (uf[:, 1:-1, 1:-1].permute(0, 3, 1, 2) - ref).abs().max().item() < 1e-5
+    border = uf.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert border.abs().max().item() == 0.0
+    assert torch.equal(ub.view_as(uf), uf.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n_bins", [3, 5, 20])
+def test_ebc_head(ops, n_bins):
+    n, g = 2, 7
+    Fm = _rand((n * (g + 2) * (g + 2), 512), 50)
+    text = _rand((n_bins, 512), 51)
+    anchors = torch.arange(n_bins, dtype=torch.float32, device="cuda") * 1.25
+    scale = math.log(1 / 0.07)
+    tmat = math.exp(scale) * F.normalize(text, dim=-1)
+    exp, logits = ops.ebc_head(Fm, tmat.contiguous(), anchors, n, g, g, want_logits=True)
+    f = Fm.view(n, g + 2, g + 2, 512)[:, 1:-1, 1:-1]
+    ref_logits = (math.exp(scale) * F.normalize(f, dim=-1)) @ F.normalize(text, dim=-1).t()
+    ref_logits = ref_logits.permute(0, 3, 1, 2)
+    ref_exp = (ref_logits.softmax(1) * anchors.view(1, -1, 1, 1)).sum(1, keepdim=True)
+    assert (logits - ref_logits).abs().max().item() < 1e-4
+    assert (exp - ref_exp).abs().max().item() < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- fold
+def _numpy_fold(preds, H, W, wh, ww, sh, sw, r):
+    """The reference loop (utils/eval_utils.py:54-95) verbatim in numpy, for bit-exact comparison."""
+    import numpy as np
+
+    nr = int(np.ceil((H - wh) / sh) + 1)
+    nc = int(np.ceil((W - ww) / sw) + 1)
+    pm = np.zeros((1, H // r, W // r), np.float32)
+    cm = np.zeros((1, H // r, W // r), np.float32)
+    idx = 0
+    for i in range(nr):
+        for j in range(nc):
+            xs, ys = i * sh, j * sw
+            xe, ye = xs + wh, ys + ww
+            if xe > H:
+                xs, xe = H - wh, H
+            if ye > W:
+                ys, ye = W - ww, W
+            pm[:, xs // r: xe // r, ys // r: ye // r] += preds[idx]
+            cm[:, xs // r: xe // r, ys // r: ye // r] += 1.0
+            idx += 1
+    return pm / cm
+
+
+@pytest.mark.parametrize("H,W,s,r", [(448, 448, 224, 8), (448, 672, 112, 8), (1536, 2048, 112, 8), (448, 672, 112, 32),
+                                     (480, 700, 100, 16)])
+def test_fold_bit_exact(ops, H, W, s, r):
+    ro, co = ops.window_origins(H, W, (224, 224), (s, s))
+    g = 224 // r
+    preds = _rand((len(ro) * len(co), 1, g, g), 60).abs()
+    dens, cnt = ops.fold_average(preds, [v // r for v in ro], [v // r for v in co], H // r, W // r, want_count=True)
+    ref = _numpy_fold(preds.cpu().numpy(), H, W, 224, 224, s, s, r)[0]
+    import numpy as np
+
+    assert np.array_equal(dens.cpu().numpy(), ref)  # bit-exact: same fp32 additions in the same order
+    assert abs(cnt.item() - float(ref.sum(dtype=np.float64))) < 1e-3 * max(1.0, abs(float(ref.sum())))
