@@ -1,0 +1,59 @@
+"""``sliding_window_predict`` -- host-side mirror of /root/reference/utils/eval_utils.py:26-96.
+
+Same signature, same assertions (AssertionError with the reference's messages) and the same return value: a **CPU**
+fp32 tensor of shape (1, 1, H // r, W // r). The body, however, is one C-ABI call: window enumeration, patch-grid
+sharing between overlapping windows, the ViT/decoder/head kernels and the atomic-free fold all run on the device; the
+only transfers are the image H2D (if the caller passed a CPU tensor) and the density map D2H.
+"""
+from __future__ import annotations
+
+from typing import Tuple, Union
+
+import torch
+from torch import Tensor, nn
+
+from .model import CLIP_EBC
+
+
+def _pair(v, what: str) -> Tuple[int, int]:
+    v = (int(v), int(v)) if isinstance(v, (int, float)) else v
+    v = tuple(v)
+    assert isinstance(v, tuple) and len(v) == 2 and v[0] > 0 and v[1] > 0, \
+        f"{what} must be a positive integer tuple (h, w), got {v}"
+    return int(v[0]), int(v[1])
+
+
+def sliding_window_predict(
+    model: nn.Module,
+    image: Tensor,
+    window_size: Union[int, Tuple[int, int]],
+    stride: Union[int, Tuple[int, int]],
+    return_device: bool = False,
+    return_count: bool = False,
+):
+    """Density map of one image by overlapping windows; overlapping regions are averaged.
+
+    Args as in the reference. Extensions (default off, so the call is a drop-in):
+      return_device: keep the result on the GPU instead of the reference's CPU tensor (throughput runs).
+      return_count:  also return ``density.sum()`` computed on the device (what eval.py:35 / test_nwpu.py:100 do next).
+    """
+    assert len(image.shape) == 4, f"Image must be a 4D tensor (1, c, h, w), got {image.shape}"
+    window_size = _pair(window_size, "Window size")
+    stride = _pair(stride, "Stride")
+    assert stride[0] <= window_size[0] and stride[1] <= window_size[1], \
+        f"Stride must be smaller than window size, got {stride} and {window_size}"
+    if not isinstance(model, CLIP_EBC):
+        raise TypeError("clip_ebc_b200.sliding_window_predict drives clip_ebc_b200.CLIP_EBC models only "
+                        f"(got {type(model).__name__}); there is no generic PyTorch fallback path")
+    assert image.shape[0] == 1, f"The batch size must be 1 due to varying image sizes, got {image.shape[0]}"
+
+    model.eval()  # eval_utils.py:73
+    dev = model._device()
+    with torch.no_grad():
+        img = image if image.device == dev else image.to(dev, non_blocking=True)
+        out = model.sliding_window_density(img, window_size, stride, with_count=return_count)
+    dens, cnt = out if return_count else (out, None)
+    if not return_device:
+        dens = dens.cpu()  # the reference returns a CPU tensor (eval_utils.py:76,96)
+        cnt = cnt.cpu() if cnt is not None else None
+    return (dens, cnt) if return_count else dens

@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference model boundary: ``get_model()`` and the ``CLIP_EBC`` module.
+
+Reference interface being mirrored (same names, argument meaning and error behaviour):
+  get_model(backbone, input_size, reduction, bins, anchor_points, **kwargs)   /root/reference/models/__init__.py:10-44
+  _clip_ebc(...) / CLIP_EBC.__init__ / CLIP_EBC.forward                        /root/reference/models/clip/model.py:30-270
+
+The module is a *parameter container* with the reference's ``state_dict`` keys (``vpt_{i}``, ``logit_scale``,
+``image_encoder.*``, ``image_decoder.0.*``, ``projection.*``) so reference checkpoints load with ``strict=True``;
+``forward`` hands raw device pointers to the C-ABI (``clipebc_forward_windows``). No arithmetic of the hot path is done
+in PyTorch and there is no fallback: a CPU tensor or a missing ``libclipebc_b200.so`` raises.
+
+Out of scope here: the CLIP text tower and tokenizer. They run once at construction in the
+reference and produce the constant ``text_features`` [N, 512]; this module takes that matrix directly (``text_features=``
+kwarg, ``set_text_features()``, or the ``text_features`` attribute exactly as in the reference object), and keeps any
+``text_encoder.*`` checkpoint entries verbatim so a ``state_dict`` round-trips.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+clip_names = ["resnet50", "resnet50x4", "resnet50x16", "resnet50x64", "resnet101", "vit_b_16", "vit_b_32", "vit_l_14"]
+resnet_backbones = ["resnet50", "resnet101", "resnet50x4", "resnet50x16", "resnet50x64"]
+vit_backbones = ["vit_b_16", "vit_b_32", "vit_l_14", "vit_l_14_336px"]
+
+_WIDTH, _LAYERS, _HEADS, _PATCH, _EMBED = 768, 12, 12, 16, 512
+
+
+class _Block(nn.Module):
+    """Parameter names of ResidualAttentionBlock (_clip/blocks.py:22-33). Never called."""
+
+    def __init__(self, d: int, heads: int) -> None:
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d, heads)
+        self.ln_1 = nn.LayerNorm(d)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d, d * 4)), ("gelu", nn.Identity()),
+                                              ("c_proj", nn.Linear(d * 4, d))]))
+        self.ln_2 = nn.LayerNorm(d)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, d: int, layers: int, heads: int) -> None:
+        super().__init__()
+        self.resblocks = nn.Sequential(*[_Block(d, heads) for _ in range(layers)])
+
+
+class _ImageEncoder(nn.Module):
+    """Parameter names of VisionTransformer(features_only=True) (_clip/image_encoder.py:118-160)."""
+
+    def __init__(self, input_size: int) -> None:
+        super().__init__()
+        scale = _WIDTH ** -0.5
+        g = input_size // _PATCH
+        self.conv1 = nn.Conv2d(3, _WIDTH, kernel_size=_PATCH, stride=_PATCH, bias=False)
+        self.class_embedding = nn.Parameter(scale * torch.randn(_WIDTH))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(g * g + 1, _WIDTH))
+        self.ln_pre = nn.LayerNorm(_WIDTH)
+        self.transformer = _Transformer(_WIDTH, _LAYERS, _HEADS)
+        self.ln_post = nn.LayerNorm(_WIDTH)
+        self.patch_size = (_PATCH, _PATCH)
+        self.channels = _WIDTH
+        self.reduction = _PATCH
+        self.clip_embed_dim = _EMBED
+
+
+class _BasicBlock(nn.Module):
+    """Parameter names of BasicBlock(768, 768) (models/utils.py:254-288)."""
+
+    def __init__(self, c: int) -> None:
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(c)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(c)
+
+
+def _init_decoder(m: nn.Module) -> None:
+    # models/utils.py:366-379
+    for mod in m.modules():
+        if isinstance(mod, nn.Conv2d):
+            nn.init.kaiming_normal_(mod.weight, mode="fan_out", nonlinearity="relu")
+            if mod.bias is not None:
+                nn.init.constant_(mod.bias, 0.0)
+        elif isinstance(mod, nn.BatchNorm2d):
+            nn.init.constant_(mod.weight, 1.0)
+            nn.init.constant_(mod.bias, 0.0)
+
+
+class CLIP_EBC(nn.Module):
+    """B200-native CLIP-EBC (ViT-B/16 + VPT). Constructor arguments as in models/clip/model.py:31-45."""
+
+    def __init__(
+        self,
+        backbone: str,
+        bins: List[Tuple[float, float]],
+        anchor_points: List[float],
+        reduction: Optional[int] = None,
+        freeze_text_encoder: bool = True,
+        prompt_type: str = "number",
+        input_size: Optional[int] = None,
+        num_vpt: Optional[int] = None,
+        deep_vpt: Optional[bool] = None,
+        vpt_drop: Optional[float] = None,
+        decoder_block: Any = None,
+        decoder_cfg: Optional[List[Union[str, int]]] = None,
+        text_features: Optional[Tensor] = None,
+        window_chunk: int = 0,
+    ) -> None:
+        super().__init__()
+        assert backbone in resnet_backbones + vit_backbones, \
+            f"Backbone should be in {resnet_backbones + vit_backbones}, got {backbone}"
+        if backbone != "vit_b_16":
+            raise NotImplementedError(
+                f"clip_ebc_b200 implements the hot path for backbone 'vit_b_16' only (got '{backbone}'); the other CLIP "
+                "backbones of the reference are outside the scope of this build (SURVEY.md section 8f).")
+        assert input_size is not None, "Expected input_size to be an integer, got None."
+        assert num_vpt is not None, "Expected num_vpt to be an integer, got None."
+        assert deep_vpt is not None, "Expected deep_vpt to be a boolean, got None."
+        assert vpt_drop is not None, "Expected vpt_drop to be a float, got None."
+        assert prompt_type in ["number", "word"], f"Expected prompt_type to be 'number' or 'word', got {prompt_type}"
+        if not freeze_text_encoder:
+            raise NotImplementedError("freeze_text_encoder=False (training the text tower) is outside the inference hot path")
+        if decoder_cfg is not None and list(decoder_cfg) != [768]:
+            raise NotImplementedError("only the reference default decoder_cfg=[768] (one BasicBlock) is implemented")
+        assert bins is not None and anchor_points is not None and len(bins) == len(anchor_points)
+
+        self.backbone = backbone
+        self.image_encoder = _ImageEncoder(int(input_size))
+        self.image_encoder_depth = _LAYERS
+        for p in self.image_encoder.parameters():
+            p.requires_grad = False
+        self.num_vpt = int(num_vpt)
+        self.deep_vpt = bool(deep_vpt)
+        self.input_size = int(input_size)
+        val = math.sqrt(6.0 / float(3 * _PATCH + _WIDTH))  # model.py:70-75
+        for idx in range(_LAYERS if self.deep_vpt else 1):
+            p = nn.Parameter(torch.empty(self.num_vpt, _WIDTH))
+            nn.init.uniform_(p, -val, val)
+            setattr(self, f"vpt_{idx}", p)
+        self.vpt_drop = float(vpt_drop)  # identity in eval mode; the inference path has no dropout
+
+        self.encoder_reduction = _PATCH
+        self.reduction = self.encoder_reduction if reduction is None else int(reduction)
+        self.channels = _WIDTH
+        self.clip_embed_dim = _EMBED
+        self.image_decoder = nn.Sequential(_BasicBlock(_WIDTH))
+        _init_decoder(self.image_decoder)
+        self.projection = nn.Conv2d(_WIDTH, _EMBED, kernel_size=1)
+        _init_decoder(self.projection)
+
+        self.prompt_type = prompt_type
+        self.freeze_text_encoder = freeze_text_encoder
+        self.bins = bins
+        self.anchor_points = torch.tensor(anchor_points, dtype=torch.float32, requires_grad=False).view(1, -1, 1, 1)
+        self.text_features: Optional[Tensor] = None
+        if text_features is not None:
+            self.set_text_features(text_features)
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07), requires_grad=True)
+
+        self._text_encoder_state: "OrderedDict[str, Tensor]" = OrderedDict()
+        self._window_chunk = int(window_chunk)
+        self._handle: Optional[C.c_void_p] = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ text features (constant input of the head)
+    def set_text_features(self, text_features: Tensor) -> None:
+        """[N, 512] output of the (out-of-scope) CLIP text tower for the bin prompts (model.py:127-129)."""
+        tf = torch.as_tensor(text_features, dtype=torch.float32).detach()
+        assert tf.dim() == 2 and tf.shape[0] == len(self.bins) and tf.shape[1] == _EMBED, \
+            f"Expected text_features of shape ({len(self.bins)}, {_EMBED}), got {tuple(tf.shape)}"
+        self.text_features = tf
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ state_dict compatibility
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+        for k, v in self._text_encoder_state.items():
+            sd[prefix + k] = v
+        return sd
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        own = OrderedDict()
+        self._text_encoder_state = OrderedDict()
+        for k, v in state_dict.items():
+            if k.startswith("text_encoder."):
+                self._text_encoder_state[k] = v  # kept verbatim; the text tower is not on the hot path
+            else:
+                own[k] = v
+        out = super().load_state_dict(own, strict=strict, **kwargs)
+        self._packed_key = None
+        return out
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float()
+        out = super()._apply(fn, *args, **kwargs)
+        self._packed_key = None
+        return out
+
+    # ------------------------------------------------------------------ native handle
+    def _device(self) -> torch.device:
+        return self.logit_scale.device
+
+    def _ensure_packed(self) -> None:
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("clip_ebc_b200.CLIP_EBC runs on a CUDA device only (no CPU fallback): call .to('cuda')")
+        tensors = self._hot_path_tensors()
+        key = (dev.index, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()))
+        if self._handle is not None and key == self._packed_key:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            if self._handle is None:
+                cfg = _lib.ClipEbcConfig(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt),
+                                         len(self.bins), self._window_chunk)
+                h = C.c_void_p()
+                _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
+                self._handle = h
+            for name, t in tensors.items():
+                t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.clipebc_model_set_tensor(self._handle, name.encode(), t.data_ptr(), shape, t.dim()),
+                           f"set_tensor({name})")
+            _lib.check(lib.clipebc_model_pack(self._handle, torch.cuda.current_stream().cuda_stream), "model_pack")
+        self._packed_key = key
+
+    def _hot_path_tensors(self) -> "OrderedDict[str, Tensor]":
+        if self.text_features is None:
+            raise RuntimeError(
+                "text_features is not set: pass text_features=[N,512] to get_model()/CLIP_EBC or call "
+                "set_text_features(); the CLIP text tower is outside this build's scope (see module docstring)")
+        out = OrderedDict()
+        for k, v in super().state_dict().items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            out[k] = v
+        out["text_features"] = self.text_features
+        out["anchor_points"] = self.anchor_points.reshape(-1)
+        return out
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().clipebc_model_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward (models/clip/model.py:191-217)
+    def forward(self, x: Tensor) -> Union[Tensor, Tuple[Tensor, Tensor]]:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"Expected input of shape (B, 3, H, W), got {tuple(x.shape)}")
+        self._ensure_packed()
+        dev = self._device()
+        if x.device != dev:
+            raise RuntimeError(f"input is on {x.device} but the model is on {dev}")
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, h, w = x.shape
+        r = self.reduction
+        exp = torch.empty((B, 1, h // r, w // r), dtype=torch.float32, device=dev)
+        logits = torch.empty((B, len(self.bins), h // r, w // r), dtype=torch.float32, device=dev) if self.training else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().clipebc_forward_windows(
+                self._handle, x.data_ptr(), B, h, w, exp.data_ptr(), None if logits is None else logits.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), "forward_windows")
+        if self.training:
+            return logits, exp
+        return exp
+
+    # ------------------------------------------------------------------ fused sliding-window entry (eval_utils.py:26-96)
+    def sliding_window_density(self, image: Tensor, window_size: Tuple[int, int], stride: Tuple[int, int],
+                               with_count: bool = False):
+        """image [1,3,H,W] on the model's device -> density [1,1,H//r,W//r] (device) and optionally its sum [1]."""
+        self._ensure_packed()
+        dev = self._device()
+        if image.device != dev:
+            raise RuntimeError(f"image is on {image.device} but the model is on {dev}")
+        if image.dim() != 4 or image.shape[0] != 1 or image.shape[1] != 3:
+            raise RuntimeError(f"Expected image of shape (1, 3, H, W), got {tuple(image.shape)}")
+        image = image.detach().to(torch.float32).contiguous()
+        H, W = image.shape[-2:]
+        r = self.reduction
+        dens = torch.empty((1, 1, H // r, W // r), dtype=torch.float32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.float32, device=dev) if with_count else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().clipebc_sliding_window_predict(
+                self._handle, image.data_ptr(), H, W, window_size[0], window_size[1], stride[0], stride[1],
+                dens.data_ptr(), None if cnt is None else cnt.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "sliding_window_predict")
+        return (dens, cnt) if with_count else dens
+
+
+def _clip_ebc(backbone: str, bins, anchor_points, reduction=None, freeze_text_encoder=True, prompt_type="number",
+              input_size=None, num_vpt=None, deep_vpt=None, vpt_drop=None, decoder_block=None, decoder_cfg=None,
+              **extra) -> CLIP_EBC:
+    """models/clip/model.py:220-270."""
+    return CLIP_EBC(backbone=backbone, bins=bins, anchor_points=anchor_points, reduction=reduction,
+                    freeze_text_encoder=freeze_text_encoder, prompt_type=prompt_type, input_size=input_size,
+                    num_vpt=num_vpt, deep_vpt=deep_vpt, vpt_drop=vpt_drop, decoder_block=decoder_block,
+                    decoder_cfg=decoder_cfg, **extra)
+
+
+def get_model(backbone: str, input_size: int, reduction: int, bins: Optional[List[Tuple[float, float]]] = None,
+              anchor_points: Optional[List[float]] = None, **kwargs: Any) -> CLIP_EBC:
+    """models/__init__.py:10-44, CLIP branch. kwargs: prompt_type, num_vpt, vpt_drop, deep_vpt (+ text_features)."""
+    backbone = backbone.lower()
+    if "clip" in backbone:
+        backbone = backbone[5:]
+        assert backbone in clip_names, f"Expected backbone to be in {clip_names}, got {backbone}"
+        return _clip_ebc(backbone=backbone, input_size=input_size, reduction=reduction, bins=bins,
+                         anchor_points=anchor_points, **kwargs)
+    raise NotImplementedError(
+        f"backbone '{backbone}': clip_ebc_b200 provides the CLIP-EBC path only; the reference's non-CLIP Classifier/"
+        "Regressor models are outside the scope of this build")

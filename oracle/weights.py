@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE -- not product code. Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import it.
+
+Seeded synthetic weights for CLIP-EBC (ViT-B/16 + VPT) under the reference's own ``state_dict`` key names, so the same
+dictionary loads into (a) the real reference module (oracle/make_golden.py, in the build container), (b) the CPU oracle
+(oracle/clip_ebc_oracle.py) and (c) the CUDA product (clip_ebc_b200.get_model(...).load_state_dict).
+
+numpy's PCG64 stream is used instead of torch's RNG so that the weights are bit-identical on every machine (the GPU box
+has no /root/reference and must regenerate exactly the tensors the golden fixtures were made with).
+
+Distributions follow the reference constructors (``variant="default"``):
+  image_encoder.*            /root/reference/models/clip/_clip/image_encoder.py:141-151, blocks.py:22-33 (torch defaults)
+  vpt_*                      /root/reference/models/clip/model.py:70-76   U(+-sqrt(6/(3*16+768)))
+  image_decoder / projection /root/reference/models/utils.py:366-379      kaiming-normal fan_out, BN (1, 0), stats (0, 1)
+  logit_scale                /root/reference/models/clip/model.py:117     ln(1/0.07)
+``variant="stress"`` additionally randomises every bias, LayerNorm/BatchNorm affine + running statistics and uses a
+sharper logit_scale, so that bias / BN-fold / epsilon paths cannot cancel out in parity tests.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+WIDTH, LAYERS, HEADS, PATCH, EMBED, HIDDEN = 768, 12, 12, 16, 512, 3072
+
+# bins / anchor points of the reference configs (configs/reduction_{8,16,32}.json), "fine" granularity, "average" anchors
+BIN_CONFIGS = {
+    # reduction 8, truncation 4, nwpu  (configs/reduction_8.json["4"]["nwpu"])
+    "r8_t4_nwpu": dict(reduction=8, bins=[(0, 0), (1, 1), (2, 2), (3, 3), (4, float("inf"))],
+                       anchor_points=[0.0, 1.0, 2.0, 3.0, 4.21931]),
+    # reduction 16, truncation key "8", qnrf (configs/reduction_16.json["8"]["qnrf"])
+    "r16_t8_qnrf": dict(reduction=16, bins=[(i, i) for i in range(8)] + [(8, float("inf"))],
+                        anchor_points=[0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 9.23349]),
+    # reduction 32, truncation 19, qnrf (configs/reduction_32.json["19"]["qnrf"])
+    "r32_t19_qnrf": dict(reduction=32, bins=[(i, i) for i in range(19)] + [(19, float("inf"))],
+                         anchor_points=[float(i) for i in range(19)] + [23.01897]),
+}
+
+
+def _u(rng, shape, bound):
+    return rng.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+def _n(rng, shape, std):
+    return (rng.standard_normal(size=shape, dtype=np.float32) * np.float32(std)).astype(np.float32)
+
+
+def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, deep_vpt: bool = True,
+                    variant: str = "default") -> Dict[str, torch.Tensor]:
+    """Reference-keyed fp32 state_dict (without ``text_encoder.*``: the text tower is not on the hot path)."""
+    assert variant in ("default", "stress")
+    rng = np.random.default_rng(seed)
+    stress = variant == "stress"
+    sd: Dict[str, np.ndarray] = {}
+    g0 = input_size // PATCH
+
+    for l in range(LAYERS if deep_vpt else 1):
+        sd[f"vpt_{l}"] = _u(rng, (num_vpt, WIDTH), math.sqrt(6.0 / (3 * PATCH + WIDTH)))
+    sd["logit_scale"] = np.array(math.log(30.0) if stress else math.log(1 / 0.07), dtype=np.float32)
+
+    ie = "image_encoder."
+    sd[ie + "class_embedding"] = _n(rng, (WIDTH,), WIDTH ** -0.5)
+    sd[ie + "positional_embedding"] = _n(rng, (g0 * g0 + 1, WIDTH), WIDTH ** -0.5)
+    sd[ie + "conv1.weight"] = _u(rng, (WIDTH, 3, PATCH, PATCH), 1.0 / math.sqrt(3 * PATCH * PATCH))
+
+    def ln(prefix):
+        if stress:
+            sd[prefix + ".weight"] = (1.0 + _n(rng, (WIDTH,), 0.1)).astype(np.float32)
+            sd[prefix + ".bias"] = _n(rng, (WIDTH,), 0.1)
+        else:
+            sd[prefix + ".weight"] = np.ones((WIDTH,), np.float32)
+            sd[prefix + ".bias"] = np.zeros((WIDTH,), np.float32)
+
+    ln(ie + "ln_pre")
+    for l in range(LAYERS):
+        p = f"{ie}transformer.resblocks.{l}."
+        sd[p + "attn.in_proj_weight"] = _u(rng, (3 * WIDTH, WIDTH), math.sqrt(6.0 / (WIDTH + 3 * WIDTH)))  # xavier
+        sd[p + "attn.in_proj_bias"] = _n(rng, (3 * WIDTH,), 0.02) if stress else np.zeros((3 * WIDTH,), np.float32)
+        sd[p + "attn.out_proj.weight"] = _u(rng, (WIDTH, WIDTH), 1.0 / math.sqrt(WIDTH))
+        sd[p + "attn.out_proj.bias"] = _n(rng, (WIDTH,), 0.02) if stress else np.zeros((WIDTH,), np.float32)
+        ln(p + "ln_1")
+        sd[p + "mlp.c_fc.weight"] = _u(rng, (HIDDEN, WIDTH), 1.0 / math.sqrt(WIDTH))
+        sd[p + "mlp.c_fc.bias"] = _u(rng, (HIDDEN,), 1.0 / math.sqrt(WIDTH))
+        sd[p + "mlp.c_proj.weight"] = _u(rng, (WIDTH, HIDDEN), 1.0 / math.sqrt(HIDDEN))
+        sd[p + "mlp.c_proj.bias"] = _u(rng, (WIDTH,), 1.0 / math.sqrt(HIDDEN))
+        ln(p + "ln_2")
+    ln(ie + "ln_post")
+
+    for k in (1, 2):
+        sd[f"image_decoder.0.conv{k}.weight"] = _n(rng, (WIDTH, WIDTH, 3, 3), math.sqrt(2.0 / (WIDTH * 9)))
+        bn = f"image_decoder.0.bn{k}."
+        if stress:
+            sd[bn + "weight"] = rng.uniform(0.5, 1.5, size=(WIDTH,)).astype(np.float32)
+            sd[bn + "bias"] = _n(rng, (WIDTH,), 0.1)
+            sd[bn + "running_mean"] = _n(rng, (WIDTH,), 0.1)
+            sd[bn + "running_var"] = rng.uniform(0.5, 1.5, size=(WIDTH,)).astype(np.float32)
+        else:
+            sd[bn + "weight"] = np.ones((WIDTH,), np.float32)
+            sd[bn + "bias"] = np.zeros((WIDTH,), np.float32)
+            sd[bn + "running_mean"] = np.zeros((WIDTH,), np.float32)
+            sd[bn + "running_var"] = np.ones((WIDTH,), np.float32)
+        sd[bn + "num_batches_tracked"] = np.array(0, dtype=np.int64)
+    sd["projection.weight"] = _n(rng, (EMBED, WIDTH, 1, 1), math.sqrt(2.0 / EMBED))
+    sd["projection.bias"] = _n(rng, (EMBED,), 0.1) if stress else np.zeros((EMBED,), np.float32)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def make_text_features(n_bins: int, seed: int = 100) -> torch.Tensor:
+    """Stand-in for ``text_encoder(prompts)`` ([N, 512]); a constant input of the hot path (model.py:127-129)."""
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(_n(rng, (n_bins, EMBED), 1.0))
+
+
+def make_image(shape: Tuple[int, ...], seed: int = 1) -> torch.Tensor:
+    """ImageNet-normalised pixels are ~unit variance (datasets/crowd.py:64): standard normal synthetic images."""
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.standard_normal(size=shape, dtype=np.float32))
+
+
+def bins_and_anchors(name: str) -> Tuple[int, List[Tuple[float, float]], List[float]]:
+    c = BIN_CONFIGS[name]
+    return c["reduction"], [(float(a), float(b)) for a, b in c["bins"]], list(c["anchor_points"])

@@ -1,0 +1,132 @@
+"""End-to-end parity on a B200: the CUDA path (through get_model()/model(x)/sliding_window_predict -> C-ABI) against
+(a) the committed fixtures produced by the real reference and (b) the CPU oracle on the same seeded inputs.
+
+Gates are BASELINE.json's north_star tolerances (tests/parity.py): density max-rel-err <= 2e-2, count rel-err <= 0.5 %,
+bin-argmax agreement >= 99.5 %, window/fold indexing bit-exact (tests/test_kernels_gpu.py::test_fold_bit_exact).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_ebc_oracle as O
+from oracle.golden_cases import CASES, case_inputs
+
+from . import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0):
+    from clip_ebc_b200 import get_model
+
+    model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+                      prompt_type="word", num_vpt=case["num_vpt"], vpt_drop=0.0, deep_vpt=case["deep_vpt"],
+                      text_features=tf, window_chunk=window_chunk)
+    model.load_state_dict(sd, strict=True)
+    return model.to("cuda").eval()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cuda_path_matches_reference_fixture(case):
+    from clip_ebc_b200 import sliding_window_predict
+
+    sd, tf, bins, anchors, reduction, x = case_inputs(case)
+    gold = parity.load_golden(case["name"])
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    if case["kind"] == "forward":
+        model.training = True  # like the reference: train-mode forward returns (logits, exp)
+        logits, exp = model(x.cuda())
+        model.training = False
+        exp_eval = model(x.cuda())
+        assert torch.equal(exp_eval, exp)
+        logits, exp = logits.cpu().numpy(), exp.cpu().numpy()
+        assert exp.shape == gold["exp"].shape and logits.shape == gold["logits"].shape
+        rel = parity.density_max_rel(exp, gold["exp"])
+        agree = parity.argmax_agreement(logits, gold["logits"])
+        agree_m = parity.margin_conditioned_agreement(logits, gold["logits"], 0.05)
+        print(f"\n[{case['name']}] exp max-rel {rel:.3e}  count-rel {parity.count_rel(exp, gold['exp']):.3e}  "
+              f"argmax {agree:.4f} (margin>0.05: {agree_m:.4f})  logits max-abs {np.abs(logits - gold['logits']).max():.3e}")
+        assert rel <= parity.DENSITY_MAX_REL
+        assert parity.count_rel(exp, gold["exp"]) <= parity.COUNT_REL
+        assert agree >= parity.ARGMAX_AGREE
+    else:
+        dens = sliding_window_predict(model, x, case["window"], case["stride"])  # CPU in, CPU out like the reference
+        assert dens.device.type == "cpu" and tuple(dens.shape) == gold["density"].shape
+        d2, cnt = sliding_window_predict(model, x.cuda(), case["window"], case["stride"], return_device=True,
+                                         return_count=True)
+        assert torch.equal(d2.cpu(), dens)
+        rel = parity.density_max_rel(dens.numpy(), gold["density"])
+        crel = parity.count_rel(dens.numpy(), gold["density"])
+        print(f"\n[{case['name']}] density max-rel {rel:.3e}  count-rel {crel:.3e}")
+        assert rel <= parity.DENSITY_MAX_REL
+        assert crel <= parity.COUNT_REL
+        assert abs(cnt.item() - float(gold["count"])) <= parity.COUNT_REL * abs(float(gold["count"]))
+
+
+def test_batch64_against_oracle():
+    """BASELINE.json configs[1] shape (64 windows) against the CPU oracle on a bounded sample of the batch."""
+    case = dict(bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32, variant="default", wseed=0, xseed=21,
+                shape=(64, 3, 224, 224))
+    sd, tf, bins, anchors, reduction, x = case_inputs(case)
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    model.training = True
+    logits, exp = model(x.cuda())
+    model.training = False
+    idx = [0, 17, 40, 63]
+    lo, eo = O.clip_ebc_forward(x[idx], sd, tf, anchors, reduction, 32, True)
+    logits, exp = logits[idx].cpu().numpy(), exp[idx].cpu().numpy()
+    assert parity.density_max_rel(exp, eo.numpy()) <= parity.DENSITY_MAX_REL
+    assert parity.count_rel(exp, eo.numpy()) <= parity.COUNT_REL
+    assert parity.argmax_agreement(logits, lo.numpy()) >= parity.ARGMAX_AGREE
+    # chunking must not change results: same windows through a model that processes 24 windows per pass
+    model2 = build_model(case, sd, tf, bins, anchors, reduction, window_chunk=24)
+    exp2 = model2(x.cuda())
+    assert torch.equal(exp2[idx].cpu(), torch.from_numpy(exp))
+
+
+def test_large_image_properties():
+    """Full-size run (2048x1536, stride 112 -> 234 windows): size-independent properties instead of a CPU oracle run.
+
+    - stride == window: the fold is a pure tiling, so the density map equals model(x) on the tiles, bit for bit;
+    - overlapping stride: every cell is an average of per-window predictions, hence bounded by the anchor range.
+    """
+    from clip_ebc_b200 import sliding_window_predict
+
+    case = dict(bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32, variant="default", wseed=0, xseed=31,
+                shape=(1, 3, 1536, 2048))
+    sd, tf, bins, anchors, reduction, img = case_inputs(case)
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    img = img.cuda()
+    dens = sliding_window_predict(model, img[:, :, :1344, :1792], 224, 224, return_device=True)  # 6 x 8 tiles
+    tiles = img[:, :, :1344, :1792].unfold(2, 224, 224).unfold(3, 224, 224)  # [1,3,6,8,224,224]
+    tiles = tiles.permute(0, 2, 3, 1, 4, 5).reshape(48, 3, 224, 224).contiguous()
+    exp = model(tiles)  # [48,1,28,28]
+    ref = exp.view(6, 8, 28, 28).permute(0, 2, 1, 3).reshape(1, 1, 168, 224)
+    assert torch.equal(dens, ref)
+    dens, cnt = sliding_window_predict(model, img, 224, 112, return_device=True, return_count=True)
+    assert tuple(dens.shape) == (1, 1, 192, 256)
+    assert torch.isfinite(dens).all()
+    assert dens.min().item() >= min(anchors) - 1e-5 and dens.max().item() <= max(anchors) + 1e-5
+    assert abs(cnt.item() - dens.double().sum().item()) <= 1e-4 * dens.double().sum().item()
+
+
+def test_errors_follow_the_reference_convention():
+    from clip_ebc_b200 import get_model, sliding_window_predict
+
+    case = CASES[0]
+    sd, tf, bins, anchors, reduction, x = case_inputs(case)
+    with pytest.raises(AssertionError):
+        get_model("clip_vit_b_99", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    with pytest.raises(AssertionError):  # ViT needs num_vpt / deep_vpt / vpt_drop (models/clip/model.py:55-58)
+        get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    with pytest.raises(AssertionError):
+        sliding_window_predict(model, x[0], 224, 224)  # not 4-D
+    with pytest.raises(AssertionError):
+        sliding_window_predict(model, x, 224, 448)  # stride > window
+    with pytest.raises(RuntimeError):
+        model(x[:, :, :200, :200].cuda())  # not a multiple of 16
+    cpu_model = get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors,
+                          num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
+    with pytest.raises(RuntimeError):
+        cpu_model(x[:, :, :224, :224])  # no CPU fallback
