@@ -38,6 +38,8 @@ SIGNATURES = {
     "clipebc_last_error": (C.c_char_p, []),
     "clipebc_abi_version": (_i, []),
     "clipebc_launch_count": (_i64, []),
+    "clipebc_profile_enable": (_i, [_i]),
+    "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_model_create": (_i, [C.POINTER(ClipEbcConfig), C.POINTER(_vp)]),
     "clipebc_model_destroy": (None, [_vp]),
     "clipebc_model_set_tensor": (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i64), _i]),

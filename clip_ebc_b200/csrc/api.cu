@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,7 +18,39 @@
 namespace cebc {
 
 static std::atomic<int64_t> g_launches{0};
-void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- launch accounting / optional per-launch CUDA-event profiling (bench.py roofline breakdown) -------------------
+namespace {
+struct ProfRec {
+  std::string tag;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double flops = 0, bytes = 0;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+thread_local const char* g_tag = nullptr;
+}  // namespace
+
+void set_launch_tag(const char* tag) { g_tag = tag; }
+
+LaunchScope::LaunchScope(cudaStream_t stream, const char* kind, double flops, double bytes) : stream_(stream), slot_(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.tag = g_tag ? std::string(kind) + ":" + g_tag : std::string(kind);
+  r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, stream);
+  g_prof.push_back(r);
+  slot_ = static_cast<int>(g_prof.size()) - 1;
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot_].e1, stream_);
+}
 
 namespace {
 
@@ -94,7 +127,10 @@ struct clipebc_model {
   std::map<int, DevBuf> pos_cache;  // key hp * 4096 + wp -> f32 [1 + hp*wp, 768]
   // workspace
   DevBuf ws_patch_rows, ws_patch_embed, ws_X, ws_Xn, ws_QKV, ws_AO, ws_Hid, ws_Y, ws_Ub, ws_Uf, ws_D1, ws_D2, ws_F,
-      ws_preds, ws_idx;
+      ws_preds;
+  // device-resident index tables (window -> patch-grid row, window origins, fold cell origins), cached per geometry so
+  // the steady state has no host->device upload and no host synchronisation
+  std::map<std::string, DevBuf> idx_cache;
 };
 
 namespace {
@@ -221,16 +257,23 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   for (int l = 0; l < kLayers; ++l) {
     const LayerPack& L = m->layer[l];
     K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, 1, M, 1, 1, 0));
+    set_launch_tag("qkv");
     K_TRY(gemm_bf16_tn(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
                        plain(M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
+    set_launch_tag(nullptr);
     K_TRY(attention_h64(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO));
+    set_launch_tag("out_proj");
     K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
                        plain(M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
+    set_launch_tag(nullptr);
     K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, 1, M, 1, 1, 0));
+    set_launch_tag("c_fc");
     K_TRY(gemm_bf16_tn(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
                        plain(M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
+    set_launch_tag("c_proj");
     K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
                        plain(M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
+    set_launch_tag(nullptr);
   }
 
   // ln_post on the patch rows only (cls / prompt rows are dropped, model.py:185-188), fp32 out
@@ -253,9 +296,11 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   __nv_bfloat16* D2 = m->ws_D2.as<__nv_bfloat16>();
   GemmParams p1 = pc;
   p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp;
+  set_launch_tag("dec_conv1");
   K_TRY(gemm_bf16_tn(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
   GemmParams p2 = pc;
   p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
+  set_launch_tag("dec_conv2");
   K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth, m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
 
   // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
@@ -264,8 +309,10 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   pp.seg_col_start[0] = 0; pp.seg_col_start[1] = kWidth; pp.seg_col_start[2] = 0;
   float* F = m->ws_F.as<float>();
   pp.out = F; pp.ldo = kEmbed; pp.bias = raw_ptr(m, "projection.bias");
+  set_launch_tag("projection");
   K_TRY(gemm_bf16_tn(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
 
+  set_launch_tag(nullptr);
   K_TRY(ebc_head(s, F, m->tmat.as<float>(), raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
   return CLIPEBC_OK;
 }
@@ -290,6 +337,42 @@ extern "C" {
 const char* clipebc_last_error(void) { return g_err.c_str(); }
 int clipebc_abi_version(void) { return CLIPEBC_ABI_VERSION; }
 int64_t clipebc_launch_count(void) { return g_launches.load(); }
+
+int clipebc_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& r : g_prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  return CLIPEBC_OK;
+}
+
+int clipebc_profile_dump(char* buf, int cap) {
+  if (!buf || cap <= 2) return fail(CLIPEBC_EINVAL, "profile_dump: no buffer");
+  CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { double ms = 0, flops = 0, bytes = 0; int64_t n = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    if (!agg.count(r.tag)) order.push_back(r.tag);
+    Agg& a = agg[r.tag];
+    a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.n += 1;
+  }
+  std::string out = "{";
+  for (size_t i = 0; i < order.size(); ++i) {
+    const Agg& a = agg[order[i]];
+    char line[256];
+    std::snprintf(line, sizeof(line), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld, \"flops\": %.6e, \"bytes\": %.6e}",
+                  i ? ", " : "", order[i].c_str(), a.ms, static_cast<long long>(a.n), a.flops, a.bytes);
+    out += line;
+  }
+  out += "}";
+  if (static_cast<int>(out.size()) + 1 > cap) return fail(CLIPEBC_EINVAL, "profile_dump: buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return CLIPEBC_OK;
+}
 
 int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (!cfg || !out) return fail(CLIPEBC_EINVAL, "null argument");
@@ -418,20 +501,28 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * kWidth * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
   K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  set_launch_tag("patch_embed");
   K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
                      kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+  set_launch_tag(nullptr);
   // window b reads patch rows [b * npatch, (b+1) * npatch)
-  std::vector<int> base(B);
-  for (int b = 0; b < B; ++b) base[b] = b * npatch;
-  CUDA_TRY(m->ws_idx.reserve(static_cast<size_t>(B) * 4));
-  CUDA_TRY(cudaMemcpyAsync(m->ws_idx.p, base.data(), static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));  // `base` is pageable host memory
+  const std::string key = "fw:" + std::to_string(B) + ":" + std::to_string(npatch);
+  auto cached = m->idx_cache.find(key);
+  if (cached == m->idx_cache.end()) {
+    std::vector<int> base(B);
+    for (int b = 0; b < B; ++b) base[b] = b * npatch;
+    DevBuf& buf = m->idx_cache[key];
+    CUDA_TRY(buf.reserve(static_cast<size_t>(B) * 4));
+    CUDA_TRY(cudaMemcpy(buf.p, base.data(), static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice));
+    cached = m->idx_cache.find(key);
+  }
+  const int* d_win_base = cached->second.as<int>();
 
   const int chunk = default_chunk(m);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nw = std::min(chunk, B - b0);
     float* lo = logits_out_dev ? logits_out_dev + static_cast<int64_t>(b0) * m->cfg.num_bins * gh * gw : nullptr;
-    if ((rc = run_windows(m, s, m->ws_idx.as<int>() + b0, wp, nw, hp, wp, pos,
+    if ((rc = run_windows(m, s, d_win_base + b0, wp, nw, hp, wp, pos,
                           exp_out_dev + static_cast<int64_t>(b0) * gh * gw, lo)))
       return rc;
   }
@@ -476,6 +567,10 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   for (int v : co) on_grid = on_grid && (v % kPatch == 0);
 
   // host-side index tables: [0, n_win) win_base | [n_win, 3 n_win) origins (y, x) | row cells | col cells
+  const std::string key = "sw:" + std::to_string(H) + ":" + std::to_string(W) + ":" + std::to_string(wh) + ":" +
+                          std::to_string(ww) + ":" + std::to_string(sh) + ":" + std::to_string(sw);
+  auto cached = m->idx_cache.find(key);
+  const bool need_upload = cached == m->idx_cache.end();
   std::vector<int> tab(static_cast<size_t>(3) * n_win + nr + nc);
   int src_pitch;
   int64_t rows;
@@ -498,10 +593,14 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
     }
   for (int i = 0; i < nr; ++i) tab[3 * n_win + i] = ro[i] / r;       // x_start // reduction (eval_utils.py:90)
   for (int j = 0; j < nc; ++j) tab[3 * n_win + nr + j] = co[j] / r;
-  CUDA_TRY(m->ws_idx.reserve(tab.size() * 4));
-  CUDA_TRY(cudaMemcpyAsync(m->ws_idx.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  const int* d_base = m->ws_idx.as<int>();
+  if (need_upload) {
+    if (m->idx_cache.size() > 64) m->idx_cache.clear();  // bound the cache for streams of differently sized images
+    DevBuf& buf = m->idx_cache[key];
+    CUDA_TRY(buf.reserve(tab.size() * 4));
+    CUDA_TRY(cudaMemcpy(buf.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    cached = m->idx_cache.find(key);
+  }
+  const int* d_base = cached->second.as<int>();
   const int* d_orig = d_base + n_win;
   const int* d_rc = d_base + 3 * n_win;
   const int* d_cc = d_rc + nr;
@@ -510,8 +609,10 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
   if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.as<__nv_bfloat16>()));
   else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  set_launch_tag("patch_embed");
   K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
                      kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+  set_launch_tag(nullptr);
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
   float* preds = m->ws_preds.as<float>();

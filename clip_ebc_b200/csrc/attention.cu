@@ -207,8 +207,12 @@ const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const _
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr_set = true;
   }
-  attention_h64_kernel<<<n_win * 12, kAttnThreads, kAttnSmem, stream>>>(qkv, const_kv, n_const, t_live, out);
-  note_launch();
+  {
+    const double tk = t_live + n_const;
+    LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
+                      2.0 * n_win * t_live * (2304.0 + 768.0));
+    attention_h64_kernel<<<n_win * 12, kAttnThreads, kAttnSmem, stream>>>(qkv, const_kv, n_const, t_live, out);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

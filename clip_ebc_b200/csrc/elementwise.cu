@@ -302,7 +302,6 @@ inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
 }
 
 inline const char* last_err() {
-  note_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -315,6 +314,7 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
   if (n_rows_out <= 0) return nullptr;
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
   const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
+  LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_is_bf16 ? 2.0 : 4.0)));
   if (out_is_bf16)
     layernorm768_kernel<true><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
                                                           rows_in_per_group, in_row_offset);
@@ -329,6 +329,7 @@ const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H
   if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
   if (y0 < 0 || x0 < 0 || y0 + gh * 16 > H || x0 + gw * 16 > W) return "patchify: grid exceeds image";
   const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * 16 * gw * 4;
+  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
   patchify16_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, n_img, H, W, y0, x0, gh, gw,
                                                                                      out);
   return last_err();
@@ -338,6 +339,7 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
                                int n_win, int hp, int wp, __nv_bfloat16* out) {
   if (n_win <= 0) return "patchify: no windows";
   const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * 16 * wp * 4;
+  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
   patchify16_windows_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, H, W, origins_yx_dev,
                                                                                              n_win, hp, wp, out);
   return last_err();
@@ -349,6 +351,7 @@ const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const
   if (n_win <= 0) return "assemble_tokens: no windows";
   if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
   const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
+  LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * kD * 8.0);
   assemble_tokens_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(
       patch_embed, win_base_dev, src_pitch, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
   return last_err();
@@ -358,6 +361,7 @@ const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, i
                                __nv_bfloat16* U_bf16, float* U_f32) {
   if (n_win <= 0) return "resample: no windows";
   const int64_t rows = static_cast<int64_t>(n_win) * (gh + 2) * (gw + 2);
+  LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * kD * 4.0 + static_cast<double>(rows) * kD * 6.0);
   resample_to_padded_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(Y, n_win, hp, wp, gh, gw, U_bf16,
                                                                                          U_f32);
   return last_err();
@@ -365,24 +369,28 @@ const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, i
 
 const char* f32_to_bf16(cudaStream_t stream, const float* in, __nv_bfloat16* out, int64_t n) {
   if (n <= 0) return nullptr;
+  LaunchScope scope(stream, "pack");
   f32_to_bf16_kernel<<<grid_for(n, 256, 4096), 256, 0, stream>>>(in, out, n);
   return last_err();
 }
 
 const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
                             const float* var, float eps, int O, int I, __nv_bfloat16* Wp, float* bias) {
+  LaunchScope scope(stream, "pack");
   fold_conv3x3_bn_kernel<<<grid_for(static_cast<int64_t>(O) * I * 9, 256, 4096), 256, 0, stream>>>(W, gamma, beta, mean,
                                                                                                    var, eps, O, I, Wp, bias);
   return last_err();
 }
 
 const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, __nv_bfloat16* out) {
+  LaunchScope scope(stream, "pack");
   split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(W, O, I, out);
   return last_err();
 }
 
 const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat) {
   if (n <= 0) return "pack_text: no bins";
+  LaunchScope scope(stream, "pack");
   pack_text_kernel<<<(n + 3) / 4, 128, 0, stream>>>(text, logit_scale, n, d, tmat);
   return last_err();
 }

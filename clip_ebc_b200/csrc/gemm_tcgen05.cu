@@ -311,8 +311,13 @@ cudaError_t launch_one(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int num_tiles = m_tiles * (p.N / BLOCK_N);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  note_launch();
+  {
+    // algorithmic work: 2*M*N*K flops; bytes = A + W + out (+ resid), each touched once
+    LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
+                      2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
+                          4.0 * p.M * static_cast<double>(p.N));
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  }
   return cudaGetLastError();
 }
 

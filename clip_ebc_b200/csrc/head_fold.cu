@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, 
 }
 
 inline const char* last_err() {
-  note_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -113,6 +112,7 @@ const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, con
   int64_t blocks = (cells + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
+  LaunchScope scope(stream, "ebc_head", 0.0, static_cast<double>(cells) * (kE * 4.0 + 4.0));
   ebc_head_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(F, tmat, anchors, n_bins, n_win, gh, gw, exp_out,
                                                                 logits_out);
   return last_err();
@@ -125,11 +125,15 @@ const char* fold_average(cudaStream_t stream, const float* preds, const int* row
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  fold_average_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(preds, row_cells_dev, col_cells_dev, n_rows, n_cols,
-                                                                    gh, gw, Ho, Wo, density);
+  {
+    LaunchScope scope(stream, "fold", 0.0, 4.0 * (static_cast<double>(n_rows) * n_cols * gh * gw + static_cast<double>(total)));
+    fold_average_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(preds, row_cells_dev, col_cells_dev, n_rows, n_cols,
+                                                                      gh, gw, Ho, Wo, density);
+  }
   const char* e = last_err();
   if (e) return e;
   if (count_out != nullptr) {
+    LaunchScope scope(stream, "count_sum", 0.0, 4.0 * static_cast<double>(total));
     sum_kernel<<<1, 1024, 0, stream>>>(density, total, count_out);
     return last_err();
   }

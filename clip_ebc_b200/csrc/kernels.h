@@ -45,8 +45,18 @@ inline GemmParams gemm_params_plain(int M, int N, int K) {
 const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                          int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
 int device_num_sms();
-// every kernel launch of this library is counted (clipebc_launch_count in the C-ABI)
-void note_launch(int n = 1);
+// Every kernel launch of this library goes through a LaunchScope: it counts the launch (clipebc_launch_count) and, when
+// profiling is enabled (clipebc_profile_enable), brackets it with CUDA events on the launching stream and books the
+// duration, algorithmic FLOPs and bytes under `tag` (the current tag set by api.cu, else `kind`).
+struct LaunchScope {
+  LaunchScope(cudaStream_t stream, const char* kind, double flops = 0.0, double bytes = 0.0);
+  ~LaunchScope();
+  LaunchScope(const LaunchScope&) = delete;
+  LaunchScope& operator=(const LaunchScope&) = delete;
+  cudaStream_t stream_;
+  int slot_;
+};
+void set_launch_tag(const char* tag);  // nullptr clears
 
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
 // out[r] = LN(in[map(r)]) * gamma + beta, eps 1e-5, fp32 statistics (two-pass, in registers). D = 768 only.

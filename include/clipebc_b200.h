@@ -50,6 +50,12 @@ int clipebc_abi_version(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 int64_t clipebc_launch_count(void);
 
+/* Optional per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
+ * clipebc_profile_dump synchronises the device and writes a JSON object {"<kernel>[:<use>]": {"ms", "launches",
+ * "flops", "bytes"}} (algorithmic work of the launches, summed since enable) into buf. Enabling clears the records. */
+int clipebc_profile_enable(int on);
+int clipebc_profile_dump(char* buf, int cap);
+
 /* ---- model lifetime: mirrors get_model() + load_state_dict() + .eval() ---------------------------------------- */
 int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out);
 void clipebc_model_destroy(clipebc_model* m);

@@ -23,9 +23,9 @@ CASES = [
          variant="stress", wseed=3, xseed=4, shape=(1, 3, 300, 500), window=224, stride=200),
     # BASELINE.json configs[3]: reduction 16 / 32 bin sets with shallow VPT
     dict(name="forward_r16_shallow_stress", kind="forward", bins="r16_t8_qnrf", deep_vpt=False, num_vpt=32,
-         variant="stress", wseed=5, xseed=6, shape=(2, 3, 224, 224)),
+         variant="stress", wseed=5, xseed=6, shape=(8, 3, 224, 224)),
     dict(name="forward_r32_shallow_stress", kind="forward", bins="r32_t19_qnrf", deep_vpt=False, num_vpt=32,
-         variant="stress", wseed=5, xseed=7, shape=(2, 3, 224, 224)),
+         variant="stress", wseed=5, xseed=7, shape=(16, 3, 224, 224)),
     # r32 with overlapping stride 112: window cell origins floor (112 // 32 = 3), reference behaviour kept
     dict(name="sliding_448x672_s112_r32_shallow", kind="sliding", bins="r32_t19_qnrf", deep_vpt=False, num_vpt=32,
          variant="default", wseed=8, xseed=9, shape=(1, 3, 448, 672), window=224, stride=112),
