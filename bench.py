@@ -247,7 +247,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.clipebc_launch_count() - l0
-    clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -313,6 +312,8 @@ def main():
         e2e = {"value": world * units_per_step * K / (t2.item() / 1000.0), "unit": "windows/s",
                "h2d_bytes_per_step": 3 * 1536 * 2048 * 4, "d2h_bytes_per_step": 192 * 256 * 4,
                "ms_per_step": t2.item() / K, "images_per_sec": world * K / (t2.item() / 1000.0)}
+
+    clocks = sampler.stop()  # sampled over both timed regions (device-resident and end-to-end)
 
     # ---- per-kernel breakdown (separate instrumented pass: CUDA events around every launch on its stream) ---------
     lib.clipebc_profile_enable(1)

@@ -29,14 +29,18 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 256;
 
+constexpr int kStageRowBytes = 144;                       // 128 B payload + 16 B pad: conflict-free 16 B accesses
+constexpr int kStagingPerWarp = 32 * kStageRowBytes;      // epilogue transpose buffer of one warp (32 rows)
+constexpr int kStagingBytes = 4 * kStagingPerWarp;
+
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N > 128) ? 4 : 6;
+  static constexpr int kStages = (BLOCK_N > 192) ? 4 : (BLOCK_N > 128 ? 5 : 6);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -44,95 +48,114 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return __fdividef(x, 1.0f + __expf(-1.702f * x));
 }
 
-// One thread owns one output row; v[32] are 32 consecutive accumulator columns starting at global column n.
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int n, const uint32_t (&r)[32]) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+constexpr bool epi_out_is_bf16() {
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16;
+}
 
-  if constexpr (EPI != EPI_F32) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+// ---- epilogues with bf16 output: 64 accumulator columns per pass --------------------------------------------------
+// Phase 1 (thread = output row, as tcgen05.ld delivers it): bias + activation, pack to bf16, write the row's 128 B into
+// the warp's staging tile. Phase 2 (after the transpose through smem): every warp store instruction writes 4 complete
+// 128 B row segments, so global stores are fully coalesced instead of 32 scattered 16 B pieces.
+template <int EPI>
+__device__ __forceinline__ void epilogue_bf16_chunk64(const GemmParams& p, uint8_t* stg, int lane, int row0, int n,
+                                                      const uint32_t (&r0)[32], const uint32_t (&r1)[32]) {
+  const int row = row0 + lane;
+  bool border = false;
+  if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
+    // zero-bordered grid: rows are (image, py, px) over a (mask_hp x mask_wp) padded grid; border rows must stay 0
+    const int rpi = p.mask_hp * p.mask_wp;
+    const int q = row % rpi;
+    const int py = q / p.mask_wp, px = q - py * p.mask_wp;
+    border = (py == 0) || (py == p.mask_hp - 1) || (px == 0) || (px == p.mask_wp - 1);
+  }
+  uint4* my = reinterpret_cast<uint4*>(stg + lane * kStageRowBytes);
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+  for (int j = 0; j < 8; ++j) {  // 8 columns per iteration
+    const uint32_t* src = (j < 4) ? &r0[8 * j] : &r1[8 * (j - 4)];
+    const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+    float v[8];
+    v[0] = __uint_as_float(src[0]) + ba.x; v[1] = __uint_as_float(src[1]) + ba.y;
+    v[2] = __uint_as_float(src[2]) + ba.z; v[3] = __uint_as_float(src[3]) + ba.w;
+    v[4] = __uint_as_float(src[4]) + bb.x; v[5] = __uint_as_float(src[5]) + bb.y;
+    v[6] = __uint_as_float(src[6]) + bb.z; v[7] = __uint_as_float(src[7]) + bb.w;
+    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = quick_gelu(v[k]);
     }
-  } else {
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+    if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
+    }
+    my[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  __syncwarp();
+  const int piece = lane & 7, rsub = lane >> 3;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * kStageRowBytes + piece * 16);
+    if (row0 + rr < p.M)
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + piece * 8) = u;
+  }
+  __syncwarp();
+}
+
+// ---- epilogues that finish in fp32 (residual stream, projection, conv2 hi/lo split): 32 columns per pass ----------
+// The raw accumulators are transposed through smem first; bias, residual add and the store all happen in the
+// coalesced layout (lane -> 4 consecutive columns of one row, a warp instruction covers 4 rows x 128 B).
+// The residual of the NEXT chunk is requested before the current chunk is processed (the output may alias the residual
+// -- the in-place residual stream -- so the compiler cannot hoist those loads itself).
+template <int EPI>
+constexpr bool epi_has_resid() { return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT; }
+
+template <int EPI>
+__device__ __forceinline__ void load_resid_chunk32(const GemmParams& p, int lane, int row0, int n, float4 (&x)[8]) {
+  if constexpr (epi_has_resid<EPI>()) {
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row0 + it * 4 + rsub;
+      x[it] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(grow) * p.ldr + n + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_f32_chunk32(const GemmParams& p, uint8_t* stg, int lane, int row0, int n,
+                                                     const uint32_t (&r)[32], const float4 (&x)[8]) {
+  uint4* my = reinterpret_cast<uint4*>(stg + lane * kStageRowBytes);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) my[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != EPI_F32 || p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n + c4));
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    const int grow = row0 + rr;
+    float4 v = *reinterpret_cast<const float4*>(stg + rr * kStageRowBytes + c4 * 4);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if constexpr (epi_has_resid<EPI>()) { v.x += x[it].x; v.y += x[it].y; v.z += x[it].z; v.w += x[it].w; }
+    if (grow < p.M) {
+      if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
+        // relu, then split into hi + lo bf16 so the next GEMM can recover ~fp32 accuracy: x ~= hi + lo
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
+        const float hz = __bfloat162float(__float2bfloat16_rn(v.z)), hw = __bfloat162float(__float2bfloat16_rn(v.w));
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4;
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+        *reinterpret_cast<uint2*>(o + p.N) = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4) = v;
       }
     }
   }
-
-  if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldr + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 x = r4[j];
-      v[4 * j + 0] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-    }
-  }
-
-  if constexpr (EPI == EPI_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32) {
-    float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16) {
-    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-    }
-    if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
-      // zero-bordered grid: rows are (image, py, px) over a (mask_hp x mask_wp) padded grid; border rows must stay 0
-      const int rpi = p.mask_hp * p.mask_wp;
-      const int q = row % rpi;
-      const int py = q / p.mask_wp, px = q - py * p.mask_wp;
-      const bool border = (py == 0) || (py == p.mask_hp - 1) || (px == 0) || (px == p.mask_wp - 1);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = border ? 0.0f : fmaxf(v[j], 0.0f);
-    }
-    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 u;
-      u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-      u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-      u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-      o4[j] = u;
-    }
-  } else if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
-    // relu, then split into hi + lo bf16 so the next GEMM can recover ~fp32 accuracy: x ~= hi + lo
-    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + n;
-    uint4* ohi = reinterpret_cast<uint4*>(o);
-    uint4* olo = reinterpret_cast<uint4*>(o + p.N);
-    float lo[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = fmaxf(v[j], 0.0f);
-      const float h = __bfloat162float(__float2bfloat16_rn(v[j]));
-      lo[j] = v[j] - h;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 u, w;
-      u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-      u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-      u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-      w.x = pack_bf16x2(lo[8 * j + 0], lo[8 * j + 1]);
-      w.y = pack_bf16x2(lo[8 * j + 2], lo[8 * j + 3]);
-      w.z = pack_bf16x2(lo[8 * j + 4], lo[8 * j + 5]);
-      w.w = pack_bf16x2(lo[8 * j + 6], lo[8 * j + 7]);
-      ohi[j] = u;
-      olo[j] = w;
-    }
-  }
+  __syncwarp();
 }
 
 template <int BLOCK_N, int EPI>
@@ -144,7 +167,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
@@ -233,20 +257,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp >= 4) {
     // ------------------------------- epilogue -------------------------------
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* stg = staging + q * kStagingPerWarp;
     uint32_t as = 0, aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
-      const int row = m_blk * kBlockM + q * 32 + lane;
+      const int row0 = m_blk * kBlockM + q * 32;
       const int n0 = n_blk * BLOCK_N;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      if constexpr (epi_out_is_bf16<EPI>()) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) epilogue_row32<EPI>(p, row, n0 + c * 32, r);
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_addr + c * 64, r0);
+          tmem_ld_32x32b_x32(t_addr + c * 64 + 32, r1);
+          tmem_ld_wait();
+          epilogue_bf16_chunk64<EPI>(p, stg, lane, row0, n0 + c * 64, r0, r1);
+        }
+      } else {
+        float4 xa[8], xb[8];
+        load_resid_chunk32<EPI>(p, lane, row0, n0, xa);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          load_resid_chunk32<EPI>(p, lane, row0, n0 + (c + 1) * 32, xb);  // in flight while chunk c is finished
+          tmem_ld_wait();
+          epilogue_f32_chunk32<EPI>(p, stg, lane, row0, n0 + c * 32, r, xa);
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r);
+          if (c + 2 < BLOCK_N / 32) load_resid_chunk32<EPI>(p, lane, row0, n0 + (c + 2) * 32, xa);
+          tmem_ld_wait();
+          epilogue_f32_chunk32<EPI>(p, stg, lane, row0, n0 + (c + 1) * 32, r, xb);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -336,6 +379,27 @@ cudaError_t launch_epi(cudaStream_t stream, int epi, const CUtensorMap& ta, cons
   }
 }
 
+// Persistent grid of one CTA per SM: the slowest SM executes ceil(tiles / SMs) tiles. Pick the tile width whose
+// (rounds x tile cost) is smallest; narrower tiles pay a fixed per-tile overhead and a lower MMA/smem efficiency.
+int pick_block_n(int M, int N, int num_sms) {
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  int best = 0;
+  double best_cost = 0.0;
+  const int cand[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (N % bn != 0) continue;
+    const long tiles = static_cast<long>(m_tiles) * (N / bn);
+    const long rounds = (tiles + num_sms - 1) / num_sms;
+    // measured on B200 (profiles/gemm_bench.py, K = 768): time per tile ~ (bn + 136); 128-wide tiles are
+    // shared-memory-bandwidth bound and cost about as much as 192-wide ones
+    const double tile_cost = (bn == 128) ? 320.0 : bn + 136.0;
+    const double cost = rounds * tile_cost;
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best ? best : 128;
+}
+
 }  // namespace
 
 int device_num_sms() {
@@ -357,9 +421,10 @@ const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, i
   if (p.seg_kblocks * p.n_seg * kBlockK != p.K) return "gemm: segments do not tile K";
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return "gemm: operands must be 16B aligned";
   if ((lda * 2) % 16 != 0 || (ldw * 2) % 16 != 0) return "gemm: row pitch must be a multiple of 16 bytes";
-  if (p.N % 32 != 0) return "gemm: N must be a multiple of 32";
-  if (block_n == 0) block_n = (p.N % 256 == 0) ? 256 : 128;
-  if (block_n != 128 && block_n != 256) return "gemm: block_n must be 128 or 256";
+  if (p.N % 64 != 0) return "gemm: N must be a multiple of 64";
+  const int num_sms = device_num_sms();
+  if (block_n == 0) block_n = pick_block_n(p.M, p.N, num_sms);
+  if (block_n != 128 && block_n != 192 && block_n != 256) return "gemm: block_n must be 128, 192 or 256";
   if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
   if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
@@ -368,9 +433,9 @@ const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, i
   CUtensorMap ta, tb;
   if (!make_tmap_bf16(&ta, A, a_rows, a_cols, lda, kBlockM)) return "gemm: cuTensorMapEncodeTiled(A) failed";
   if (!make_tmap_bf16(&tb, W, p.N, p.K, ldw, block_n)) return "gemm: cuTensorMapEncodeTiled(W) failed";
-  const int num_sms = device_num_sms();
-  cudaError_t e = (block_n == 256) ? launch_epi<256>(stream, epi, ta, tb, p, num_sms)
-                                   : launch_epi<128>(stream, epi, ta, tb, p, num_sms);
+  cudaError_t e = (block_n == 256)   ? launch_epi<256>(stream, epi, ta, tb, p, num_sms)
+                  : (block_n == 192) ? launch_epi<192>(stream, epi, ta, tb, p, num_sms)
+                                     : launch_epi<128>(stream, epi, ta, tb, p, num_sms);
   if (e != cudaSuccess) return cudaGetErrorString(e);
   return nullptr;
 }

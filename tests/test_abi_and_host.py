@@ -1,0 +1,148 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/clipebc_b200.h declares, the host-only integer
+logic (window enumeration) matches the oracle and its plain-C restatement bit for bit, and the Python host mirrors the
+reference's error conventions. No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(os.path.join(ROOT, "clip_ebc_b200", "libclipebc_b200.so")):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    from clip_ebc_b200 import _lib
+
+    return _lib.load()
+
+
+@pytest.fixture(scope="module")
+def fold_c():
+    path = os.path.join(ROOT, "oracle", "_build", "libfold_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make"], cwd=os.path.join(ROOT, "oracle"))
+    so = C.CDLL(path)
+    so.oracle_num_windows.restype = C.c_int
+    so.oracle_fold.restype = C.c_int
+    return so
+
+
+def test_every_header_symbol_is_exported_and_bound(lib):
+    from clip_ebc_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "clipebc_b200.h")).read()
+    declared = set(re.findall(r"\b(clipebc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert lib.clipebc_abi_version() == 1
+    assert lib.clipebc_launch_count() == 0  # nothing ran on this CPU box
+
+
+def test_library_is_self_contained():
+    """The boundary is a plain C-ABI: no torch / python symbols, no libcuda.so link-time dependency."""
+    out = subprocess.check_output(["ldd", os.path.join(ROOT, "clip_ebc_b200", "libclipebc_b200.so")], text=True)
+    assert "libtorch" not in out and "libc10" not in out and "libpython" not in out
+    assert "libcuda.so" not in out and "not found" not in out
+
+
+CASES = [(448, 448, 224, 224), (1536, 2048, 224, 112), (3072, 4096, 224, 224), (3072, 4096, 224, 112),
+         (448, 672, 224, 112), (300, 500, 224, 200), (224, 224, 224, 224), (225, 1000, 224, 7), (480, 700, 224, 100)]
+
+
+@pytest.mark.parametrize("H,W,win,s", CASES)
+def test_window_origins_bit_exact(lib, fold_c, H, W, win, s):
+    from clip_ebc_b200 import ops
+    from oracle import clip_ebc_oracle as O
+
+    ro, co = ops.window_origins(H, W, (win, win), (s, s))
+    ref_r, ref_c = O.window_origins(H, W, (win, win), (s, s))
+    assert (ro, co) == (ref_r, ref_c)
+    # plain-C restatement
+    n = fold_c.oracle_num_windows(H, win, s)
+    arr = (C.c_int * n)()
+    fold_c.oracle_window_origins(H, win, s, arr)
+    assert list(arr) == ro
+
+
+def test_c_fold_oracle_matches_numpy_oracle(fold_c):
+    from oracle import clip_ebc_oracle as O
+
+    rng = np.random.default_rng(0)
+    for (H, W, win, s, r) in [(448, 672, 224, 112, 8), (300, 500, 224, 200, 8), (448, 672, 224, 112, 32)]:
+        ro, co = O.window_origins(H, W, (win, win), (s, s))
+        g = win // r
+        preds = rng.standard_normal((len(ro) * len(co), 1, g, g), dtype=np.float32)
+        ref = O.fold_average(preds, H, W, (win, win), (s, s), r)[0]
+        out = np.empty((H // r, W // r), np.float32)
+        rc = fold_c.oracle_fold(preds.ctypes.data_as(C.c_void_p), H, W, win, win, s, s, r, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.array_equal(out, ref)
+
+
+def test_window_origins_errors(lib):
+    nr, nc = C.c_int(), C.c_int()
+    assert lib.clipebc_window_origins(448, 448, 224, 224, 448, 224, C.byref(nr), C.byref(nc), None, None) == 1  # stride > window
+    assert b"stride" in lib.clipebc_last_error()
+    assert lib.clipebc_window_origins(100, 448, 224, 224, 224, 224, C.byref(nr), C.byref(nc), None, None) == 1  # image < window
+    assert lib.clipebc_window_origins(448, 448, 0, 224, 224, 224, C.byref(nr), C.byref(nc), None, None) == 1
+
+
+def test_model_create_validates_config(lib):
+    from clip_ebc_b200 import _lib
+
+    h = C.c_void_p()
+    bad = _lib.ClipEbcConfig(224, 12, 32, 1, 5, 0)  # reduction 12
+    assert lib.clipebc_model_create(C.byref(bad), C.byref(h)) == 1
+    ok = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0)
+    assert lib.clipebc_model_create(C.byref(ok), C.byref(h)) == 0
+    # packing without tensors is a state error, reported by name
+    assert lib.clipebc_model_pack(h, None) == 3
+    assert b"missing tensor" in lib.clipebc_last_error()
+    # forward before pack is refused as well
+    assert lib.clipebc_forward_windows(h, C.c_void_p(16), 1, 224, 224, C.c_void_p(16), None, None) == 3
+    lib.clipebc_model_destroy(h)
+
+
+def test_python_host_mirrors_reference_interface():
+    from clip_ebc_b200 import get_model, sliding_window_predict
+    from oracle import weights
+
+    r, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
+    with pytest.raises(AssertionError):
+        get_model("clip_vit_b_99", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    with pytest.raises(AssertionError, match="num_vpt"):
+        get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    with pytest.raises(NotImplementedError):
+        get_model("clip_resnet50", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    model = get_model("CLIP_ViT_B_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors, prompt_type="word",
+                      num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=weights.make_text_features(5))
+    assert model.reduction == 8 and model.bins == bins and tuple(model.anchor_points.shape) == (1, 5, 1, 1)
+    sd = weights.make_state_dict(0)
+    assert set(sd) == set(model.state_dict())  # reference key names, strict round-trip
+    model.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError, match="unexpected|Unexpected|Missing|missing"):
+        model.load_state_dict({**sd, "bogus.weight": torch.zeros(1)}, strict=True)
+    # text_encoder.* entries of a reference checkpoint are accepted and round-trip
+    model.load_state_dict({**sd, "text_encoder.ln_final.weight": torch.ones(512)}, strict=True)
+    assert "text_encoder.ln_final.weight" in model.state_dict()
+    x = torch.zeros(1, 3, 448, 448)
+    with pytest.raises(AssertionError, match="4D"):
+        sliding_window_predict(model, x[0], 224, 224)
+    with pytest.raises(AssertionError, match="Stride must be smaller"):
+        sliding_window_predict(model, x, 224, 448)
+    with pytest.raises(RuntimeError, match="CUDA device only"):  # no CPU fallback
+        sliding_window_predict(model, x, 224, 224)
+    shallow = get_model("clip_vit_b_16", input_size=224, reduction=16, bins=bins, anchor_points=anchors, num_vpt=32,
+                        vpt_drop=0.0, deep_vpt=False)
+    assert [k for k in shallow.state_dict() if k.startswith("vpt_")] == ["vpt_0"]
+    with pytest.raises(RuntimeError, match="text_features"):
+        shallow._hot_path_tensors()

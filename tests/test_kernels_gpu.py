@@ -30,10 +30,12 @@ def _rel(a, b):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (300, 768, 768), (1000, 2304, 768),
                                    (777, 768, 3072), (32, 2304, 768), (12608, 768, 768)])
 def test_gemm_plain_f32(ops, M, N, K, block_n):
+    if block_n and N % block_n:
+        pytest.skip("N is not a multiple of this tile width")
     a, w = _bf(_rand((M, K), 1)), _bf(_rand((N, K), 2, 0.05))
     out = ops.gemm(a, w, ops.EPI_F32, block_n=block_n)
     ref = a.float() @ w.float().t()
@@ -41,24 +43,27 @@ def test_gemm_plain_f32(ops, M, N, K, block_n):
     assert _rel(out, ref) < 2e-5
 
 
-def test_gemm_bias_bf16_and_gelu(ops):
+@pytest.mark.parametrize("block_n", [128, 192, 256])
+def test_gemm_bias_bf16_and_gelu(ops, block_n):
     M, N, K = 1234, 3072, 768
     a, w, b = _bf(_rand((M, K), 3)), _bf(_rand((N, K), 4, 0.04)), _rand((N,), 5)
     ref = a.float() @ w.float().t() + b
-    out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b)
+    out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b, block_n=block_n)
     assert out.dtype == torch.bfloat16
     assert _rel(out, ref) < 6e-3  # one bf16 rounding of the output (2^-8)
-    out = ops.gemm(a, w, ops.EPI_BIAS_GELU_BF16, bias=b)
+    assert torch.equal(out, ref.to(torch.bfloat16)) or (out.float() - ref).abs().max() < 0.05
+    out = ops.gemm(a, w, ops.EPI_BIAS_GELU_BF16, bias=b, block_n=block_n)
     refg = ref * torch.sigmoid(1.702 * ref)
     assert _rel(out, refg) < 6e-3
 
 
-def test_gemm_bias_resid_inplace(ops):
+@pytest.mark.parametrize("block_n", [128, 192, 256])
+def test_gemm_bias_resid_inplace(ops, block_n):
     M, N, K = 2000, 768, 3072
     a, w, b = _bf(_rand((M, K), 6)), _bf(_rand((N, K), 7, 0.02)), _rand((N,), 8)
     x = _rand((M, N), 9)
     ref = x + a.float() @ w.float().t() + b
-    out = ops.gemm(a, w, ops.EPI_BIAS_RESID_F32, bias=b, resid=x, out=x)  # in place on the residual stream
+    out = ops.gemm(a, w, ops.EPI_BIAS_RESID_F32, bias=b, resid=x, out=x, block_n=block_n)  # in place on the residual stream
     assert out.data_ptr() == x.data_ptr()
     assert _rel(out, ref) < 2e-5
 
