@@ -38,6 +38,7 @@ SIGNATURES = {
     "clipebc_last_error": (C.c_char_p, []),
     "clipebc_abi_version": (_i, []),
     "clipebc_launch_count": (_i64, []),
+    "clipebc_set_gemm_impl": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_model_create": (_i, [C.POINTER(ClipEbcConfig), C.POINTER(_vp)]),

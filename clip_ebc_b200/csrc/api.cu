@@ -52,6 +52,15 @@ LaunchScope::~LaunchScope() {
   if (slot_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot_].e1, stream_);
 }
 
+// which GEMM kernel serves the hot path: 1 = one CTA per 128-row tile, 2 = CTA pair (cta_group::2, 256-row tiles)
+static std::atomic<int> g_gemm_impl{2};
+
+const char* gemm_dispatch(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols, int64_t lda,
+                          const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
+  return g_gemm_impl.load() == 2 ? gemm2_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n)
+                                 : gemm_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n);
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -258,20 +267,20 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
     const LayerPack& L = m->layer[l];
     K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, 1, M, 1, 1, 0));
     set_launch_tag("qkv");
-    K_TRY(gemm_bf16_tn(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
+    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
                        plain(M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
     set_launch_tag(nullptr);
     K_TRY(attention_h64(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO));
     set_launch_tag("out_proj");
-    K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
                        plain(M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
     set_launch_tag(nullptr);
     K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, 1, M, 1, 1, 0));
     set_launch_tag("c_fc");
-    K_TRY(gemm_bf16_tn(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
+    K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
                        plain(M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
     set_launch_tag("c_proj");
-    K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
                        plain(M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
     set_launch_tag(nullptr);
   }
@@ -297,11 +306,11 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   GemmParams p1 = pc;
   p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp;
   set_launch_tag("dec_conv1");
-  K_TRY(gemm_bf16_tn(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
+  K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
   GemmParams p2 = pc;
   p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
   set_launch_tag("dec_conv2");
-  K_TRY(gemm_bf16_tn(s, EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth, m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
+  K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth, m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
 
   // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
   GemmParams pp = gemm_params_plain(Mp, kEmbed, 3 * kWidth);
@@ -310,7 +319,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   float* F = m->ws_F.as<float>();
   pp.out = F; pp.ldo = kEmbed; pp.bias = raw_ptr(m, "projection.bias");
   set_launch_tag("projection");
-  K_TRY(gemm_bf16_tn(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
+  K_TRY(gemm_dispatch(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
 
   set_launch_tag(nullptr);
   K_TRY(ebc_head(s, F, m->tmat.as<float>(), raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
@@ -337,6 +346,12 @@ extern "C" {
 const char* clipebc_last_error(void) { return g_err.c_str(); }
 int clipebc_abi_version(void) { return CLIPEBC_ABI_VERSION; }
 int64_t clipebc_launch_count(void) { return g_launches.load(); }
+
+int clipebc_set_gemm_impl(int impl) {
+  if (impl != 1 && impl != 2) return fail(CLIPEBC_EINVAL, "gemm impl must be 1 (single CTA) or 2 (CTA pair)");
+  g_gemm_impl.store(impl);
+  return CLIPEBC_OK;
+}
 
 int clipebc_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -460,7 +475,7 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
       CUDA_TRY(m->pack_tmp_bf16.reserve(static_cast<size_t>(c.num_vpt) * kWidth * 2));
       CUDA_TRY(L.const_kv.reserve(static_cast<size_t>(c.num_vpt) * 3 * kWidth * 2));
       K_TRY(layernorm768(s, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_bf16.p, 1, c.num_vpt, 1, 1, 0));
-      K_TRY(gemm_bf16_tn(s, EPI_BIAS_BF16, m->pack_tmp_bf16.as<__nv_bfloat16>(), c.num_vpt, kWidth, kWidth,
+      K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->pack_tmp_bf16.as<__nv_bfloat16>(), c.num_vpt, kWidth, kWidth,
                          L.w_qkv.as<__nv_bfloat16>(), kWidth,
                          plain(c.num_vpt, 3 * kWidth, kWidth, L.const_kv.p, 3 * kWidth, L.b_qkv), 0));
     }
@@ -502,7 +517,7 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
   K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
                      kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
   set_launch_tag(nullptr);
   // window b reads patch rows [b * npatch, (b+1) * npatch)
@@ -610,7 +625,7 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.as<__nv_bfloat16>()));
   else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_bf16_tn(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
                      kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
   set_launch_tag(nullptr);
 
@@ -647,7 +662,7 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
     p.seg_col_start[i] = seg_col_start ? seg_col_start[i] : 0;
   }
   p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp;
-  const char* e = gemm_bf16_tn(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
+  const char* e = gemm_dispatch(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
                                lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);
   if (e) return fail(std::strncmp(e, "gemm:", 5) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
   return CLIPEBC_OK;

@@ -1,0 +1,436 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM:  D[M,N] = A[M,K] * W[N,K]^T, bf16 x bf16 -> fp32 in TMEM.
+//
+// Why a pair: with one CTA per 128xBLOCK_N tile the shared-memory port carries the TMA writes *and* the MMA operand
+// reads of A (16 KB) + B (32 KB) per 64-deep k-block (96 KB per 512 MMA cycles > 128 B/clk) -- measured ~800 cycles per
+// k-block on B200 (profiles/r01_*). A CTA pair computes a 256xBLOCK_N tile with M split over the two SMs and each SM
+// holding only half of B: 32 KB written + 32 KB read per k-block and SM.
+//
+// Cluster of 2 CTAs (one per SM of a TPC), 384 threads each:
+//   warp 0      TMA producer (both CTAs): own 128 rows of A + own half (BLOCK_N/2 rows) of W; transaction bytes of both
+//               CTAs are reported to the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2 256 x BLOCK_N x 16; tcgen05.commit multicast
+//               releases the smem slot in both CTAs and publishes the accumulator to both epilogues
+//   warp 2      TMEM allocator (both CTAs, cta_group::2)
+//   warps 4-11  epilogue (both CTAs): 2 warps per TMEM lane quadrant, each owning half of the tile's columns;
+//               tcgen05.ld -> XOR-swizzled smem transpose -> coalesced global accesses; the tile's bias lives in smem
+// Same fused epilogues and K-segment addressing as gemm_tcgen05.cu (see kernels.h).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cebc {
+
+namespace {
+
+constexpr int kBlockM = 128;   // rows per CTA (256 per pair)
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kStagingPerWarp = 32 * 128;  // 32 rows x 128 B, XOR-swizzled 16 B slots
+
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N > 192) ? 5 : 6;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float quick_gelu2(float x) {
+  // x * sigmoid(1.702 x)   (reference: blocks.py:17-19)
+  return __fdividef(x, 1.0f + __expf(-1.702f * x));
+}
+
+template <int EPI>
+constexpr bool out_is_bf16() {
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16;
+}
+template <int EPI>
+constexpr bool has_resid() { return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT; }
+
+// ---- bf16-output epilogues, 32 accumulator columns per pass -------------------------------------------------------
+// phase 1: thread = output row (as tcgen05.ld delivers it): bias (smem broadcast) + activation, pack, 4 x 16 B into the
+// warp's staging tile (64 B rows, slot ^= (row >> 1) & 3). phase 2: lane -> (row = it*8 + lane/4, slot = lane%4): one
+// warp store writes 8 complete 64 B row segments.
+template <int EPI>
+__device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* stg, const float* bias_s, int lane, int row0,
+                                                 int n, const uint32_t (&r)[32]) {
+  const int row = row0 + lane;
+  bool border = false;
+  if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
+    const int rpi = p.mask_hp * p.mask_wp;
+    const int q = row % rpi;
+    const int py = q / p.mask_wp, px = q - py * p.mask_wp;
+    border = (py == 0) || (py == p.mask_hp - 1) || (px == 0) || (px == p.mask_wp - 1);
+  }
+  const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+    float v[8];
+    v[0] = __uint_as_float(r[8 * j + 0]) + ba.x; v[1] = __uint_as_float(r[8 * j + 1]) + ba.y;
+    v[2] = __uint_as_float(r[8 * j + 2]) + ba.z; v[3] = __uint_as_float(r[8 * j + 3]) + ba.w;
+    v[4] = __uint_as_float(r[8 * j + 4]) + bb.x; v[5] = __uint_as_float(r[8 * j + 5]) + bb.y;
+    v[6] = __uint_as_float(r[8 * j + 6]) + bb.z; v[7] = __uint_as_float(r[8 * j + 7]) + bb.w;
+    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
+    }
+    if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
+    }
+    *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  __syncwarp();
+  const int slot = lane & 3, rsub = lane >> 2;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + rsub;
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((slot ^ ((rr >> 1) & 3)) << 4));
+    if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + slot * 8) = u;
+  }
+  __syncwarp();
+}
+
+// ---- fp32-finishing epilogues, 32 columns per pass (128 B rows, slot ^= row & 7) ----------------------------------
+template <int EPI>
+__device__ __forceinline__ void load_resid32(const GemmParams& p, int lane, int row0, int n, float4 (&x)[8]) {
+  if constexpr (has_resid<EPI>()) {
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row0 + it * 4 + rsub;
+      x[it] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(grow) * p.ldr + n + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* stg, const float* bias_s, int lane, int row0,
+                                                int n, const uint32_t (&r)[32], const float4 (&x)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  const int slot = lane & 7, c4 = slot * 4, rsub = lane >> 3;
+  const float4 b = *reinterpret_cast<const float4*>(bias_s + c4);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    const int grow = row0 + rr;
+    float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((slot ^ (rr & 7)) << 4));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if constexpr (has_resid<EPI>()) { v.x += x[it].x; v.y += x[it].y; v.z += x[it].z; v.w += x[it].w; }
+    if (grow < p.M) {
+      if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
+        const float hz = __bfloat162float(__float2bfloat16_rn(v.z)), hw = __bfloat162float(__float2bfloat16_rn(v.w));
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4;
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+        *reinterpret_cast<uint2*>(o + p.N) = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4) = v;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ GemmParams p) {
+  using Cfg = Cfg2<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int HALF_N = BLOCK_N / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + Cfg::kBiasBytes);
+  uint64_t* full_bar = bars;                         // [STAGES]  used in the leader CTA only
+  uint64_t* empty_bar = bars + STAGES;               // [STAGES]  one set per CTA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]       one set per CTA
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]       used in the leader CTA only
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row pair tiles
+  const int n_tiles = p.N / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / kBlockK;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
+      mbar_init(&empty_bar[s], 1);  // tcgen05.commit multicast from the leader
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // every epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------------------
+    uint32_t stage = 0, phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int m0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
+      const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
+      int seg = 0, kk = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);  // own slot free (released by the leader's commit multicast)
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_cluster(leader_full);
+          tma_load_2d_pair(sa, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK, m0 + p.seg_row_shift[seg]);
+          tma_load_2d_pair(sb, &tma_b, leader_full, kb * kBlockK, n0);
+        }
+        __syncwarp();
+        if (++kk == p.seg_kblocks) { kk = 0; ++seg; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ------------------------------- MMA issuer (leader CTA) -------------------------------
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+    uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_desc_sw128_kmajor(a_addr + k * kUmmaK * 2);
+            const uint64_t db = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 2);
+            umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair_mcast(&empty_bar[stage], 3);                          // smem slot free in both CTAs
+          if (kb == num_kb - 1) umma_commit_pair_mcast(&tmem_full_bar[as], 3);  // accumulator ready in both CTAs
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------- epilogue (both CTAs, 8 warps) -------------------------------
+    const int ew = warp - 4;
+    const int q = ew & 3;        // TMEM lane quadrant (== warp % 4)
+    const int half = ew >> 2;    // which half of the tile's columns
+    const int et = threadIdx.x - 128;
+    uint8_t* stg = staging + ew * kStagingPerWarp;
+    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    uint32_t as = 0, aphase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int row0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
+      const int n0 = n_blk * BLOCK_N;
+      // the tile's bias -> smem (double-buffered by accumulator stage); overlaps the wait for the accumulator
+      float* bs = bias_s + as * BLOCK_N;
+      if (et < BLOCK_N) bs[et] = (EPI != EPI_F32 || p.bias != nullptr) ? __ldg(p.bias + n0 + et) : 0.0f;
+      named_bar_sync(1, kEpiWarps * 32);
+      const int cbase = half * HALF_N;
+      float4 xa[8], xb[8];
+      if constexpr (!out_is_bf16<EPI>()) load_resid32<EPI>(p, lane, row0, n0 + cbase, xa);
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
+      if constexpr (out_is_bf16<EPI>()) {
+#pragma unroll 1
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          tmem_ld_wait();
+          epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r);
+        }
+      } else {
+        constexpr int NC = HALF_N / 32;
+#pragma unroll 1
+        for (int c = 0; c < NC; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          if (c + 1 < NC) load_resid32<EPI>(p, lane, row0, n0 + cbase + (c + 1) * 32, xb);
+          tmem_ld_wait();
+          epi_f32_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, xa);
+          if (c + 1 < NC) {
+            tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r);
+            if (c + 2 < NC) load_resid32<EPI>(p, lane, row0, n0 + cbase + (c + 2) * 32, xa);
+            tmem_ld_wait();
+            epi_f32_chunk32<EPI>(p, stg, bs + cbase + (c + 1) * 32, lane, row0, n0 + cbase + (c + 1) * 32, r, xb);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn2() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+bool make_tmap2(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn2();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int EPI>
+cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                        int num_sms) {
+  using Cfg = Cfg2<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int num_tiles = m_tiles * (p.N / BLOCK_N);
+  const int max_pairs = num_sms / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  {
+    LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
+                      2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
+                          4.0 * p.M * static_cast<double>(p.N));
+    kern<<<2 * pairs, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  }
+  return cudaGetLastError();
+}
+
+template <int BLOCK_N>
+cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                        int num_sms) {
+  switch (epi) {
+    case EPI_F32: return launch_one2<BLOCK_N, EPI_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_F32: return launch_one2<BLOCK_N, EPI_BIAS_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_BF16: return launch_one2<BLOCK_N, EPI_BIAS_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_GELU_BF16: return launch_one2<BLOCK_N, EPI_BIAS_GELU_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT>(stream, ta, tb, p, num_sms);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ceil(tiles / pairs) rounds; measured on B200 (profiles/gemm_bench.py) the time of one round is ~ (block_n + 320):
+// pick the cheapest tile width that divides N
+int pick_block_n2(int M, int N, int num_sms) {
+  const int m_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int pairs = num_sms / 2;
+  int best = 0;
+  double best_cost = 0.0;
+  const int cand[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (N % bn != 0) continue;
+    const long tiles = static_cast<long>(m_tiles) * (N / bn);
+    const long rounds = (tiles + pairs - 1) / pairs;
+    const double cost = rounds * (bn + 320.0);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best ? best : 128;
+}
+
+}  // namespace
+
+const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
+                          int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
+  if (p.K % kBlockK != 0) return "gemm: K must be a multiple of 64";
+  if (p.n_seg < 1 || p.n_seg > kMaxGemmSegs) return "gemm: bad segment count";
+  if (p.seg_kblocks * p.n_seg * kBlockK != p.K) return "gemm: segments do not tile K";
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return "gemm: operands must be 16B aligned";
+  if ((lda * 2) % 16 != 0 || (ldw * 2) % 16 != 0) return "gemm: row pitch must be a multiple of 16 bytes";
+  if (p.N % 64 != 0) return "gemm: N must be a multiple of 64";
+  const int num_sms = device_num_sms();
+  if (block_n == 0) block_n = pick_block_n2(p.M, p.N, num_sms);
+  if (block_n != 128 && block_n != 192 && block_n != 256) return "gemm: block_n must be 128, 192 or 256";
+  if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
+  if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
+  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
+  if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 3 || p.mask_wp < 3)) return "gemm: mask grid missing";
+
+  CUtensorMap ta, tb;
+  if (!make_tmap2(&ta, A, a_rows, a_cols, lda, kBlockM)) return "gemm: cuTensorMapEncodeTiled(A) failed";
+  if (!make_tmap2(&tb, W, p.N, p.K, ldw, block_n / 2)) return "gemm: cuTensorMapEncodeTiled(W) failed";
+  cudaError_t e = (block_n == 256)   ? launch_epi2<256>(stream, epi, ta, tb, p, num_sms)
+                  : (block_n == 192) ? launch_epi2<192>(stream, epi, ta, tb, p, num_sms)
+                                     : launch_epi2<128>(stream, epi, ta, tb, p, num_sms);
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  return nullptr;
+}
+
+}  // namespace cebc

@@ -44,6 +44,9 @@ inline GemmParams gemm_params_plain(int M, int N, int K) {
 // D[M,N] = A[M,K] * W[N,K]^T. A: bf16 [a_rows, a_cols] pitch lda; W: bf16 [N, K] pitch ldw. block_n: 0 = auto.
 const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                          int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
+// CTA-pair (cta_group::2) implementation of the same contract (gemm2_tcgen05.cu).
+const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
+                          int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
 int device_num_sms();
 // Every kernel launch of this library goes through a LaunchScope: it counts the launch (clipebc_launch_count) and, when
 // profiling is enabled (clipebc_profile_enable), brackets it with CUDA events on the launching stream and books the

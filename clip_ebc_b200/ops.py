@@ -15,6 +15,11 @@ EPI_F32, EPI_BIAS_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EP
     EPI_BIAS_RESID_RELU_SPLIT = range(7)
 
 
+def set_gemm_impl(impl: int) -> None:
+    """1 = single-CTA tcgen05 GEMM, 2 = CTA-pair (cta_group::2) GEMM (default)."""
+    _lib.check(_lib.load().clipebc_set_gemm_impl(int(impl)), "set_gemm_impl")
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -50,6 +50,10 @@ int clipebc_abi_version(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 int64_t clipebc_launch_count(void);
 
+/* Selects the tcgen05 GEMM kernel used by the hot path and by clipebc_gemm_bf16: 1 = one CTA per 128-row tile,
+ * 2 = CTA pair (cta_group::2, 256-row tiles; default). Both implement the same contract; tests run both. */
+int clipebc_set_gemm_impl(int impl);
+
 /* Optional per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
  * clipebc_profile_dump synchronises the device and writes a JSON object {"<kernel>[:<use>]": {"ms", "launches",
  * "flops", "bytes"}} (algorithmic work of the launches, summed since enable) into buf. Enabling clears the records. */

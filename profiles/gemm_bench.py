@@ -22,6 +22,7 @@ shapes = [
     ("c_fc", M, 3072, 768, ops.EPI_BIAS_GELU_BF16),
     ("c_proj", M, 768, 3072, ops.EPI_BIAS_RESID_F32),
     ("projection", Mp, 512, 2304, ops.EPI_BIAS_F32),
+    ("conv_like", Mp, 768, 6912, ops.EPI_BIAS_BF16),
 ]
 for name, m, n, k, epi in shapes:
     a = torch.randn(m, k, device=dev).to(torch.bfloat16)
@@ -30,9 +31,10 @@ for name, m, n, k, epi in shapes:
     resid = torch.randn(m, n, device=dev) if epi == ops.EPI_BIAS_RESID_F32 else None
     out = resid if resid is not None else None
     res = []
-    for bn in (128, 192, 256, 0):
+    for impl, bn in [(i, b) for i in (1, 2) for b in (128, 192, 256, 0)]:
         if bn and n % bn:
             continue
+        ops.set_gemm_impl(impl)
         o = ops.gemm(a, w, epi, bias=bias, resid=resid, out=out, block_n=bn)
         for _ in range(3):
             ops.gemm(a, w, epi, bias=bias, resid=resid, out=o, block_n=bn)
@@ -45,5 +47,5 @@ for name, m, n, k, epi in shapes:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        res.append(f"bn={bn or 'auto'}: {ms * 1e3:7.1f} us {2.0 * m * n * k / ms / 1e9:7.0f} TF/s")
-    print(f"{name:11s} M={m} N={n} K={k}  " + " | ".join(res))
+        res.append(f"{impl}cta bn={bn or 'auto':>4}: {ms * 1e3:6.1f} us {2.0 * m * n * k / ms / 1e9:5.0f} TF/s")
+    print(f"{name:11s} M={m} N={n} K={k}\n   " + "\n   ".join(res))

@@ -9,11 +9,14 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=[1, 2], ids=["gemm1cta", "gemm2cta"])
+def ops(request):
+    """All kernel tests run once per GEMM implementation (single CTA / CTA pair with cta_group::2)."""
     from clip_ebc_b200 import ops as _ops
 
-    return _ops
+    _ops.set_gemm_impl(request.param)
+    yield _ops
+    _ops.set_gemm_impl(2)
 
 
 def _rand(shape, seed, scale=1.0, device="cuda"):
