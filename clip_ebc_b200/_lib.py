@@ -27,6 +27,7 @@ class ClipEbcConfig(C.Structure):
         ("deep_vpt", C.c_int),
         ("num_bins", C.c_int),
         ("window_chunk", C.c_int),
+        ("operand_fp16", C.c_int),
     ]
 
 
@@ -39,6 +40,7 @@ SIGNATURES = {
     "clipebc_abi_version": (_i, []),
     "clipebc_launch_count": (_i64, []),
     "clipebc_set_gemm_impl": (_i, [_i]),
+    "clipebc_set_attention_impl": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_model_create": (_i, [C.POINTER(ClipEbcConfig), C.POINTER(_vp)]),
@@ -48,13 +50,13 @@ SIGNATURES = {
     "clipebc_forward_windows": (_i, [_vp, _fp, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_sliding_window_predict": (_i, [_vp, _fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_window_origins": (_i, [_i, _i, _i, _i, _i, _i, _ip, _ip, _ip, _ip]),
-    "clipebc_f32_to_bf16": (_i, [_fp, _vp, _i64, _vp]),
+    "clipebc_f32_to_16": (_i, [_fp, _vp, _i64, _i, _vp]),
     "clipebc_gemm_bf16": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _ip, _ip, _vp, _i, _fp, _fp, _i,
-                               _i, _i, _i, _vp]),
+                               _i, _i, _i, _i, _i, _vp]),
     "clipebc_layernorm768": (_i, [_fp, _fp, _fp, _vp, _i, _i64, _i, _i, _i, _vp]),
-    "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _vp, _fp, _vp]),
+    "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
     "clipebc_ebc_head": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_fold_average": (_i, [_fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
 }

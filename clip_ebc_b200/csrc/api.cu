@@ -61,6 +61,18 @@ const char* gemm_dispatch(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
                                  : gemm_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n);
 }
 
+// which attention kernel serves the hot path: 1 = mma.sync (legacy tensor path), 2 = tcgen05 one CTA per query tile,
+// 3 = tcgen05 persistent warp-specialised (P in TMEM)
+static std::atomic<int> g_attn_impl{3};
+
+const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                               int n_win, int t_live, void* out, int out_fp16) {
+  const int impl = g_attn_impl.load();
+  if (impl == 3 && n_const % 8 == 0) return attention_h64_fa(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
+  if (impl == 2 && n_const % 8 == 0) return attention_h64_tc(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
+  return attention_h64(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -165,9 +177,9 @@ std::string blk(int l, const char* tail) {
   return "image_encoder.transformer.resblocks." + std::to_string(l) + "." + tail;
 }
 
-int to_bf16(cudaStream_t s, const float* src, int64_t n, DevBuf* dst) {
+int to_16(cudaStream_t s, const float* src, int64_t n, DevBuf* dst, int fp16) {
   CUDA_TRY(dst->reserve(static_cast<size_t>(n) * 2));
-  K_TRY(f32_to_bf16(s, src, dst->as<__nv_bfloat16>(), n));
+  K_TRY(f32_to_16(s, src, dst->p, n, fp16));
   return CLIPEBC_OK;
 }
 
@@ -220,9 +232,21 @@ int get_pos(clipebc_model* m, int hp, int wp, cudaStream_t stream, const float**
   return CLIPEBC_OK;
 }
 
-GemmParams plain(int M, int N, int K, void* out, int ldo, const float* bias, const float* resid = nullptr, int ldr = 0) {
+// fp16: 16-bit format of the operands (A, W); out16_fp16: format of a 16-bit output (QKV stays bf16 for the attention)
+GemmParams plain(int fp16, int out16_fp16, int M, int N, int K, void* out, int ldo, const float* bias,
+                 const float* resid = nullptr, int ldr = 0) {
   GemmParams p = gemm_params_plain(M, N, K);
   p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr;
+  p.ab_fp16 = fp16; p.out_fp16 = out16_fp16;
+  return p;
+}
+
+// patch embedding as a split-precision GEMM: rows [hi | lo] (2*768) x W3 = [Whi | Whi | Wlo] (3*768), segments hi, lo, hi
+GemmParams patch_embed_params(int fp16, int rows, void* out) {
+  GemmParams p = gemm_params_plain(rows, 768, 3 * 768);
+  p.n_seg = 3; p.seg_kblocks = 768 / 64;
+  p.seg_col_start[0] = 0; p.seg_col_start[1] = 768; p.seg_col_start[2] = 0;
+  p.out = out; p.ldo = 768; p.bias = nullptr; p.ab_fp16 = fp16; p.out_fp16 = fp16;
   return p;
 }
 
@@ -231,6 +255,8 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
                 const float* pos, float* exp_out, float* logits_out) {
   const clipebc_config& c = m->cfg;
   const bool deep = c.deep_vpt != 0;
+  const int fp16 = c.operand_fp16 != 0;   // 16-bit operand format of every GEMM of the path
+  const int ln16 = fp16 ? 2 : 1;          // layernorm768 out_kind
   const int n_prompt_live = deep ? 0 : c.num_vpt;
   const int n_const = deep ? c.num_vpt : 0;
   const int npatch = hp * wp;
@@ -265,23 +291,23 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 
   for (int l = 0; l < kLayers; ++l) {
     const LayerPack& L = m->layer[l];
-    K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, 1, M, 1, 1, 0));
+    K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, ln16, M, 1, 1, 0));
     set_launch_tag("qkv");
     K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
-                       plain(M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
+                       plain(fp16, 0, M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
     set_launch_tag(nullptr);
-    K_TRY(attention_h64(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO));
+    K_TRY(attention_dispatch(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO, fp16));
     set_launch_tag("out_proj");
     K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
-                       plain(M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
+                       plain(fp16, fp16, M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
     set_launch_tag(nullptr);
-    K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, 1, M, 1, 1, 0));
+    K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, ln16, M, 1, 1, 0));
     set_launch_tag("c_fc");
     K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
-                       plain(M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
+                       plain(fp16, fp16, M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
     set_launch_tag("c_proj");
     K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
-                       plain(M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
+                       plain(fp16, fp16, M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
     set_launch_tag(nullptr);
   }
 
@@ -291,10 +317,11 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
                      static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch));
   __nv_bfloat16* Ub = m->ws_Ub.as<__nv_bfloat16>();
   float* Uf = m->ws_Uf.as<float>();
-  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf));
+  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf, fp16));
 
   // decoder BasicBlock as two implicit GEMMs over the zero-bordered grid: 9 taps = 9 row-shifted K-segments
   GemmParams pc = gemm_params_plain(Mp, kWidth, 9 * kWidth);
+  pc.ab_fp16 = fp16; pc.out_fp16 = fp16;
   pc.n_seg = 9; pc.seg_kblocks = kWidth / 64;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) {
@@ -314,6 +341,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 
   // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
   GemmParams pp = gemm_params_plain(Mp, kEmbed, 3 * kWidth);
+  pp.ab_fp16 = fp16; pp.out_fp16 = fp16;
   pp.n_seg = 3; pp.seg_kblocks = kWidth / 64;
   pp.seg_col_start[0] = 0; pp.seg_col_start[1] = kWidth; pp.seg_col_start[2] = 0;
   float* F = m->ws_F.as<float>();
@@ -350,6 +378,12 @@ int64_t clipebc_launch_count(void) { return g_launches.load(); }
 int clipebc_set_gemm_impl(int impl) {
   if (impl != 1 && impl != 2) return fail(CLIPEBC_EINVAL, "gemm impl must be 1 (single CTA) or 2 (CTA pair)");
   g_gemm_impl.store(impl);
+  return CLIPEBC_OK;
+}
+
+int clipebc_set_attention_impl(int impl) {
+  if (impl < 1 || impl > 3) return fail(CLIPEBC_EINVAL, "attention impl must be 1 (mma.sync), 2 or 3 (tcgen05)");
+  g_attn_impl.store(impl);
   return CLIPEBC_OK;
 }
 
@@ -396,6 +430,7 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (cfg->input_size <= 0 || cfg->input_size % kPatch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of 16");
   if (cfg->num_vpt < 0 || cfg->num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
   if (cfg->num_bins < 1 || cfg->num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
+  if (cfg->operand_fp16 != 0 && cfg->operand_fp16 != 1) return fail(CLIPEBC_EINVAL, "operand_fp16 must be 0 (bf16) or 1 (fp16)");
   clipebc_model* m = new clipebc_model();
   m->cfg = *cfg;
   *out = m;
@@ -424,6 +459,7 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   if (!m) return fail(CLIPEBC_EINVAL, "null model");
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const clipebc_config& c = m->cfg;
+  const int fp16 = c.operand_fp16 != 0;
   const int g0 = c.input_size / kPatch;
   std::string err;
   const int n_vpt_layers = c.deep_vpt ? kLayers : 1;
@@ -457,13 +493,14 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   if (!ok) return fail(CLIPEBC_ESTATE, "pack: " + err);
 
   int rc;
-  if ((rc = to_bf16(s, raw_ptr(m, "image_encoder.conv1.weight"), static_cast<int64_t>(kWidth) * kWidth, &m->w_patch))) return rc;
+  CUDA_TRY(m->w_patch.reserve(static_cast<size_t>(kWidth) * 3 * kWidth * 2));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "image_encoder.conv1.weight"), kWidth, kWidth, m->w_patch.p, fp16));
   for (int l = 0; l < kLayers; ++l) {
     LayerPack& L = m->layer[l];
-    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * kWidth * kWidth, &L.w_qkv))) return rc;
-    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "attn.out_proj.weight")), static_cast<int64_t>(kWidth) * kWidth, &L.w_out))) return rc;
-    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), static_cast<int64_t>(kHidden) * kWidth, &L.w_fc))) return rc;
-    if ((rc = to_bf16(s, raw_ptr(m, blk(l, "mlp.c_proj.weight")), static_cast<int64_t>(kWidth) * kHidden, &L.w_proj))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * kWidth * kWidth, &L.w_qkv, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.out_proj.weight")), static_cast<int64_t>(kWidth) * kWidth, &L.w_out, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), static_cast<int64_t>(kHidden) * kWidth, &L.w_fc, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_proj.weight")), static_cast<int64_t>(kWidth) * kHidden, &L.w_proj, fp16))) return rc;
     L.b_qkv = raw_ptr(m, blk(l, "attn.in_proj_bias"));
     L.b_out = raw_ptr(m, blk(l, "attn.out_proj.bias"));
     L.b_fc = raw_ptr(m, blk(l, "mlp.c_fc.bias"));
@@ -474,10 +511,10 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
       // constant prompt K/V of layer l: in_proj(LN1_l(vpt_l)) -- same kernels as the live path
       CUDA_TRY(m->pack_tmp_bf16.reserve(static_cast<size_t>(c.num_vpt) * kWidth * 2));
       CUDA_TRY(L.const_kv.reserve(static_cast<size_t>(c.num_vpt) * 3 * kWidth * 2));
-      K_TRY(layernorm768(s, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_bf16.p, 1, c.num_vpt, 1, 1, 0));
+      K_TRY(layernorm768(s, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_bf16.p, fp16 ? 2 : 1, c.num_vpt, 1, 1, 0));
       K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->pack_tmp_bf16.as<__nv_bfloat16>(), c.num_vpt, kWidth, kWidth,
                          L.w_qkv.as<__nv_bfloat16>(), kWidth,
-                         plain(c.num_vpt, 3 * kWidth, kWidth, L.const_kv.p, 3 * kWidth, L.b_qkv), 0));
+                         plain(fp16, 0, c.num_vpt, 3 * kWidth, kWidth, L.const_kv.p, 3 * kWidth, L.b_qkv), 0));
     }
   }
   for (int k = 1; k <= 2; ++k) {
@@ -487,10 +524,10 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
     CUDA_TRY(W.reserve(static_cast<size_t>(kWidth) * 9 * kWidth * 2));
     CUDA_TRY(B.reserve(kWidth * 4));
     K_TRY(fold_conv3x3_bn(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".bias"), raw_ptr(m, bn + ".running_mean"),
-                          raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth, kWidth, W.as<__nv_bfloat16>(), B.as<float>()));
+                          raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth, kWidth, W.p, B.as<float>(), fp16));
   }
   CUDA_TRY(m->w_p3.reserve(static_cast<size_t>(kEmbed) * 3 * kWidth * 2));
-  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), kEmbed, kWidth, m->w_p3.as<__nv_bfloat16>()));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), kEmbed, kWidth, m->w_p3.p, fp16));
   CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * kEmbed * 4));
   K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, kEmbed, m->tmat.as<float>()));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -513,12 +550,14 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   if ((rc = get_pos(m, hp, wp, s, &pos))) return rc;
 
   const int64_t rows = static_cast<int64_t>(B) * npatch;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * kWidth * 2));
+  const int fp16 = m->cfg.operand_fp16 != 0;
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kWidth * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.p, fp16));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
-                     kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kWidth, 2 * kWidth,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
+                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p), 0));
   set_launch_tag(nullptr);
   // window b reads patch rows [b * npatch, (b+1) * npatch)
   const std::string key = "fw:" + std::to_string(B) + ":" + std::to_string(npatch);
@@ -620,13 +659,15 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   const int* d_rc = d_base + 3 * n_win;
   const int* d_cc = d_rc + nr;
 
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * kWidth * 2));
+  const int fp16 = m->cfg.operand_fp16 != 0;
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kWidth * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.as<__nv_bfloat16>()));
-  else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.as<__nv_bfloat16>()));
+  if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.p, fp16));
+  else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.p, fp16));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, kWidth, kWidth, m->w_patch.as<__nv_bfloat16>(),
-                     kWidth, plain(static_cast<int>(rows), kWidth, kWidth, m->ws_patch_embed.p, kWidth, nullptr), 0));
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kWidth, 2 * kWidth,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
+                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p), 0));
   set_launch_tag(nullptr);
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
@@ -642,15 +683,15 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
 }
 
 // ------------------------------------------------------------------------------------------------ single kernels
-int clipebc_f32_to_bf16(const float* in_dev, void* out, int64_t n, void* stream) {
-  K_TRY(f32_to_bf16(static_cast<cudaStream_t>(stream), in_dev, static_cast<__nv_bfloat16*>(out), n));
+int clipebc_f32_to_16(const float* in_dev, void* out, int64_t n, int fp16, void* stream) {
+  K_TRY(f32_to_16(static_cast<cudaStream_t>(stream), in_dev, out, n, fp16));
   return CLIPEBC_OK;
 }
 
 int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* W, int64_t ldw,
                       int M, int N, int K, int n_seg, const int* seg_row_shift, const int* seg_col_start, void* out,
                       int ldo, const float* bias, const float* resid, int ldr, int mask_hp, int mask_wp, int block_n,
-                      void* stream) {
+                      int ab_fp16, int out_fp16, void* stream) {
   if (!A || !W || !out) return fail(CLIPEBC_EINVAL, "null argument");
   if (n_seg < 1 || n_seg > kMaxGemmSegs) return fail(CLIPEBC_EINVAL, "n_seg must be in 1..9");
   if (K <= 0 || K % (64 * n_seg) != 0) return fail(CLIPEBC_EINVAL, "K must be a positive multiple of 64 * n_seg");
@@ -662,32 +703,37 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
     p.seg_col_start[i] = seg_col_start ? seg_col_start[i] : 0;
   }
   p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp;
+  p.ab_fp16 = ab_fp16 != 0; p.out_fp16 = out_fp16 != 0;
   const char* e = gemm_dispatch(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
                                lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);
   if (e) return fail(std::strncmp(e, "gemm:", 5) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
   return CLIPEBC_OK;
 }
 
-int clipebc_layernorm768(const float* in, const float* g, const float* b, void* out, int out_is_bf16, int64_t n_rows_out,
+int clipebc_layernorm768(const float* in, const float* g, const float* b, void* out, int out_kind, int64_t n_rows_out,
                          int rows_out_per_group, int rows_in_per_group, int in_row_offset, void* stream) {
-  K_TRY(layernorm768(static_cast<cudaStream_t>(stream), in, g, b, out, out_is_bf16, n_rows_out, rows_out_per_group,
+  if (out_kind < 0 || out_kind > 2) return fail(CLIPEBC_EINVAL, "layernorm: out_kind must be 0 (f32), 1 (bf16) or 2 (fp16)");
+  K_TRY(layernorm768(static_cast<cudaStream_t>(stream), in, g, b, out, out_kind, n_rows_out, rows_out_per_group,
                      rows_in_per_group, in_row_offset));
   return CLIPEBC_OK;
 }
 
-int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_win, int t_live, void* out, void* stream) {
-  K_TRY(attention_h64(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
-                      static_cast<const __nv_bfloat16*>(const_kv), n_const, n_win, t_live, static_cast<__nv_bfloat16*>(out)));
+int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_win, int t_live, void* out, int out_fp16,
+                      void* stream) {
+  K_TRY(attention_dispatch(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
+                           static_cast<const __nv_bfloat16*>(const_kv), n_const, n_win, t_live, out, out_fp16 != 0));
   return CLIPEBC_OK;
 }
 
-int clipebc_patchify16(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, void* out, void* stream) {
-  K_TRY(patchify16(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, static_cast<__nv_bfloat16*>(out)));
+int clipebc_patchify16(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, void* out, int fp16,
+                       void* stream) {
+  K_TRY(patchify16(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, out, fp16 != 0));
   return CLIPEBC_OK;
 }
 
-int clipebc_resample_to_padded(const float* Y, int n_win, int hp, int wp, int gh, int gw, void* Ub, float* Uf, void* stream) {
-  K_TRY(resample_to_padded(static_cast<cudaStream_t>(stream), Y, n_win, hp, wp, gh, gw, static_cast<__nv_bfloat16*>(Ub), Uf));
+int clipebc_resample_to_padded(const float* Y, int n_win, int hp, int wp, int gh, int gw, void* Ub, float* Uf, int fp16,
+                               void* stream) {
+  K_TRY(resample_to_padded(static_cast<cudaStream_t>(stream), Y, n_win, hp, wp, gh, gw, Ub, Uf, fp16 != 0));
   return CLIPEBC_OK;
 }
 

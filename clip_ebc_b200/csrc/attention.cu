@@ -35,7 +35,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __global__ void __launch_bounds__(kAttnThreads) attention_h64_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                     const __nv_bfloat16* __restrict__ const_kv,
                                                                     int n_const, int t_live,
-                                                                    __nv_bfloat16* __restrict__ out) {
+                                                                    uint16_t* __restrict__ out, int out_fp16) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + kMaxSeq * 128;
@@ -181,15 +181,15 @@ __global__ void __launch_bounds__(kAttnThreads) attention_h64_kernel(const __nv_
     }
     const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
     const int r0 = q0 + g, r1 = q0 + g + 8;
-    __nv_bfloat16* obase = out + static_cast<int64_t>(win) * t_live * 768 + head * kHeadDim + 2 * tq;
+    uint16_t* obase = out + static_cast<int64_t>(win) * t_live * 768 + head * kHeadDim + 2 * tq;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (r0 < Tq)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r0) * 768 + 8 * j) =
-            pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+            pack16x2(o[j][0] * inv0, o[j][1] * inv0, out_fp16);
       if (r1 < Tq)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r1) * 768 + 8 * j) =
-            pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+            pack16x2(o[j][2] * inv1, o[j][3] * inv1, out_fp16);
     }
   }
 }
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_h64_kernel(const __nv_
 }  // namespace
 
 const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                          int n_win, int t_live, __nv_bfloat16* out) {
+                          int n_win, int t_live, void* out, int out_fp16) {
   if (n_win <= 0 || t_live <= 0) return "attention: empty problem";
   if (n_const < 0 || (n_const > 0 && const_kv == nullptr)) return "attention: constant keys missing";
   if (t_live + n_const > kMaxSeq) return "attention: sequence longer than 256 keys is not supported";
@@ -211,7 +211,8 @@ const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const _
     const double tk = t_live + n_const;
     LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
                       2.0 * n_win * t_live * (2304.0 + 768.0));
-    attention_h64_kernel<<<n_win * 12, kAttnThreads, kAttnSmem, stream>>>(qkv, const_kv, n_const, t_live, out);
+    attention_h64_kernel<<<n_win * 12, kAttnThreads, kAttnSmem, stream>>>(qkv, const_kv, n_const, t_live,
+                                                                          static_cast<uint16_t*>(out), out_fp16);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <cstdio>
@@ -45,6 +46,28 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 16-bit tensor-core operand formats: bf16 (8-bit mantissa) or fp16 (11-bit mantissa, values saturated to +-65504).
+// Both run on the same tcgen05 kind::f16 path; `fp16` is a warp-uniform runtime flag chosen per model.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fp16) {
+  return fp16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+// x rounded to the 16-bit format, as fp32 (for hi/lo splits: lo = x - round16(x))
+__device__ __forceinline__ float round16(float x, int fp16) {
+  if (fp16) return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ uint16_t cvt16(float x, int fp16) {
+  if (fp16) { __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<uint16_t*>(&b);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -154,11 +177,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr_by
   return d;
 }
 
-// Instruction descriptor for kind::f16, A=B=bf16 (K-major both), D=f32, dense.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+// Instruction descriptor for kind::f16, A and B both bf16 (format 1) or both fp16 (format 0), K-major, D=f32, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N, int fp16 = 0) {
   return (1u << 4)                                  // D format: f32
-         | (1u << 7)                                // A format: bf16
-         | (1u << 10)                               // B format: bf16
+         | ((fp16 ? 0u : 1u) << 7)                  // A format: 0 = f16, 1 = bf16
+         | ((fp16 ? 0u : 1u) << 10)                 // B format
          | (0u << 15) | (0u << 16)                  // A, B K-major
          | (static_cast<uint32_t>(N >> 3) << 17)    // N >> 3
          | (static_cast<uint32_t>(M >> 4) << 24);   // M >> 4

@@ -65,19 +65,19 @@ __device__ __forceinline__ void store_row_f32(float* p, const Row768& r, int lan
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) p4[i * 32 + lane] = r.v[i];
 }
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* p, const Row768& r, int lane) {
+__device__ __forceinline__ void store_row_16(void* p, const Row768& r, int lane, int fp16) {
   uint2* p2 = reinterpret_cast<uint2*>(p);
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i)
-    p2[i * 32 + lane] = make_uint2(pack_bf16x2(r.v[i].x, r.v[i].y), pack_bf16x2(r.v[i].z, r.v[i].w));
+    p2[i * 32 + lane] = make_uint2(pack16x2(r.v[i].x, r.v[i].y, fp16), pack16x2(r.v[i].z, r.v[i].w, fp16));
 }
 
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
-template <bool OUT_BF16>
+template <bool OUT_16>
 __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, void* __restrict__ out,
                                                            int64_t n_rows_out, int rows_out_per_group,
-                                                           int rows_in_per_group, int in_row_offset) {
+                                                           int rows_in_per_group, int in_row_offset, int fp16) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows_out;
@@ -86,19 +86,27 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
     const int64_t in_row = g * rows_in_per_group + in_row_offset + (r - g * rows_out_per_group);
     Row768 x = load_row(in + in_row * kD, lane);
     layernorm_row(x, gamma, beta, lane);
-    if constexpr (OUT_BF16)
-      store_row_bf16(static_cast<__nv_bfloat16*>(out) + r * kD, x, lane);
+    if constexpr (OUT_16)
+      store_row_16(static_cast<uint16_t*>(out) + r * kD, x, lane, fp16);
     else
       store_row_f32(static_cast<float*>(out) + r * kD, x, lane);
   }
 }
 
 // ------------------------------------------------------------------ patchify -----------------------------------
+__device__ __forceinline__ void store_hi_lo(uint16_t* dst, const float4& v, int fp16) {
+  const float hx = round16(v.x, fp16), hy = round16(v.y, fp16), hz = round16(v.z, fp16), hw = round16(v.w, fp16);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack16x2(hx, hy, fp16), pack16x2(hz, hw, fp16));
+  *reinterpret_cast<uint2*>(dst + kD) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
+}
+
 // One thread per 4 horizontally adjacent pixels; consecutive threads walk along an image row (coalesced 16B reads),
 // each writes 4 bf16 (8 B) into its patch row; 4 consecutive threads fill one 32 B sector.
+// Rows are written as [hi(768) | lo(768)] with hi = round16(x), lo = round16(x - hi): the patch-embed GEMM multiplies
+// [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9 (the stem is 0.4 % of the FLOPs).
 __global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict__ image, int n_img, int H, int W,
-                                                         int y0, int x0, int gh, int gw,
-                                                         __nv_bfloat16* __restrict__ out) {
+                                                         int y0, int x0, int gh, int gw, uint16_t* __restrict__ out,
+                                                         int fp16) {
   const int64_t quads_per_row = static_cast<int64_t>(gw) * 4;            // 4 quads per patch row of 16 px
   const int64_t per_img = static_cast<int64_t>(3) * gh * 16 * quads_per_row;
   const int64_t total = per_img * n_img;
@@ -119,14 +127,13 @@ __global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict
       v = make_float4(src[0], src[1], src[2], src[3]);
     }
     const int64_t patch = (static_cast<int64_t>(img) * gh + gy) * gw + gx;
-    uint2* dst = reinterpret_cast<uint2*>(out + patch * kD + c * 256 + py * 16 + px4 * 4);
-    *dst = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    store_hi_lo(out + patch * 2 * kD + c * 256 + py * 16 + px4 * 4, v, fp16);
   }
 }
 
 __global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __restrict__ image, int H, int W,
                                                                  const int* __restrict__ origins_yx, int n_win, int hp,
-                                                                 int wp, __nv_bfloat16* __restrict__ out) {
+                                                                 int wp, uint16_t* __restrict__ out, int fp16) {
   const int64_t quads_per_row = static_cast<int64_t>(wp) * 4;
   const int64_t per_win = static_cast<int64_t>(3) * hp * 16 * quads_per_row;
   const int64_t total = per_win * n_win;
@@ -143,8 +150,7 @@ __global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __
     const float* src = image + (static_cast<int64_t>(c) * H + (oy + yy)) * W + ox + qx * 4;
     const float4 v = make_float4(src[0], src[1], src[2], src[3]);
     const int64_t patch = (static_cast<int64_t>(win) * hp + gy) * wp + gx;
-    uint2* dst = reinterpret_cast<uint2*>(out + patch * kD + c * 256 + py * 16 + px4 * 4);
-    *dst = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    store_hi_lo(out + patch * 2 * kD + c * 256 + py * 16 + px4 * 4, v, fp16);
   }
 }
 
@@ -196,8 +202,8 @@ __device__ __forceinline__ void bilinear_src(int dst, float inv_scale, int in_si
 }
 
 __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __restrict__ Y, int n_win, int hp, int wp,
-                                                                 int gh, int gw, __nv_bfloat16* __restrict__ U_bf16,
-                                                                 float* __restrict__ U_f32) {
+                                                                 int gh, int gw, uint16_t* __restrict__ U_16,
+                                                                 float* __restrict__ U_f32, int fp16) {
   const int lane = threadIdx.x & 31;
   const int Hp = gh + 2, Wp = gw + 2;
   const int64_t n_rows = static_cast<int64_t>(n_win) * Hp * Wp;
@@ -234,16 +240,16 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
         o.v[i].w = w00 * a.v[i].w + w01 * b.v[i].w + w10 * c.v[i].w + w11 * d.v[i].w;
       }
     }
-    store_row_bf16(U_bf16 + r * kD, o, lane);
+    store_row_16(U_16 + r * kD, o, lane, fp16);
     store_row_f32(U_f32 + r * kD, o, lane);
   }
 }
 
 // ------------------------------------------------------------------ pack-time ----------------------------------
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+__global__ void f32_to_16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int64_t n, int fp16) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    out[i] = __float2bfloat16_rn(in[i]);
+    out[i] = cvt16(in[i], fp16);
 }
 
 // BN(eval) folds exactly into the bias-free conv: W' = W * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)
@@ -251,7 +257,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 __global__ void fold_conv3x3_bn_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                        const float* __restrict__ var, float eps, int O, int I,
-                                       __nv_bfloat16* __restrict__ Wp, float* __restrict__ bias) {
+                                       uint16_t* __restrict__ Wp, float* __restrict__ bias, int fp16) {
   const int64_t total = static_cast<int64_t>(O) * I * 9;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -260,21 +266,22 @@ __global__ void fold_conv3x3_bn_kernel(const float* __restrict__ W, const float*
     const int tap = static_cast<int>((idx / I) % 9);
     const int o = static_cast<int>(idx / (static_cast<int64_t>(I) * 9));
     const float s = gamma[o] / sqrtf(var[o] + eps);
-    Wp[idx] = __float2bfloat16_rn(W[(static_cast<int64_t>(o) * I + i) * 9 + tap] * s);
+    Wp[idx] = cvt16(W[(static_cast<int64_t>(o) * I + i) * 9 + tap] * s, fp16);
     if (i == 0 && tap == 0) bias[o] = beta[o] - mean[o] * s;
   }
 }
 
-__global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, __nv_bfloat16* __restrict__ out) {
+__global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, uint16_t* __restrict__ out, int fp16) {
   const int64_t total = static_cast<int64_t>(O) * I;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(idx % I);
     const int64_t o = idx / I;
     const float w = W[idx];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    __nv_bfloat16* row = out + o * 3 * I;
+    const float hf = round16(w, fp16);
+    const uint16_t hi = cvt16(hf, fp16);
+    const uint16_t lo = cvt16(w - hf, fp16);
+    uint16_t* row = out + o * 3 * I;
     row[i] = hi;
     row[I + i] = hi;
     row[2 * I + i] = lo;
@@ -309,39 +316,39 @@ inline const char* last_err() {
 }  // namespace
 
 const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
-                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
                          int in_row_offset) {
   if (n_rows_out <= 0) return nullptr;
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
   const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
-  LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_is_bf16 ? 2.0 : 4.0)));
-  if (out_is_bf16)
+  LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_kind ? 2.0 : 4.0)));
+  if (out_kind)
     layernorm768_kernel<true><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
-                                                          rows_in_per_group, in_row_offset);
+                                                          rows_in_per_group, in_row_offset, out_kind == 2);
   else
     layernorm768_kernel<false><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
-                                                           rows_in_per_group, in_row_offset);
+                                                           rows_in_per_group, in_row_offset, 0);
   return last_err();
 }
 
 const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       __nv_bfloat16* out) {
+                       void* out, int fp16) {
   if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
   if (y0 < 0 || x0 < 0 || y0 + gh * 16 > H || x0 + gw * 16 > W) return "patchify: grid exceeds image";
   const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * 16 * gw * 4;
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  patchify16_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, n_img, H, W, y0, x0, gh, gw,
-                                                                                     out);
+  patchify16_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(
+      image, n_img, H, W, y0, x0, gh, gw, static_cast<uint16_t*>(out), fp16);
   return last_err();
 }
 
 const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                               int n_win, int hp, int wp, __nv_bfloat16* out) {
+                               int n_win, int hp, int wp, void* out, int fp16) {
   if (n_win <= 0) return "patchify: no windows";
   const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * 16 * wp * 4;
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  patchify16_windows_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(image, H, W, origins_yx_dev,
-                                                                                             n_win, hp, wp, out);
+  patchify16_windows_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(
+      image, H, W, origins_yx_dev, n_win, hp, wp, static_cast<uint16_t*>(out), fp16);
   return last_err();
 }
 
@@ -358,33 +365,34 @@ const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const
 }
 
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
-                               __nv_bfloat16* U_bf16, float* U_f32) {
+                               void* U_16, float* U_f32, int fp16) {
   if (n_win <= 0) return "resample: no windows";
   const int64_t rows = static_cast<int64_t>(n_win) * (gh + 2) * (gw + 2);
   LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * kD * 4.0 + static_cast<double>(rows) * kD * 6.0);
-  resample_to_padded_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(Y, n_win, hp, wp, gh, gw, U_bf16,
-                                                                                         U_f32);
+  resample_to_padded_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(
+      Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);
   return last_err();
 }
 
-const char* f32_to_bf16(cudaStream_t stream, const float* in, __nv_bfloat16* out, int64_t n) {
+const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n, int fp16) {
   if (n <= 0) return nullptr;
   LaunchScope scope(stream, "pack");
-  f32_to_bf16_kernel<<<grid_for(n, 256, 4096), 256, 0, stream>>>(in, out, n);
+  f32_to_16_kernel<<<grid_for(n, 256, 4096), 256, 0, stream>>>(in, static_cast<uint16_t*>(out), n, fp16);
   return last_err();
 }
 
 const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
-                            const float* var, float eps, int O, int I, __nv_bfloat16* Wp, float* bias) {
+                            const float* var, float eps, int O, int I, void* Wp, float* bias, int fp16) {
   LaunchScope scope(stream, "pack");
-  fold_conv3x3_bn_kernel<<<grid_for(static_cast<int64_t>(O) * I * 9, 256, 4096), 256, 0, stream>>>(W, gamma, beta, mean,
-                                                                                                   var, eps, O, I, Wp, bias);
+  fold_conv3x3_bn_kernel<<<grid_for(static_cast<int64_t>(O) * I * 9, 256, 4096), 256, 0, stream>>>(
+      W, gamma, beta, mean, var, eps, O, I, static_cast<uint16_t*>(Wp), bias, fp16);
   return last_err();
 }
 
-const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, __nv_bfloat16* out) {
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, void* out, int fp16) {
   LaunchScope scope(stream, "pack");
-  split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(W, O, I, out);
+  split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(
+      W, O, I, static_cast<uint16_t*>(out), fp16);
   return last_err();
 }
 

@@ -86,7 +86,8 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
       for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
     }
     *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        make_uint4(pack16x2(v[0], v[1], p.out_fp16), pack16x2(v[2], v[3], p.out_fp16), pack16x2(v[4], v[5], p.out_fp16),
+                   pack16x2(v[6], v[7], p.out_fp16));
   }
   __syncwarp();
   const int slot = lane & 3, rsub = lane >> 2;
@@ -134,11 +135,12 @@ __device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* st
     if (grow < p.M) {
       if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
-        const float hz = __bfloat162float(__float2bfloat16_rn(v.z)), hw = __bfloat162float(__float2bfloat16_rn(v.w));
+        const float hx = round16(v.x, p.out_fp16), hy = round16(v.y, p.out_fp16);
+        const float hz = round16(v.z, p.out_fp16), hw = round16(v.w, p.out_fp16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4;
-        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
-        *reinterpret_cast<uint2*>(o + p.N) = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(hx, hy, p.out_fp16), pack16x2(hz, hw, p.out_fp16));
+        *reinterpret_cast<uint2*>(o + p.N) =
+            make_uint2(pack16x2(v.x - hx, v.y - hy, p.out_fp16), pack16x2(v.z - hz, v.w - hw, p.out_fp16));
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4) = v;
       }
@@ -224,7 +226,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
   } else if (warp == 1 && leader) {
     // ------------------------------- MMA issuer (leader CTA) -------------------------------
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+    const uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N, p.ab_fp16);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);

@@ -88,7 +88,8 @@ __device__ __forceinline__ void epilogue_bf16_chunk64(const GemmParams& p, uint8
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
     }
-    my[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    my[j] = make_uint4(pack16x2(v[0], v[1], p.out_fp16), pack16x2(v[2], v[3], p.out_fp16), pack16x2(v[4], v[5], p.out_fp16),
+                   pack16x2(v[6], v[7], p.out_fp16));
   }
   __syncwarp();
   const int piece = lane & 7, rsub = lane >> 3;
@@ -145,11 +146,12 @@ __device__ __forceinline__ void epilogue_f32_chunk32(const GemmParams& p, uint8_
       if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
         // relu, then split into hi + lo bf16 so the next GEMM can recover ~fp32 accuracy: x ~= hi + lo
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
-        const float hz = __bfloat162float(__float2bfloat16_rn(v.z)), hw = __bfloat162float(__float2bfloat16_rn(v.w));
+        const float hx = round16(v.x, p.out_fp16), hy = round16(v.y, p.out_fp16);
+        const float hz = round16(v.z, p.out_fp16), hw = round16(v.w, p.out_fp16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4;
-        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
-        *reinterpret_cast<uint2*>(o + p.N) = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(hx, hy, p.out_fp16), pack16x2(hz, hw, p.out_fp16));
+        *reinterpret_cast<uint2*>(o + p.N) =
+            make_uint2(pack16x2(v.x - hx, v.y - hy, p.out_fp16), pack16x2(v.z - hz, v.w - hw, p.out_fp16));
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4) = v;
       }
@@ -227,7 +229,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
+    const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N, p.ab_fp16);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);

@@ -32,6 +32,8 @@ struct GemmParams {
   const float* resid;                 // f32 [M, ldr]
   int ldr;
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
+  int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
+  int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
 };
 
 inline GemmParams gemm_params_plain(int M, int N, int K) {
@@ -63,19 +65,20 @@ void set_launch_tag(const char* tag);  // nullptr clears
 
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
 // out[r] = LN(in[map(r)]) * gamma + beta, eps 1e-5, fp32 statistics (two-pass, in registers). D = 768 only.
+// out_kind: 0 = f32, 1 = bf16, 2 = fp16.
 // Row map: in_row = (r / rows_out_per_group) * rows_in_per_group + in_row_offset + r % rows_out_per_group.
 const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
-                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
                          int in_row_offset);
 
 // ------------------------------------------------------------------ stem ---------------------------------------
-// image f32 [n_img, 3, H, W] -> patch rows bf16 [n_img * gh * gw, 768], k = c*256 + py*16 + px, on the grid whose
-// (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches).
+// image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * 768] = [hi | lo] split of the
+// pixels, k = c*256 + py*16 + px, on the grid whose (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches).
 const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       __nv_bfloat16* out);
-// per-window patchify when window origins are not on the 16-pixel grid: out rows [n_win * hp * wp, 768]
+                       void* out, int fp16);
+// per-window patchify when window origins are not on the 16-pixel grid: out rows [n_win * hp * wp, 2 * 768]
 const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                               int n_win, int hp, int wp, __nv_bfloat16* out);
+                               int n_win, int hp, int wp, void* out, int fp16);
 
 // Assemble the residual stream X f32 [n_win * t_live, 768]:
 //   row 0            : LN_pre(class_emb + pos[0])
@@ -89,15 +92,24 @@ const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const
 // ------------------------------------------------------------------ attention ----------------------------------
 // qkv bf16 [n_win * t_live, 3*768] (q | k | v, head h at columns 64h..64h+63 of each third); const_kv bf16
 // [n_const, 3*768] rows appended as extra keys/values for every window (deep-VPT prompt tokens); out bf16
-// [n_win * t_live, 768]. softmax(q k^T / 8) v per (window, head), no mask. t_live + n_const <= 256.
+// [n_win * t_live, 768] (bf16, or fp16 when out_fp16). softmax(q k^T / 8) v per (window, head), no mask.
+// t_live + n_const <= 256.
 const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                          int n_win, int t_live, __nv_bfloat16* out);
+                          int n_win, int t_live, void* out, int out_fp16);
+
+// tcgen05 / TMEM implementation of the same contract (attention_tc.cu); needs n_const % 8 == 0.
+const char* attention_h64_tc(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                             int n_win, int t_live, void* out, int out_fp16);
+
+// persistent warp-specialised tcgen05 implementation (attention_fa.cu): P stays in TMEM, loads of the next item overlap
+const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                             int n_win, int t_live, void* out, int out_fp16);
 
 // ------------------------------------------------------------------ decoder / head -----------------------------
 // Y f32 [n_win * hp * wp, 768] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
 // zero-bordered NHWC grids U_bf16 / U_f32 [n_win, gh + 2, gw + 2, 768]  (model.py:195-196).
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
-                               __nv_bfloat16* U_bf16, float* U_f32);
+                               void* U_16, float* U_f32, int fp16);
 
 // F f32 [n_win * (gh+2) * (gw+2), 512] projected features on the padded grid -> EBC head on interior cells:
 // normalise, logits against tmat f32 [n_bins, 512] (= logit_scale * normalised text features), softmax, expectation
@@ -112,12 +124,12 @@ const char* fold_average(cudaStream_t stream, const float* preds, const int* row
                          int n_rows, int n_cols, int gh, int gw, int Ho, int Wo, float* density, float* count_out);
 
 // ------------------------------------------------------------------ pack-time helpers --------------------------
-const char* f32_to_bf16(cudaStream_t stream, const float* in, __nv_bfloat16* out, int64_t n);
+const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n, int fp16);
 // W f32 [O, I, 3, 3] + BN(gamma, beta, mean, var, eps) -> Wp bf16 [O, 9*I] (tap-major K: k = (ky*3+kx)*I + i), bias f32 [O]
 const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
-                            const float* var, float eps, int O, int I, __nv_bfloat16* Wp, float* bias);
+                            const float* var, float eps, int O, int I, void* Wp, float* bias, int fp16);
 // W f32 [O, I] -> bf16 [O, 3*I] = [hi | hi | lo]
-const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, __nv_bfloat16* out);
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, void* out, int fp16);
 // text f32 [n, d] -> tmat = exp(logit_scale) * text / max(||text||, 1e-12)
 const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat);
 

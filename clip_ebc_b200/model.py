@@ -113,6 +113,7 @@ class CLIP_EBC(nn.Module):
         decoder_cfg: Optional[List[Union[str, int]]] = None,
         text_features: Optional[Tensor] = None,
         window_chunk: int = 0,
+        operand_dtype: str = "fp16",
     ) -> None:
         super().__init__()
         assert backbone in resnet_backbones + vit_backbones, \
@@ -165,6 +166,8 @@ class CLIP_EBC(nn.Module):
             self.set_text_features(text_features)
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07), requires_grad=True)
 
+        assert operand_dtype in ("fp16", "bf16"), f"operand_dtype must be 'fp16' or 'bf16', got {operand_dtype}"
+        self.operand_dtype = operand_dtype  # 16-bit tensor-core operand format (accumulation / residual stay fp32)
         self._text_encoder_state: "OrderedDict[str, Tensor]" = OrderedDict()
         self._window_chunk = int(window_chunk)
         self._handle: Optional[C.c_void_p] = None
@@ -220,7 +223,7 @@ class CLIP_EBC(nn.Module):
         with torch.cuda.device(dev):
             if self._handle is None:
                 cfg = _lib.ClipEbcConfig(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt),
-                                         len(self.bins), self._window_chunk)
+                                         len(self.bins), self._window_chunk, int(self.operand_dtype == "fp16"))
                 h = C.c_void_p()
                 _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
                 self._handle = h

@@ -20,6 +20,11 @@ def set_gemm_impl(impl: int) -> None:
     _lib.check(_lib.load().clipebc_set_gemm_impl(int(impl)), "set_gemm_impl")
 
 
+def set_attention_impl(impl: int) -> None:
+    """1 = mma.sync attention, 2 = tcgen05 / TMEM attention (default)."""
+    _lib.check(_lib.load().clipebc_set_attention_impl(int(impl)), "set_attention_impl")
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -48,18 +53,25 @@ def window_origins(H: int, W: int, window: Tuple[int, int], stride: Tuple[int, i
     return list(ro), list(co)
 
 
-def to_bf16(x: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.load().clipebc_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "f32_to_bf16")
+def _dt16(fp16: bool) -> torch.dtype:
+    return torch.float16 if fp16 else torch.bfloat16
+
+
+def to_16(x: torch.Tensor, fp16: bool = False) -> torch.Tensor:
+    out = torch.empty(x.shape, dtype=_dt16(fp16), device=x.device)
+    _lib.check(_lib.load().clipebc_f32_to_16(_ptr(x), _ptr(out), x.numel(), int(fp16), _stream()), "f32_to_16")
     return out
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, M: Optional[int] = None, K: Optional[int] = None,
          seg_row_shift: Optional[Sequence[int]] = None, seg_col_start: Optional[Sequence[int]] = None,
-         mask_hw: Tuple[int, int] = (0, 0), block_n: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """D = A[M,K] @ W[N,K]^T with a fused epilogue. a, w: bf16 2-D contiguous."""
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+         mask_hw: Tuple[int, int] = (0, 0), block_n: int = 0, out: Optional[torch.Tensor] = None,
+         out_fp16: Optional[bool] = None) -> torch.Tensor:
+    """D = A[M,K] @ W[N,K]^T with a fused epilogue. a, w: both bf16 or both fp16, 2-D contiguous."""
+    assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16) and a.dim() == 2 and w.dim() == 2
+    ab_fp16 = a.dtype == torch.float16
+    out_fp16 = ab_fp16 if out_fp16 is None else out_fp16
     N = w.shape[0]
     K = w.shape[1] if K is None else K
     M = a.shape[0] if M is None else M
@@ -70,53 +82,57 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
         if epi in (EPI_F32, EPI_BIAS_F32, EPI_BIAS_RESID_F32):
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
         elif epi == EPI_BIAS_RESID_RELU_SPLIT:
-            out = torch.empty((M, 2 * N), dtype=torch.bfloat16, device=a.device)
+            out = torch.empty((M, 2 * N), dtype=_dt16(out_fp16), device=a.device)
         else:
-            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+            out = torch.empty((M, N), dtype=_dt16(out_fp16), device=a.device)
     _lib.check(_lib.load().clipebc_gemm_bf16(
         epi, _ptr(a), a.shape[0], a.shape[1], a.stride(0), _ptr(w), w.stride(0), M, N, K, n_seg, rs, cs, _ptr(out),
         out.stride(0), _ptr(bias), _ptr(resid), resid.stride(0) if resid is not None else 0, mask_hw[0], mask_hw[1],
-        block_n, _stream()), "gemm")
+        block_n, int(ab_fp16), int(out_fp16), _stream()), "gemm")
     return out
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_bf16: bool = True,
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype = torch.bfloat16,
               n_rows_out: Optional[int] = None, rows_out_per_group: int = 1, rows_in_per_group: int = 1,
               in_row_offset: int = 0) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.shape[-1] == 768
     n = x.numel() // 768 if n_rows_out is None else n_rows_out
-    out = torch.empty((n, 768), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    _lib.check(_lib.load().clipebc_layernorm768(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), int(out_bf16), n,
+    kind = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out_dtype]
+    out = torch.empty((n, 768), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.load().clipebc_layernorm768(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, n,
                                                 rows_out_per_group, rows_in_per_group, in_row_offset, _stream()),
                "layernorm")
     return out
 
 
-def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[torch.Tensor] = None,
+              out_fp16: bool = False) -> torch.Tensor:
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (n_win * t_live, 2304)
     n_const = 0 if const_kv is None else const_kv.shape[0]
-    out = torch.empty((n_win * t_live, 768), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.load().clipebc_attention(_ptr(qkv), _ptr(const_kv), n_const, n_win, t_live, _ptr(out), _stream()),
-               "attention")
+    out = torch.empty((n_win * t_live, 768), dtype=_dt16(out_fp16), device=qkv.device)
+    _lib.check(_lib.load().clipebc_attention(_ptr(qkv), _ptr(const_kv), n_const, n_win, t_live, _ptr(out),
+                                             int(out_fp16), _stream()), "attention")
     return out
 
 
 def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = None,
-             gw: Optional[int] = None) -> torch.Tensor:
+             gw: Optional[int] = None, fp16: bool = False) -> torch.Tensor:
+    """-> [n*gh*gw, 2*768]: columns [0, 768) = hi, [768, 1536) = lo of the hi/lo split of the pixels."""
     n, c, H, W = image.shape
     assert c == 3 and image.dtype == torch.float32
     gh = (H - y0) // 16 if gh is None else gh
     gw = (W - x0) // 16 if gw is None else gw
-    out = torch.empty((n * gh * gw, 768), dtype=torch.bfloat16, device=image.device)
-    _lib.check(_lib.load().clipebc_patchify16(_ptr(image), n, H, W, y0, x0, gh, gw, _ptr(out), _stream()), "patchify")
+    out = torch.empty((n * gh * gw, 2 * 768), dtype=_dt16(fp16), device=image.device)
+    _lib.check(_lib.load().clipebc_patchify16(_ptr(image), n, H, W, y0, x0, gh, gw, _ptr(out), int(fp16), _stream()),
+               "patchify")
     return out
 
 
-def resample_to_padded(Y: torch.Tensor, n_win: int, hp: int, wp: int, gh: int, gw: int):
-    ub = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=torch.bfloat16, device=Y.device)
+def resample_to_padded(Y: torch.Tensor, n_win: int, hp: int, wp: int, gh: int, gw: int, fp16: bool = False):
+    ub = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=_dt16(fp16), device=Y.device)
     uf = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=torch.float32, device=Y.device)
-    _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, _ptr(ub), _ptr(uf), _stream()),
-               "resample")
+    _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, _ptr(ub), _ptr(uf), int(fp16),
+                                                      _stream()), "resample")
     return ub, uf
 
 

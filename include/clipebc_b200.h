@@ -30,7 +30,7 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 1
+#define CLIPEBC_ABI_VERSION 2
 
 typedef struct clipebc_model clipebc_model;
 
@@ -43,6 +43,9 @@ typedef struct clipebc_config {
   int deep_vpt;     /* 1: per-layer prompts vpt_0..vpt_11, 0: shallow (vpt_0 only, propagated) */
   int num_bins;     /* N = len(bins) = len(anchor_points), 1..32                              */
   int window_chunk; /* windows per internal pass (0 = library default)                         */
+  int operand_fp16; /* 16-bit tensor-core operand format: 1 = fp16 (11-bit mantissa; CLIP's released weights are fp16,
+                       all operands are range-bounded and saturated), 0 = bf16. Accumulation, residual stream,
+                       LayerNorm statistics, softmax and the head are fp32 either way.         */
 } clipebc_config;
 
 const char* clipebc_last_error(void);
@@ -53,6 +56,10 @@ int64_t clipebc_launch_count(void);
 /* Selects the tcgen05 GEMM kernel used by the hot path and by clipebc_gemm_bf16: 1 = one CTA per 128-row tile,
  * 2 = CTA pair (cta_group::2, 256-row tiles; default). Both implement the same contract; tests run both. */
 int clipebc_set_gemm_impl(int impl);
+/* Selects the attention kernel: 1 = mma.sync (legacy tensor path), 2 = tcgen05 / TMEM, one CTA per 128-query tile,
+ * 3 = tcgen05 persistent warp-specialised with P kept in TMEM (default). 2 and 3 fall back to 1 when the constant-key
+ * count is not a multiple of 8. */
+int clipebc_set_attention_impl(int impl);
 
 /* Optional per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
  * clipebc_profile_dump synchronises the device and writes a JSON object {"<kernel>[:<use>]": {"ms", "launches",
@@ -90,22 +97,27 @@ int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_
                            int* col_origins);
 
 /* ---- single kernels (unit/parity tests and profiling; all pointers are device pointers) ------------------------ */
-int clipebc_f32_to_bf16(const float* in_dev, void* out_bf16_dev, int64_t n, void* stream);
-/* epi: 0 f32, 1 bias f32, 2 bias bf16, 3 bias+quickgelu bf16, 4 bias+resid f32, 5 bias+relu+border-mask bf16,
- *      6 bias+resid+relu hi/lo split bf16. See clip_ebc_b200/csrc/kernels.h for the contract. */
-int clipebc_gemm_bf16(int epi, const void* A_bf16_dev, int64_t a_rows, int64_t a_cols, int64_t lda,
-                      const void* W_bf16_dev, int64_t ldw, int M, int N, int K, int n_seg, const int* seg_row_shift,
+/* "16" = a 16-bit floating format selected by an fp16 flag: 0 = bf16, 1 = fp16 (saturating). */
+int clipebc_f32_to_16(const float* in_dev, void* out_16_dev, int64_t n, int fp16, void* stream);
+/* epi: 0 f32, 1 bias f32, 2 bias ->16, 3 bias+quickgelu ->16, 4 bias+resid f32, 5 bias+relu+border-mask ->16,
+ *      6 bias+resid+relu hi/lo split ->16. ab_fp16: format of A and W; out_fp16: format of a 16-bit output.
+ *      See clip_ebc_b200/csrc/kernels.h for the contract. */
+int clipebc_gemm_bf16(int epi, const void* A_16_dev, int64_t a_rows, int64_t a_cols, int64_t lda,
+                      const void* W_16_dev, int64_t ldw, int M, int N, int K, int n_seg, const int* seg_row_shift,
                       const int* seg_col_start, void* out_dev, int ldo, const float* bias_dev, const float* resid_dev,
-                      int ldr, int mask_hp, int mask_wp, int block_n, void* stream);
+                      int ldr, int mask_hp, int mask_wp, int block_n, int ab_fp16, int out_fp16, void* stream);
+/* out_kind: 0 = f32, 1 = bf16, 2 = fp16 */
 int clipebc_layernorm768(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
-                         int out_is_bf16, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
                          int in_row_offset, void* stream);
+/* q, k, v (and the constant keys/values) are bf16; the output is bf16 or fp16 (out_fp16) */
 int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
-                      void* out_bf16_dev, void* stream);
+                      void* out_16_dev, int out_fp16, void* stream);
+/* out: [n_img*gh*gw, 2*768] = [hi | lo] split of the pixels in the 16-bit format */
 int clipebc_patchify16(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       void* out_bf16_dev, void* stream);
-int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, void* U_bf16_dev,
-                               float* U_f32_dev, void* stream);
+                       void* out_16_dev, int fp16, void* stream);
+int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, void* U_16_dev,
+                               float* U_f32_dev, int fp16, void* stream);
 int clipebc_ebc_head(const float* F_dev, const float* tmat_dev, const float* anchors_dev, int n_bins, int n_win, int gh,
                      int gw, float* exp_out_dev, float* logits_out_dev, void* stream);
 /* preds_dev f32 [n_rows*n_cols, gh, gw]; row_cells/col_cells: HOST arrays of window origins // reduction. */

@@ -1,0 +1,27 @@
+"""Micro-benchmark of the attention kernels (mma.sync vs tcgen05) at the hot-path shape."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from clip_ebc_b200 import ops  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+for t_live, n_const in [(197, 32), (229, 0)]:
+    qkv = torch.randn(B * t_live, 2304, device="cuda").to(torch.bfloat16)
+    ckv = torch.randn(n_const, 2304, device="cuda").to(torch.bfloat16) if n_const else None
+    for impl in (1, 2, 3):
+        ops.set_attention_impl(impl)
+        for _ in range(3):
+            ops.attention(qkv, B, t_live, ckv)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.attention(qkv, B, t_live, ckv)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        fl = 4.0 * B * 12 * t_live * (t_live + n_const) * 64
+        print(f"T={t_live}+{n_const} impl={impl}: {ms * 1e3:7.1f} us  {fl / ms / 1e9:6.0f} TF/s")

@@ -28,6 +28,12 @@ def _bf(x):
     return x.to(torch.bfloat16)
 
 
+DT16 = [torch.bfloat16, torch.float16]
+DT16_IDS = ["bf16", "fp16"]
+# relative size of one rounding of a value to the 16-bit format (half an ulp of the worst-case mantissa)
+ROUND16 = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}
+
+
 def _rel(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
 
@@ -36,28 +42,31 @@ def _rel(a, b):
 @pytest.mark.parametrize("block_n", [0, 128, 192, 256])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (300, 768, 768), (1000, 2304, 768),
                                    (777, 768, 3072), (32, 2304, 768), (12608, 768, 768)])
-def test_gemm_plain_f32(ops, M, N, K, block_n):
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_gemm_plain_f32(ops, M, N, K, block_n, dt):
     if block_n and N % block_n:
         pytest.skip("N is not a multiple of this tile width")
-    a, w = _bf(_rand((M, K), 1)), _bf(_rand((N, K), 2, 0.05))
+    a, w = _rand((M, K), 1).to(dt), _rand((N, K), 2, 0.05).to(dt)
     out = ops.gemm(a, w, ops.EPI_F32, block_n=block_n)
     ref = a.float() @ w.float().t()
-    # bf16 inputs are exact in both; only fp32 accumulation order differs -> 1e-5 relative to the output scale
+    # the 16-bit inputs are exact in both; only fp32 accumulation order differs -> 1e-5 relative to the output scale
     assert _rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
 @pytest.mark.parametrize("block_n", [128, 192, 256])
-def test_gemm_bias_bf16_and_gelu(ops, block_n):
+def test_gemm_bias_16_and_gelu(ops, block_n, dt):
     M, N, K = 1234, 3072, 768
-    a, w, b = _bf(_rand((M, K), 3)), _bf(_rand((N, K), 4, 0.04)), _rand((N,), 5)
+    a, w, b = _rand((M, K), 3).to(dt), _rand((N, K), 4, 0.04).to(dt), _rand((N,), 5)
     ref = a.float() @ w.float().t() + b
     out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b, block_n=block_n)
-    assert out.dtype == torch.bfloat16
-    assert _rel(out, ref) < 6e-3  # one bf16 rounding of the output (2^-8)
-    assert torch.equal(out, ref.to(torch.bfloat16)) or (out.float() - ref).abs().max() < 0.05
+    assert out.dtype == dt
+    assert _rel(out, ref) < 1.5 * ROUND16[dt]  # one rounding of the output
+    out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b, block_n=block_n, out_fp16=False)  # QKV: bf16 out for the attention
+    assert out.dtype == torch.bfloat16 and _rel(out, ref) < 1.5 * ROUND16[torch.bfloat16]
     out = ops.gemm(a, w, ops.EPI_BIAS_GELU_BF16, bias=b, block_n=block_n)
     refg = ref * torch.sigmoid(1.702 * ref)
-    assert _rel(out, refg) < 6e-3
+    assert _rel(out, refg) < 1.5 * ROUND16[dt] + 2e-6
 
 
 @pytest.mark.parametrize("block_n", [128, 192, 256])
@@ -71,15 +80,16 @@ def test_gemm_bias_resid_inplace(ops, block_n):
     assert _rel(out, ref) < 2e-5
 
 
-def test_gemm_conv_segments_match_conv2d(ops):
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_gemm_conv_segments_match_conv2d(ops, dt):
     """3x3 conv over the zero-bordered NHWC grid as 9 row-shifted K-segments == F.conv2d(padding=1)."""
     B, g, Cc = 3, 14, 768
     Hp = Wp = g + 2
-    x = _bf(_rand((B, Cc, g, g), 10))
-    wt = _bf(_rand((Cc, Cc, 3, 3), 11, 0.02))
+    x = _rand((B, Cc, g, g), 10).to(dt)
+    wt = _rand((Cc, Cc, 3, 3), 11, 0.02).to(dt)
     bias = _rand((Cc,), 12)
     ref = F.relu(F.conv2d(x.float(), wt.float(), padding=1) + bias.view(1, -1, 1, 1))
-    xp = torch.zeros((B, Hp, Wp, Cc), dtype=torch.bfloat16, device="cuda")
+    xp = torch.zeros((B, Hp, Wp, Cc), dtype=dt, device="cuda")
     xp[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1)
     wk = wt.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).contiguous()  # [O, (ky, kx, I)]
     shifts = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
@@ -91,13 +101,14 @@ def test_gemm_conv_segments_match_conv2d(ops):
     border[:, 1:-1, 1:-1, :] = 0
     assert border.abs().max().item() == 0.0
     got = out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
-    assert _rel(got, ref) < 6e-3  # bf16 output rounding
+    assert _rel(got, ref) < 1.5 * ROUND16[dt]  # output rounding
 
 
-def test_gemm_resid_relu_split_and_split_projection(ops):
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_gemm_resid_relu_split_and_split_projection(ops, dt):
     """conv2-style epilogue writes hi|lo; the [hi|lo|hi] x [Whi|Whi|Wlo] GEMM reproduces an fp32 linear to ~1e-5."""
     M, Cc, E = 900, 768, 512
-    a, w, b = _bf(_rand((M, Cc), 13)), _bf(_rand((Cc, Cc), 14, 0.03)), _rand((Cc,), 15)
+    a, w, b = _rand((M, Cc), 13).to(dt), _rand((Cc, Cc), 14, 0.03).to(dt), _rand((Cc,), 15)
     u = _rand((M, Cc), 16)
     t_ref = F.relu(a.float() @ w.float().t() + b + u)
     split = ops.gemm(a, w, ops.EPI_BIAS_RESID_RELU_SPLIT, bias=b, resid=u)
@@ -105,8 +116,8 @@ def test_gemm_resid_relu_split_and_split_projection(ops):
     assert _rel(hi + lo, t_ref) < 3e-5  # hi + lo carries ~16 mantissa bits
     wp = _rand((E, Cc), 17, 0.05)
     bp = _rand((E,), 18)
-    w_hi = wp.to(torch.bfloat16)
-    w_lo = (wp - w_hi.float()).to(torch.bfloat16)
+    w_hi = wp.to(dt)
+    w_lo = (wp - w_hi.float()).to(dt)
     w3 = torch.cat([w_hi, w_hi, w_lo], dim=1).contiguous()
     out = ops.gemm(split, w3, ops.EPI_BIAS_F32, bias=bp, K=3 * Cc, seg_row_shift=[0, 0, 0],
                    seg_col_start=[0, Cc, 0])
@@ -125,47 +136,79 @@ def test_layernorm(ops):
     x = _rand((1000, 768), 20, 3.0) + 0.5
     g, b = _rand((768,), 21) * 0.1 + 1.0, _rand((768,), 22) * 0.1
     ref = F.layer_norm(x, (768,), g, b, 1e-5)
-    out = ops.layernorm(x, g, b, out_bf16=False)
+    out = ops.layernorm(x, g, b, out_dtype=torch.float32)
     assert (out - ref).abs().max().item() < 2e-5
-    outb = ops.layernorm(x, g, b, out_bf16=True)
-    assert torch.equal(outb, out.to(torch.bfloat16))
+    for dt in DT16:
+        out16 = ops.layernorm(x, g, b, out_dtype=dt)
+        assert torch.equal(out16, out.to(dt))
     # row map: take the last 196 rows of every group of 229 (ln_post on the patch rows)
     x = _rand((3 * 229, 768), 23)
-    out = ops.layernorm(x, g, b, out_bf16=False, n_rows_out=3 * 196, rows_out_per_group=196, rows_in_per_group=229,
+    out = ops.layernorm(x, g, b, out_dtype=torch.float32, n_rows_out=3 * 196, rows_out_per_group=196, rows_in_per_group=229,
                         in_row_offset=33)
     ref = F.layer_norm(x.view(3, 229, 768)[:, 33:], (768,), g, b, 1e-5).reshape(-1, 768)
     assert (out - ref).abs().max().item() < 2e-5
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("n_win,t_live,n_const", [(2, 197, 32), (3, 229, 0), (1, 50, 0), (2, 17, 5), (1, 256, 0)])
-def test_attention(ops, n_win, t_live, n_const):
+@pytest.mark.parametrize("impl", [1, 2, 3], ids=["mma_sync", "tcgen05", "tcgen05_persistent"])
+@pytest.mark.parametrize("n_win,t_live,n_const", [(2, 197, 32), (3, 229, 0), (1, 50, 0), (2, 17, 5), (1, 256, 0),
+                                                  (5, 197, 32), (2, 128, 8), (1, 129, 0), (40, 197, 32)])
+@pytest.mark.parametrize("out_fp16", [False, True], ids=["out_bf16", "out_fp16"])
+def test_attention(ops, n_win, t_live, n_const, impl, out_fp16):
+    ops.set_attention_impl(impl)  # impl 2 falls back to 1 when n_const % 8 != 0
     qkv = _bf(_rand((n_win * t_live, 2304), 30))
     ckv = _bf(_rand((n_const, 2304), 31)) if n_const else None
-    out = ops.attention(qkv, n_win, t_live, ckv).float().view(n_win, t_live, 12, 64)
+    out = ops.attention(qkv, n_win, t_live, ckv, out_fp16=out_fp16)
+    assert out.dtype == (torch.float16 if out_fp16 else torch.bfloat16)
+    out = out.float().view(n_win, t_live, 12, 64)
     q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
     if n_const:
         ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
         k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
         v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
     ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    ops.set_attention_impl(3)
     # P is rounded to bf16 before P@V and the output is bf16: 2^-8 relative
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("impl", [1, 2, 3], ids=["mma_sync", "tcgen05", "tcgen05_persistent"])
+def test_attention_large_scores(ops, impl):
+    """Peaky softmax (|score| up to ~40): the single-pass reference-max scheme must stay exact up to bf16 rounding."""
+    ops.set_attention_impl(impl)
+    n_win, t_live, n_const = 3, 197, 32
+    qkv = _bf(_rand((n_win * t_live, 2304), 32, 3.0))
+    ckv = _bf(_rand((n_const, 2304), 33, 3.0))
+    out = ops.attention(qkv, n_win, t_live, ckv).float().view(n_win, t_live, 12, 64)
+    ops.set_attention_impl(3)
+    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
+    ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
+    k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
+    v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
 # ----------------------------------------------------------------------------------------------- stem / decoder
-def test_patchify_matches_unfold(ops):
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_patchify_matches_unfold(ops, dt):
     img = _rand((2, 3, 64, 96), 40)
-    out = ops.patchify(img).float().view(2, 4 * 6, 768)
+    out = ops.patchify(img, fp16=dt == torch.float16).float().view(2, 4 * 6, 2, 768)
     ref = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2)  # [n, L, c*256 + py*16 + px]
-    assert torch.equal(out, ref.to(torch.bfloat16).float())
+    hi = ref.to(dt).float()
+    assert torch.equal(out[:, :, 0], hi)
+    assert torch.equal(out[:, :, 1], (ref - hi).to(dt).float())
+    # hi + lo carries the pixels to ~2 roundings of the 16-bit format
+    assert (out[:, :, 0] + out[:, :, 1] - ref).abs().max().item() < 4 * ROUND16[dt] ** 2 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("g", [28, 14, 7])
-def test_resample_matches_interpolate(ops, g):
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_resample_matches_interpolate(ops, g, dt):
     n = 2
     Y = _rand((n * 196, 768), 41)
-    ub, uf = ops.resample_to_padded(Y, n, 14, 14, g, g)
+    ub, uf = ops.resample_to_padded(Y, n, 14, 14, g, g, fp16=dt == torch.float16)
     x = Y.view(n, 14, 14, 768).permute(0, 3, 1, 2)
     ref = x if g == 14 else F.interpolate(x, scale_factor=g / 14, mode="bilinear")
     uf = uf.view(n, g + 2, g + 2, 768)
@@ -173,7 +216,7 @@ def test_resample_matches_interpolate(ops, g):
     border = uf.clone()
     border[:, 1:-1, 1:-1] = 0
     assert border.abs().max().item() == 0.0
-    assert torch.equal(ub.view_as(uf), uf.to(torch.bfloat16))
+    assert torch.equal(ub.view_as(uf), uf.to(dt))
 
 
 @pytest.mark.parametrize("n_bins", [3, 5, 20])
