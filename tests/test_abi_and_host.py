@@ -44,7 +44,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.clipebc_abi_version() == 1
+    assert lib.clipebc_abi_version() == 2
     assert lib.clipebc_launch_count() == 0  # nothing ran on this CPU box
 
 
@@ -100,9 +100,11 @@ def test_model_create_validates_config(lib):
     from clip_ebc_b200 import _lib
 
     h = C.c_void_p()
-    bad = _lib.ClipEbcConfig(224, 12, 32, 1, 5, 0)  # reduction 12
+    bad = _lib.ClipEbcConfig(224, 12, 32, 1, 5, 0, 1)  # reduction 12
     assert lib.clipebc_model_create(C.byref(bad), C.byref(h)) == 1
-    ok = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0)
+    bad2 = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0, 7)  # operand format
+    assert lib.clipebc_model_create(C.byref(bad2), C.byref(h)) == 1
+    ok = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0, 1)
     assert lib.clipebc_model_create(C.byref(ok), C.byref(h)) == 0
     # packing without tensors is a state error, reported by name
     assert lib.clipebc_model_pack(h, None) == 3
