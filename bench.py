@@ -214,7 +214,8 @@ def main():
         units_per_step = BATCH
         step = lambda i: model(ring[i % len(ring)])  # noqa: E731
         workload = ("configs[1]: ViT-B/16 deep-VPT(32) forward + decoder + EBC head, batch 64 synthetic 224x224 windows, "
-                    "reduction 8 (5 bins), bf16 tensor-core GEMMs / fp32 accumulate+residual, 1 process per GPU")
+                    "reduction 8 (5 bins), 16-bit tensor-core GEMMs (fp16 operands) / fp32 accumulate+residual, "
+                    "1 process per GPU")
         l2 = "ring of 4 distinct input batches (154 MB > 126 MB L2); per-step weights+activations > L2"
     else:
         H, Wd = 1536, 2048
@@ -353,7 +354,7 @@ def main():
         line = {
             "metric": "windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "fp16/bf16 tensor-core operands (tcgen05 kind::f16), fp32 accumulate/residual/softmax/head", "data": "synthetic",
             "config": {"workload": workload, "l2": l2, "global_batch_windows": world * units_per_step,
                        "parallelism": f"dp{world} (independent windows/images per rank)",
                        "weights": "seeded random init with the reference's init distributions (oracle/weights.py)"},
