@@ -6,14 +6,15 @@
 // One CTA per SM loops over (window, head) items; all stages of consecutive items overlap:
 //   warp 0       TMA producer: Q [256 x 64], K, V [256 x 64] (constant prompt rows first) of item i+1 are fetched into
 //                the second smem stage while item i is being processed
-//   warps 1, 3   MMA issuers, one per 128-query tile t (so the two tiles run decoupled and their softmax phases stagger):
-//                S_t = Q_t K^T (128 x 256 x 64), later O_t = P_t V with P_t read straight from TMEM (tcgen05.mma
-//                A-operand in tensor memory) and V consumed in place as MN-major B
-//   warp 2       TMEM allocator (all 512 columns: S_0 | S_1, each 128 lanes x 256 fp32)
-//   warps 4-7    softmax group of tile 0, warps 8-11 of tile 1: thread = query row = TMEM lane; row max, exp2, row sum from
-//                TMEM; P is written back to TMEM as packed bf16 over the consumed S columns (no smem round trip);
-//                finally O_t * 1/rowsum -> bf16 -> global
+//   warp 1       MMA issuer: S = Q_t K^T (128 x 256 x 64) of the NEXT 128-query tile into the free TMEM buffer, and
+//                O = P V of the current one with P read straight from TMEM (tcgen05.mma A-operand in tensor memory) and
+//                V consumed in place as MN-major B
+//   warp 2       TMEM allocator (all 512 columns: two S buffers of 128 lanes x 256 fp32)
+//   warps 4-11   two softmax groups that split the keys of one tile (group h: keys [128h, 128h+128)): thread = query row
+//                = TMEM lane; exp2 and row sum from TMEM in a single pass, P written back to TMEM as packed bf16 over
+//                the consumed S columns (no smem round trip); finally O * 1/rowsum -> 16-bit -> global
 // Scores and probabilities never leave the SM: HBM traffic is Q, K, V in and O out.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,7 +27,8 @@ constexpr int kQTileBytes = 128 * 128;   // one 128-query tile
 constexpr int kQBytes = 2 * kQTileBytes; // 256 query rows x 64 dims bf16
 constexpr int kKVBytes = 256 * 128;      // 256 key rows x 64 dims bf16
 constexpr int kStageBytesF = kQBytes + 2 * kKVBytes;  // 96 KB
-constexpr int kSmemF = 2 * kStageBytesF + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;   // row max / row sum exchange between the two softmax groups
+constexpr int kSmemF = 2 * kStageBytesF + kXchgBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kQkvLdF = 3 * 768;
 
 __device__ __forceinline__ uint64_t desc_sw128_mn(uint32_t smem_addr_bytes) {
@@ -87,9 +89,16 @@ __device__ __forceinline__ void chunk_max(const uint32_t (&v)[32], int lim, floa
 // p_j = exp2(min(s_j * scale - m_scaled, 120)) (0 beyond the real keys), row sum in fp32, P as packed bf16 pairs into TMEM.
 // The P columns [16c, 16c+16) overlay S columns that have already been consumed (16c + 16 <= 32c + 32).
 __device__ __forceinline__ void chunk_exp_store(const uint32_t (&v)[32], int lim, float scale, float m_scaled,
-                                                float& row_sum, uint32_t p_taddr) {
+                                                float& row_sum, uint32_t p_taddr, int dbg = 0) {
   uint32_t pk[16];
-  if (lim >= 32) {
+  if (dbg & 1) {  // EXPERIMENT: no exp
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float p0 = __uint_as_float(v[2 * j]) * scale - m_scaled, p1 = __uint_as_float(v[2 * j + 1]) * scale - m_scaled;
+      row_sum += p0 + p1;
+      pk[j] = pack_bf16x2(p0, p1);
+    }
+  } else if (lim >= 32) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float p0 = ex2f(fminf(__uint_as_float(v[2 * j]) * scale - m_scaled, 120.f));
@@ -106,28 +115,37 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&v)[32], int lim
       pk[j] = pack_bf16x2(p0, p1);
     }
   }
-  tmem_st_32x32b_x16(p_taddr, pk);
+  if (!(dbg & 4)) tmem_st_32x32b_x16(p_taddr, pk);
 }
 
+// Kernel structure: a CTA walks over "tiles" u = (item, 128-query tile); tile u lives in TMEM buffer u & 1 (256 columns):
+//   S (fp32, 256 cols)  ->  P0 packed bf16 [0,64) | O fp32 [64,128) | P1 packed bf16 [128,192)
+// The two softmax groups split the COLUMNS (keys) of one tile: group h owns keys [128h, 128h+128). While they work on
+// tile u, the tensor core computes S of tile u+1 into the other buffer and O of tile u-1 behind them; the epilogue of
+// tile u-1 is interleaved in the middle of tile u's softmax so its buffer is free again in time for S of tile u+1.
 __global__ void __launch_bounds__(kThreadsF, 1)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items,
-                    uint16_t* __restrict__ out, int out_fp16) {
+                    uint16_t* __restrict__ out, int out_fp16, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytesF);
-  uint64_t* qk_full = bars + 0;     // [2] TMA -> MMA
-  uint64_t* v_full = bars + 2;      // [2]
-  uint64_t* qk_empty = bars + 4;    // [2] MMA (commit) -> TMA
-  uint64_t* v_empty = bars + 6;     // [2]
-  uint64_t* s_full = bars + 8;      // [2 tiles] MMA (commit) -> softmax group
-  uint64_t* p_ready = bars + 10;    // [2 tiles] softmax group (4 warps) -> MMA
-  uint64_t* o_full = bars + 12;     // [2 tiles] MMA (commit) -> softmax group
-  uint64_t* tmem_free = bars + 14;  // [2 tiles] softmax group (4 warps) -> MMA
+  float* xchg = reinterpret_cast<float*>(smem + 2 * kStageBytesF);  // [2 buffers][2 kinds: max, sum][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytesF + kXchgBytes);
+  uint64_t* qk_full = bars + 0;    // [2 stages] TMA -> MMA
+  uint64_t* v_full = bars + 2;     // [2 stages]
+  uint64_t* qk_empty = bars + 4;   // [2 stages] MMA (commit) -> TMA
+  uint64_t* v_empty = bars + 6;    // [2 stages]
+  uint64_t* s_full = bars + 8;     // [2 buffers] MMA (commit) -> softmax groups
+  uint64_t* p_ready = bars + 10;   // [2 buffers] softmax groups (8 warps) -> MMA
+  uint64_t* o_full = bars + 12;    // [2 buffers] MMA (commit) -> softmax groups
+  uint64_t* buf_free = bars + 14;  // [2 buffers] softmax groups (8 warps) -> MMA
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tk = n_const + t_live;
+  const int n_qt = (t_live + 127) >> 7;  // 128-query tiles per item (1 or 2)
+  const int n_local = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total_tiles = n_local * n_qt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -136,8 +154,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&qk_empty[i], 2); mbar_init(&v_empty[i], 2);
-      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&tmem_free[i], 4);
+      mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&qk_empty[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 8); mbar_init(&o_full[i], 1); mbar_init(&buf_free[i], 8);
     }
     fence_mbar_init();
   }
@@ -149,8 +167,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int it = 0; it < n_local; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
       const int s = it & 1, ph = (it >> 1) & 1;
       const int head = item % 12, win = item / 12;
       const int row_base = win * t_live;
@@ -159,137 +177,165 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       uint8_t* sV = sK + kKVBytes;
       mbar_wait(&qk_empty[s], ph ^ 1);
       if (lane == 0) {
+        if (dbg & 64) { mbar_arrive(&qk_full[s]); } else {
         mbar_arrive_expect_tx(&qk_full[s], kQBytes + kKVBytes);
         tma_load_2d(sQ, &tm_q, &qk_full[s], head * 64, row_base);
         if (n_const > 0) tma_load_2d(sK, &tm_const, &qk_full[s], 768 + head * 64, 0);
         tma_load_2d(sK + n_const * 128, &tm_kv, &qk_full[s], 768 + head * 64, row_base);
+        }
       }
       __syncwarp();
       mbar_wait(&v_empty[s], ph ^ 1);
       if (lane == 0) {
+        if (dbg & 64) { mbar_arrive(&v_full[s]); } else {
         mbar_arrive_expect_tx(&v_full[s], kKVBytes);
         if (n_const > 0) tma_load_2d(sV, &tm_const, &v_full[s], 1536 + head * 64, 0);
         tma_load_2d(sV + n_const * 128, &tm_kv, &v_full[s], 1536 + head * 64, row_base);
+        }
       }
       __syncwarp();
     }
-  } else if (warp == 1 || warp == 3) {
-    // ------------------------------------ MMA issuer of query tile t ------------------------------------
-    const int t = warp >> 1;  // warp 1 -> tile 0, warp 3 -> tile 1
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
     constexpr uint32_t idesc_s = idesc_f(128, 256, false);
     constexpr uint32_t idesc_o = idesc_f(128, 64, true);
     const int k_steps = (Tk + 15) >> 4;
-    const uint32_t s_tmem = tmem_base + t * 256;  // S_t; packed bf16 P_t overlays columns [0, 128)
-    const uint32_t o_tmem = s_tmem + 128;         // O_t overlays S_t columns [128, 192)
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1, ip = it & 1;
+    // S of tile u: Q_t K^T into buffer u & 1
+    auto issue_s = [&](int u) {
+      const int it = u / n_qt, t = u - it * n_qt;
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int b = u & 1, j = u >> 1;
       const uint32_t q_addr = smem_u32(smem + s * kStageBytesF) + t * kQTileBytes;
       const uint32_t k_addr = smem_u32(smem + s * kStageBytesF) + kQBytes;
-      const uint32_t v_addr = k_addr + kKVBytes;
       mbar_wait(&qk_full[s], ph);
-      mbar_wait(&tmem_free[t], ip ^ 1);  // O_t of the previous item has been read out
+      mbar_wait(&buf_free[b], (j & 1) ^ 1);  // the tile that used this buffer two tiles ago has been written out
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(s_tmem, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
-                       k != 0 ? 1u : 0u);
-        umma_commit(&s_full[t]);
-        umma_commit(&qk_empty[s]);  // Q/K of this stage are dead once both tiles' S MMAs have retired (2 arrivals)
+        for (int k = 0; k < ((dbg & 16) ? 0 : 4); ++k)
+          umma_bf16_ss(tmem_base + b * 256, umma_desc_sw128_kmajor(q_addr + k * 32),
+                       umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+        if (t == n_qt - 1) umma_commit(&qk_empty[s]);  // Q / K of this stage are dead after the item's last S
       }
       __syncwarp();
+    };
+    if (total_tiles > 0) issue_s(0);
+    if (total_tiles > 1) issue_s(1);
+    for (int u = 0; u < total_tiles; ++u) {
+      const int it = u / n_qt, t = u - it * n_qt;
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int b = u & 1, j = u >> 1;
+      const uint32_t v_addr = smem_u32(smem + s * kStageBytesF) + kQBytes + kKVBytes;
       mbar_wait(&v_full[s], ph);
-      mbar_wait(&p_ready[t], ip);
+      mbar_wait(&p_ready[b], j & 1);
       tc_fence_after();
       if (lane == 0) {
-        for (int ks = 0; ks < k_steps; ++ks)
-          umma_bf16_ts(o_tmem, s_tmem + ks * 8, desc_sw128_mn(v_addr + ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
-        umma_commit(&o_full[t]);
-        umma_commit(&v_empty[s]);
+        const uint32_t buf = tmem_base + b * 256;
+        for (int ks = 0; ks < ((dbg & 8) ? 0 : k_steps); ++ks) {
+          // keys [0,128): packed P at columns [0,64); keys [128,256): packed P at columns [128,192)
+          const uint32_t p_tmem = buf + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8);
+          umma_bf16_ts(buf + 64, p_tmem, desc_sw128_mn(v_addr + ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[b]);
+        if (t == n_qt - 1) umma_commit(&v_empty[s]);
       }
       __syncwarp();
+      if (u + 2 < total_tiles) issue_s(u + 2);
     }
   } else if (warp >= 4) {
     // ------------------------------------ softmax groups ------------------------------------
-    const int t = (warp - 4) >> 2;            // query tile of this group
-    const int q = warp & 3;                   // TMEM lane quadrant
-    const int r = q * 32 + lane;              // row inside the tile
-    const int q_row = t * 128 + r;            // row inside the window
-    const bool warp_active = t * 128 + q * 32 < t_live;
-    const int n_chunks = (Tk + 31) >> 5;
+    const int h = (warp - 4) >> 2;  // column half owned by this group: keys [128h, 128h + 128)
+    const int q = warp & 3;         // TMEM lane quadrant
+    const int r = q * 32 + lane;    // row inside the tile
     const float kScale = 0.125f * 1.4426950408889634f;
-    const uint32_t s_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int ip = it & 1;
+    const int keys_mine = min(max(Tk - 128 * h, 0), 128);  // real keys in this half
+    const int n_chunks = (keys_mine + 31) >> 5;            // 0..4
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    // O of tile u (this group's 32 of the 64 output dims) -> global, then release the buffer
+    auto epilogue = [&](int u) {
+      const int it = u / n_qt, t = u - it * n_qt;
+      const int item = blockIdx.x + it * gridDim.x;
       const int head = item % 12, win = item / 12;
-      float row_sum = 0.f;
-      mbar_wait(&s_full[t], ip);
+      const int b = u & 1, j = u >> 1;
+      const int q_row = t * 128 + r;
+      const bool active = t * 128 + q * 32 < t_live;
+      mbar_wait(&o_full[b], j & 1);
       tc_fence_after();
-      if (warp_active) {
-        // Single pass over S (TMEM reads are the scarce resource: ~64 B/clk/SM). Softmax is shift invariant, so the
-        // reference maximum only has to keep exp2 in range: the max over the first 32 keys is used and the exponent is
-        // clamped at +120 (a row whose other scores exceed that reference by > 660 would saturate instead of overflow).
-        uint32_t va[32], vb[32];
-        float mx = -INFINITY;
-        tmem_ld_32x32b_x32(s_row, va);
+      if (active) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(lane_base + b * 256 + 64 + h * 32, o);
         tmem_ld_wait();
-        chunk_max(va, Tk, mx);
-        // pass 2: p = exp2((s - max) / 8 * log2 e), row sum, packed bf16 P back into TMEM
-        const float m_scaled = mx * kScale;
-#pragma unroll 1
-        for (int c = 0; c < n_chunks; c += 2) {
-          if (c + 1 < n_chunks) tmem_ld_32x32b_x32(s_row + (c + 1) * 32, vb);
-          chunk_exp_store(va, Tk - c * 32, kScale, m_scaled, row_sum, s_row + c * 16);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&buf_free[b]);
+        if (q_row < t_live && !(dbg & 32)) {
+          const float* sums = xchg + (b * 2 + 1) * 256;  // [2 halves][128 rows]
+          const float inv = 1.0f / (sums[r] + sums[128 + r]);
+          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(win) * t_live + q_row) * 768 + head * 64 + h * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            dst[g] = make_uint4(pack16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv, out_fp16),
+                                pack16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, out_fp16),
+                                pack16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, out_fp16),
+                                pack16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, out_fp16));
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&buf_free[b]);
+      }
+    };
+
+    for (int u = 0; u < total_tiles; ++u) {
+      const int it = u / n_qt, t = u - it * n_qt;
+      const int b = u & 1, j = u >> 1;
+      const bool active = (t * 128 + q * 32 < t_live) && n_chunks > 0;
+      const uint32_t s_row = lane_base + b * 256 + h * 128;  // this group's S columns; its P overlays their first half
+      float* maxs = xchg + (b * 2 + 0) * 256;
+      float* sums = xchg + (b * 2 + 1) * 256;
+      float row_sum = 0.f;
+      uint32_t va[32], vb[32];
+      mbar_wait(&s_full[b], j & 1);
+      tc_fence_after();
+      // Reference maximum (softmax is shift invariant; it only has to keep exp2 in range): max over the first 32 keys of
+      // each half, combined across the two groups through smem. The exponent is clamped at +120.
+      float mx = -INFINITY;
+      if (active) {
+        if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row, va);
+        tmem_ld_wait();
+        chunk_max(va, keys_mine, mx);
+      }
+      maxs[h * 128 + r] = mx;
+      named_bar_sync(1, 256);
+      const float m_scaled = fmaxf(mx, maxs[(1 - h) * 128 + r]) * kScale;
+      if (active) {
+        if (n_chunks > 1) { if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row + 32, vb); }
+        chunk_exp_store(va, keys_mine, kScale, m_scaled, row_sum, s_row, dbg);
+        tmem_ld_wait();
+        if (n_chunks > 1) {
+          if (n_chunks > 2) { if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row + 64, va); }
+          chunk_exp_store(vb, keys_mine - 32, kScale, m_scaled, row_sum, s_row + 16, dbg);
           tmem_ld_wait();
-          if (c + 1 < n_chunks) {
-            if (c + 2 < n_chunks) tmem_ld_32x32b_x32(s_row + (c + 2) * 32, va);
-            chunk_exp_store(vb, Tk - (c + 1) * 32, kScale, m_scaled, row_sum, s_row + (c + 1) * 16);
-            tmem_ld_wait();
-          }
+        }
+      }
+      if (u >= 1) epilogue(u - 1);  // mid-softmax: frees the other buffer in time for S of tile u + 1
+      if (active) {
+        if (n_chunks > 2) {
+          if (n_chunks > 3) { if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row + 96, vb); }
+          chunk_exp_store(va, keys_mine - 64, kScale, m_scaled, row_sum, s_row + 32, dbg);
+          tmem_ld_wait();
+          if (n_chunks > 3) chunk_exp_store(vb, keys_mine - 96, kScale, m_scaled, row_sum, s_row + 48, dbg);
         }
         tmem_st_wait();
       }
+      sums[h * 128 + r] = row_sum;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[t]);
-
-      mbar_wait(&o_full[t], ip);
-      tc_fence_after();
-      if (warp_active) {
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(s_row + 128, o0);
-        tmem_ld_32x32b_x32(s_row + 160, o1);
-        tmem_ld_wait();
-        // O is in registers: hand the TMEM tile back before the global stores so the next S MMA can start
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_free[t]);
-        if (q_row < t_live) {
-          const float inv = 1.0f / row_sum;
-          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(win) * t_live + q_row) * 768 + head * 64);
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(pack16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv, out_fp16));
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            dst[4 + g] =
-                make_uint4(pack16x2(__uint_as_float(o1[8 * g + 0]) * inv, __uint_as_float(o1[8 * g + 1]) * inv, out_fp16),
-                           pack16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv, out_fp16),
-                           pack16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv, out_fp16),
-                           pack16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv, out_fp16));
-        }
-      }
-      if (!warp_active) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_free[t]);
-      }
+      if (lane == 0) mbar_arrive(&p_ready[b]);
     }
+    if (total_tiles > 0) epilogue(total_tiles - 1);
   }
 
   tc_fence_before();
@@ -353,8 +399,9 @@ const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, cons
     const double tk = t_live + n_const;
     LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
                       2.0 * n_win * t_live * (2304.0 + 768.0));
+    static int dbg = getenv("CLIPEBC_ATTN_DBG") ? atoi(getenv("CLIPEBC_ATTN_DBG")) : 0;  // experiment knob
     attention_fa_kernel<<<grid, kThreadsF, kSmemF, stream>>>(tq, tkv, tc, n_const, t_live, n_items,
-                                                             static_cast<uint16_t*>(out), out_fp16);
+                                                             static_cast<uint16_t*>(out), out_fp16, dbg);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

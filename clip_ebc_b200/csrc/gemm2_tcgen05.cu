@@ -14,6 +14,7 @@
 //   warps 4-11  epilogue (both CTAs): 2 warps per TMEM lane quadrant, each owning half of the tile's columns;
 //               tcgen05.ld -> XOR-swizzled smem transpose -> coalesced global accesses; the tile's bias lives in smem
 // Same fused epilogues and K-segment addressing as gemm_tcgen05.cu (see kernels.h).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -96,7 +97,7 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
   for (int it = 0; it < 4; ++it) {
     const int rr = it * 8 + rsub;
     const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((slot ^ ((rr >> 1) & 3)) << 4));
-    if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + slot * 8) = u;
+    if (row0 + rr < p.M && !(p.dbg & 1)) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + slot * 8) = u;
   }
   __syncwarp();
 }
@@ -281,9 +282,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll 1
         for (int c = 0; c < HALF_N / 32; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          if (!(p.dbg & 4)) tmem_ld_32x32b_x32(t_addr + c * 32, r);
           tmem_ld_wait();
-          epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r);
+          if (!(p.dbg & 2)) epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r);
         }
       } else {
         constexpr int NC = HALF_N / 32;
@@ -410,6 +411,8 @@ int pick_block_n2(int M, int N, int num_sms) {
 
 const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                           int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
+  static const int dbg_env = getenv("CLIPEBC_GEMM_DBG") ? atoi(getenv("CLIPEBC_GEMM_DBG")) : 0;  // experiment knob
+  p.dbg = dbg_env;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
   if (p.K % kBlockK != 0) return "gemm: K must be a multiple of 64";
   if (p.n_seg < 1 || p.n_seg > kMaxGemmSegs) return "gemm: bad segment count";

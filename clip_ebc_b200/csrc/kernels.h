@@ -34,6 +34,7 @@ struct GemmParams {
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
   int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
+  int dbg;                            // experiment knob (profiles/): 0 in production
 };
 
 inline GemmParams gemm_params_plain(int M, int N, int K) {
