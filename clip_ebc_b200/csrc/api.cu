@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -33,6 +34,11 @@ thread_local const char* g_tag = nullptr;
 }  // namespace
 
 void set_launch_tag(const char* tag) { g_tag = tag; }
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("CLIPEBC_NO_PDL") == nullptr;
+  return on;
+}
 
 LaunchScope::LaunchScope(cudaStream_t stream, const char* kind, double flops, double bytes) : stream_(stream), slot_(-1) {
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -164,6 +164,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();  // QKV of this layer comes from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -400,8 +402,9 @@ const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, cons
     LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
                       2.0 * n_win * t_live * (2304.0 + 768.0));
     static int dbg = getenv("CLIPEBC_ATTN_DBG") ? atoi(getenv("CLIPEBC_ATTN_DBG")) : 0;  // experiment knob
-    attention_fa_kernel<<<grid, kThreadsF, kSmemF, stream>>>(tq, tkv, tc, n_const, t_live, n_items,
-                                                             static_cast<uint16_t*>(out), out_fp16, dbg);
+    cudaError_t le = launch_pdl(attention_fa_kernel, dim3(grid), dim3(kThreadsF), kSmemF, stream, 1, tq, tkv, tc, n_const,
+                                t_live, n_items, static_cast<uint16_t*>(out), out_fp16, dbg);
+    if (le != cudaSuccess) return cudaGetErrorString(le);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

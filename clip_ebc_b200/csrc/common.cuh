@@ -71,6 +71,15 @@ __device__ __forceinline__ uint16_t cvt16(float x, int fp16) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: every hot-path kernel is launched with programmaticStreamSerialization, so its CTAs
+// may become resident (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous
+// kernel of the stream drains. pdl_wait() must precede the first access to global memory a predecessor may have
+// written or may still read; pdl_launch_dependents() lets the next kernel of the stream start its own prologue.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

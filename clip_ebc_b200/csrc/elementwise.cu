@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
                                                            const float* __restrict__ beta, void* __restrict__ out,
                                                            int64_t n_rows_out, int rows_out_per_group,
                                                            int rows_in_per_group, int in_row_offset, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows_out;
@@ -107,6 +109,8 @@ __device__ __forceinline__ void store_hi_lo(uint16_t* dst, const float4& v, int 
 __global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict__ image, int n_img, int H, int W,
                                                          int y0, int x0, int gh, int gw, uint16_t* __restrict__ out,
                                                          int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t quads_per_row = static_cast<int64_t>(gw) * 4;            // 4 quads per patch row of 16 px
   const int64_t per_img = static_cast<int64_t>(3) * gh * 16 * quads_per_row;
   const int64_t total = per_img * n_img;
@@ -134,6 +138,8 @@ __global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __restrict__ image, int H, int W,
                                                                  const int* __restrict__ origins_yx, int n_win, int hp,
                                                                  int wp, uint16_t* __restrict__ out, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t quads_per_row = static_cast<int64_t>(wp) * 4;
   const int64_t per_win = static_cast<int64_t>(3) * hp * 16 * quads_per_row;
   const int64_t total = per_win * n_win;
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
                                                               const float* __restrict__ ln_b,
                                                               const float* __restrict__ vpt0, int n_prompt, int n_win,
                                                               int hp, int wp, float* __restrict__ X) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t_live = 1 + n_prompt + hp * wp;
   const int64_t n_rows = static_cast<int64_t>(n_win) * t_live;
@@ -204,6 +212,8 @@ __device__ __forceinline__ void bilinear_src(int dst, float inv_scale, int in_si
 __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __restrict__ Y, int n_win, int hp, int wp,
                                                                  int gh, int gw, uint16_t* __restrict__ U_16,
                                                                  float* __restrict__ U_f32, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int Hp = gh + 2, Wp = gw + 2;
   const int64_t n_rows = static_cast<int64_t>(n_win) * Hp * Wp;
@@ -322,13 +332,11 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
   const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
   LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_kind ? 2.0 : 4.0)));
-  if (out_kind)
-    layernorm768_kernel<true><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
-                                                          rows_in_per_group, in_row_offset, out_kind == 2);
-  else
-    layernorm768_kernel<false><<<blocks, 256, 0, stream>>>(in, gamma, beta, out, n_rows_out, rows_out_per_group,
-                                                           rows_in_per_group, in_row_offset, 0);
-  return last_err();
+  cudaError_t e = out_kind ? launch_pdl(layernorm768_kernel<true>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
+                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, out_kind == 2)
+                           : launch_pdl(layernorm768_kernel<false>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
+                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, 0);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
@@ -337,9 +345,9 @@ const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H
   if (y0 < 0 || x0 < 0 || y0 + gh * 16 > H || x0 + gw * 16 > W) return "patchify: grid exceeds image";
   const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * 16 * gw * 4;
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  patchify16_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(
-      image, n_img, H, W, y0, x0, gh, gw, static_cast<uint16_t*>(out), fp16);
-  return last_err();
+  cudaError_t e = launch_pdl(patchify16_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0, stream, 1,
+                             image, n_img, H, W, y0, x0, gh, gw, static_cast<uint16_t*>(out), fp16);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
@@ -347,9 +355,9 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
   if (n_win <= 0) return "patchify: no windows";
   const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * 16 * wp * 4;
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  patchify16_windows_kernel<<<grid_for(total, 256, device_num_sms() * 16), 256, 0, stream>>>(
-      image, H, W, origins_yx_dev, n_win, hp, wp, static_cast<uint16_t*>(out), fp16);
-  return last_err();
+  cudaError_t e = launch_pdl(patchify16_windows_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0,
+                             stream, 1, image, H, W, origins_yx_dev, n_win, hp, wp, static_cast<uint16_t*>(out), fp16);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
@@ -359,9 +367,9 @@ const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const
   if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
   const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
   LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * kD * 8.0);
-  assemble_tokens_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(
-      patch_embed, win_base_dev, src_pitch, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
-  return last_err();
+  cudaError_t e = launch_pdl(assemble_tokens_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
+                             patch_embed, win_base_dev, src_pitch, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
@@ -369,9 +377,9 @@ const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, i
   if (n_win <= 0) return "resample: no windows";
   const int64_t rows = static_cast<int64_t>(n_win) * (gh + 2) * (gw + 2);
   LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * kD * 4.0 + static_cast<double>(rows) * kD * 6.0);
-  resample_to_padded_kernel<<<grid_for(rows, 8, device_num_sms() * 8), 256, 0, stream>>>(
-      Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);
-  return last_err();
+  cudaError_t e = launch_pdl(resample_to_padded_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
+                             Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n, int fp16) {

@@ -14,6 +14,12 @@
 //   warps 4-11  epilogue (both CTAs): 2 warps per TMEM lane quadrant, each owning half of the tile's columns;
 //               tcgen05.ld -> XOR-swizzled smem transpose -> coalesced global accesses; the tile's bias lives in smem
 // Same fused epilogues and K-segment addressing as gemm_tcgen05.cu (see kernels.h).
+//
+// MC = 2 (cluster of 4 CTAs = two pairs working on vertically adjacent 256-row tiles of the same N-tile): at 32 KB of
+// operands per k-block and SM the pair kernel pulls ~10.6 TB/s out of L2, which is the chip's L2 slice throughput
+// (~6300 B/clk) -- the tensor pipe waits on it (~450 ns per k-block instead of 270). The two pairs need the same weight
+// tile, so each CTA fetches only a quarter of it (64 rows) and TMA-multicasts it to its counterpart in the other pair:
+// 24 KB per k-block and SM leave L2. The price is placement: only 33 clusters of 4 fit on the 148 SMs (132 SMs).
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
@@ -150,13 +156,28 @@ __device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* st
   __syncwarp();
 }
 
-template <int BLOCK_N, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// TMA load multicast to the CTAs of `cta_mask`; with cta_group::2 the transaction bytes of every destination CTA are
+// reported to the barrier of that CTA's pair leader (the peer bit, bit 24 of the shared address, is cleared).
+__device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                       int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
+
+template <int BLOCK_N, int EPI, int MC>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ GemmParams p) {
   using Cfg = Cfg2<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int CL = 2 * MC;  // CTAs per cluster
+  static_assert(MC == 1 || MC == 2, "one or two CTA pairs per cluster");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -171,14 +192,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;          // rank inside the CTA pair
+  const uint32_t pr = crank >> 1;           // pair inside the cluster
+  const uint32_t leader_crank = crank & ~1u;
   const bool leader = rank == 0;
 
   const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row pair tiles
   const int n_tiles = p.N / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = ((m_tiles + MC - 1) / MC) * n_tiles;   // cluster tiles: MC vertically adjacent pair tiles
   const int num_kb = p.K / kBlockK;
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -187,7 +211,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
-      mbar_init(&empty_bar[s], 1);  // tcgen05.commit multicast from the leader
+      mbar_init(&empty_bar[s], MC);  // tcgen05.commit multicast from the leader of every pair of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -200,25 +224,42 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above overlapped the tail of the previous kernel; its results (A, the residual) are needed from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
     uint32_t stage = 0, phase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
-      const int m0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
+      const int m0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
       const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
       int seg = 0, kk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);  // own slot free (released by the leader's commit multicast)
+        // slot free in every CTA of the cluster (each pair leader's commit is multicast to all of them), so multicast
+        // writes into the other pair's slot are safe too
+        mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), leader_crank);
+          const uint32_t tx = ((p.dbg & 16) ? 0u : 2u * Cfg::kABytes) + ((p.dbg & 8) ? 0u : 2u * Cfg::kBBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx);
           else mbar_arrive_cluster(leader_full);
-          tma_load_2d_pair(sa, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK, m0 + p.seg_row_shift[seg]);
-          tma_load_2d_pair(sb, &tma_b, leader_full, kb * kBlockK, n0);
+          if (!(p.dbg & 16))
+            tma_load_2d_pair(sa, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK, m0 + p.seg_row_shift[seg]);
+          if (p.dbg & 8) {
+          } else if constexpr (MC == 1) {
+            tma_load_2d_pair(sb, &tma_b, leader_full, kb * kBlockK, n0);
+          } else {
+            // this CTA's share of the weight half-tile, delivered to the same slot of the CTA with the same pair rank in
+            // every pair of the cluster
+            constexpr int kShareRows = HALF_N / MC;
+            const uint16_t mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
+            tma_load_2d_pair_mcast(sb + pr * (Cfg::kBBytes / MC), &tma_b, &full_bar[stage], kb * kBlockK,
+                                   n0 + static_cast<int>(pr) * kShareRows, mask);
+          }
         }
         __syncwarp();
         if (++kk == p.seg_kblocks) { kk = 0; ++seg; }
@@ -229,7 +270,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // ------------------------------- MMA issuer (leader CTA) -------------------------------
     const uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N, p.ab_fp16);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
+    constexpr uint16_t kAllCtas = (1u << CL) - 1;
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pr));
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -245,8 +288,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             const uint64_t db = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 2);
             umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_pair_mcast(&empty_bar[stage], 3);                          // smem slot free in both CTAs
-          if (kb == num_kb - 1) umma_commit_pair_mcast(&tmem_full_bar[as], 3);  // accumulator ready in both CTAs
+          umma_commit_pair_mcast(&empty_bar[stage], kAllCtas);                           // this pair is done with the slot
+          if (kb == num_kb - 1) umma_commit_pair_mcast(&tmem_full_bar[as], pair_mask);  // accumulator ready in both CTAs
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -261,12 +304,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int half = ew >> 2;    // which half of the tile's columns
     const int et = threadIdx.x - 128;
     uint8_t* stg = staging + ew * kStagingPerWarp;
-    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
-    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), leader_crank);
+    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), leader_crank);
     uint32_t as = 0, aphase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
-      const int row0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
+      const int row0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
       const int n0 = n_blk * BLOCK_N;
       // the tile's bias -> smem (double-buffered by accumulator stage); overlaps the wait for the accumulator
       float* bs = bias_s + as * BLOCK_N;
@@ -349,41 +392,57 @@ bool make_tmap2(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int EPI>
+// clusters of 2*MC CTAs (1 CTA per SM) that can be co-resident: 74 pairs, but only 33 clusters of 4 on B200
+template <int BLOCK_N, int EPI, int MC>
+int max_clusters2(int num_sms) {
+  static int cached = 0;
+  if (cached) return cached;
+  using Cfg = Cfg2<BLOCK_N>;
+  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * MC * 64); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2 * MC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / (2 * MC); }
+  cached = n;
+  return n;
+}
+
+template <int BLOCK_N, int EPI, int MC>
 cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_sms) {
   using Cfg = Cfg2<BLOCK_N>;
-  static bool attr_set = false;
-  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
+  const int max_cl = max_clusters2<BLOCK_N, EPI, MC>(num_sms);  // also sets the dynamic smem attribute (once)
+  if (max_cl <= 0) return cudaErrorInvalidConfiguration;
   const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
-  const int num_tiles = m_tiles * (p.N / BLOCK_N);
-  const int max_pairs = num_sms / 2;
-  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  const int num_tiles = ((m_tiles + MC - 1) / MC) * (p.N / BLOCK_N);
+  const int clusters = num_tiles < max_cl ? num_tiles : max_cl;
+  cudaError_t e;
   {
     LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
                       2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
                           4.0 * p.M * static_cast<double>(p.N));
-    kern<<<2 * pairs, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, p);
   }
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MC>
 cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_sms) {
   switch (epi) {
-    case EPI_F32: return launch_one2<BLOCK_N, EPI_F32>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_F32: return launch_one2<BLOCK_N, EPI_BIAS_F32>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_BF16: return launch_one2<BLOCK_N, EPI_BIAS_BF16>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_GELU_BF16: return launch_one2<BLOCK_N, EPI_BIAS_GELU_BF16>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT>(stream, ta, tb, p, num_sms);
+    case EPI_F32: return launch_one2<BLOCK_N, EPI_F32, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_F32: return launch_one2<BLOCK_N, EPI_BIAS_F32, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_BF16: return launch_one2<BLOCK_N, EPI_BIAS_BF16, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_GELU_BF16: return launch_one2<BLOCK_N, EPI_BIAS_GELU_BF16, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT, MC>(stream, ta, tb, p, num_sms);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -428,12 +487,21 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
   if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 3 || p.mask_wp < 3)) return "gemm: mask grid missing";
 
+  static const int mc_env = getenv("CLIPEBC_GEMM_MC") ? atoi(getenv("CLIPEBC_GEMM_MC")) : 0;  // experiment knob
+  const int mc = (mc_env == 1 || mc_env == 2) ? mc_env : 1;  // measured on B200: no gain from the multicast variant (power-bound)
+
   CUtensorMap ta, tb;
   if (!make_tmap2(&ta, A, a_rows, a_cols, lda, kBlockM)) return "gemm: cuTensorMapEncodeTiled(A) failed";
-  if (!make_tmap2(&tb, W, p.N, p.K, ldw, block_n / 2)) return "gemm: cuTensorMapEncodeTiled(W) failed";
-  cudaError_t e = (block_n == 256)   ? launch_epi2<256>(stream, epi, ta, tb, p, num_sms)
-                  : (block_n == 192) ? launch_epi2<192>(stream, epi, ta, tb, p, num_sms)
-                                     : launch_epi2<128>(stream, epi, ta, tb, p, num_sms);
+  if (!make_tmap2(&tb, W, p.N, p.K, ldw, block_n / 2 / mc)) return "gemm: cuTensorMapEncodeTiled(W) failed";
+  cudaError_t e;
+  if (mc == 2)
+    e = (block_n == 256)   ? launch_epi2<256, 2>(stream, epi, ta, tb, p, num_sms)
+        : (block_n == 192) ? launch_epi2<192, 2>(stream, epi, ta, tb, p, num_sms)
+                           : launch_epi2<128, 2>(stream, epi, ta, tb, p, num_sms);
+  else
+    e = (block_n == 256)   ? launch_epi2<256, 1>(stream, epi, ta, tb, p, num_sms)
+        : (block_n == 192) ? launch_epi2<192, 1>(stream, epi, ta, tb, p, num_sms)
+                           : launch_epi2<128, 1>(stream, epi, ta, tb, p, num_sms);
   if (e != cudaSuccess) return cudaGetErrorString(e);
   return nullptr;
 }

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__
                                                        const float* __restrict__ anchors, int n_bins, int n_win, int gh,
                                                        int gw, float* __restrict__ exp_out,
                                                        float* __restrict__ logits_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int Hp = gh + 2, Wp = gw + 2;
   const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(256) fold_average_kernel(const float* __restri
                                                            const int* __restrict__ row_cells,
                                                            const int* __restrict__ col_cells, int n_rows, int n_cols,
                                                            int gh, int gw, int Ho, int Wo, float* __restrict__ density) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(Ho) * Wo;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -85,6 +89,8 @@ __global__ void __launch_bounds__(256) fold_average_kernel(const float* __restri
 
 // Deterministic single-block sum (fixed association order, independent of grid size / GPU count).
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[1024];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += 1024) s += x[i];
@@ -113,9 +119,9 @@ const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, con
   const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   LaunchScope scope(stream, "ebc_head", 0.0, static_cast<double>(cells) * (kE * 4.0 + 4.0));
-  ebc_head_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(F, tmat, anchors, n_bins, n_win, gh, gw, exp_out,
-                                                                logits_out);
-  return last_err();
+  cudaError_t e = launch_pdl(ebc_head_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, F, tmat, anchors,
+                             n_bins, n_win, gh, gw, exp_out, logits_out);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
 const char* fold_average(cudaStream_t stream, const float* preds, const int* row_cells_dev, const int* col_cells_dev,
@@ -127,15 +133,16 @@ const char* fold_average(cudaStream_t stream, const float* preds, const int* row
   if (blocks > cap) blocks = cap;
   {
     LaunchScope scope(stream, "fold", 0.0, 4.0 * (static_cast<double>(n_rows) * n_cols * gh * gw + static_cast<double>(total)));
-    fold_average_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(preds, row_cells_dev, col_cells_dev, n_rows, n_cols,
-                                                                      gh, gw, Ho, Wo, density);
+    cudaError_t le = launch_pdl(fold_average_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, preds,
+                                row_cells_dev, col_cells_dev, n_rows, n_cols, gh, gw, Ho, Wo, density);
+    if (le != cudaSuccess) return cudaGetErrorString(le);
   }
   const char* e = last_err();
   if (e) return e;
   if (count_out != nullptr) {
     LaunchScope scope(stream, "count_sum", 0.0, 4.0 * static_cast<double>(total));
-    sum_kernel<<<1, 1024, 0, stream>>>(density, total, count_out);
-    return last_err();
+    cudaError_t le = launch_pdl(sum_kernel, dim3(1), dim3(1024), 0, stream, 1, density, total, count_out);
+    return le != cudaSuccess ? cudaGetErrorString(le) : last_err();
   }
   return nullptr;
 }

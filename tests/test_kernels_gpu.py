@@ -125,6 +125,52 @@ def test_gemm_resid_relu_split_and_split_projection(ops, dt):
     assert _rel(out, ref.float()) < 5e-5
 
 
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+@pytest.mark.parametrize("rem", [8, 64, 100, 128])
+def test_gemm_remainder_rows_all_epilogues(ops, rem, dt):
+    """M = 2 full 256-row tiles + a small remainder: every fused epilogue must mask the padded rows of the last tile and
+    give the same answer on the remainder rows as on full tiles."""
+    M, N, K = 512 + rem, 768, 768
+    a, w, b = _rand((M, K), 30).to(dt), _rand((N, K), 31, 0.04).to(dt), _rand((N,), 32)
+    x = _rand((M, N), 33)
+    ref = a.float() @ w.float().t() + b
+    out = ops.gemm(a, w, ops.EPI_BIAS_F32, bias=b)
+    assert _rel(out, ref) < 2e-5 and _rel(out[512:], ref[512:]) < 2e-5
+    out = ops.gemm(a, w, ops.EPI_BIAS_BF16, bias=b)
+    assert _rel(out[512:], ref[512:]) < 1.5 * ROUND16[dt]
+    out = ops.gemm(a, w, ops.EPI_BIAS_GELU_BF16, bias=b)
+    refg = ref * torch.sigmoid(1.702 * ref)
+    assert _rel(out, refg) < 1.5 * ROUND16[dt] + 2e-6 and _rel(out[512:], refg[512:]) < 1.5 * ROUND16[dt] + 2e-6
+    xr = x.clone()
+    out = ops.gemm(a, w, ops.EPI_BIAS_RESID_F32, bias=b, resid=xr, out=xr)
+    assert _rel(out, ref + x) < 2e-5 and _rel(out[512:], (ref + x)[512:]) < 2e-5
+    split = ops.gemm(a, w, ops.EPI_BIAS_RESID_RELU_SPLIT, bias=b, resid=x)
+    t_ref = F.relu(ref + x)
+    got = split[:, :N].float() + split[:, N:].float()
+    assert _rel(got, t_ref) < 3e-5 and _rel(got[512:], t_ref[512:]) < 3e-5
+
+
+def test_gemm_remainder_rows_conv_segments(ops):
+    """Row-shifted K-segments + border mask on a shape with a remainder (2 windows x 30 x 30 = 1800 = 7 x 256 + 8)."""
+    dt = torch.float16
+    B, g, Cc = 2, 28, 768
+    Hp = Wp = g + 2
+    x = _rand((B, Cc, g, g), 40).to(dt)
+    wt = _rand((Cc, Cc, 3, 3), 41, 0.02).to(dt)
+    bias = _rand((Cc,), 42)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), padding=1) + bias.view(1, -1, 1, 1))
+    xp = torch.zeros((B, Hp, Wp, Cc), dtype=dt, device="cuda")
+    xp[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1)
+    wk = wt.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).contiguous()
+    shifts = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+    out = ops.gemm(xp.view(-1, Cc), wk, ops.EPI_BIAS_RELU_MASK_BF16, bias=bias, K=9 * Cc, seg_row_shift=shifts,
+                   seg_col_start=[0] * 9, mask_hw=(Hp, Wp)).view(B, Hp, Wp, Cc)
+    border = out.clone()
+    border[:, 1:-1, 1:-1, :] = 0
+    assert border.abs().max().item() == 0.0
+    assert _rel(out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), ref) < 1.5 * ROUND16[dt]
+
+
 def test_gemm_rejects_bad_shapes(ops):
     a, w = _bf(_rand((64, 100), 1)), _bf(_rand((256, 100), 2))
     with pytest.raises(RuntimeError):
