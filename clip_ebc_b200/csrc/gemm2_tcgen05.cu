@@ -169,6 +169,9 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUt
       : "memory");
 }
 
+// time line of CTA 0 (experiment): slot i <- clock64()
+#define CEBC_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (slot) < 256) p.trace[(slot)] = clock64(); } while (0)
+
 template <int BLOCK_N, int EPI, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -192,6 +195,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 3) CEBC_TRACE(0);
   const uint32_t crank = cluster_ctarank();
   const uint32_t rank = crank & 1;          // rank inside the CTA pair
   const uint32_t pr = crank >> 1;           // pair inside the cluster
@@ -225,8 +229,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above overlapped the tail of the previous kernel; its results (A, the residual) are needed from here on
+  if (warp == 3) CEBC_TRACE(1);
   pdl_launch_dependents();
   pdl_wait();
+  if (warp == 3) CEBC_TRACE(2);
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if ((p.dbg & 32) && blockIdx.x == 0 && threadIdx.x == 96) {  // experiment: effective SM clock during the kernel
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
@@ -236,6 +248,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int m0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
       const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
       int seg = 0, kk = 0;
+      CEBC_TRACE(16 + 4 * ((t - cluster_id) / num_clusters));
       for (int kb = 0; kb < num_kb; ++kb) {
         // slot free in every CTA of the cluster (each pair leader's commit is multicast to all of them), so multicast
         // writes into the other pair's slot are safe too
@@ -276,8 +289,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      CEBC_TRACE(17 + 4 * ((t - cluster_id) / num_clusters));
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (kb == 0) CEBC_TRACE(18 + 4 * ((t - cluster_id) / num_clusters));
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -319,6 +334,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       float4 xa[8], xb[8];
       if constexpr (!out_is_bf16<EPI>()) load_resid32<EPI>(p, lane, row0, n0 + cbase, xa);
       mbar_wait(&tmem_full_bar[as], aphase);
+      if (ew == 0) CEBC_TRACE(19 + 4 * ((t - cluster_id) / num_clusters));
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
       if constexpr (out_is_bf16<EPI>()) {
@@ -349,6 +365,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
+      if (ew == 0) CEBC_TRACE(8 + ((t - cluster_id) / num_clusters));  // epilogue of tile i done
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -356,6 +373,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal its barriers / read its smem
+  if (warp == 3) CEBC_TRACE(3);
+  if ((p.dbg & 32) && blockIdx.x == 0 && threadIdx.x == 96) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("[gemm2] %lld cycles in %llu ns -> %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0, 1e3 * (c1 - dbg_c0) / (double)(t1 - dbg_t0));
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
@@ -487,6 +511,13 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
   if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 3 || p.mask_wp < 3)) return "gemm: mask grid missing";
 
+  static const bool trace_env = getenv("CLIPEBC_GEMM_TRACE") != nullptr;  // experiment: print CTA 0's time line
+  static long long* trace_dev = nullptr;
+  if (trace_env) {
+    if (!trace_dev) cudaMalloc(&trace_dev, 256 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, 256 * sizeof(long long), stream);
+    p.trace = trace_dev;
+  }
   static const int mc_env = getenv("CLIPEBC_GEMM_MC") ? atoi(getenv("CLIPEBC_GEMM_MC")) : 0;  // experiment knob
   const int mc = (mc_env == 1 || mc_env == 2) ? mc_env : 1;  // measured on B200: no gain from the multicast variant (power-bound)
 
@@ -503,6 +534,17 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
         : (block_n == 192) ? launch_epi2<192, 1>(stream, epi, ta, tb, p, num_sms)
                            : launch_epi2<128, 1>(stream, epi, ta, tb, p, num_sms);
   if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (trace_env) {
+    long long h[256];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    printf("[trace] setup %lld pdl %lld end %lld |", h[1] - t0, h[2] - t0, h[3] - t0);
+    for (int i = 0; i < 8 && h[16 + 4 * i]; ++i)
+      printf(" tile%d: tma %lld mma_free %lld first_full %lld acc_full %lld epi_done %lld |", i, h[16 + 4 * i] - t0,
+             h[17 + 4 * i] - t0, h[18 + 4 * i] - t0, h[19 + 4 * i] - t0, h[8 + i] - t0);
+    printf("\n");
+  }
   return nullptr;
 }
 

@@ -35,6 +35,7 @@ struct GemmParams {
   int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
   int dbg;                            // experiment knob (profiles/): 0 in production
+  long long* trace;                   // experiment: clock64 time line of CTA 0 (profiles/gemm_trace.py), nullptr in production
 };
 
 inline GemmParams gemm_params_plain(int M, int N, int K) {
