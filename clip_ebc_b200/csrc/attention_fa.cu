@@ -126,7 +126,8 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&v)[32], int lim
 __global__ void __launch_bounds__(kThreadsF, 1)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items,
-                    uint16_t* __restrict__ out, int out_fp16, int dbg) {
+                    uint16_t* __restrict__ out, int out_fp16, int dbg, long long* trace) {
+#define ATT_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && (slot) < 256) trace[(slot)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* xchg = reinterpret_cast<float*>(smem + 2 * kStageBytesF);  // [2 buffers][2 kinds: max, sum][2 halves][128 rows]
@@ -166,6 +167,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
   pdl_wait();  // QKV of this layer comes from the previous kernel
+  if (warp == 3) ATT_TRACE(0);
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -210,7 +212,9 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t q_addr = smem_u32(smem + s * kStageBytesF) + t * kQTileBytes;
       const uint32_t k_addr = smem_u32(smem + s * kStageBytesF) + kQBytes;
       mbar_wait(&qk_full[s], ph);
+      ATT_TRACE(8 + 8 * u + 0);
       mbar_wait(&buf_free[b], (j & 1) ^ 1);  // the tile that used this buffer two tiles ago has been written out
+      ATT_TRACE(8 + 8 * u + 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -231,6 +235,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t v_addr = smem_u32(smem + s * kStageBytesF) + kQBytes + kKVBytes;
       mbar_wait(&v_full[s], ph);
       mbar_wait(&p_ready[b], j & 1);
+      ATT_TRACE(8 + 8 * u + 2);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t buf = tmem_base + b * 256;
@@ -243,6 +248,10 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (t == n_qt - 1) umma_commit(&v_empty[s]);
       }
       __syncwarp();
+      if (trace != nullptr && blockIdx.x == 0) {  // experiment: when does the PV chain retire?
+        mbar_wait(&o_full[b], j & 1);
+        ATT_TRACE(128 + 8 * u + 4);
+      }
       if (u + 2 < total_tiles) issue_s(u + 2);
     }
   } else if (warp >= 4) {
@@ -264,6 +273,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int q_row = t * 128 + r;
       const bool active = t * 128 + q * 32 < t_live;
       mbar_wait(&o_full[b], j & 1);
+      if (warp == 4) ATT_TRACE(8 + 8 * u + 5);
       tc_fence_after();
       if (active) {
         uint32_t o[32];
@@ -299,7 +309,9 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       float* sums = xchg + (b * 2 + 1) * 256;
       float row_sum = 0.f;
       uint32_t va[32], vb[32];
+      if (warp == 4) ATT_TRACE(8 + 8 * u + 6);
       mbar_wait(&s_full[b], j & 1);
+      if (warp == 4) ATT_TRACE(8 + 8 * u + 3);
       tc_fence_after();
       // Reference maximum (softmax is shift invariant; it only has to keep exp2 in range): max over the first 32 keys of
       // each half, combined across the two groups through smem. The exponent is clamped at +120.
@@ -310,7 +322,9 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         chunk_max(va, keys_mine, mx);
       }
       maxs[h * 128 + r] = mx;
+      if (warp == 4) ATT_TRACE(128 + 8 * u + 0);
       named_bar_sync(1, 256);
+      if (warp == 4) ATT_TRACE(128 + 8 * u + 1);
       const float m_scaled = fmaxf(mx, maxs[(1 - h) * 128 + r]) * kScale;
       if (active) {
         if (n_chunks > 1) { if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row + 32, vb); }
@@ -322,7 +336,9 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_ld_wait();
         }
       }
+      if (warp == 4) ATT_TRACE(128 + 8 * u + 2);
       if (u >= 1) epilogue(u - 1);  // mid-softmax: frees the other buffer in time for S of tile u + 1
+      if (warp == 4) ATT_TRACE(128 + 8 * u + 3);
       if (active) {
         if (n_chunks > 2) {
           if (n_chunks > 3) { if (!(dbg & 2)) tmem_ld_32x32b_x32(s_row + 96, vb); }
@@ -336,6 +352,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[b]);
+      if (warp == 4) ATT_TRACE(8 + 8 * u + 4);
     }
     if (total_tiles > 0) epilogue(total_tiles - 1);
   }
@@ -402,9 +419,27 @@ const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, cons
     LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
                       2.0 * n_win * t_live * (2304.0 + 768.0));
     static int dbg = getenv("CLIPEBC_ATTN_DBG") ? atoi(getenv("CLIPEBC_ATTN_DBG")) : 0;  // experiment knob
+    static const bool trace_env = getenv("CLIPEBC_ATTN_TRACE") != nullptr;  // experiment: time line of CTA 0
+    static long long* trace_dev = nullptr;
+    if (trace_env) {
+      if (!trace_dev) cudaMalloc(&trace_dev, 256 * sizeof(long long));
+      cudaMemsetAsync(trace_dev, 0, 256 * sizeof(long long), stream);
+    }
     cudaError_t le = launch_pdl(attention_fa_kernel, dim3(grid), dim3(kThreadsF), kSmemF, stream, 1, tq, tkv, tc, n_const,
-                                t_live, n_items, static_cast<uint16_t*>(out), out_fp16, dbg);
+                                t_live, n_items, static_cast<uint16_t*>(out), out_fp16, dbg, trace_env ? trace_dev : nullptr);
     if (le != cudaSuccess) return cudaGetErrorString(le);
+    if (trace_env) {
+      long long h[256];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      printf("[attn trace] columns: qk_full buf_free(S issued) p_ready(PV issued) | softmax: wait_s s_full p_done o_full\n");
+      for (int u = 0; u < 10 && h[8 + 8 * u + 3]; ++u)
+        printf("  tile%d: %6lld %6lld %6lld (pv done %6lld) | %6lld %6lld %6lld %6lld | max_written %6lld exchanged %6lld half %6lld epi_done %6lld\n",
+               u, h[8 + 8 * u] - t0, h[8 + 8 * u + 1] - t0, h[8 + 8 * u + 2] - t0, h[128 + 8 * u + 4] - t0, h[8 + 8 * u + 6] - t0,
+               h[8 + 8 * u + 3] - t0, h[8 + 8 * u + 4] - t0, h[8 + 8 * u + 5] - t0, h[128 + 8 * u] - t0, h[128 + 8 * u + 1] - t0,
+               h[128 + 8 * u + 2] - t0, h[128 + 8 * u + 3] - t0);
+    }
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -74,7 +74,7 @@ __device__ __forceinline__ void store_row_16(void* p, const Row768& r, int lane,
 
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
 template <bool OUT_16>
-__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, void* __restrict__ out,
                                                            int64_t n_rows_out, int rows_out_per_group,
                                                            int rows_in_per_group, int in_row_offset, int fp16) {
