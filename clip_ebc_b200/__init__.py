@@ -6,7 +6,8 @@ hand-written CUDA kernels behind the C-ABI of ``include/clipebc_b200.h``; there 
 """
 from ._lib import LIB_PATH, load  # noqa: F401
 
-__all__ = ["get_model", "sliding_window_predict", "CLIP_EBC", "load", "LIB_PATH"]
+__all__ = ["get_model", "sliding_window_predict", "resize_density_map", "calculate_errors", "evaluate", "CLIP_EBC",
+           "Resize2Multiple", "ZeroPad2Multiple", "load", "LIB_PATH"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require torch.cuda
@@ -14,8 +15,16 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         from . import model
 
         return getattr(model, name)
-    if name == "sliding_window_predict":
-        from .eval_utils import sliding_window_predict
+    if name in ("sliding_window_predict", "resize_density_map", "calculate_errors"):
+        from . import eval_utils
 
-        return sliding_window_predict
+        return getattr(eval_utils, name)
+    if name in ("Resize2Multiple", "ZeroPad2Multiple"):
+        from . import transforms
+
+        return getattr(transforms, name)
+    if name == "evaluate":
+        from .eval_loop import evaluate
+
+        return evaluate
     raise AttributeError(name)

@@ -33,6 +33,7 @@ class ClipEbcConfig(C.Structure):
 
 _vp, _i, _i64, _fp = C.c_void_p, C.c_int, C.c_int64, C.c_void_p  # float* passed as raw addresses
 _ip = C.POINTER(C.c_int)
+_cfp = C.POINTER(C.c_float)  # HOST float arrays
 
 # name -> (restype, argtypes): every symbol declared in include/clipebc_b200.h
 SIGNATURES = {
@@ -59,6 +60,10 @@ SIGNATURES = {
     "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
     "clipebc_ebc_head": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_fold_average": (_i, [_fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "clipebc_resize_bicubic_aa": (_i, [_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _cfp, _cfp, _vp]),
+    "clipebc_pad_normalize": (_i, [_vp, _i, _i, _i, _i, _fp, _i, _i, _cfp, _cfp, _vp]),
+    "clipebc_resize_density_workspace_floats": (_i, []),
+    "clipebc_resize_density_map": (_i, [_fp, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
 }
 
 
@@ -95,3 +100,7 @@ def check(rc: int, what: str = "") -> None:
 def int_array(values):
     arr = (C.c_int * len(values))(*[int(v) for v in values])
     return arr
+
+
+def float_array(values):
+    return (C.c_float * len(values))(*[float(v) for v in values])

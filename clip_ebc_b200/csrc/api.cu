@@ -768,4 +768,35 @@ int clipebc_fold_average(const float* preds, const int* row_cells_host, const in
   return CLIPEBC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ pre / post steps
+int clipebc_resize_bicubic_aa(const void* in_dev, int in_is_u8, int C, int h, int w, float* tmp_dev, float* out_dev, int H,
+                              int W, const float* mean_host, const float* std_host, void* stream) {
+  if (!in_dev || !tmp_dev || !out_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  if ((mean_host == nullptr) != (std_host == nullptr)) return fail(CLIPEBC_EINVAL, "mean and std must be given together");
+  const char* e = resize_bicubic_aa(static_cast<cudaStream_t>(stream), in_dev, in_is_u8 != 0, C, h, w, tmp_dev, out_dev, H, W,
+                                    mean_host, std_host);
+  if (e) return fail(std::strncmp(e, "resize:", 7) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
+  return CLIPEBC_OK;
+}
+
+int clipebc_pad_normalize(const void* in_dev, int in_is_u8, int C, int h, int w, float* out_dev, int H, int W,
+                          const float* mean_host, const float* std_host, void* stream) {
+  if (!in_dev || !out_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  if ((mean_host == nullptr) != (std_host == nullptr)) return fail(CLIPEBC_EINVAL, "mean and std must be given together");
+  const char* e = pad_normalize(static_cast<cudaStream_t>(stream), in_dev, in_is_u8 != 0, C, h, w, out_dev, H, W, mean_host,
+                                std_host);
+  if (e) return fail(std::strncmp(e, "pad:", 4) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
+  return CLIPEBC_OK;
+}
+
+int clipebc_resize_density_workspace_floats(void) { return resize_density_workspace_floats(); }
+
+int clipebc_resize_density_map(const float* x_dev, int h, int w, int H, int W, float* out_dev, float* workspace_dev,
+                               float* sums_out_dev, void* stream) {
+  if (!x_dev || !out_dev || !workspace_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  const char* e = resize_density_map(static_cast<cudaStream_t>(stream), x_dev, h, w, H, W, out_dev, workspace_dev, sums_out_dev);
+  if (e) return fail(std::strncmp(e, "resize_density_map:", 19) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
+  return CLIPEBC_OK;
+}
+
 }  // extern "C"

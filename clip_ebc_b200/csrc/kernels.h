@@ -148,6 +148,21 @@ const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, con
 const char* fold_average(cudaStream_t stream, const float* preds, const int* row_cells_dev, const int* col_cells_dev,
                          int n_rows, int n_cols, int gh, int gw, int Ho, int Wo, float* density, float* count_out);
 
+// ------------------------------------------------------------------ before / after the hot path ----------------
+// in [C, h, w] (uint8 when in_is_u8, else f32 in [0,1]) -> out f32 [C, H, W]: bicubic antialiased resize as
+// TF.resize(BICUBIC, antialias=True) (datasets/transforms.py:27-35); tmp f32 [C, h, W]; mean/std (host, nullable
+// together) apply torchvision Normalize to the result (datasets/crowd.py:64).
+const char* resize_bicubic_aa(cudaStream_t stream, const void* in, int in_is_u8, int C, int h, int w, float* tmp, float* out,
+                              int H, int W, const float* mean_host, const float* std_host);
+// right / bottom zero padding of the [0,1] image to [C, H, W] (datasets/transforms.py:138-140), then Normalize
+const char* pad_normalize(cudaStream_t stream, const void* in, int in_is_u8, int C, int h, int w, float* out, int H, int W,
+                          const float* mean_host, const float* std_host);
+// x f32 [h, w] -> out f32 [H, W] = bilinear(x) * nan_to_num(sum(bilinear(x)) / sum(x))   (utils/eval_utils.py:19-23);
+// workspace: resize_density_workspace_floats() floats; sums_out (nullable) <- [sum(x), sum(bilinear(x))]
+int resize_density_workspace_floats();
+const char* resize_density_map(cudaStream_t stream, const float* x, int h, int w, int H, int W, float* out, float* workspace,
+                               float* sums_out);
+
 // ------------------------------------------------------------------ pack-time helpers --------------------------
 const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n, int fp16);
 // W f32 [O, I, 3, 3] + BN(gamma, beta, mean, var, eps) -> Wp bf16 [O, 9*I] (tap-major K: k = (ky*3+kx)*I + i), bias f32 [O]

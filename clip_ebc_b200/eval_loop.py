@@ -1,0 +1,91 @@
+"""Evaluation-loop plumbing around the hot path: host-side mirror of
+``evaluate()`` (/root/reference/eval.py:11-40) and of the NWPU test loop / result file (test_nwpu.py:89-116).
+
+Same signature and return value as the reference. What differs is where the work happens: every image goes through one
+C-ABI call (unfold, ViT, decoder, head, fold and the per-image count all on the device) and the per-image counts stay
+on the GPU until the loop ends, so there is no host synchronisation per image (the reference does `.cpu()` on every
+count, eval.py:35): the host only enqueues -- the H2D copy of image i+1 overlaps the kernels of image i.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from .eval_utils import calculate_errors, sliding_window_predict
+from .model import CLIP_EBC
+
+
+def _device_counts(model: CLIP_EBC, image: Tensor, sliding_window: bool, window_size, stride) -> Tensor:
+    """counts [B] (device) of a batch of same-sized images [B,3,H,W] already on the model's device."""
+    if sliding_window:
+        outs = []
+        for b in range(image.shape[0]):  # the reference asserts nothing here, but its fold only handles one image
+            _, cnt = sliding_window_predict(model, image[b:b + 1], window_size, stride, return_device=True, return_count=True)
+            outs.append(cnt.reshape(1))
+        return torch.cat(outs)
+    return model(image).sum(dim=(1, 2, 3))  # eval.py:33,35 on the device
+
+
+def evaluate(
+    model: nn.Module,
+    data_loader: Iterable,
+    device: torch.device,
+    sliding_window: bool = False,
+    window_size: Optional[int] = None,
+    stride: Optional[int] = None,
+) -> Dict[str, float]:
+    """MAE / RMSE of the predicted counts over `data_loader` (batches of `(image, target_points, density)`)."""
+    if not isinstance(model, CLIP_EBC):
+        raise TypeError(f"clip_ebc_b200.evaluate drives clip_ebc_b200.CLIP_EBC models only (got {type(model).__name__})")
+    model.eval()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("clip_ebc_b200.evaluate needs a CUDA device (there is no CPU fallback)")
+    pred_counts, target_counts = [], []
+    if sliding_window:
+        assert window_size is not None, f"Window size must be provided when sliding_window is True, but got {window_size}"
+        assert stride is not None, f"Stride must be provided when sliding_window is True, but got {stride}"
+
+    for image, target_points, _ in data_loader:
+        image = image.to(device, non_blocking=True)
+        target_counts.append([len(p) for p in target_points])
+        with torch.set_grad_enabled(False):
+            pred_counts.append(_device_counts(model, image, sliding_window, window_size, stride))
+
+    if pred_counts:
+        pred = torch.cat(pred_counts).cpu().numpy().astype(np.float64)  # the only device->host transfer of the loop
+    else:
+        pred = np.array([])
+    target = np.array([item for sublist in target_counts for item in sublist])
+    assert len(pred) == len(target), f"Length of predictions and ground truths should be equal, but got {len(pred)} and {len(target)}"
+    return calculate_errors(pred, target)
+
+
+def predict_counts(model: nn.Module, images: Iterable[Tensor], device: torch.device, sliding_window: bool = False,
+                   window_size: Optional[int] = None, stride: Optional[int] = None) -> List[float]:
+    """The loop of test_nwpu.py:89-106: one predicted count per image ([3,H,W] or [1,3,H,W] tensors), in order."""
+    if not isinstance(model, CLIP_EBC):
+        raise TypeError(f"clip_ebc_b200.predict_counts drives clip_ebc_b200.CLIP_EBC models only (got {type(model).__name__})")
+    model.eval()
+    device = torch.device(device)
+    outs = []
+    for image in images:
+        image = image.unsqueeze(0) if image.dim() == 3 else image
+        image = image.to(device, non_blocking=True)
+        with torch.set_grad_enabled(False):
+            outs.append(_device_counts(model, image, sliding_window, window_size, stride))
+    return torch.cat(outs).cpu().tolist() if outs else []
+
+
+def nwpu_result_text(image_ids: Sequence[str], preds: Sequence[float]) -> str:
+    """The submission format of test_nwpu.py:111-116: '<id> <count>' per line, no newline at the end of the file."""
+    assert len(image_ids) == len(preds), f"{len(image_ids)} ids but {len(preds)} predictions"
+    return "\n".join(f"{image_id} {pred}" for image_id, pred in zip(image_ids, preds))
+
+
+def write_nwpu_results(path: str, image_ids: Sequence[str], preds: Sequence[float]) -> None:
+    with open(path, "w") as f:
+        f.write(nwpu_result_text(image_ids, preds))

@@ -1,4 +1,7 @@
-"""``sliding_window_predict`` -- host-side mirror of /root/reference/utils/eval_utils.py:26-96.
+"""Host-side mirror of /root/reference/utils/eval_utils.py: ``sliding_window_predict`` (:26-96), ``resize_density_map``
+(:19-23) and ``calculate_errors`` (:8-16).
+
+``sliding_window_predict``:
 
 Same signature, same assertions (AssertionError with the reference's messages) and the same return value: a **CPU**
 fp32 tensor of shape (1, 1, H // r, W // r). The body, however, is one C-ABI call: window enumeration, patch-grid
@@ -7,8 +10,9 @@ only transfers are the image H2D (if the caller passed a CPU tensor) and the den
 """
 from __future__ import annotations
 
-from typing import Tuple, Union
+from typing import Dict, Tuple, Union
 
+import numpy as np
 import torch
 from torch import Tensor, nn
 
@@ -57,3 +61,39 @@ def sliding_window_predict(
         dens = dens.cpu()  # the reference returns a CPU tensor (eval_utils.py:76,96)
         cnt = cnt.cpu() if cnt is not None else None
     return (dens, cnt) if return_count else dens
+
+
+def calculate_errors(pred_counts: np.ndarray, gt_counts: np.ndarray) -> Dict[str, float]:
+    """MAE / RMSE of per-image counts (reference utils/eval_utils.py:8-16; host arithmetic on a few hundred numbers)."""
+    assert isinstance(pred_counts, np.ndarray), f"Expected numpy.ndarray, got {type(pred_counts)}"
+    assert isinstance(gt_counts, np.ndarray), f"Expected numpy.ndarray, got {type(gt_counts)}"
+    assert len(pred_counts) == len(gt_counts), \
+        f"Length of predictions and ground truths should be equal, but got {len(pred_counts)} and {len(gt_counts)}"
+    errors = {
+        "mae": np.mean(np.abs(pred_counts - gt_counts)),
+        "rmse": np.sqrt(np.mean((pred_counts - gt_counts) ** 2)),
+    }
+    return errors
+
+
+def resize_density_map(x: Tensor, size: Tuple[int, int]) -> Tensor:
+    """Bilinear resize of a density map times nan_to_num(sum(resized) / sum(x)) (reference utils/eval_utils.py:19-23; the
+    reference multiplies by this ratio rather than its inverse -- kept bit for bit in meaning).
+
+    The reference expression ``x * scale_factor`` (scale_factor of shape [B, C]) only broadcasts for one single-channel
+    map, which is what its callers pass (notebooks/model.ipynb); other shapes raise here as they do there. A CPU input
+    (what ``sliding_window_predict`` returns by default) is moved to the GPU, resized there (csrc/preproc.cu) and
+    returned on its original device.
+    """
+    if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 1:
+        raise RuntimeError(f"The size of tensor a ({tuple(x.shape)}) must be (1, 1, h, w): the reference's "
+                           "x * scale_factor does not broadcast for batched or multi-channel maps")
+    if not torch.cuda.is_available():
+        raise RuntimeError("clip_ebc_b200.resize_density_map needs a CUDA device (there is no CPU fallback)")
+    from . import ops
+
+    dev = x.device
+    xd = x if x.is_cuda else x.cuda()
+    out = ops.resize_density_map(xd.float().contiguous()[0, 0], (int(size[0]), int(size[1])))
+    out = out[None, None]
+    return out if dev.type == "cuda" else out.to(dev)

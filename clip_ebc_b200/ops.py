@@ -157,3 +157,52 @@ def fold_average(preds: torch.Tensor, row_cells: Sequence[int], col_cells: Seque
                                                 len(row_cells), len(col_cells), gh, gw, Ho, Wo, _ptr(dens), _ptr(cnt),
                                                 _stream()), "fold")
     return (dens, cnt) if want_count else dens
+
+
+# ------------------------------------------------------------------------------------ pre / post steps (section 8f)
+def _image_in(image: torch.Tensor):
+    if image.dim() != 3 or image.shape[0] > 4:
+        raise RuntimeError(f"expected a [C<=4, H, W] image, got {tuple(image.shape)}")
+    if image.dtype not in (torch.uint8, torch.float32):
+        raise RuntimeError(f"image must be uint8 or float32, got {image.dtype}")
+    return _ptr(image), int(image.dtype == torch.uint8), int(image.shape[0]), int(image.shape[1]), int(image.shape[2])
+
+
+def _stats(mean, std):
+    if mean is None and std is None:
+        return None, None
+    return _lib.float_array(mean), _lib.float_array(std)
+
+
+def resize_bicubic_aa(image: torch.Tensor, height: int, width: int, mean=None, std=None) -> torch.Tensor:
+    """TF.resize(image, (height, width), BICUBIC, antialias=True) on a [C,H,W] uint8 (-> /255) or [0,1] float image,
+    optionally followed by Normalize(mean, std) -- one pair of kernels (width pass, height pass)."""
+    ptr, u8, c, h, w = _image_in(image)
+    tmp = torch.empty((c, h, width), dtype=torch.float32, device=image.device)
+    out = torch.empty((c, height, width), dtype=torch.float32, device=image.device)
+    m, s = _stats(mean, std)
+    _lib.check(_lib.load().clipebc_resize_bicubic_aa(ptr, u8, c, h, w, _ptr(tmp), _ptr(out), int(height), int(width), m, s,
+                                                     _stream()), "resize_bicubic_aa")
+    return out
+
+
+def pad_normalize(image: torch.Tensor, height: int, width: int, mean=None, std=None) -> torch.Tensor:
+    """Right/bottom zero padding of a [C,H,W] uint8 (-> /255) or [0,1] float image to (height, width), then Normalize."""
+    ptr, u8, c, h, w = _image_in(image)
+    out = torch.empty((c, int(height), int(width)), dtype=torch.float32, device=image.device)
+    m, s = _stats(mean, std)
+    _lib.check(_lib.load().clipebc_pad_normalize(ptr, u8, c, h, w, _ptr(out), int(height), int(width), m, s, _stream()),
+               "pad_normalize")
+    return out
+
+
+def resize_density_map(x: torch.Tensor, size: Tuple[int, int], return_sums: bool = False):
+    """One density map [h, w] -> [H, W]: bilinear resize times nan_to_num(sum(resized) / sum(x))."""
+    assert x.dtype == torch.float32 and x.dim() == 2
+    lib = _lib.load()
+    ws = torch.empty(lib.clipebc_resize_density_workspace_floats(), dtype=torch.float32, device=x.device)
+    out = torch.empty((int(size[0]), int(size[1])), dtype=torch.float32, device=x.device)
+    sums = torch.empty(2, dtype=torch.float32, device=x.device) if return_sums else None
+    _lib.check(lib.clipebc_resize_density_map(_ptr(x), int(x.shape[0]), int(x.shape[1]), int(size[0]), int(size[1]),
+                                              _ptr(out), _ptr(ws), _ptr(sums), _stream()), "resize_density_map")
+    return (out, sums) if return_sums else out

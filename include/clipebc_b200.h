@@ -30,7 +30,7 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 2
+#define CLIPEBC_ABI_VERSION 3
 
 typedef struct clipebc_model clipebc_model;
 
@@ -124,6 +124,25 @@ int clipebc_ebc_head(const float* F_dev, const float* tmat_dev, const float* anc
 int clipebc_fold_average(const float* preds_dev, const int* row_cells_host, const int* col_cells_host, int n_rows,
                          int n_cols, int gh, int gw, int Ho, int Wo, float* density_out_dev, float* count_out_dev,
                          void* stream);
+
+/* ---- the steps either side of the hot path ------------------------------------------------
+ * Pre-step: what datasets/crowd.py:213-228 does to an image before sliding_window_predict -- uint8 -> [0,1]
+ * (`/ 255.`), Resize2Multiple (datasets/transforms.py:69-105: TF.resize BICUBIC antialias=True) or ZeroPad2Multiple
+ * (:108-140: right/bottom zero pad), torchvision Normalize (datasets/crowd.py:64). Post-step: resize_density_map
+ * (utils/eval_utils.py:19-23).
+ *
+ * in_dev: [C, h, w], uint8 when in_is_u8 != 0, else f32 already in [0,1]; C <= 4. mean/std: HOST arrays of C floats, or
+ * both NULL for no normalisation. tmp_dev: f32 [C, h, W] scratch. out_dev: f32 [C, H, W]. */
+int clipebc_resize_bicubic_aa(const void* in_dev, int in_is_u8, int C, int h, int w, float* tmp_dev, float* out_dev,
+                              int H, int W, const float* mean_host, const float* std_host, void* stream);
+int clipebc_pad_normalize(const void* in_dev, int in_is_u8, int C, int h, int w, float* out_dev, int H, int W,
+                          const float* mean_host, const float* std_host, void* stream);
+/* x_dev f32 [h, w] (one density map, the only shape the reference function broadcasts for) -> out_dev f32 [H, W] =
+ * bilinear(x) * nan_to_num(sum(bilinear(x)) / sum(x), 0, 0, 0). workspace_dev: clipebc_resize_density_workspace_floats()
+ * floats. sums_out_dev (nullable): [sum(x), sum(bilinear(x))]. Sums are two-stage with a fixed order (deterministic). */
+int clipebc_resize_density_workspace_floats(void);
+int clipebc_resize_density_map(const float* x_dev, int h, int w, int H, int W, float* out_dev, float* workspace_dev,
+                               float* sums_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,3 +43,63 @@ def case_inputs(case: dict):
     tf = weights.make_text_features(len(bins), seed=100 + case["wseed"])
     x = weights.make_image(case["shape"], seed=case["xseed"])
     return sd, tf, bins, anchors, reduction, x
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the steps either side of the hot path (oracle/eval_oracle.py, clip_ebc_b200/{transforms,
+# eval_utils,eval_loop}.py). Fixtures tests/golden/eval_*.npz come from the reference's own functions.
+# ---------------------------------------------------------------------------------------------------------------
+RESIZE_DENSITY_CASES = [
+    # (name, seed, input shape [B,1,h,w], target size (H,W), zero_image: index of an all-zero map or None)
+    # the reference function only broadcasts for [1,1,h,w] inputs (x * scale_factor with scale_factor [B,C]), which is
+    # what its callers pass (notebooks/model.ipynb): one density map per call
+    dict(name="eval_resize_density_up8", seed=21, shape=(1, 1, 24, 32), size=(192, 256), zero_image=None),
+    dict(name="eval_resize_density_zero_map", seed=22, shape=(1, 1, 28, 28), size=(224, 224), zero_image=0),
+    dict(name="eval_resize_density_odd", seed=23, shape=(1, 1, 37, 53), size=(300, 421), zero_image=None),
+    dict(name="eval_resize_density_down", seed=24, shape=(1, 1, 56, 84), size=(30, 41), zero_image=None),
+]
+
+TRANSFORM_CASES = [
+    # uint8 image [3,H,W] from a seed; window / stride; subsample steps for the stored outputs
+    dict(name="eval_transform_500x731_s112", seed=31, shape=(3, 500, 731), window=224, stride=112, n_points=40),
+    dict(name="eval_transform_300x350_s224", seed=32, shape=(3, 300, 350), window=224, stride=224, n_points=7),
+    dict(name="eval_transform_200x260_s112", seed=33, shape=(3, 200, 260), window=224, stride=112, n_points=0),  # upscale to the window
+    dict(name="eval_transform_448x672_s112", seed=34, shape=(3, 448, 672), window=224, stride=112, n_points=3),  # already a multiple
+]
+SUB_Y, SUB_X = 7, 5  # stored outputs are out[:, ::SUB_Y, ::SUB_X] plus per-channel float64 sums
+
+
+def make_u8_image(shape, seed):
+    """Smooth-ish uint8 test image (low-frequency pattern + noise) so that resampling has something to resample."""
+    import numpy as np
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    c, h, w = shape
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    img = np.empty(shape, dtype=np.float64)
+    for ch in range(c):
+        fy, fx, ph = rng.uniform(0.01, 0.08), rng.uniform(0.01, 0.08), rng.uniform(0, 6.28)
+        img[ch] = 127.5 + 90.0 * np.sin(fy * yy + fx * xx + ph) + rng.normal(0, 20.0, size=(h, w))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_points(n, h, w, seed):
+    import numpy as np
+    import torch
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if n == 0:
+        return torch.zeros((0, 2), dtype=torch.float32)
+    pts = np.stack([rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n)], axis=1)
+    return torch.from_numpy(pts.astype(np.float32))
+
+
+def make_density(shape, seed, zero_image=None):
+    import numpy as np
+    import torch
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x = np.abs(rng.normal(0.0, 0.5, size=shape)).astype(np.float32)
+    if zero_image is not None:
+        x[zero_image] = 0.0
+    return torch.from_numpy(x)
