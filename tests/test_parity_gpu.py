@@ -129,6 +129,53 @@ def test_large_image_properties():
     assert abs(cnt.item() - dens.double().sum().item()) <= 1e-4 * dens.double().sum().item()
 
 
+@pytest.mark.parametrize("bins_key,g", [("r16_t8_qnrf", 14), ("r32_t19_qnrf", 7)])
+def test_batch256_shallow_vpt_reduction_16_32(bins_key, g):
+    """BASELINE.json configs[3] at full size: 256 windows, shallow VPT (229 live rows), reduction 16 / 32 bin sets.
+    A sample of the batch against the CPU oracle (north_star gates), chunk invariance over the whole batch."""
+    case = dict(bins=bins_key, deep_vpt=False, num_vpt=32, variant="stress", wseed=5, xseed=41, shape=(256, 3, 224, 224))
+    sd, tf, bins, anchors, reduction, x = case_inputs(case)
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    model.training = True
+    logits, exp = model(x.cuda())
+    model.training = False
+    assert tuple(exp.shape) == (256, 1, g, g) and tuple(logits.shape) == (256, len(bins), g, g)
+    idx = [0, 95, 96, 255]  # both sides of the internal 96-window chunk boundary
+    lo, eo = O.clip_ebc_forward(x[idx], sd, tf, anchors, reduction, 32, False)
+    assert parity.density_max_rel(exp[idx].cpu().numpy(), eo.numpy()) <= parity.DENSITY_MAX_REL
+    assert parity.count_rel(exp[idx].cpu().numpy(), eo.numpy()) <= parity.COUNT_REL
+    assert parity.argmax_agreement(logits[idx].cpu().numpy(), lo.numpy()) >= parity.ARGMAX_AGREE
+    model2 = build_model(case, sd, tf, bins, anchors, reduction, window_chunk=64)
+    assert torch.equal(model2(x.cuda()), exp)
+
+
+@pytest.mark.parametrize("stride,n_rows,n_cols", [(224, 14, 19), (112, 27, 36)])
+def test_qnrf_scale_image_properties(stride, n_rows, n_cols):
+    """BASELINE.json configs[4] at full size (4096 x 3072: 266 / 972 windows). Size-independent properties:
+    the map is finite and inside the anchor range, the fused count equals the sum of the map, and every cell covered by
+    exactly one window (stride 224: the interior tiles) equals model(tile) bit for bit."""
+    from clip_ebc_b200 import ops, sliding_window_predict
+
+    case = dict(bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32, variant="default", wseed=0, xseed=51, shape=(1, 3, 3072, 4096))
+    sd, tf, bins, anchors, reduction, img = case_inputs(case)
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    ro, co = ops.window_origins(3072, 4096, (224, 224), (stride, stride))
+    assert (len(ro), len(co)) == (n_rows, n_cols) and ro[-1] == 2848 and co[-1] == 3872  # SURVEY.md appendix B
+    img = img.cuda()
+    dens, cnt = sliding_window_predict(model, img, 224, stride, return_device=True, return_count=True)
+    assert tuple(dens.shape) == (1, 1, 384, 512)
+    assert torch.isfinite(dens).all()
+    assert dens.min().item() >= min(anchors) - 1e-5 and dens.max().item() <= max(anchors) + 1e-5
+    assert abs(cnt.item() - dens.double().sum().item()) <= 1e-4 * dens.double().sum().item()
+    if stride == 224:
+        tiles = torch.cat([img[:, :, y:y + 224, x:x + 224] for (y, x) in [(0, 0), (224, 448), (2464, 3584)]]).contiguous()
+        exp = model(tiles)
+        for t, (y, x) in enumerate([(0, 0), (224, 448), (2464, 3584)]):
+            assert torch.equal(dens[0, 0, y // 8:y // 8 + 28, x // 8:x // 8 + 28], exp[t, 0])
+    # a second call on the same image is bit-identical (no atomics anywhere on the path)
+    assert torch.equal(sliding_window_predict(model, img, 224, stride, return_device=True), dens)
+
+
 def test_errors_follow_the_reference_convention():
     from clip_ebc_b200 import get_model, sliding_window_predict
 
