@@ -47,9 +47,18 @@ struct Cfg2 {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float quick_gelu2(float x) {
+__device__ __forceinline__ float quick_gelu2_exact(float x) {
   // x * sigmoid(1.702 x)   (reference: blocks.py:17-19)
   return __fdividef(x, 1.0f + __expf(-1.702f * x));
+}
+// Same function through sigmoid(z) = (1 + tanh(z / 2)) / 2: ONE special-function op (MUFU.TANH) per element instead of
+// two (EX2 + RCP). The c_fc epilogue is MUFU-bound (32768 elements per 128 x 256 tile and SM against a ~9.4k-cycle
+// mainloop); tanh.approx has 2^-11 relative error, the size of the fp16 rounding that follows.
+__device__ __forceinline__ float quick_gelu2(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 template <int EPI>
@@ -85,8 +94,13 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
     v[4] = __uint_as_float(r[8 * j + 4]) + bb.x; v[5] = __uint_as_float(r[8 * j + 5]) + bb.y;
     v[6] = __uint_as_float(r[8 * j + 6]) + bb.z; v[7] = __uint_as_float(r[8 * j + 7]) + bb.w;
     if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+      if (p.dbg & 64) {  // experiment: the two-MUFU form
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
+        for (int k = 0; k < 8; ++k) v[k] = quick_gelu2_exact(v[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
+      }
     }
     if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
 #pragma unroll
