@@ -28,7 +28,8 @@ constexpr int kQBytes = 2 * kQTileBytes; // 256 query rows x 64 dims bf16
 constexpr int kKVBytes = 256 * 128;      // 256 key rows x 64 dims bf16
 constexpr int kStageBytesF = kQBytes + 2 * kKVBytes;  // 96 KB
 constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;   // row max / row sum exchange between the two softmax groups
-constexpr int kSmemF = 2 * kStageBytesF + kXchgBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kOutStageBytes = 8 * 32 * 64;        // per softmax warp: 32 rows x 64 B of packed output, XOR-swizzled
+constexpr int kSmemF = 2 * kStageBytesF + kXchgBytes + kOutStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kQkvLdF = 3 * 768;
 
 __device__ __forceinline__ uint64_t desc_sw128_mn(uint32_t smem_addr_bytes) {
@@ -131,7 +132,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* xchg = reinterpret_cast<float*>(smem + 2 * kStageBytesF);  // [2 buffers][2 kinds: max, sum][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytesF + kXchgBytes);
+  uint8_t* out_stage = smem + 2 * kStageBytesF + kXchgBytes;  // [8 warps][32 rows][64 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytesF + kXchgBytes + kOutStageBytes);
   uint64_t* qk_full = bars + 0;    // [2 stages] TMA -> MMA
   uint64_t* v_full = bars + 2;     // [2 stages]
   uint64_t* qk_empty = bars + 4;   // [2 stages] MMA (commit) -> TMA
@@ -282,16 +284,32 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&buf_free[b]);
-        if (q_row < t_live && !(dbg & 32)) {
+        if (!(dbg & 32)) {
+          // thread = row holds 64 B of its output row; a direct store would touch 32 rows with 16 B each. Stage the
+          // warp's 32 x 64 B in smem (slot ^= (row >> 1) & 3: conflict-free both ways) and write 8 complete 64 B row
+          // segments per instruction instead.
           const float* sums = xchg + (b * 2 + 1) * 256;  // [2 halves][128 rows]
           const float inv = 1.0f / (sums[r] + sums[128 + r]);
-          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(win) * t_live + q_row) * 768 + head * 64 + h * 32);
+          uint8_t* stg = out_stage + (warp - 4) * (32 * 64);
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(pack16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, out_fp16),
-                                pack16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, out_fp16));
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ sw) << 4)) =
+                make_uint4(pack16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv, out_fp16),
+                           pack16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, out_fp16),
+                           pack16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, out_fp16),
+                           pack16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, out_fp16));
+          __syncwarp();
+          const int slot = lane & 3, rsub = lane >> 2;
+          const int row0 = t * 128 + q * 32;
+          uint16_t* obase = out + (static_cast<int64_t>(win) * t_live + row0) * 768 + head * 64 + h * 32 + slot * 8;
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int rr = it4 * 8 + rsub;
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((slot ^ ((rr >> 1) & 3)) << 4));
+            if (row0 + rr < t_live) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(rr) * 768) = v;
+          }
+          __syncwarp();
         }
       } else {
         tc_fence_before();
