@@ -331,9 +331,27 @@ def main():
     total_ms = sum(v["ms"] for v in prof.values())
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks["bf16_sustained"]
+    # DRAM traffic per launch of the same kernel family from the committed ncu capture (dram__bytes_read + write per
+    # launch, weighted by how often each GEMM of the step is launched); cold-L2 figures, so an upper bound in-step.
+    traffic, traffic_note = None, "no ncu capture committed"
+    tpath = os.path.join(ROOT, "profiles", "r01g_gemm_dram.json")
+    if args.workload == "windows64" and os.path.exists(tpath):
+        per_tag = json.load(open(tpath))["per_tag"]
+        num = den = 0.0
+        for k, v in prof.items():
+            tag = k.split(":", 1)[1] if k.startswith("gemm:") else None
+            if tag in per_tag:
+                n = v["launches"] / prof_steps
+                num += n * (per_tag[tag]["dram_read_bytes_per_launch"] + per_tag[tag]["dram_write_bytes_per_launch"])
+                den += n
+        if den > 0:
+            traffic = num / den
+            traffic_note = ("bytes per launch, launch-weighted mean over the GEMMs of a step, from profiles/r01g_gemm_dram.json "
+                            "(ncu dram__bytes_read.sum + dram__bytes_write.sum, cold L2 per launch)")
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues)", "achieved": achieved, "peak": peak,
-        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "bound": "tensor", "kernel": "gemm2_tcgen05_kernel (all epilogues)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+        "algorithmic_bytes_per_launch": (sum(v["bytes"] for k, v in prof.items() if k.startswith("gemm")) / max(1, gemm_launches)),
         "peak_source": f"bf16_tflops_sustained of {peaks['source']} (kernel timed inside a long step)",
         "avg_launch_ms": gemm_ms / max(1, gemm_launches), "gflop_per_launch": gemm_flops / max(1, gemm_launches) / 1e9,
         "share_of_step": gemm_ms / total_ms if total_ms else None,
@@ -354,7 +372,8 @@ def main():
         line = {
             "metric": "windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16/bf16 tensor-core operands (tcgen05 kind::f16), fp32 accumulate/residual/softmax/head", "data": "synthetic",
+            "dtype": "fp16 operands on tcgen05 kind::f16 (bf16 selectable, same rate); fp32 accumulate / residual / LayerNorm / softmax / head",
+            "data": "synthetic",
             "config": {"workload": workload, "l2": l2, "global_batch_windows": world * units_per_step,
                        "parallelism": f"dp{world} (independent windows/images per rank)",
                        "weights": "seeded random init with the reference's init distributions (oracle/weights.py)"},
