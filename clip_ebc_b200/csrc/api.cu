@@ -68,12 +68,14 @@ const char* gemm_dispatch(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
 }
 
 // which attention kernel serves the hot path: 1 = mma.sync (legacy tensor path), 2 = tcgen05 one CTA per query tile,
-// 3 = tcgen05 persistent warp-specialised (P in TMEM)
-static std::atomic<int> g_attn_impl{3};
+// 3 = tcgen05 persistent warp-specialised (P in TMEM, the softmax groups split the keys of a tile),
+// 4 = tcgen05 persistent, two independent chains (a thread owns a query row)
+static std::atomic<int> g_attn_impl{4};
 
 const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                                int n_win, int t_live, void* out, int out_fp16) {
   const int impl = g_attn_impl.load();
+  if (impl == 4 && n_const % 8 == 0) return attention_h64_pp(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   if (impl == 3 && n_const % 8 == 0) return attention_h64_fa(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   if (impl == 2 && n_const % 8 == 0) return attention_h64_tc(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   return attention_h64(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
@@ -388,7 +390,7 @@ int clipebc_set_gemm_impl(int impl) {
 }
 
 int clipebc_set_attention_impl(int impl) {
-  if (impl < 1 || impl > 3) return fail(CLIPEBC_EINVAL, "attention impl must be 1 (mma.sync), 2 or 3 (tcgen05)");
+  if (impl < 1 || impl > 4) return fail(CLIPEBC_EINVAL, "attention impl must be 1 (mma.sync), 2, 3 or 4 (tcgen05)");
   g_attn_impl.store(impl);
   return CLIPEBC_OK;
 }

@@ -204,7 +204,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
     constexpr uint32_t idesc_s = idesc_f(128, 256, false);
-    constexpr uint32_t idesc_o = idesc_f(128, 64, true);
+    // experiment (timing only, results garbage): other N for the P.V MMAs
+    const uint32_t idesc_o = (dbg & 128) ? idesc_f(128, 128, true) : (dbg & 256) ? idesc_f(128, 16, true) : idesc_f(128, 64, true);
     const int k_steps = (Tk + 15) >> 4;
     // S of tile u: Q_t K^T into buffer u & 1
     auto issue_s = [&](int u) {

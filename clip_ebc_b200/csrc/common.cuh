@@ -51,9 +51,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // 16-bit tensor-core operand formats: bf16 (8-bit mantissa) or fp16 (11-bit mantissa, values saturated to +-65504).
 // Both run on the same tcgen05 kind::f16 path; `fp16` is a warp-uniform runtime flag chosen per model.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  // convert first (out-of-range values become +-inf), then saturate both halves with two packed min / max instead of
+  // four fp32 ones: the packs sit in ALU-bound epilogues
   __half2 v = __floats2half2_rn(lo, hi);
+  const __half2 lim = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x7BFF)));  // 65504
+  v = __hmin2(__hmax2(v, __hneg2(lim)), lim);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fp16) {

@@ -130,6 +130,11 @@ const char* attention_h64_tc(cudaStream_t stream, const __nv_bfloat16* qkv, cons
 const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                              int n_win, int t_live, void* out, int out_fp16);
 
+// two independent chains per CTA, one per TMEM buffer (attention_pp.cu): a thread owns a whole query row, the softmax of
+// one chain overlaps the tensor work of the other
+const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                             int n_win, int t_live, void* out, int out_fp16);
+
 // ------------------------------------------------------------------ decoder / head -----------------------------
 // Y f32 [n_win * hp * wp, 768] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
 // zero-bordered NHWC grids U_bf16 / U_f32 [n_win, gh + 2, gw + 2, 768]  (model.py:195-196).

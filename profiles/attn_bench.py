@@ -11,7 +11,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 for t_live, n_const in [(197, 32), (229, 0)]:
     qkv = torch.randn(B * t_live, 2304, device="cuda").to(torch.bfloat16)
     ckv = torch.randn(n_const, 2304, device="cuda").to(torch.bfloat16) if n_const else None
-    for impl in (1, 2, 3):
+    for impl in (1, 2, 3, 4):
         ops.set_attention_impl(impl)
         for _ in range(3):
             ops.attention(qkv, B, t_live, ckv)

@@ -196,7 +196,7 @@ def test_layernorm(ops):
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("impl", [1, 2, 3], ids=["mma_sync", "tcgen05", "tcgen05_persistent"])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["mma_sync", "tcgen05", "tcgen05_persistent", "tcgen05_two_chains"])
 @pytest.mark.parametrize("n_win,t_live,n_const", [(2, 197, 32), (3, 229, 0), (1, 50, 0), (2, 17, 5), (1, 256, 0),
                                                   (5, 197, 32), (2, 128, 8), (1, 129, 0), (40, 197, 32)])
 @pytest.mark.parametrize("out_fp16", [False, True], ids=["out_bf16", "out_fp16"])
@@ -213,12 +213,12 @@ def test_attention(ops, n_win, t_live, n_const, impl, out_fp16):
         k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
         v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
     ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
-    ops.set_attention_impl(3)
+    ops.set_attention_impl(4)
     # P is rounded to bf16 before P@V and the output is bf16: 2^-8 relative
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3], ids=["mma_sync", "tcgen05", "tcgen05_persistent"])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["mma_sync", "tcgen05", "tcgen05_persistent", "tcgen05_two_chains"])
 def test_attention_large_scores(ops, impl):
     """Peaky softmax (|score| up to ~40): the single-pass reference-max scheme must stay exact up to bf16 rounding."""
     ops.set_attention_impl(impl)
@@ -226,7 +226,7 @@ def test_attention_large_scores(ops, impl):
     qkv = _bf(_rand((n_win * t_live, 2304), 32, 3.0))
     ckv = _bf(_rand((n_const, 2304), 33, 3.0))
     out = ops.attention(qkv, n_win, t_live, ckv).float().view(n_win, t_live, 12, 64)
-    ops.set_attention_impl(3)
+    ops.set_attention_impl(4)
     q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
     ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
     k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
