@@ -133,8 +133,15 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tk = n_const + t_live;
   const int n_qt = (t_live + 127) >> 7;  // 128-query tiles per item (1 or 2)
-  const int n_local = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int total_tiles = n_local * n_qt;
+  // Work is dealt in 128-query tiles, a contiguous range per CTA (1536 tiles on 148 CTAs = 10 or 11 each; dealing whole
+  // items would give 10 or 12). The two tiles of an item are consecutive, so they land on the two chains and share one
+  // K / V stage; an item cut by a range boundary is simply loaded by both CTAs.
+  const int64_t n_tiles_all = static_cast<int64_t>(n_items) * n_qt;
+  const int g0 = static_cast<int>(n_tiles_all * blockIdx.x / gridDim.x);
+  const int g1 = static_cast<int>(n_tiles_all * (blockIdx.x + 1) / gridDim.x);
+  const int total_tiles = g1 - g0;
+  const int item0 = g0 / n_qt;
+  const int n_local = total_tiles > 0 ? (g1 - 1) / n_qt - item0 + 1 : 0;  // items touched by this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -144,7 +151,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1);
-      mbar_init(&qk_empty[i], n_qt); mbar_init(&v_empty[i], n_qt);  // one commit per tile of the item
+      mbar_init(&qk_empty[i], 2); mbar_init(&v_empty[i], 2);  // two commits per item (see the MMA issuers)
       mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&buf_free[i], 4);
     }
     fence_mbar_init();
@@ -161,7 +168,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     for (int it = 0; it < n_local; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
+      const int item = item0 + it;
       const int s = it & 1, ph = (it >> 1) & 1;
       const int head = item % 12, win = item / 12;
       const int row_base = win * t_live;
@@ -197,8 +204,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (b == 1 && total_tiles > 1) mbar_wait(&p_ready[0], 0);
     int k = 0;
     for (int u = b; u < total_tiles; u += 2, ++k) {
-      const int it = u / n_qt, t = u - it * n_qt;
+      const int g = g0 + u;
+      const int item = g / n_qt, t = g - item * n_qt;
+      const int it = item - item0;
       const int s = it & 1, ph = (it >> 1) & 1;
+      // the stage of an item is released by two commits: one per tile, or both from here when this CTA only has one
+      // tile of the item (single-tile windows, or an item cut by the range boundary)
+      const int lo = item * n_qt > g0 ? item * n_qt : g0, hi = (item + 1) * n_qt < g1 ? (item + 1) * n_qt : g1;
+      const bool sole = (hi - lo) == 1;
       const uint32_t stage_addr = smem_u32(smem + s * kStageBytesP);
       const uint32_t q_addr = stage_addr + t * kQTileBytesP;
       const uint32_t k_addr = stage_addr + kQBytesP;
@@ -215,6 +228,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                        kk != 0 ? 1u : 0u);
         umma_commit(&s_full[b]);
         umma_commit(&qk_empty[s]);  // Q / K of the stage are dead once every tile of the item has done this
+        if (sole) umma_commit(&qk_empty[s]);
       }
       __syncwarp();
       // O = P V once the softmax group has written P
@@ -227,6 +241,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           umma_bf16_ts_p(buf + 128, buf + ks * 8, desc_sw128_mn_p(v_addr + ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
         umma_commit(&o_full[b]);
         umma_commit(&v_empty[s]);
+        if (sole) umma_commit(&v_empty[s]);
       }
       __syncwarp();
     }
@@ -241,8 +256,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     uint8_t* stg = out_stage + (warp - 4) * (32 * 64);
     int k = 0;
     for (int u = b; u < total_tiles; u += 2, ++k) {
-      const int it = u / n_qt, t = u - it * n_qt;
-      const int item = blockIdx.x + it * gridDim.x;
+      const int g = g0 + u;
+      const int item = g / n_qt, t = g - item * n_qt;
       const int head = item % 12, win = item / 12;
       const int row0 = t * 128 + q * 32;          // first row of this warp inside the window
       const bool active = row0 < t_live;          // warps whose 32 rows are all padding only keep the protocol going
@@ -382,7 +397,8 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
     tc = tkv;
   }
   const int n_items = n_win * 12;
-  const int grid = n_items < device_num_sms() ? n_items : device_num_sms();
+  const int64_t n_tiles_all = static_cast<int64_t>(n_items) * ((t_live + 127) / 128);
+  const int grid = n_tiles_all < device_num_sms() ? static_cast<int>(n_tiles_all) : device_num_sms();
   {
     const double tk = t_live + n_const;
     LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
