@@ -6,7 +6,7 @@ hand-written CUDA kernels behind the C-ABI of ``include/clipebc_b200.h``; there 
 """
 from ._lib import LIB_PATH, load  # noqa: F401
 
-__all__ = ["get_model", "sliding_window_predict", "resize_density_map", "calculate_errors", "evaluate", "CLIP_EBC",
+__all__ = ["get_model", "sliding_window_predict", "sliding_window_predict_batch", "resize_density_map", "calculate_errors", "evaluate", "CLIP_EBC",
            "Resize2Multiple", "ZeroPad2Multiple", "load", "LIB_PATH"]
 
 
@@ -15,7 +15,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         from . import model
 
         return getattr(model, name)
-    if name in ("sliding_window_predict", "resize_density_map", "calculate_errors"):
+    if name in ("sliding_window_predict", "sliding_window_predict_batch", "resize_density_map", "calculate_errors"):
         from . import eval_utils
 
         return getattr(eval_utils, name)

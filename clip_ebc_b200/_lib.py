@@ -50,6 +50,7 @@ SIGNATURES = {
     "clipebc_model_pack": (_i, [_vp, _vp]),
     "clipebc_forward_windows": (_i, [_vp, _fp, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_sliding_window_predict": (_i, [_vp, _fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "clipebc_sliding_window_predict_batch": (_i, [_vp, _i, C.POINTER(_vp), _ip, _ip, _i, _i, _i, _i, C.POINTER(_vp), _fp, _vp]),
     "clipebc_window_origins": (_i, [_i, _i, _i, _i, _i, _i, _ip, _ip, _ip, _ip]),
     "clipebc_f32_to_16": (_i, [_fp, _vp, _i64, _i, _vp]),
     "clipebc_gemm_bf16": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _ip, _ip, _vp, _i, _fp, _fp, _i,

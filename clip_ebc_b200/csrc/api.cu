@@ -260,7 +260,7 @@ GemmParams patch_embed_params(int fp16, int rows, void* out) {
 
 // The ViT blocks + decoder + head for `nw` windows whose patch embeddings are already in m->ws_patch_embed.
 int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int src_pitch, int nw, int hp, int wp,
-                const float* pos, float* exp_out, float* logits_out) {
+                const float* pos, float* exp_out, float* logits_out, const int* win_pitch_dev = nullptr) {
   const clipebc_config& c = m->cfg;
   const bool deep = c.deep_vpt != 0;
   const int fp16 = c.operand_fp16 != 0;   // 16-bit operand format of every GEMM of the path
@@ -292,7 +292,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   __nv_bfloat16* AO = m->ws_AO.as<__nv_bfloat16>();
   __nv_bfloat16* Hid = m->ws_Hid.as<__nv_bfloat16>();
 
-  K_TRY(assemble_tokens(s, m->ws_patch_embed.as<float>(), win_base_dev, src_pitch,
+  K_TRY(assemble_tokens(s, m->ws_patch_embed.as<float>(), win_base_dev, src_pitch, win_pitch_dev,
                         raw_ptr(m, "image_encoder.class_embedding"), pos, raw_ptr(m, "image_encoder.ln_pre.weight"),
                         raw_ptr(m, "image_encoder.ln_pre.bias"), deep ? nullptr : raw_ptr(m, "vpt_0"), n_prompt_live, nw,
                         hp, wp, X));
@@ -687,6 +687,110 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
       return rc;
   }
   K_TRY(fold_average(s, preds, d_rc, d_cc, nr, nc, gh, gw, H / r, W / r, density_out_dev, count_out_dev));
+  return CLIPEBC_OK;
+}
+
+
+int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const float* const* images_dev, const int* heights,
+                                         const int* widths, int wh, int ww, int sh, int sw, float* const* density_out_dev,
+                                         float* counts_out_dev, void* stream_) {
+  if (!m || !images_dev || !heights || !widths || !density_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
+  if (n_images <= 0) return fail(CLIPEBC_EINVAL, "batch must contain at least one image");
+  if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
+  int rc;
+  if ((rc = check_window_geometry(m, wh, ww))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int r = m->cfg.reduction;
+  const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
+  const int gh = wh / r, gw = ww / r;
+  const float* pos;
+  if ((rc = get_pos(m, hp, wp, s, &pos))) return rc;
+
+  // geometry of every image: windows (utils/eval_utils.py:54-66), patch rows (shared grid when all origins are on it)
+  struct Geom { int H, W, nr, nc, n_win, pitch; bool on_grid; int64_t rows, row_off; int win_off, tab_off; std::vector<int> ro, co; };
+  std::vector<Geom> gs(n_images);
+  int64_t total_rows = 0;
+  int total_win = 0;
+  std::string key = "swb:" + std::to_string(wh) + ":" + std::to_string(ww) + ":" + std::to_string(sh) + ":" + std::to_string(sw);
+  for (int i = 0; i < n_images; ++i) {
+    Geom& g = gs[i];
+    if (!images_dev[i] || !density_out_dev[i]) return fail(CLIPEBC_EINVAL, "null image or output pointer in the batch");
+    g.H = heights[i]; g.W = widths[i];
+    if ((rc = clipebc_window_origins(g.H, g.W, wh, ww, sh, sw, &g.nr, &g.nc, nullptr, nullptr))) return rc;
+    g.ro.resize(g.nr); g.co.resize(g.nc);
+    clipebc_window_origins(g.H, g.W, wh, ww, sh, sw, &g.nr, &g.nc, g.ro.data(), g.co.data());
+    g.n_win = g.nr * g.nc;
+    g.on_grid = true;
+    for (int v : g.ro) g.on_grid = g.on_grid && (v % kPatch == 0);
+    for (int v : g.co) g.on_grid = g.on_grid && (v % kPatch == 0);
+    g.rows = g.on_grid ? static_cast<int64_t>(g.H / kPatch) * (g.W / kPatch) : static_cast<int64_t>(g.n_win) * npatch;
+    g.pitch = g.on_grid ? g.W / kPatch : wp;
+    g.row_off = total_rows; g.win_off = total_win;
+    total_rows += g.rows; total_win += g.n_win;
+    key += ":" + std::to_string(g.H) + "x" + std::to_string(g.W);
+  }
+  if (total_rows > 0x7fffffff) return fail(CLIPEBC_EINVAL, "batch too large");
+
+  // index tables: win_base | win_pitch | origins (y, x) | per image: row cells, col cells
+  size_t tab_len = static_cast<size_t>(4) * total_win;
+  for (Geom& g : gs) { g.tab_off = static_cast<int>(tab_len); tab_len += g.nr + g.nc; }
+  auto cached = m->idx_cache.find(key);
+  if (cached == m->idx_cache.end()) {
+    std::vector<int> tab(tab_len);
+    for (const Geom& g : gs) {
+      for (int i = 0; i < g.nr; ++i)
+        for (int j = 0; j < g.nc; ++j) {
+          const int w = g.win_off + i * g.nc + j;
+          tab[w] = static_cast<int>(g.row_off) +
+                   (g.on_grid ? (g.ro[i] / kPatch) * g.pitch + g.co[j] / kPatch : (i * g.nc + j) * npatch);
+          tab[total_win + w] = g.pitch;
+          tab[2 * total_win + 2 * w] = g.ro[i];
+          tab[2 * total_win + 2 * w + 1] = g.co[j];
+        }
+      for (int i = 0; i < g.nr; ++i) tab[g.tab_off + i] = g.ro[i] / r;
+      for (int j = 0; j < g.nc; ++j) tab[g.tab_off + g.nr + j] = g.co[j] / r;
+    }
+    if (m->idx_cache.size() > 64) m->idx_cache.clear();
+    DevBuf& buf = m->idx_cache[key];
+    CUDA_TRY(buf.reserve(tab.size() * 4));
+    CUDA_TRY(cudaMemcpy(buf.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    cached = m->idx_cache.find(key);
+  }
+  const int* d_tab = cached->second.as<int>();
+  const int* d_base = d_tab;
+  const int* d_pitch = d_tab + total_win;
+  const int* d_orig = d_tab + 2 * total_win;
+
+  // patch rows of all images, one patch-embedding GEMM over all of them
+  const int fp16 = m->cfg.operand_fp16 != 0;
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(total_rows) * 2 * kWidth * 2));
+  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(total_rows) * kWidth * 4));
+  for (int i = 0; i < n_images; ++i) {
+    const Geom& g = gs[i];
+    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * kWidth;
+    if (g.on_grid) K_TRY(patchify16(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, dst, fp16));
+    else K_TRY(patchify16_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, dst, fp16));
+  }
+  set_launch_tag("patch_embed");
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), total_rows, 2 * kWidth, 2 * kWidth,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
+                      patch_embed_params(fp16, static_cast<int>(total_rows), m->ws_patch_embed.p), 0));
+  set_launch_tag(nullptr);
+
+  // the windows of all images share the passes of the ViT / decoder / head (chunks may span image boundaries)
+  CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(total_win) * gh * gw * 4));
+  float* preds = m->ws_preds.as<float>();
+  const int chunk = default_chunk(m);
+  for (int b0 = 0; b0 < total_win; b0 += chunk) {
+    const int nw = std::min(chunk, total_win - b0);
+    if ((rc = run_windows(m, s, d_base + b0, 0, nw, hp, wp, pos, preds + static_cast<int64_t>(b0) * gh * gw, nullptr, d_pitch + b0)))
+      return rc;
+  }
+  for (int i = 0; i < n_images; ++i) {
+    const Geom& g = gs[i];
+    K_TRY(fold_average(s, preds + static_cast<int64_t>(g.win_off) * gh * gw, d_tab + g.tab_off, d_tab + g.tab_off + g.nr, g.nr,
+                       g.nc, gh, gw, g.H / r, g.W / r, density_out_dev[i], counts_out_dev ? counts_out_dev + i : nullptr));
+  }
   return CLIPEBC_OK;
 }
 

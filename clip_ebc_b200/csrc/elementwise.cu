@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __
 // ------------------------------------------------------------------ token assembly -----------------------------
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch_embed,
                                                               const int* __restrict__ win_base, int src_pitch,
+                                                              const int* __restrict__ win_pitch,
                                                               const float* __restrict__ class_emb,
                                                               const float* __restrict__ pos,
                                                               const float* __restrict__ ln_g,
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
     } else {
       const int pidx = t - 1 - n_prompt;
       const int py = pidx / wp, px = pidx - py * wp;
-      const int64_t src = static_cast<int64_t>(win_base[win]) + static_cast<int64_t>(py) * src_pitch + px;
+      const int pitch = win_pitch != nullptr ? win_pitch[win] : src_pitch;  // windows of different images in one pass
+      const int64_t src = static_cast<int64_t>(win_base[win]) + static_cast<int64_t>(py) * pitch + px;
       x = load_row(patch_embed + src * kD, lane);
       add_row(x, load_row_ldg(pos + static_cast<int64_t>(1 + pidx) * kD, lane));
       layernorm_row(x, ln_g, ln_b, lane);
@@ -361,14 +363,15 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
 }
 
 const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
-                            const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
+                            const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
                             const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X) {
   if (n_win <= 0) return "assemble_tokens: no windows";
   if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
   const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
   LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * kD * 8.0);
   cudaError_t e = launch_pdl(assemble_tokens_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
-                             patch_embed, win_base_dev, src_pitch, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
+                             patch_embed, win_base_dev, src_pitch, win_pitch_dev, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp,
+                             wp, X);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 

@@ -109,9 +109,10 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
 //   row 0            : LN_pre(class_emb + pos[0])
 //   rows 1..n_prompt : vpt0 rows (shallow VPT only; n_prompt = 0 for deep)            (model.py:161-168)
 //   remaining rows   : LN_pre(patch_embed[src_row(win, p)] + pos[1 + p])              (model.py:147-157)
-// src_row = win_base[win] + (p / wp) * src_pitch + p % wp  (gather from a shared per-image patch grid or per-window rows)
+// src_row = win_base[win] + (p / wp) * pitch + p % wp  (gather from a shared per-image patch grid or per-window rows);
+// pitch = win_pitch_dev[win] when given (windows of several images in one pass), else src_pitch
 const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
-                            const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
+                            const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
                             const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X);
 
 // ------------------------------------------------------------------ attention ----------------------------------

@@ -14,8 +14,45 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
-from .eval_utils import calculate_errors, sliding_window_predict
+from .eval_utils import calculate_errors, sliding_window_predict, sliding_window_predict_batch
 from .model import CLIP_EBC
+
+# Cross-image window batching: images are collected until their windows fill at least one internal pass (96 windows)
+# and then go through ONE C-ABI call (clipebc_sliding_window_predict_batch). Images that fill a pass on their own
+# (NWPU / QNRF scale) are unaffected; small ones (a dozen windows each) no longer leave most SMs idle.
+BATCH_WINDOWS = 96
+
+
+def _n_windows(h: int, w: int, window, stride) -> int:
+    wh, ww = (window, window) if isinstance(window, (int, float)) else window
+    sh, sw = (stride, stride) if isinstance(stride, (int, float)) else stride
+    return (int(np.ceil((h - wh) / sh) + 1)) * (int(np.ceil((w - ww) / sw) + 1))
+
+
+class _WindowBatcher:
+    """Collects same-model images and flushes them through sliding_window_predict_batch; counts come back in order."""
+
+    def __init__(self, model, window_size, stride, target_windows=BATCH_WINDOWS):
+        self.model, self.window_size, self.stride, self.target = model, window_size, stride, target_windows
+        self.pending, self.pending_windows, self.out = [], 0, []
+
+    def add(self, image: Tensor) -> None:
+        for b in range(image.shape[0]):
+            im = image[b:b + 1]
+            self.pending.append(im)
+            self.pending_windows += _n_windows(im.shape[-2], im.shape[-1], self.window_size, self.stride)
+            if self.pending_windows >= self.target:
+                self.flush()
+
+    def flush(self) -> None:
+        if self.pending:
+            _, cnt = sliding_window_predict_batch(self.model, self.pending, self.window_size, self.stride, return_device=True)
+            self.out.append(cnt)
+            self.pending, self.pending_windows = [], 0
+
+    def counts(self) -> Tensor:
+        self.flush()
+        return torch.cat(self.out) if self.out else torch.empty(0)
 
 
 def _device_counts(model: CLIP_EBC, image: Tensor, sliding_window: bool, window_size, stride) -> Tensor:
@@ -48,15 +85,21 @@ def evaluate(
     if sliding_window:
         assert window_size is not None, f"Window size must be provided when sliding_window is True, but got {window_size}"
         assert stride is not None, f"Stride must be provided when sliding_window is True, but got {stride}"
+    batcher = _WindowBatcher(model, window_size, stride) if sliding_window else None
 
     for image, target_points, _ in data_loader:
         image = image.to(device, non_blocking=True)
         target_counts.append([len(p) for p in target_points])
         with torch.set_grad_enabled(False):
-            pred_counts.append(_device_counts(model, image, sliding_window, window_size, stride))
+            if batcher is not None:
+                batcher.add(image)
+            else:
+                pred_counts.append(_device_counts(model, image, sliding_window, window_size, stride))
 
-    if pred_counts:
-        pred = torch.cat(pred_counts).cpu().numpy().astype(np.float64)  # the only device->host transfer of the loop
+    if batcher is not None:
+        pred = batcher.counts().cpu().numpy().astype(np.float64)     # the only device->host transfer of the loop
+    elif pred_counts:
+        pred = torch.cat(pred_counts).cpu().numpy().astype(np.float64)
     else:
         pred = np.array([])
     target = np.array([item for sublist in target_counts for item in sublist])
@@ -72,11 +115,17 @@ def predict_counts(model: nn.Module, images: Iterable[Tensor], device: torch.dev
     model.eval()
     device = torch.device(device)
     outs = []
+    batcher = _WindowBatcher(model, window_size, stride) if sliding_window else None
     for image in images:
         image = image.unsqueeze(0) if image.dim() == 3 else image
         image = image.to(device, non_blocking=True)
         with torch.set_grad_enabled(False):
-            outs.append(_device_counts(model, image, sliding_window, window_size, stride))
+            if batcher is not None:
+                batcher.add(image)
+            else:
+                outs.append(_device_counts(model, image, sliding_window, window_size, stride))
+    if batcher is not None:
+        return batcher.counts().cpu().tolist()
     return torch.cat(outs).cpu().tolist() if outs else []
 
 

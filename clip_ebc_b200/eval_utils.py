@@ -63,6 +63,35 @@ def sliding_window_predict(
     return (dens, cnt) if return_count else dens
 
 
+def sliding_window_predict_batch(model: nn.Module, images, window_size: Union[int, Tuple[int, int]],
+                                 stride: Union[int, Tuple[int, int]], return_device: bool = False):
+    """`sliding_window_predict` for a list of images of different sizes in ONE pass (extension, not in the reference:
+    eval.py processes one image per iteration). The windows of all images are batched through the ViT / decoder / head
+    together, every image is folded on its own; results are identical to per-image calls.
+
+    Returns (densities, counts): a list of [1,1,H_i//r,W_i//r] maps and a [n] tensor of their sums -- CPU tensors like the
+    reference unless `return_device`.
+    """
+    window_size = _pair(window_size, "Window size")
+    stride = _pair(stride, "Stride")
+    assert stride[0] <= window_size[0] and stride[1] <= window_size[1], \
+        f"Stride must be smaller than window size, got {stride} and {window_size}"
+    if not isinstance(model, CLIP_EBC):
+        raise TypeError("clip_ebc_b200.sliding_window_predict_batch drives clip_ebc_b200.CLIP_EBC models only "
+                        f"(got {type(model).__name__})")
+    for image in images:
+        assert len(image.shape) == 4, f"Image must be a 4D tensor (1, c, h, w), got {image.shape}"
+        assert image.shape[0] == 1, f"The batch size must be 1 due to varying image sizes, got {image.shape[0]}"
+    model.eval()
+    dev = model._device()
+    with torch.no_grad():
+        imgs = [im if im.device == dev else im.to(dev, non_blocking=True) for im in images]
+        dens, cnt = model.sliding_window_density_batch(imgs, window_size, stride)
+    if not return_device:
+        dens, cnt = [d.cpu() for d in dens], cnt.cpu()
+    return dens, cnt
+
+
 def calculate_errors(pred_counts: np.ndarray, gt_counts: np.ndarray) -> Dict[str, float]:
     """MAE / RMSE of per-image counts (reference utils/eval_utils.py:8-16; host arithmetic on a few hundred numbers)."""
     assert isinstance(pred_counts, np.ndarray), f"Expected numpy.ndarray, got {type(pred_counts)}"

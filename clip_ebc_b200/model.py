@@ -301,6 +301,35 @@ class CLIP_EBC(nn.Module):
         return (dens, cnt) if with_count else dens
 
 
+    def sliding_window_density_batch(self, images, window_size: Tuple[int, int], stride: Tuple[int, int]):
+        """images: list of [1,3,H_i,W_i] tensors on the model's device (sizes may differ) -> (list of densities
+        [1,1,H_i//r,W_i//r], counts [n] on the device). One C-ABI call: the windows of all images share the ViT passes."""
+        self._ensure_packed()
+        dev = self._device()
+        n = len(images)
+        if n == 0:
+            raise RuntimeError("empty image batch")
+        imgs, hs, ws, dens = [], [], [], []
+        r = self.reduction
+        for im in images:
+            if im.device != dev:
+                raise RuntimeError(f"image is on {im.device} but the model is on {dev}")
+            if im.dim() != 4 or im.shape[0] != 1 or im.shape[1] != 3:
+                raise RuntimeError(f"Expected image of shape (1, 3, H, W), got {tuple(im.shape)}")
+            im = im.detach().to(torch.float32).contiguous()
+            imgs.append(im)
+            hs.append(int(im.shape[-2])); ws.append(int(im.shape[-1]))
+            dens.append(torch.empty((1, 1, hs[-1] // r, ws[-1] // r), dtype=torch.float32, device=dev))
+        cnt = torch.empty((n,), dtype=torch.float32, device=dev)
+        img_ptrs = (C.c_void_p * n)(*[im.data_ptr() for im in imgs])
+        den_ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in dens])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().clipebc_sliding_window_predict_batch(
+                self._handle, n, img_ptrs, _lib.int_array(hs), _lib.int_array(ws), window_size[0], window_size[1], stride[0],
+                stride[1], den_ptrs, cnt.data_ptr(), torch.cuda.current_stream().cuda_stream), "sliding_window_predict_batch")
+        return dens, cnt
+
+
 def _clip_ebc(backbone: str, bins, anchor_points, reduction=None, freeze_text_encoder=True, prompt_type="number",
               input_size=None, num_vpt=None, deep_vpt=None, vpt_drop=None, decoder_block=None, decoder_cfg=None,
               **extra) -> CLIP_EBC:

@@ -91,6 +91,17 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
 int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int H, int W, int wh, int ww, int sh,
                                    int sw, float* density_out_dev, float* count_out_dev, void* stream);
 
+/* The same for a batch of images of arbitrary (different) sizes: the windows of all images share the passes of the
+ * ViT / decoder / head, so small images (a handful of windows each) still fill the GPU; each image is folded on its
+ * own. This is the cross-image window batching of the evaluation loop (eval.py:25-35 processes one image per
+ * iteration because sizes vary). images_dev / heights / widths / density_out_dev: HOST arrays of n_images entries
+ * (device pointers / sizes); counts_out_dev: device array of n_images floats or NULL. Results are identical to
+ * n_images separate clipebc_sliding_window_predict calls. */
+int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const float* const* images_dev,
+                                         const int* heights, const int* widths, int window_h, int window_w,
+                                         int stride_h, int stride_w, float* const* density_out_dev,
+                                         float* counts_out_dev, void* stream);
+
 /* ---- integer part of sliding_window_predict, host only (utils/eval_utils.py:54-66) ----------------------------- */
 /* Writes n_rows/n_cols and, when the arrays are non-NULL (capacity >= n_rows / n_cols), the clamped window origins. */
 int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_rows, int* n_cols, int* row_origins,

@@ -126,3 +126,30 @@ def test_evaluate_loop_matches_oracle():
         assert abs(c - r) <= parity.COUNT_REL * abs(r)
     assert abs(err["mae"] - ref_err["mae"]) <= parity.COUNT_REL * max(abs(r) for r in ref_counts)
     assert abs(err["rmse"] - ref_err["rmse"]) <= parity.COUNT_REL * max(abs(r) for r in ref_counts)
+
+
+def test_cross_image_window_batching_is_bit_identical_to_per_image_calls():
+    """clipebc_sliding_window_predict_batch: images of different sizes (shared-grid, off-grid and single-window ones) in
+    one pass give exactly the maps and counts of separate sliding_window_predict calls, chunk boundaries inside images
+    included (window_chunk=8 forces them)."""
+    from clip_ebc_b200 import get_model, sliding_window_predict, sliding_window_predict_batch
+
+    case = CASES[0]
+    sd, tf, bins, anchors, reduction, _ = case_inputs(case)
+    from oracle import weights
+
+    for chunk in (0, 8):
+        model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+                          prompt_type="word", num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf, window_chunk=chunk)
+        model.load_state_dict(sd, strict=True)
+        model = model.to("cuda").eval()
+        images = [weights.make_image((1, 3, h, w), seed=400 + i).cuda()
+                  for i, (h, w) in enumerate([(448, 672), (300, 500), (224, 224), (448, 448), (230, 700)])]
+        dens, cnt = sliding_window_predict_batch(model, images, 224, 112, return_device=True)
+        assert len(dens) == len(images) and tuple(cnt.shape) == (len(images),)
+        for i, im in enumerate(images):
+            d1, c1 = sliding_window_predict(model, im, 224, 112, return_device=True, return_count=True)
+            assert torch.equal(dens[i], d1), f"image {i} differs"
+            assert torch.equal(cnt[i:i + 1], c1.reshape(1))
+        dens_cpu, cnt_cpu = sliding_window_predict_batch(model, [im.cpu() for im in images], 224, 112)
+        assert all(d.device.type == "cpu" for d in dens_cpu) and torch.equal(cnt_cpu, cnt.cpu())
