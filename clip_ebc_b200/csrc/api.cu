@@ -353,7 +353,21 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   pp.n_seg = 3; pp.seg_kblocks = kWidth / 64;
   pp.seg_col_start[0] = 0; pp.seg_col_start[1] = kWidth; pp.seg_col_start[2] = 0;
   float* F = m->ws_F.as<float>();
-  pp.out = F; pp.ldo = kEmbed; pp.bias = raw_ptr(m, "projection.bias");
+  pp.bias = raw_ptr(m, "projection.bias");
+  static const bool unfused_head = std::getenv("CLIPEBC_HEAD_UNFUSED") != nullptr;  // A/B knob (profiles/)
+  if (g_gemm_impl.load() == 2 && !unfused_head) {
+    // projection fused with the head: the 512 projected features of a cell are never written; the GEMM epilogue
+    // leaves ||f||^2 and the N bin dot products per half tile (4 partials per row), ebc_head_finish does the rest
+    constexpr int kParts = 2 * (kEmbed / 256);
+    pp.out = F; pp.ldo = kParts * (1 + c.num_bins);
+    pp.head_tmat = m->tmat.as<float>(); pp.head_bins = c.num_bins;
+    set_launch_tag("projection+head");
+    K_TRY(gemm_dispatch(s, EPI_BIAS_HEAD_PARTIAL, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 256));
+    set_launch_tag(nullptr);
+    K_TRY(ebc_head_finish(s, F, kParts, raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
+    return CLIPEBC_OK;
+  }
+  pp.out = F; pp.ldo = kEmbed;
   set_launch_tag("projection");
   K_TRY(gemm_dispatch(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
 

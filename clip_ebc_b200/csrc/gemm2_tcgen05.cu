@@ -170,6 +170,49 @@ __device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* st
   __syncwarp();
 }
 
+// ---- projection fused with the first half of the EBC head (EPI_BIAS_HEAD_PARTIAL) ---------------------------------
+// thread = output row; over its `ncols` columns of the tile: ss += f^2, dot[b] += f * tmat[b][col], f = acc + bias.
+// tm_s: the tile's slice of the text matrix in smem, [NB][tile_n] f32 (rows >= head_bins are zero); reads are warp
+// broadcasts of 16 B. Nothing of f is written to memory.
+template <int NB>
+__device__ __forceinline__ void head_partial_cols(uint32_t t_addr, const float* tm_s, int tile_n, const float* bias_s, int ncols,
+                                                  float& ss, float (&dot)[NB]) {
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_addr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j);
+      const float f0 = __uint_as_float(r[j]) + b4.x, f1 = __uint_as_float(r[j + 1]) + b4.y;
+      const float f2 = __uint_as_float(r[j + 2]) + b4.z, f3 = __uint_as_float(r[j + 3]) + b4.w;
+      ss += (f0 * f0 + f1 * f1) + (f2 * f2 + f3 * f3);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 t = *reinterpret_cast<const float4*>(tm_s + b * tile_n + c + j);
+        dot[b] += (f0 * t.x + f1 * t.y) + (f2 * t.z + f3 * t.w);
+      }
+    }
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ void head_partial_tile(const GemmParams& p, uint32_t t_addr, const float* tm_s, int tile_n,
+                                                  const float* bias_s, int ncols, int row, int part) {
+  float ss = 0.f, dot[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dot[b] = 0.f;
+  head_partial_cols<NB>(t_addr, tm_s, tile_n, bias_s, ncols, ss, dot);
+  if (row < p.M) {
+    float* o = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + static_cast<size_t>(part) * (1 + p.head_bins);
+    o[0] = ss;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (b < p.head_bins) o[1 + b] = dot[b];
+  }
+}
+
 // TMA load multicast to the CTAs of `cta_mask`; with cta_group::2 the transaction bytes of every destination CTA are
 // reported to the barrier of that CTA's pair leader (the peer bit, bit 24 of the shared address, is cleared).
 __device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
@@ -342,6 +385,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int n0 = n_blk * BLOCK_N;
       // the tile's bias -> smem (double-buffered by accumulator stage); overlaps the wait for the accumulator
       float* bs = bias_s + as * BLOCK_N;
+      if constexpr (EPI == EPI_BIAS_HEAD_PARTIAL) {
+        // the tile's slice of the text matrix lives in the (otherwise unused) staging area: wait until every warp is
+        // done with the previous tile's slice before overwriting it
+        named_bar_sync(1, kEpiWarps * 32);
+        float* tm_s = reinterpret_cast<float*>(staging);
+        const int nb_pad = p.head_bins <= 8 ? 8 : (p.head_bins <= 16 ? 16 : 32);
+        for (int i = et; i < nb_pad * BLOCK_N; i += kEpiWarps * 32) {
+          const int b = i / BLOCK_N, col = i - b * BLOCK_N;
+          tm_s[i] = b < p.head_bins ? __ldg(p.head_tmat + static_cast<size_t>(b) * p.N + n0 + col) : 0.0f;
+        }
+      }
       if (et < BLOCK_N) bs[et] = (EPI != EPI_F32 || p.bias != nullptr) ? __ldg(p.bias + n0 + et) : 0.0f;
       named_bar_sync(1, kEpiWarps * 32);
       const int cbase = half * HALF_N;
@@ -351,7 +405,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       if (ew == 0) CEBC_TRACE(19 + 4 * ((t - cluster_id) / num_clusters));
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
-      if constexpr (out_is_bf16<EPI>()) {
+      if constexpr (EPI == EPI_BIAS_HEAD_PARTIAL) {
+        const float* tm_s = reinterpret_cast<const float*>(staging) + cbase;
+        const int row = row0 + lane, part = 2 * n_blk + half;
+        if (p.head_bins <= 8) head_partial_tile<8>(p, t_addr, tm_s, BLOCK_N, bs + cbase, HALF_N, row, part);
+        else if (p.head_bins <= 16) head_partial_tile<16>(p, t_addr, tm_s, BLOCK_N, bs + cbase, HALF_N, row, part);
+        else head_partial_tile<32>(p, t_addr, tm_s, BLOCK_N, bs + cbase, HALF_N, row, part);
+      } else if constexpr (out_is_bf16<EPI>()) {
 #pragma unroll 1
         for (int c = 0; c < HALF_N / 32; ++c) {
           uint32_t r[32];
@@ -481,6 +541,9 @@ cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, con
     case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_HEAD_PARTIAL:
+      if constexpr (BLOCK_N == 256 && MC == 1) return launch_one2<256, EPI_BIAS_HEAD_PARTIAL, 1>(stream, ta, tb, p, num_sms);
+      else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }
@@ -524,6 +587,11 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
   if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
   if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 3 || p.mask_wp < 3)) return "gemm: mask grid missing";
+  if (epi == EPI_BIAS_HEAD_PARTIAL) {
+    if (p.head_tmat == nullptr || p.head_bins < 1 || p.head_bins > 32) return "gemm: head epilogue needs the text matrix and 1..32 bins";
+    if (p.N % 256 != 0) return "gemm: head epilogue needs N to be a multiple of 256";
+    block_n = 256;
+  }
 
   static const bool trace_env = getenv("CLIPEBC_GEMM_TRACE") != nullptr;  // experiment: print CTA 0's time line
   static long long* trace_dev = nullptr;

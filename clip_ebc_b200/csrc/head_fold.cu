@@ -60,6 +60,49 @@ __global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__
   }
 }
 
+// Second half of the fused head: one thread per interior cell sums the per-half-tile partials of the projection GEMM
+// (EPI_BIAS_HEAD_PARTIAL) in a fixed order and finishes normalise / softmax / expectation (models/clip/model.py:203-212).
+__global__ void __launch_bounds__(256) ebc_head_finish_kernel(const float* __restrict__ partial, int n_part,
+                                                              const float* __restrict__ anchors, int n_bins, int n_win,
+                                                              int gh, int gw, float* __restrict__ exp_out,
+                                                              float* __restrict__ logits_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Hp = gh + 2, Wp = gw + 2;
+  const int S = 1 + n_bins;
+  const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
+  for (int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; cell < n_cells;
+       cell += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int win = static_cast<int>(cell / (gh * gw));
+    const int q = static_cast<int>(cell - static_cast<int64_t>(win) * gh * gw);
+    const int y = q / gw, x = q - y * gw;
+    const int64_t row = (static_cast<int64_t>(win) * Hp + (y + 1)) * Wp + (x + 1);
+    const float* pr = partial + row * n_part * S;
+    float ss = 0.f;
+    for (int k = 0; k < n_part; ++k) ss += pr[k * S];
+    const float inv_norm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    float lg[32];
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int b = 0; b < n_bins; ++b) {
+      float d = 0.f;
+      for (int k = 0; k < n_part; ++k) d += pr[k * S + 1 + b];
+      d *= inv_norm;
+      lg[b] = d;
+      mx = fmaxf(mx, d);
+    }
+    float den = 0.f, num = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < n_bins; ++b) {
+      const float e = __expf(lg[b] - mx);
+      den += e;
+      num += e * __ldg(anchors + b);
+      if (logits_out != nullptr) logits_out[((static_cast<int64_t>(win) * n_bins + b) * gh + y) * gw + x] = lg[b];
+    }
+    exp_out[cell] = num / den;
+  }
+}
+
 // One thread per output cell; windows covering the cell are visited in ascending window index (row-major i, j), which
 // reproduces the fp32 summation order of the reference loop (utils/eval_utils.py:79-95) bit for bit. No atomics.
 __global__ void __launch_bounds__(256) fold_average_kernel(const float* __restrict__ preds,
@@ -121,6 +164,20 @@ const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, con
   LaunchScope scope(stream, "ebc_head", 0.0, static_cast<double>(cells) * (kE * 4.0 + 4.0));
   cudaError_t e = launch_pdl(ebc_head_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, F, tmat, anchors,
                              n_bins, n_win, gh, gw, exp_out, logits_out);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+
+const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,
+                            int gh, int gw, float* exp_out, float* logits_out) {
+  if (n_bins < 1 || n_bins > 32) return "ebc_head: 1..32 bins supported";
+  if (n_win <= 0 || n_part < 1) return "ebc_head: no windows";
+  const int64_t cells = static_cast<int64_t>(n_win) * gh * gw;
+  int64_t blocks = (cells + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  LaunchScope scope(stream, "ebc_head_finish", 0.0, static_cast<double>(cells) * (n_part * (1.0 + n_bins) * 4.0 + 4.0));
+  cudaError_t e = launch_pdl(ebc_head_finish_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, partial,
+                             n_part, anchors, n_bins, n_win, gh, gw, exp_out, logits_out);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 

@@ -16,7 +16,10 @@ enum GemmEpilogue : int {
   EPI_BIAS_GELU_BF16 = 3,       // out bf16 = quickgelu(acc + bias)
   EPI_BIAS_RESID_F32 = 4,       // out f32 = acc + bias + resid   (out may alias resid)
   EPI_BIAS_RELU_MASK_BF16 = 5,  // out bf16 = border ? 0 : relu(acc + bias)          (decoder conv1 on the padded grid)
-  EPI_BIAS_RESID_RELU_SPLIT = 6 // t = relu(acc + bias + resid); out[:, n] = hi(t), out[:, N + n] = lo(t)  (bf16 pair)
+  EPI_BIAS_RESID_RELU_SPLIT = 6,// t = relu(acc + bias + resid); out[:, n] = hi(t), out[:, N + n] = lo(t)  (bf16 pair)
+  EPI_BIAS_HEAD_PARTIAL = 7     // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
+                                // tiles) out[row][2 * n_blk + half][0] = sum f^2, [1 + b] = sum f * head_tmat[b][n]
+                                // -- the projection fused with the first half of the EBC head (ebc_head_finish)
 };
 
 constexpr int kMaxGemmSegs = 9;
@@ -34,6 +37,8 @@ struct GemmParams {
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
   int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
+  const float* head_tmat;             // EPI_BIAS_HEAD_PARTIAL: f32 [head_bins, N] (logit_scale * normalised text features)
+  int head_bins;                      // 1..32
   int dbg;                            // experiment knob (profiles/): 0 in production
   long long* trace;                   // experiment: clock64 time line of CTA 0 (profiles/gemm_trace.py), nullptr in production
 };
@@ -147,6 +152,12 @@ const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, i
 // over anchors. exp_out f32 [n_win, 1, gh, gw]; logits_out (nullable) f32 [n_win, n_bins, gh, gw]. (model.py:200-212)
 const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
                      int n_win, int gh, int gw, float* exp_out, float* logits_out);
+
+// Second half of the fused head: partial f32 [n_win * (gh+2) * (gw+2), n_part, 1 + n_bins] written by the projection GEMM
+// with EPI_BIAS_HEAD_PARTIAL -> sums over the n_part partials in a fixed order, 1 / max(||f||, 1e-12), softmax over the
+// bins, anchor expectation on the interior cells. Same outputs as ebc_head.
+const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,
+                            int gh, int gw, float* exp_out, float* logits_out);
 
 // ------------------------------------------------------------------ fold ---------------------------------------
 // preds f32 [n_rows * n_cols, 1, gh, gw] -> density f32 [Ho, Wo]: average of overlapping windows, summed in ascending
