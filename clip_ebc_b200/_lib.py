@@ -54,7 +54,7 @@ SIGNATURES = {
     "clipebc_window_origins": (_i, [_i, _i, _i, _i, _i, _i, _ip, _ip, _ip, _ip]),
     "clipebc_f32_to_16": (_i, [_fp, _vp, _i64, _i, _vp]),
     "clipebc_gemm_bf16": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _ip, _ip, _vp, _i, _fp, _fp, _i,
-                               _i, _i, _i, _i, _i, _vp]),
+                               _i, _i, _i, _i, _i, _i, _vp]),
     "clipebc_layernorm768": (_i, [_fp, _fp, _fp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -271,8 +271,8 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   const int T = 1 + n_prompt_live + npatch;
   const int M = nw * T;
   const int gh = hp * kPatch / c.reduction, gw = wp * kPatch / c.reduction;
-  const int Hp = gh + 2, Wp = gw + 2;
-  const int Mp = nw * Hp * Wp;
+  const int Hp = gh + 1, Wp = gw + 1;  // shared-border decoder grid (kernels.h: resample_to_padded): 841 rows per r8
+  const int Mp = nw * Hp * Wp;         // window instead of 900 on a grid bordered on all four sides
 
   CUDA_TRY(m->ws_X.reserve(static_cast<size_t>(M) * kWidth * 4));
   CUDA_TRY(m->ws_Xn.reserve(static_cast<size_t>(M) * kWidth * 2));
@@ -339,7 +339,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   __nv_bfloat16* D1 = m->ws_D1.as<__nv_bfloat16>();
   __nv_bfloat16* D2 = m->ws_D2.as<__nv_bfloat16>();
   GemmParams p1 = pc;
-  p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp;
+  p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp; p1.mask_lead = 0;
   set_launch_tag("dec_conv1");
   K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
   GemmParams p2 = pc;
@@ -816,7 +816,7 @@ int clipebc_f32_to_16(const float* in_dev, void* out, int64_t n, int fp16, void*
 
 int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* W, int64_t ldw,
                       int M, int N, int K, int n_seg, const int* seg_row_shift, const int* seg_col_start, void* out,
-                      int ldo, const float* bias, const float* resid, int ldr, int mask_hp, int mask_wp, int block_n,
+                      int ldo, const float* bias, const float* resid, int ldr, int mask_hp, int mask_wp, int mask_lead, int block_n,
                       int ab_fp16, int out_fp16, void* stream) {
   if (!A || !W || !out) return fail(CLIPEBC_EINVAL, "null argument");
   if (n_seg < 1 || n_seg > kMaxGemmSegs) return fail(CLIPEBC_EINVAL, "n_seg must be in 1..9");
@@ -828,7 +828,7 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
     p.seg_row_shift[i] = seg_row_shift ? seg_row_shift[i] : 0;
     p.seg_col_start[i] = seg_col_start ? seg_col_start[i] : 0;
   }
-  p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp;
+  p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp; p.mask_lead = mask_lead != 0;
   p.ab_fp16 = ab_fp16 != 0; p.out_fp16 = out_fp16 != 0;
   const char* e = gemm_dispatch(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
                                lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int Hp = gh + 2, Wp = gw + 2;
+  const int Hp = gh + 1, Wp = gw + 1;  // shared-border grid: one trailing zero column per line, one zero row per window
   const int64_t n_rows = static_cast<int64_t>(n_win) * Hp * Wp;
   const float inv_sy = static_cast<float>(hp) / static_cast<float>(gh);
   const float inv_sx = static_cast<float>(wp) / static_cast<float>(gw);
@@ -228,16 +228,16 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
     const int q = static_cast<int>(r - static_cast<int64_t>(win) * Hp * Wp);
     const int py = q / Wp, px = q - py * Wp;
     Row768 o;
-    if (py == 0 || py == Hp - 1 || px == 0 || px == Wp - 1) {
+    if (py == gh || px == gw) {
 #pragma unroll
       for (int i = 0; i < kVecPerLane; ++i) o.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (gh == hp && gw == wp) {
-      o = load_row(Y + (static_cast<int64_t>(win) * hp * wp + static_cast<int64_t>(py - 1) * wp + (px - 1)) * kD, lane);
+      o = load_row(Y + (static_cast<int64_t>(win) * hp * wp + static_cast<int64_t>(py) * wp + px) * kD, lane);
     } else {
       int y0, y1, x0, x1;
       float ly, lx;
-      bilinear_src(py - 1, inv_sy, hp, y0, y1, ly);
-      bilinear_src(px - 1, inv_sx, wp, x0, x1, lx);
+      bilinear_src(py, inv_sy, hp, y0, y1, ly);
+      bilinear_src(px, inv_sx, wp, x0, x1, lx);
       const float* base = Y + static_cast<int64_t>(win) * hp * wp * kD;
       const Row768 a = load_row(base + (static_cast<int64_t>(y0) * wp + x0) * kD, lane);
       const Row768 b = load_row(base + (static_cast<int64_t>(y0) * wp + x1) * kD, lane);
@@ -378,7 +378,7 @@ const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
                                void* U_16, float* U_f32, int fp16) {
   if (n_win <= 0) return "resample: no windows";
-  const int64_t rows = static_cast<int64_t>(n_win) * (gh + 2) * (gw + 2);
+  const int64_t rows = static_cast<int64_t>(n_win) * (gh + 1) * (gw + 1);
   LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * kD * 4.0 + static_cast<double>(rows) * kD * 6.0);
   cudaError_t e = launch_pdl(resample_to_padded_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
                              Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);

@@ -67,7 +67,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk64(const GemmParams& p, uint8
     const int rpi = p.mask_hp * p.mask_wp;
     const int q = row % rpi;
     const int py = q / p.mask_wp, px = q - py * p.mask_wp;
-    border = (py == 0) || (py == p.mask_hp - 1) || (px == 0) || (px == p.mask_wp - 1);
+    border = (py == p.mask_hp - 1) || (px == p.mask_wp - 1) || (p.mask_lead && (py == 0 || px == 0));
   }
   uint4* my = reinterpret_cast<uint4*>(stg + lane * kStageRowBytes);
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -430,7 +430,7 @@ const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, i
   if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
   if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
-  if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 3 || p.mask_wp < 3)) return "gemm: mask grid missing";
+  if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 2 || p.mask_wp < 2)) return "gemm: mask grid missing";
 
   CUtensorMap ta, tb;
   if (!make_tmap_bf16(&ta, A, a_rows, a_cols, lda, kBlockM)) return "gemm: cuTensorMapEncodeTiled(A) failed";

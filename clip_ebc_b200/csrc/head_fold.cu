@@ -9,7 +9,7 @@ namespace {
 
 constexpr int kE = 512;  // CLIP embed dim of ViT-B/16
 
-// One warp per interior cell of the padded decoder grid. Reference: models/clip/model.py:200-212
+// One warp per interior cell of the shared-border decoder grid. Reference: models/clip/model.py:200-212
 //   f^ = f / max(||f||, 1e-12);  logits = (exp(logit_scale) * f^) @ t^T;  probs = softmax;  exp = sum probs * anchor
 // tmat already holds exp(logit_scale) * t^ (pack_text).
 __global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__ F, const float* __restrict__ tmat,
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int Hp = gh + 2, Wp = gw + 2;
+  const int Hp = gh + 1, Wp = gw + 1;  // shared-border grid (kernels.h: resample_to_padded)
   const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   for (int64_t cell = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < n_cells;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__
     const int win = static_cast<int>(cell / (gh * gw));
     const int q = static_cast<int>(cell - static_cast<int64_t>(win) * gh * gw);
     const int y = q / gw, x = q - y * gw;
-    const int64_t row = (static_cast<int64_t>(win) * Hp + (y + 1)) * Wp + (x + 1);
+    const int64_t row = (static_cast<int64_t>(win) * Hp + y) * Wp + x;
     const float4* f4 = reinterpret_cast<const float4*>(F + row * kE);
     float4 f[4];
 #pragma unroll
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) ebc_head_finish_kernel(const float* __res
                                                               float* __restrict__ logits_out) {
   pdl_launch_dependents();
   pdl_wait();
-  const int Hp = gh + 2, Wp = gw + 2;
+  const int Hp = gh + 1, Wp = gw + 1;  // shared-border grid (kernels.h: resample_to_padded)
   const int S = 1 + n_bins;
   const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
   for (int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; cell < n_cells;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) ebc_head_finish_kernel(const float* __res
     const int win = static_cast<int>(cell / (gh * gw));
     const int q = static_cast<int>(cell - static_cast<int64_t>(win) * gh * gw);
     const int y = q / gw, x = q - y * gw;
-    const int64_t row = (static_cast<int64_t>(win) * Hp + (y + 1)) * Wp + (x + 1);
+    const int64_t row = (static_cast<int64_t>(win) * Hp + y) * Wp + x;
     const float* pr = partial + row * n_part * S;
     float ss = 0.f;
     for (int k = 0; k < n_part; ++k) ss += pr[k * S];

@@ -35,6 +35,9 @@ struct GemmParams {
   const float* resid;                 // f32 [M, ldr]
   int ldr;
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
+  int mask_lead;                      // 1: first AND last row / column of the grid are border; 0: only the last ones
+                                      // (shared-border grid: the trailing zero column / row of one line / image is the
+                                      // leading border of the next)
   int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
   const float* head_tmat;             // EPI_BIAS_HEAD_PARTIAL: f32 [head_bins, N] (logit_scale * normalised text features)
@@ -143,17 +146,20 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
 
 // ------------------------------------------------------------------ decoder / head -----------------------------
 // Y f32 [n_win * hp * wp, 768] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
-// zero-bordered NHWC grids U_bf16 / U_f32 [n_win, gh + 2, gw + 2, 768]  (model.py:195-196).
+// shared-border NHWC grids U_16 / U_f32 [n_win, gh + 1, gw + 1, 768]: cell (y, x) of a window at row y * (gw + 1) + x,
+// column gw and row gh are zero. The zero column that ends one line is the left border of the next line, the zero row
+// that ends one window is the top border of the next (rows before the buffer are zero-filled by TMA): every 3x3 tap
+// r + dy * (gw + 1) + dx of an interior cell lands on the right neighbour or on a zero  (model.py:195-196).
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
                                void* U_16, float* U_f32, int fp16);
 
-// F f32 [n_win * (gh+2) * (gw+2), 512] projected features on the padded grid -> EBC head on interior cells:
+// F f32 [n_win * (gh+1) * (gw+1), 512] projected features on the shared-border grid -> EBC head on interior cells:
 // normalise, logits against tmat f32 [n_bins, 512] (= logit_scale * normalised text features), softmax, expectation
 // over anchors. exp_out f32 [n_win, 1, gh, gw]; logits_out (nullable) f32 [n_win, n_bins, gh, gw]. (model.py:200-212)
 const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
                      int n_win, int gh, int gw, float* exp_out, float* logits_out);
 
-// Second half of the fused head: partial f32 [n_win * (gh+2) * (gw+2), n_part, 1 + n_bins] written by the projection GEMM
+// Second half of the fused head: partial f32 [n_win * (gh+1) * (gw+1), n_part, 1 + n_bins] written by the projection GEMM
 // with EPI_BIAS_HEAD_PARTIAL -> sums over the n_part partials in a fixed order, 1 / max(||f||, 1e-12), softmax over the
 // bins, anchor expectation on the interior cells. Same outputs as ebc_head.
 const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,

@@ -66,7 +66,7 @@ def to_16(x: torch.Tensor, fp16: bool = False) -> torch.Tensor:
 def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, M: Optional[int] = None, K: Optional[int] = None,
          seg_row_shift: Optional[Sequence[int]] = None, seg_col_start: Optional[Sequence[int]] = None,
-         mask_hw: Tuple[int, int] = (0, 0), block_n: int = 0, out: Optional[torch.Tensor] = None,
+         mask_hw: Tuple[int, int] = (0, 0), mask_lead: bool = True, block_n: int = 0, out: Optional[torch.Tensor] = None,
          out_fp16: Optional[bool] = None) -> torch.Tensor:
     """D = A[M,K] @ W[N,K]^T with a fused epilogue. a, w: both bf16 or both fp16, 2-D contiguous."""
     assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16) and a.dim() == 2 and w.dim() == 2
@@ -88,7 +88,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
     _lib.check(_lib.load().clipebc_gemm_bf16(
         epi, _ptr(a), a.shape[0], a.shape[1], a.stride(0), _ptr(w), w.stride(0), M, N, K, n_seg, rs, cs, _ptr(out),
         out.stride(0), _ptr(bias), _ptr(resid), resid.stride(0) if resid is not None else 0, mask_hw[0], mask_hw[1],
-        block_n, int(ab_fp16), int(out_fp16), _stream()), "gemm")
+        int(mask_lead), block_n, int(ab_fp16), int(out_fp16), _stream()), "gemm")
     return out
 
 
@@ -129,8 +129,8 @@ def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = 
 
 
 def resample_to_padded(Y: torch.Tensor, n_win: int, hp: int, wp: int, gh: int, gw: int, fp16: bool = False):
-    ub = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=_dt16(fp16), device=Y.device)
-    uf = torch.empty((n_win * (gh + 2) * (gw + 2), 768), dtype=torch.float32, device=Y.device)
+    ub = torch.empty((n_win * (gh + 1) * (gw + 1), 768), dtype=_dt16(fp16), device=Y.device)
+    uf = torch.empty((n_win * (gh + 1) * (gw + 1), 768), dtype=torch.float32, device=Y.device)
     _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, _ptr(ub), _ptr(uf), int(fp16),
                                                       _stream()), "resample")
     return ub, uf

@@ -30,7 +30,7 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 3
+#define CLIPEBC_ABI_VERSION 4
 
 typedef struct clipebc_model clipebc_model;
 
@@ -112,11 +112,14 @@ int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_
 int clipebc_f32_to_16(const float* in_dev, void* out_16_dev, int64_t n, int fp16, void* stream);
 /* epi: 0 f32, 1 bias f32, 2 bias ->16, 3 bias+quickgelu ->16, 4 bias+resid f32, 5 bias+relu+border-mask ->16,
  *      6 bias+resid+relu hi/lo split ->16. ab_fp16: format of A and W; out_fp16: format of a 16-bit output.
+ *      mask_hp x mask_wp: rows per image of the zero-bordered grid of epi 5; mask_lead 1: first and last row/column are
+ *      border, 0: only the last ones (shared-border grid, see clipebc_resample_to_padded).
  *      See clip_ebc_b200/csrc/kernels.h for the contract. */
 int clipebc_gemm_bf16(int epi, const void* A_16_dev, int64_t a_rows, int64_t a_cols, int64_t lda,
                       const void* W_16_dev, int64_t ldw, int M, int N, int K, int n_seg, const int* seg_row_shift,
                       const int* seg_col_start, void* out_dev, int ldo, const float* bias_dev, const float* resid_dev,
-                      int ldr, int mask_hp, int mask_wp, int block_n, int ab_fp16, int out_fp16, void* stream);
+                      int ldr, int mask_hp, int mask_wp, int mask_lead, int block_n, int ab_fp16, int out_fp16,
+                      void* stream);
 /* out_kind: 0 = f32, 1 = bf16, 2 = fp16 */
 int clipebc_layernorm768(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
                          int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
@@ -127,8 +130,11 @@ int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, i
 /* out: [n_img*gh*gw, 2*768] = [hi | lo] split of the pixels in the 16-bit format */
 int clipebc_patchify16(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw,
                        void* out_16_dev, int fp16, void* stream);
+/* Shared-border grid [n_win, gh+1, gw+1, 768]: cell (y, x) at row y*(gw+1)+x, column gw and row gh are zero; the zero
+ * column ending a line is the left border of the next line, the zero row ending a window the top border of the next. */
 int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, void* U_16_dev,
                                float* U_f32_dev, int fp16, void* stream);
+/* F_dev f32 [n_win*(gh+1)*(gw+1), 512] on the shared-border grid; evaluated on the gh x gw interior cells */
 int clipebc_ebc_head(const float* F_dev, const float* tmat_dev, const float* anchors_dev, int n_bins, int n_win, int gh,
                      int gw, float* exp_out_dev, float* logits_out_dev, void* stream);
 /* preds_dev f32 [n_rows*n_cols, gh, gw]; row_cells/col_cells: HOST arrays of window origins // reduction. */

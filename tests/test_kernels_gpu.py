@@ -150,6 +150,28 @@ def test_gemm_remainder_rows_all_epilogues(ops, rem, dt):
     assert _rel(got, t_ref) < 3e-5 and _rel(got[512:], t_ref[512:]) < 3e-5
 
 
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_gemm_conv_segments_on_shared_border_grid(ops, dt):
+    """The decoder's layout: one trailing zero column per line and one zero row per image ((g+1)^2 rows instead of
+    (g+2)^2); rows before the buffer are zero-filled by TMA. 3x3 conv as 9 row-shifted K-segments == F.conv2d(padding=1)."""
+    B, g, Cc = 3, 14, 768
+    Wp = g + 1
+    x = _rand((B, Cc, g, g), 20).to(dt)
+    wt = _rand((Cc, Cc, 3, 3), 21, 0.02).to(dt)
+    bias = _rand((Cc,), 22)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), padding=1) + bias.view(1, -1, 1, 1))
+    xp = torch.zeros((B, Wp, Wp, Cc), dtype=dt, device="cuda")
+    xp[:, :-1, :-1, :] = x.permute(0, 2, 3, 1)
+    wk = wt.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).contiguous()
+    shifts = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+    out = ops.gemm(xp.view(-1, Cc), wk, ops.EPI_BIAS_RELU_MASK_BF16, bias=bias, K=9 * Cc, seg_row_shift=shifts,
+                   seg_col_start=[0] * 9, mask_hw=(Wp, Wp), mask_lead=False).view(B, Wp, Wp, Cc)
+    border = out.clone()
+    border[:, :-1, :-1, :] = 0
+    assert border.abs().max().item() == 0.0
+    assert _rel(out[:, :-1, :-1, :].permute(0, 3, 1, 2), ref) < 1.5 * ROUND16[dt]
+
+
 def test_gemm_remainder_rows_conv_segments(ops):
     """Row-shifted K-segments + border mask on a shape with a remainder (2 windows x 30 x 30 = 1800 = 7 x 256 + 8)."""
     dt = torch.float16
@@ -257,10 +279,10 @@ def test_resample_matches_interpolate(ops, g, dt):
     ub, uf = ops.resample_to_padded(Y, n, 14, 14, g, g, fp16=dt == torch.float16)
     x = Y.view(n, 14, 14, 768).permute(0, 3, 1, 2)
     ref = x if g == 14 else F.interpolate(x, scale_factor=g / 14, mode="bilinear")
-    uf = uf.view(n, g + 2, g + 2, 768)
-    assert (uf[:, 1:-1, 1:-1].permute(0, 3, 1, 2) - ref).abs().max().item() < 1e-5
+    uf = uf.view(n, g + 1, g + 1, 768)  # shared-border grid: one trailing zero column per line, one zero row per window
+    assert (uf[:, :-1, :-1].permute(0, 3, 1, 2) - ref).abs().max().item() < 1e-5
     border = uf.clone()
-    border[:, 1:-1, 1:-1] = 0
+    border[:, :-1, :-1] = 0
     assert border.abs().max().item() == 0.0
     assert torch.equal(ub.view_as(uf), uf.to(dt))
 
@@ -268,13 +290,13 @@ def test_resample_matches_interpolate(ops, g, dt):
 @pytest.mark.parametrize("n_bins", [3, 5, 20])
 def test_ebc_head(ops, n_bins):
     n, g = 2, 7
-    Fm = _rand((n * (g + 2) * (g + 2), 512), 50)
+    Fm = _rand((n * (g + 1) * (g + 1), 512), 50)
     text = _rand((n_bins, 512), 51)
     anchors = torch.arange(n_bins, dtype=torch.float32, device="cuda") * 1.25
     scale = math.log(1 / 0.07)
     tmat = math.exp(scale) * F.normalize(text, dim=-1)
     exp, logits = ops.ebc_head(Fm, tmat.contiguous(), anchors, n, g, g, want_logits=True)
-    f = Fm.view(n, g + 2, g + 2, 512)[:, 1:-1, 1:-1]
+    f = Fm.view(n, g + 1, g + 1, 512)[:, :-1, :-1]
     ref_logits = (math.exp(scale) * F.normalize(f, dim=-1)) @ F.normalize(text, dim=-1).t()
     ref_logits = ref_logits.permute(0, 3, 1, 2)
     ref_exp = (ref_logits.softmax(1) * anchors.view(1, -1, 1, 1)).sum(1, keepdim=True)
