@@ -42,6 +42,7 @@ SIGNATURES = {
     "clipebc_launch_count": (_i64, []),
     "clipebc_set_gemm_impl": (_i, [_i]),
     "clipebc_set_attention_impl": (_i, [_i]),
+    "clipebc_set_ln_fold": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_model_create": (_i, [C.POINTER(ClipEbcConfig), C.POINTER(_vp)]),
@@ -55,6 +56,10 @@ SIGNATURES = {
     "clipebc_f32_to_16": (_i, [_fp, _vp, _i64, _i, _vp]),
     "clipebc_gemm_bf16": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _ip, _ip, _vp, _i, _fp, _fp, _i,
                                _i, _i, _i, _i, _i, _i, _vp]),
+    "clipebc_gemm_resid_stats": (_i, [_vp, _i64, _i64, _vp, _i64, _i, _i, _i, _fp, _fp, _vp, _vp, _i, _i, _i, _vp]),
+    "clipebc_gemm_ln": (_i, [_i, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _fp, _vp, _i, _fp, _i, _i, _i, _vp]),
+    "clipebc_rowstats768": (_i, [_fp, _i64, _vp, _vp, _i, _vp]),
+    "clipebc_fold_ln_linear": (_i, [_fp, _fp, _fp, _fp, _i, _vp, _fp, _fp, _i, _vp]),
     "clipebc_layernorm768": (_i, [_fp, _fp, _fp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),

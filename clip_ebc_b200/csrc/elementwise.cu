@@ -72,6 +72,23 @@ __device__ __forceinline__ void store_row_16(void* p, const Row768& r, int lane,
     p2[i * 32 + lane] = make_uint2(pack16x2(r.v[i].x, r.v[i].y, fp16), pack16x2(r.v[i].z, r.v[i].w, fp16));
 }
 
+// (mean, sum of squared deviations) of one row held by a warp, two-pass in registers -> slot 0 of its statistics row
+// (kernels.h: EPI_LN_* with ln_parts = 1)
+__device__ __forceinline__ void store_row_stats(const Row768& r, int lane, float2* stats) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  q = warp_sum(q);
+  if (lane == 0) stats[0] = make_float2(mean, q);
+}
+
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
 template <bool OUT_16>
 __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
@@ -169,7 +186,9 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
                                                               const float* __restrict__ ln_g,
                                                               const float* __restrict__ ln_b,
                                                               const float* __restrict__ vpt0, int n_prompt, int n_win,
-                                                              int hp, int wp, float* __restrict__ X) {
+                                                              int hp, int wp, float* __restrict__ X,
+                                                              uint16_t* __restrict__ X16, float2* __restrict__ stats,
+                                                              int fp16) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -197,6 +216,24 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
       layernorm_row(x, ln_g, ln_b, lane);
     }
     store_row_f32(X + r * kD, x, lane);
+    if (X16 != nullptr) {
+      store_row_16(X16 + r * kD, x, lane, fp16);
+      store_row_stats(x, lane, stats + r * kLnStatSlots);
+    }
+  }
+}
+
+// rows f32 -> 16-bit copy + (mean, M2): the inputs of an LN-folded GEMM for rows that no GEMM epilogue produced
+__global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restrict__ in, int64_t n_rows,
+                                                          uint16_t* __restrict__ X16, float2* __restrict__ stats, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
+    const Row768 x = load_row(in + r * kD, lane);
+    store_row_16(X16 + r * kD, x, lane, fp16);
+    store_row_stats(x, lane, stats + r * kLnStatSlots);
   }
 }
 
@@ -300,6 +337,26 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, u
   }
 }
 
+// LayerNorm folded into the following Linear (I = 768): one warp per output row
+__global__ void fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int O, uint16_t* __restrict__ Wf,
+                                      float* __restrict__ colsum, float* __restrict__ bias_f, int fp16) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < kD; k += 32) {
+    const float w = W[static_cast<int64_t>(o) * kD + k];
+    const float wf = round16(w * gamma[k], fp16);
+    Wf[static_cast<int64_t>(o) * kD + k] = cvt16(wf, fp16);
+    cs += wf;
+    bb += w * beta[k];
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) { colsum[o] = cs; bias_f[o] = b[o] + bb; }
+}
+
 // F.normalize(text, p=2, dim=-1) (eps 1e-12) scaled by exp(logit_scale)  (model.py:204,207-208); one warp per bin
 __global__ void pack_text_kernel(const float* __restrict__ text, const float* __restrict__ logit_scale, int n, int d,
                                  float* __restrict__ tmat) {
@@ -364,14 +421,25 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
 
 const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
                             const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
-                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X) {
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X, void* X16, float2* stats,
+                            int fp16) {
   if (n_win <= 0) return "assemble_tokens: no windows";
   if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
+  if ((X16 == nullptr) != (stats == nullptr)) return "assemble_tokens: X16 and stats go together";
   const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
   LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * kD * 8.0);
   cudaError_t e = launch_pdl(assemble_tokens_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
                              patch_embed, win_base_dev, src_pitch, win_pitch_dev, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp,
-                             wp, X);
+                             wp, X, static_cast<uint16_t*>(X16), stats, fp16);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+
+const char* rowstats768(cudaStream_t stream, const float* in, int64_t n_rows, void* X16, float2* stats, int fp16) {
+  if (n_rows <= 0) return nullptr;
+  if (X16 == nullptr || stats == nullptr) return "rowstats: null output";
+  LaunchScope scope(stream, "rowstats", 0.0, static_cast<double>(n_rows) * kD * 6.0);
+  cudaError_t e = launch_pdl(rowstats768_kernel, dim3(grid_for(n_rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1, in,
+                             n_rows, static_cast<uint16_t*>(X16), stats, fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
@@ -404,6 +472,14 @@ const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, in
   LaunchScope scope(stream, "pack");
   split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(
       W, O, I, static_cast<uint16_t*>(out), fp16);
+  return last_err();
+}
+
+const char* fold_ln_linear(cudaStream_t stream, const float* W, const float* b, const float* gamma, const float* beta, int O,
+                           void* Wf, float* colsum, float* bias_f, int fp16) {
+  if (O <= 0) return "fold_ln_linear: empty";
+  LaunchScope scope(stream, "pack");
+  fold_ln_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(W, b, gamma, beta, O, static_cast<uint16_t*>(Wf), colsum, bias_f, fp16);
   return last_err();
 }
 

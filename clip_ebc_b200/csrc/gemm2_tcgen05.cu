@@ -35,15 +35,24 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kStagingPerWarp = 32 * 128;  // 32 rows x 128 B, XOR-swizzled 16 B slots
 
-template <int BLOCK_N>
+// The statistics epilogue moves the residual tile with TMA (see the TR branch of the epilogue). Measured on B200 the plain
+// residual epilogue is 2 us (out_proj) / 5 us (c_proj) per launch FASTER through registers (the TMA round trip doubles the
+// shared-memory traffic of the epilogue, and the shared-memory port is what the mainloop competes for), so only
+// EPI_BIAS_RESID_STATS -- which needs a thread to own its row -- takes this path.
+template <int BLOCK_N, int EPI>
+constexpr bool tma_resid() { return BLOCK_N == 192 && EPI == EPI_BIAS_RESID_STATS; }
+constexpr int kResidBoxBytes = 32 * 32 * 4;  // TMA box of the residual tile: 32 rows x 32 fp32 columns, 128B-swizzled
+
+template <int BLOCK_N, bool TR = false>
 struct Cfg2 {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N > 192) ? 5 : 6;
+  static constexpr int kStages = TR ? 4 : ((BLOCK_N > 192) ? 5 : 6);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;
-  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
+  // TR: every epilogue warp owns the residual of its 32 rows x BLOCK_N / 2 columns (BLOCK_N / 64 boxes of 4 KB)
+  static constexpr int kStagingBytes = TR ? kEpiWarps * (BLOCK_N / 64) * kResidBoxBytes : kEpiWarps * kStagingPerWarp;
+  static constexpr int kBiasBytes = 4 * BLOCK_N * 4;  // [2][BLOCK_N] bias + [2][BLOCK_N] LN column sums (EPI_LN_*)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -62,11 +71,15 @@ __device__ __forceinline__ float quick_gelu2(float x) {
 }
 
 template <int EPI>
+constexpr bool is_ln() { return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16; }
+template <int EPI>
 constexpr bool out_is_bf16() {
-  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16;
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16 || is_ln<EPI>();
 }
 template <int EPI>
-constexpr bool has_resid() { return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT; }
+constexpr bool has_resid() {
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_RESID_STATS;
+}
 
 // ---- bf16-output epilogues, 32 accumulator columns per pass -------------------------------------------------------
 // phase 1: thread = output row (as tcgen05.ld delivers it): bias (smem broadcast) + activation, pack, 4 x 16 B into the
@@ -74,7 +87,8 @@ constexpr bool has_resid() { return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS
 // warp store writes 8 complete 64 B row segments.
 template <int EPI>
 __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* stg, const float* bias_s, int lane, int row0,
-                                                 int n, const uint32_t (&r)[32]) {
+                                                 int n, const uint32_t (&r)[32], const float* cs_s = nullptr, float ra = 1.f,
+                                                 float rc = 0.f) {
   const int row = row0 + lane;
   bool border = false;
   if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
@@ -93,7 +107,16 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
     v[2] = __uint_as_float(r[8 * j + 2]) + ba.z; v[3] = __uint_as_float(r[8 * j + 3]) + ba.w;
     v[4] = __uint_as_float(r[8 * j + 4]) + bb.x; v[5] = __uint_as_float(r[8 * j + 5]) + bb.y;
     v[6] = __uint_as_float(r[8 * j + 6]) + bb.z; v[7] = __uint_as_float(r[8 * j + 7]) + bb.w;
-    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+    if constexpr (is_ln<EPI>()) {
+      // LayerNorm applied after the contraction: rstd * (acc - mean * colsum[n]) + bias'[n]; ra = rstd, rc = -rstd * mean
+      const float4* c4p = reinterpret_cast<const float4*>(cs_s);
+      const float4 ca = c4p[2 * j], cb = c4p[2 * j + 1];
+      v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ra, fmaf(rc, ca.x, ba.x)); v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ra, fmaf(rc, ca.y, ba.y));
+      v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ra, fmaf(rc, ca.z, ba.z)); v[3] = fmaf(__uint_as_float(r[8 * j + 3]), ra, fmaf(rc, ca.w, ba.w));
+      v[4] = fmaf(__uint_as_float(r[8 * j + 4]), ra, fmaf(rc, cb.x, bb.x)); v[5] = fmaf(__uint_as_float(r[8 * j + 5]), ra, fmaf(rc, cb.y, bb.y));
+      v[6] = fmaf(__uint_as_float(r[8 * j + 6]), ra, fmaf(rc, cb.z, bb.z)); v[7] = fmaf(__uint_as_float(r[8 * j + 7]), ra, fmaf(rc, cb.w, bb.w));
+    }
+    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16) {
       if (p.dbg & 64) {  // experiment: the two-MUFU form
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = quick_gelu2_exact(v[k]);
@@ -232,8 +255,10 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUt
 template <int BLOCK_N, int EPI, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_r, const __grid_constant__ CUtensorMap tma_o,
                      const __grid_constant__ GemmParams p) {
-  using Cfg = Cfg2<BLOCK_N>;
+  constexpr bool TR = tma_resid<BLOCK_N, EPI>();
+  using Cfg = Cfg2<BLOCK_N, TR>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int HALF_N = BLOCK_N / 2;
   constexpr int CL = 2 * MC;  // CTAs per cluster
@@ -242,13 +267,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BLOCK_N]
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BLOCK_N] bias, then [2][BLOCK_N] LN column sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;                         // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + STAGES;               // [STAGES]  one set per CTA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]       one set per CTA
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]       used in the leader CTA only
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* resid_bar = bars + 2 * STAGES + 5;       // [kEpiWarps]  TR: residual boxes of one epilogue warp have landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -268,6 +294,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if constexpr (TR) { tma_prefetch_desc(&tma_r); tma_prefetch_desc(&tma_o); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -278,6 +305,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // every epilogue warp of both CTAs
     }
+    if constexpr (TR)
+      for (int s = 0; s < kEpiWarps; ++s) mbar_init(&resid_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -379,6 +408,104 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), leader_crank);
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), leader_crank);
     uint32_t as = 0, aphase = 0;
+    if constexpr (TR) {
+      // ---- fp32 residual tiles through TMA ------------------------------------------------------------------------
+      // The register-staged epilogue below keeps only one 32-column chunk of the residual in flight per warp and is
+      // latency-bound (out_proj: ~10 us per tile against a 4.5 us mainloop). Here every epilogue warp owns the residual of
+      // its 32 rows x 96 columns as three 128B-swizzled 4 KB boxes in shared memory: the boxes of the NEXT tile are
+      // requested as soon as the store of the current one has been read out of shared memory, thread = accumulator row
+      // adds accumulator + bias in place (16 B accesses, conflict-free under the swizzle) and lane 0 sends the boxes
+      // back with a bulk tensor store; rows >= M are clipped by the hardware. No predicates, no staging transposes, and
+      // the row statistics of EPI_BIAS_RESID_STATS are plain per-thread sums (a thread owns its row).
+      constexpr int NB = HALF_N / 32;
+      uint8_t* Rw = staging + ew * (NB * kResidBoxBytes);
+      uint64_t* rbar = &resid_bar[ew];
+      uint32_t rphase = 0;
+      const int cbase = half * HALF_N;
+      auto request_resid = [&](int t) {
+        const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
+        const int r0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
+        mbar_arrive_expect_tx(rbar, NB * kResidBoxBytes);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) tma_load_2d(Rw + c * kResidBoxBytes, &tma_r, rbar, n_blk * BLOCK_N + cbase + c * 32, r0);
+      };
+      if (lane == 0 && cluster_id < num_tiles) request_resid(cluster_id);
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
+        const int row0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
+        const int n0 = n_blk * BLOCK_N;
+        float* bs = bias_s + as * BLOCK_N;
+        if (et < BLOCK_N) bs[et] = __ldg(p.bias + n0 + et);
+        named_bar_sync(1, kEpiWarps * 32);
+        mbar_wait(rbar, rphase);
+        rphase ^= 1;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
+        const int row = row0 + lane;
+        uint16_t* x16 = nullptr;
+        if constexpr (EPI == EPI_BIAS_RESID_STATS)
+          x16 = static_cast<uint16_t*>(p.x16_out) + static_cast<size_t>(row) * p.N + n0 + cbase;
+        float pivot = 0.f, sd = 0.f, sq = 0.f;   // sum (v - pivot), sum (v - pivot)^2 over the thread's 96 columns
+#pragma unroll 1
+        for (int c = 0; c < NB; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* rowp = Rw + c * kResidBoxBytes + lane * 128;
+          const float4* b4 = reinterpret_cast<const float4*>(bs + cbase + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float4* s0 = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
+            float4* s1 = reinterpret_cast<float4*>(rowp + (((j + 1) ^ (lane & 7)) << 4));
+            float4 v0 = *s0, v1 = *s1;
+            const float4 ba = b4[j], bb = b4[j + 1];
+            v0.x += __uint_as_float(r[4 * j + 0]) + ba.x; v0.y += __uint_as_float(r[4 * j + 1]) + ba.y;
+            v0.z += __uint_as_float(r[4 * j + 2]) + ba.z; v0.w += __uint_as_float(r[4 * j + 3]) + ba.w;
+            v1.x += __uint_as_float(r[4 * j + 4]) + bb.x; v1.y += __uint_as_float(r[4 * j + 5]) + bb.y;
+            v1.z += __uint_as_float(r[4 * j + 6]) + bb.z; v1.w += __uint_as_float(r[4 * j + 7]) + bb.w;
+            *s0 = v0;
+            *s1 = v1;
+            if constexpr (EPI == EPI_BIAS_RESID_STATS) {
+              if (c == 0 && j == 0) pivot = v0.x;
+              const float d0 = v0.x - pivot, d1 = v0.y - pivot, d2 = v0.z - pivot, d3 = v0.w - pivot;
+              const float d4 = v1.x - pivot, d5 = v1.y - pivot, d6 = v1.z - pivot, d7 = v1.w - pivot;
+              sd += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+              sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+              sq = fmaf(d4, d4, sq); sq = fmaf(d5, d5, sq); sq = fmaf(d6, d6, sq); sq = fmaf(d7, d7, sq);
+              if (row < p.M)
+                *reinterpret_cast<uint4*>(x16 + c * 32 + 4 * j) =
+                    make_uint4(pack16x2(v0.x, v0.y, p.out_fp16), pack16x2(v0.z, v0.w, p.out_fp16),
+                               pack16x2(v1.x, v1.y, p.out_fp16), pack16x2(v1.z, v1.w, p.out_fp16));
+            }
+          }
+        }
+        // the accumulator has been read: hand the TMEM buffer back before the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
+        fence_proxy_async_smem();  // this thread's generic-proxy writes -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < NB; ++c) tma_store_2d(&tma_o, Rw + c * kResidBoxBytes, n0 + cbase + c * 32, row0);
+          bulk_commit_group();
+          bulk_wait_group_read0();  // the boxes have left shared memory: refill them with the next tile's residual
+          if (t + num_clusters < num_tiles) request_resid(t + num_clusters);
+        }
+        if constexpr (EPI == EPI_BIAS_RESID_STATS) {
+          if (row < p.M) {
+            const float mean_d = sd * (1.0f / HALF_N);
+            p.stats_out[static_cast<size_t>(row) * kLnStatSlots + 2 * n_blk + half] =
+                make_float2(pivot + mean_d, fmaxf(sq - sd * mean_d, 0.f));
+          }
+        }
+        __syncwarp();
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      if (lane == 0) bulk_wait_group0();  // all stores complete before the CTA may exit
+    } else
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
       const int row0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
@@ -397,6 +524,39 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         }
       }
       if (et < BLOCK_N) bs[et] = (EPI != EPI_F32 || p.bias != nullptr) ? __ldg(p.bias + n0 + et) : 0.0f;
+      float* cs = bias_s + (2 + as) * BLOCK_N;
+      float ln_a = 1.f, ln_c = 0.f;
+      if constexpr (is_ln<EPI>()) {
+        if (et < BLOCK_N) cs[et] = __ldg(p.ln_colsum + n0 + et);
+        // this thread's row: merge the partials (mean, M2) left by the producer of the rows -> rstd, -rstd * mean
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const float4* st = reinterpret_cast<const float4*>(p.ln_stats + static_cast<size_t>(row) * kLnStatSlots);
+          float mean, m2;
+          if (p.ln_parts == 1) {
+            const float2 v = *reinterpret_cast<const float2*>(st);
+            mean = v.x; m2 = v.y;
+          } else {
+            float4 v[kLnStatSlots / 2];
+#pragma unroll
+            for (int j = 0; j < kLnStatSlots / 2; ++j) v[j] = st[j];  // two partials each; independent loads
+            float ms = 0.f;
+            m2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kLnStatSlots / 2; ++j) { ms += v[j].x + v[j].z; m2 += v[j].y + v[j].w; }
+            mean = ms * (1.0f / kLnStatSlots);
+            float dv = 0.f;
+#pragma unroll
+            for (int j = 0; j < kLnStatSlots / 2; ++j) {
+              const float a = v[j].x - mean, b = v[j].z - mean;
+              dv += a * a + b * b;
+            }
+            m2 += static_cast<float>(kLnPartCols) * dv;
+          }
+          ln_a = rsqrtf(m2 * (1.0f / 768.0f) + 1e-5f);
+          ln_c = -ln_a * mean;
+        }
+      }
       named_bar_sync(1, kEpiWarps * 32);
       const int cbase = half * HALF_N;
       float4 xa[8], xb[8];
@@ -417,7 +577,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           uint32_t r[32];
           if (!(p.dbg & 4)) tmem_ld_32x32b_x32(t_addr + c * 32, r);
           tmem_ld_wait();
-          if (!(p.dbg & 2)) epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r);
+          if (!(p.dbg & 2))
+            epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cs + cbase + c * 32, ln_a, ln_c);
         }
       } else {
         constexpr int NC = HALF_N / 32;
@@ -490,12 +651,25 @@ bool make_tmap2(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 [rows, cols] pitch ld: 32 x 32 boxes, 128B-swizzled (the residual / output tile of the TR epilogue)
+bool make_tmap2_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn2();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // clusters of 2*MC CTAs (1 CTA per SM) that can be co-resident: 74 pairs, but only 33 clusters of 4 on B200
 template <int BLOCK_N, int EPI, int MC>
 int max_clusters2(int num_sms) {
   static int cached = 0;
   if (cached) return cached;
-  using Cfg = Cfg2<BLOCK_N>;
+  using Cfg = Cfg2<BLOCK_N, tma_resid<BLOCK_N, EPI>()>;
   auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg = {};
@@ -513,7 +687,13 @@ int max_clusters2(int num_sms) {
 template <int BLOCK_N, int EPI, int MC>
 cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_sms) {
-  using Cfg = Cfg2<BLOCK_N>;
+  using Cfg = Cfg2<BLOCK_N, tma_resid<BLOCK_N, EPI>()>;
+  CUtensorMap tr = ta, to = ta;  // placeholders for the kernels that do not use them
+  if constexpr (tma_resid<BLOCK_N, EPI>()) {
+    if ((reinterpret_cast<uintptr_t>(p.resid) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldr % 4) || (p.ldo % 4))
+      return cudaErrorMisalignedAddress;
+    if (!make_tmap2_f32(&tr, p.resid, p.M, p.N, p.ldr) || !make_tmap2_f32(&to, p.out, p.M, p.N, p.ldo)) return cudaErrorInvalidValue;
+  }
   auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
   const int max_cl = max_clusters2<BLOCK_N, EPI, MC>(num_sms);  // also sets the dynamic smem attribute (once)
   if (max_cl <= 0) return cudaErrorInvalidConfiguration;
@@ -525,7 +705,7 @@ cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtens
     LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
                       2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
                           4.0 * p.M * static_cast<double>(p.N));
-    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, p);
+    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, tr, to, p);
   }
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -541,6 +721,15 @@ cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, con
     case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_STATS:
+      if constexpr (MC == 1 && BLOCK_N == 192) return launch_one2<192, EPI_BIAS_RESID_STATS, 1>(stream, ta, tb, p, num_sms);
+      else return cudaErrorInvalidValue;
+    case EPI_LN_BIAS_BF16:
+      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_LN_BIAS_BF16, 1>(stream, ta, tb, p, num_sms);
+      else return cudaErrorInvalidValue;
+    case EPI_LN_BIAS_GELU_BF16:
+      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_LN_BIAS_GELU_BF16, 1>(stream, ta, tb, p, num_sms);
+      else return cudaErrorInvalidValue;
     case EPI_BIAS_HEAD_PARTIAL:
       if constexpr (BLOCK_N == 256 && MC == 1) return launch_one2<256, EPI_BIAS_HEAD_PARTIAL, 1>(stream, ta, tb, p, num_sms);
       else return cudaErrorInvalidValue;
@@ -569,6 +758,8 @@ int pick_block_n2(int M, int N, int num_sms) {
 
 }  // namespace
 
+int gemm2_pick_block_n(int M, int N) { return pick_block_n2(M, N, device_num_sms()); }
+
 const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                           int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
   static const int dbg_env = getenv("CLIPEBC_GEMM_DBG") ? atoi(getenv("CLIPEBC_GEMM_DBG")) : 0;  // experiment knob
@@ -581,11 +772,22 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if ((lda * 2) % 16 != 0 || (ldw * 2) % 16 != 0) return "gemm: row pitch must be a multiple of 16 bytes";
   if (p.N % 64 != 0) return "gemm: N must be a multiple of 64";
   const int num_sms = device_num_sms();
-  if (block_n == 0) block_n = pick_block_n2(p.M, p.N, num_sms);
+  if (block_n == 0) block_n = (epi == EPI_BIAS_RESID_STATS) ? 192 : pick_block_n2(p.M, p.N, num_sms);
   if (block_n != 128 && block_n != 192 && block_n != 256) return "gemm: block_n must be 128, 192 or 256";
   if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
-  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT) && p.resid == nullptr) return "gemm: epilogue needs a residual";
+  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT || epi == EPI_BIAS_RESID_STATS) && p.resid == nullptr)
+    return "gemm: epilogue needs a residual";
+  if (epi == EPI_BIAS_RESID_STATS) {
+    if (p.x16_out == nullptr || p.stats_out == nullptr) return "gemm: statistics epilogue needs x16_out and stats_out";
+    if (p.N != 2 * kLnPartCols * (kLnStatSlots / 2)) return "gemm: statistics epilogue: N must be 768";
+    if (block_n != 192) return "gemm: statistics epilogue exists for 192-wide tiles only";
+  }
+  if (epi == EPI_LN_BIAS_BF16 || epi == EPI_LN_BIAS_GELU_BF16) {
+    if (p.ln_stats == nullptr || p.ln_colsum == nullptr) return "gemm: LayerNorm epilogue needs ln_stats and ln_colsum";
+    if (p.K != 768) return "gemm: LayerNorm epilogue: K must be 768";
+    if (p.ln_parts != 1 && p.ln_parts != kLnStatSlots) return "gemm: LayerNorm epilogue: ln_parts must be 1 or 8";
+  }
   if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 2 || p.mask_wp < 2)) return "gemm: mask grid missing";
   if (epi == EPI_BIAS_HEAD_PARTIAL) {
     if (p.head_tmat == nullptr || p.head_bins < 1 || p.head_bins > 32) return "gemm: head epilogue needs the text matrix and 1..32 bins";

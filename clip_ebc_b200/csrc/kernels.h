@@ -17,10 +17,22 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID_F32 = 4,       // out f32 = acc + bias + resid   (out may alias resid)
   EPI_BIAS_RELU_MASK_BF16 = 5,  // out bf16 = border ? 0 : relu(acc + bias)          (decoder conv1 on the padded grid)
   EPI_BIAS_RESID_RELU_SPLIT = 6,// t = relu(acc + bias + resid); out[:, n] = hi(t), out[:, N + n] = lo(t)  (bf16 pair)
-  EPI_BIAS_HEAD_PARTIAL = 7     // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
+  EPI_BIAS_HEAD_PARTIAL = 7,    // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
                                 // tiles) out[row][2 * n_blk + half][0] = sum f^2, [1 + b] = sum f * head_tmat[b][n]
                                 // -- the projection fused with the first half of the EBC head (ebc_head_finish)
+  // LayerNorm folded into the GEMMs either side of it (CTA-pair kernel only; DESIGN.md section 2, rewrite 7):
+  EPI_BIAS_RESID_STATS = 8,     // EPI_BIAS_RESID_F32 + x16_out[row, n] = 16-bit copy of the new residual row and, per row and
+                                // half tile of 96 columns, stats_out[row][n / 96] = (mean, sum of squared deviations) of those
+                                // columns. 192-wide tiles only (N = 768 -> 8 partials per row), so the partition -- and with it
+                                // every bit of a row's statistics -- does not depend on the batch the row is part of
+  EPI_LN_BIAS_BF16 = 9,         // out bf16 = rstd[row] * (acc - mean[row] * ln_colsum[n]) + bias[n]: A holds the RAW rows,
+                                // W = W * diag(gamma), bias = b + W beta, ln_colsum[n] = sum_k W'[n, k]; (mean, rstd) merged
+                                // per row in the epilogue from the ln_parts (1 or 8) partials of ln_stats (K = 768)
+  EPI_LN_BIAS_GELU_BF16 = 10    // quickgelu of the same
 };
+
+constexpr int kLnStatSlots = 8;   // float2 slots per row of a LayerNorm statistics buffer
+constexpr int kLnPartCols = 96;   // columns per partial written by EPI_BIAS_RESID_STATS (half of a 192-wide tile)
 
 constexpr int kMaxGemmSegs = 9;
 
@@ -42,6 +54,11 @@ struct GemmParams {
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
   const float* head_tmat;             // EPI_BIAS_HEAD_PARTIAL: f32 [head_bins, N] (logit_scale * normalised text features)
   int head_bins;                      // 1..32
+  void* x16_out;                      // EPI_BIAS_RESID_STATS: 16-bit [M, N] copy of the output rows (format out_fp16)
+  float2* stats_out;                  // EPI_BIAS_RESID_STATS: [M, kLnStatSlots] (mean, M2) per 96-column half tile
+  const float2* ln_stats;             // EPI_LN_*: [M, kLnStatSlots]; ln_parts = 8: eight partials of 96 columns,
+  int ln_parts;                       //           ln_parts = 1: slot 0 holds (mean, M2) of the whole row
+  const float* ln_colsum;             // EPI_LN_*: [N]
   int dbg;                            // experiment knob (profiles/): 0 in production
   long long* trace;                   // experiment: clock64 time line of CTA 0 (profiles/gemm_trace.py), nullptr in production
 };
@@ -59,6 +76,7 @@ const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, i
 // CTA-pair (cta_group::2) implementation of the same contract (gemm2_tcgen05.cu).
 const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                           int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
+int gemm2_pick_block_n(int M, int N);  // the tile width gemm2_bf16_tn chooses for block_n = 0
 int device_num_sms();
 // Every kernel launch of this library goes through a LaunchScope: it counts the launch (clipebc_launch_count) and, when
 // profiling is enabled (clipebc_profile_enable), brackets it with CUDA events on the launching stream and books the
@@ -119,9 +137,14 @@ const char* patchify16_windows(cudaStream_t stream, const float* image, int H, i
 //   remaining rows   : LN_pre(patch_embed[src_row(win, p)] + pos[1 + p])              (model.py:147-157)
 // src_row = win_base[win] + (p / wp) * pitch + p % wp  (gather from a shared per-image patch grid or per-window rows);
 // pitch = win_pitch_dev[win] when given (windows of several images in one pass), else src_pitch
+// X16 / stats (nullable together): 16-bit copy of the rows and their (mean, M2) in slot 0 of the statistics row -- what
+// the first LN-folded GEMM (EPI_LN_*, ln_parts = 1) consumes.
 const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
                             const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
-                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X);
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X, void* X16 = nullptr,
+                            float2* stats = nullptr, int fp16 = 0);
+// rows f32 [n, 768] -> 16-bit copy + (mean, M2) in slot 0 (the same outputs for arbitrary rows)
+const char* rowstats768(cudaStream_t stream, const float* in, int64_t n_rows, void* X16, float2* stats, int fp16);
 
 // ------------------------------------------------------------------ attention ----------------------------------
 // qkv bf16 [n_win * t_live, 3*768] (q | k | v, head h at columns 64h..64h+63 of each third); const_kv bf16
@@ -193,6 +216,11 @@ const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* ga
                             const float* var, float eps, int O, int I, void* Wp, float* bias, int fp16);
 // W f32 [O, I] -> bf16 [O, 3*I] = [hi | hi | lo]
 const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, void* out, int fp16);
+// LayerNorm folded into the Linear that follows it: W f32 [O, 768], b f32 [O], gamma / beta f32 [768] ->
+// Wf 16-bit [O, 768] = W * diag(gamma); colsum f32 [O] = sum_k Wf[o, k] (of the ROUNDED weights, what the MMA sees);
+// bias_f f32 [O] = b + W beta
+const char* fold_ln_linear(cudaStream_t stream, const float* W, const float* b, const float* gamma, const float* beta, int O,
+                           void* Wf, float* colsum, float* bias_f, int fp16);
 // text f32 [n, d] -> tmat = exp(logit_scale) * text / max(||text||, 1e-12)
 const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat);
 

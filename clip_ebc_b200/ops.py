@@ -20,6 +20,11 @@ def set_gemm_impl(impl: int) -> None:
     _lib.check(_lib.load().clipebc_set_gemm_impl(int(impl)), "set_gemm_impl")
 
 
+def set_ln_fold(on: bool) -> None:
+    """LayerNorm folded into the GEMMs either side of it (default off; see clipebc_set_ln_fold)."""
+    _lib.check(_lib.load().clipebc_set_ln_fold(int(bool(on))), "set_ln_fold")
+
+
 def set_attention_impl(impl: int) -> None:
     """1 = mma.sync attention, 2 = tcgen05 / TMEM attention (default)."""
     _lib.check(_lib.load().clipebc_set_attention_impl(int(impl)), "set_attention_impl")
@@ -89,6 +94,62 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
         epi, _ptr(a), a.shape[0], a.shape[1], a.stride(0), _ptr(w), w.stride(0), M, N, K, n_seg, rs, cs, _ptr(out),
         out.stride(0), _ptr(bias), _ptr(resid), resid.stride(0) if resid is not None else 0, mask_hw[0], mask_hw[1],
         int(mask_lead), block_n, int(ab_fp16), int(out_fp16), _stream()), "gemm")
+    return out
+
+
+LN_STAT_SLOTS = 8  # float2 slots per row of a LayerNorm statistics buffer (kernels.h: kLnStatSlots)
+
+
+def rowstats(x: torch.Tensor, fp16: bool = False):
+    """rows f32 [n, 768] -> (16-bit copy, stats f32 [n, 8, 2]) with slot 0 = (mean, sum of squared deviations) of the row."""
+    assert x.dtype == torch.float32 and x.shape[-1] == 768
+    n = x.numel() // 768
+    x16 = torch.empty((n, 768), dtype=_dt16(fp16), device=x.device)
+    stats = torch.zeros((n, LN_STAT_SLOTS, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().clipebc_rowstats768(_ptr(x), n, _ptr(x16), _ptr(stats), int(fp16), _stream()), "rowstats")
+    return x16, stats
+
+
+def fold_ln_linear(W: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, fp16: bool = False):
+    """LayerNorm(768) folded into the Linear behind it -> (W diag(gamma) in 16 bits, its column sums, b + W beta)."""
+    assert W.dtype == torch.float32 and W.shape[1] == 768
+    O = W.shape[0]
+    wf = torch.empty((O, 768), dtype=_dt16(fp16), device=W.device)
+    colsum = torch.empty((O,), dtype=torch.float32, device=W.device)
+    bias_f = torch.empty((O,), dtype=torch.float32, device=W.device)
+    _lib.check(_lib.load().clipebc_fold_ln_linear(_ptr(W), _ptr(b), _ptr(gamma), _ptr(beta), O, _ptr(wf), _ptr(colsum),
+                                                  _ptr(bias_f), int(fp16), _stream()), "fold_ln_linear")
+    return wf, colsum, bias_f
+
+
+def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias: torch.Tensor, block_n: int = 0,
+                     out_fp16: Optional[bool] = None):
+    """x f32 [M, 768] += a @ w^T + bias in place -> (x16, stats [M, 8, 2]): the residual GEMM of a block that also leaves
+    the 16-bit rows and the (mean, M2) partials of every 96 columns for the next LN-folded GEMM."""
+    assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16) and x.dtype == torch.float32
+    ab_fp16 = a.dtype == torch.float16
+    out_fp16 = ab_fp16 if out_fp16 is None else out_fp16
+    M, N = x.shape
+    x16 = torch.empty((M, N), dtype=_dt16(out_fp16), device=x.device)
+    stats = torch.zeros((M, LN_STAT_SLOTS, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().clipebc_gemm_resid_stats(_ptr(a), a.shape[0], a.stride(0), _ptr(w), w.stride(0), M, N, w.shape[1],
+                                                    _ptr(x), _ptr(bias), _ptr(x16), _ptr(stats), block_n,
+                                                    int(ab_fp16), int(out_fp16), _stream()), "gemm_resid_stats")
+    return x16, stats
+
+
+def gemm_ln(a16: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, stats: torch.Tensor, colsum: torch.Tensor,
+            ln_parts: int, gelu: bool = False, block_n: int = 0, out_fp16: Optional[bool] = None) -> torch.Tensor:
+    """act(LayerNorm(rows) @ W^T + b) from the RAW 16-bit rows, the folded weights and the row statistics."""
+    assert a16.dtype == wf.dtype and a16.dtype in (torch.bfloat16, torch.float16)
+    ab_fp16 = a16.dtype == torch.float16
+    out_fp16 = ab_fp16 if out_fp16 is None else out_fp16
+    M, K = a16.shape
+    N = wf.shape[0]
+    out = torch.empty((M, N), dtype=_dt16(out_fp16), device=a16.device)
+    _lib.check(_lib.load().clipebc_gemm_ln(int(gelu), _ptr(a16), M, a16.stride(0), _ptr(wf), wf.stride(0), M, N, K, _ptr(out),
+                                           out.stride(0), _ptr(bias_f), _ptr(stats), int(ln_parts), _ptr(colsum), block_n,
+                                           int(ab_fp16), int(out_fp16), _stream()), "gemm_ln")
     return out
 
 

@@ -80,6 +80,114 @@ def test_gemm_bias_resid_inplace(ops, block_n):
     assert _rel(out, ref) < 2e-5
 
 
+# ------------------------------------------------------------------- LayerNorm folded into the GEMMs either side of it
+def _ln_ref(x, gamma, beta):
+    """nn.LayerNorm(768, eps=1e-5) in float64 (reference: _clip/blocks.py:8-14)."""
+    xd = x.double()
+    mu = xd.mean(-1, keepdim=True)
+    var = ((xd - mu) ** 2).mean(-1, keepdim=True)
+    return ((xd - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()).float()
+
+
+def _merge_stats(stats, parts):
+    """Chan merge of the per-row partials (equal counts), in float64 -> (mean, variance)."""
+    st = stats[:, :parts].double()
+    n = 768 // parts
+    mean = st[..., 0].mean(1)
+    m2 = st[..., 1].sum(1) + n * ((st[..., 0] - mean[:, None]) ** 2).sum(1)
+    return mean, m2 / 768
+
+
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_rowstats_and_fold_ln_linear(dt):
+    from clip_ebc_b200 import ops as _ops
+
+    fp16 = dt == torch.float16
+    x = _rand((333, 768), 60, 2.0) + 3.0 * _rand((333, 1), 61)   # rows with a non-zero mean
+    x16, stats = _ops.rowstats(x, fp16=fp16)
+    assert torch.equal(x16, x.to(dt))
+    mean, var = _merge_stats(stats, 1)
+    assert (mean - x.double().mean(1)).abs().max().item() < 1e-5
+    assert ((var - x.double().var(1, unbiased=False)).abs() / x.double().var(1, unbiased=False)).max().item() < 1e-5
+    W, b = _rand((2304, 768), 62, 0.03), _rand((2304,), 63)
+    gamma, beta = 1.0 + 0.3 * _rand((768,), 64), 0.2 * _rand((768,), 65)
+    wf, colsum, bias_f = _ops.fold_ln_linear(W, b, gamma, beta, fp16=fp16)
+    assert torch.equal(wf, (W * gamma).to(dt))
+    assert (colsum - wf.double().sum(1)).abs().max().item() < 1e-4   # sums of the ROUNDED weights
+    assert (bias_f - (b.double() + W.double() @ beta.double())).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("block_n", [0, 192])
+@pytest.mark.parametrize("M,K", [(2000, 768), (777, 3072), (12608, 768), (31, 768)])
+def test_gemm_resid_stats(block_n, M, K):
+    """out_proj / c_proj with the statistics epilogue (residual tiles through TMA): same residual update as epilogue 4 plus
+    the 16-bit rows and the (mean, M2) partials of every 96 columns."""
+    from clip_ebc_b200 import ops as _ops
+
+    dt = torch.float16
+    a, w, b = _rand((M, K), 66).to(dt), _rand((768, K), 67, 0.02).to(dt), _rand((768,), 68)
+    x = _rand((M, 768), 69) + 2.0
+    ref = x + a.float() @ w.float().t() + b
+    x16, stats = _ops.gemm_resid_stats(a, w, x, b, block_n=block_n)
+    assert _rel(x, ref) < 2e-5                                   # in place, as EPI_BIAS_RESID_F32
+    assert torch.equal(x16, x.to(dt))                            # the 16-bit copy is the rounding of what was written
+    xc = x.double().view(M, 8, 96)
+    assert (stats[..., 0].double() - xc.mean(2)).abs().max().item() < 2e-5              # partial means
+    assert _rel(stats[..., 1], ((xc - xc.mean(2, keepdim=True)) ** 2).sum(2)) < 2e-5      # partial M2
+    mean, var = _merge_stats(stats, 8)
+    xd = x.double()
+    assert (mean - xd.mean(1)).abs().max().item() < 2e-5
+    assert ((var - xd.var(1, unbiased=False)).abs() / xd.var(1, unbiased=False)).max().item() < 2e-5
+
+
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+@pytest.mark.parametrize("gelu", [False, True], ids=["qkv", "c_fc"])
+@pytest.mark.parametrize("M,N", [(1234, 2304), (12608, 3072), (50, 768)])
+def test_gemm_ln_matches_layernorm_linear(dt, gelu, M, N):
+    """LN folded into the GEMM (raw 16-bit rows, W diag(gamma), epilogue rstd * (acc - mean * colsum) + b') against
+    LayerNorm -> Linear (-> QuickGELU) in fp32/fp64 on the same rows. The only differences are one 16-bit rounding of the
+    raw rows (instead of the normalised ones) and of the folded weights: a few output roundings."""
+    from clip_ebc_b200 import ops as _ops
+
+    fp16 = dt == torch.float16
+    x = _rand((M, 768), 70, 1.5) + 2.0 * _rand((M, 1), 71) + 0.5 * _rand((1, 768), 72)
+    W, b = _rand((N, 768), 73, 0.03), _rand((N,), 74)
+    gamma, beta = 1.0 + 0.3 * _rand((768,), 75), 0.2 * _rand((768,), 76)
+    ref = _ln_ref(x, gamma, beta) @ W.t() + b
+    if gelu:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    x16, stats = _ops.rowstats(x, fp16=fp16)
+    wf, colsum, bias_f = _ops.fold_ln_linear(W, b, gamma, beta, fp16=fp16)
+    out = _ops.gemm_ln(x16, wf, bias_f, stats, colsum, 1, gelu=gelu)
+    # what the separate-kernel path computes: 16-bit LN output x 16-bit weights
+    xn16 = _ln_ref(x, gamma, beta).to(dt).float()
+    unfused = xn16 @ W.to(dt).float().t() + b
+    if gelu:
+        unfused = unfused * torch.sigmoid(1.702 * unfused)
+    err, err_unfused = _rel(out, ref), _rel(unfused.to(dt), ref)
+    assert err < 4 * ROUND16[dt], (err, err_unfused)
+    assert err < 3 * err_unfused + 1e-4, (err, err_unfused)      # no worse than the path it replaces (same error class)
+
+
+def test_gemm_resid_stats_feeds_gemm_ln():
+    """The pair as the hot path chains it: residual GEMM -> (x16, chunk statistics) -> LN-folded GEMM."""
+    from clip_ebc_b200 import ops as _ops
+
+    dt = torch.float16
+    M = 3000
+    a, w, b = _rand((M, 768), 77).to(dt), _rand((768, 768), 78, 0.03).to(dt), _rand((768,), 79)
+    x = _rand((M, 768), 80)
+    W2, b2 = _rand((3072, 768), 81, 0.03), _rand((3072,), 82)
+    gamma, beta = 1.0 + 0.3 * _rand((768,), 83), 0.2 * _rand((768,), 84)
+    wf, colsum, bias_f = _ops.fold_ln_linear(W2, b2, gamma, beta, fp16=True)
+    xc = x.clone()
+    x16, stats = _ops.gemm_resid_stats(a, w, xc, b)
+    out = _ops.gemm_ln(x16, wf, bias_f, stats, colsum, 8, gelu=True)
+    r = _ln_ref(xc, gamma, beta) @ W2.t() + b2
+    r = r * torch.sigmoid(1.702 * r)
+    assert _rel(out, r) < 4 * ROUND16[dt]
+
+
 @pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
 def test_gemm_conv_segments_match_conv2d(ops, dt):
     """3x3 conv over the zero-bordered NHWC grid as 9 row-shifted K-segments == F.conv2d(padding=1)."""

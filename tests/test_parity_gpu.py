@@ -26,8 +26,18 @@ def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0, operand_
     return model.to("cuda").eval()
 
 
+@pytest.fixture(params=[False, True], ids=["ln_kernels", "ln_folded"])
+def ln_fold(request):
+    """Both forms of the LayerNorms inside the blocks: separate kernels (default) and folded into the GEMMs."""
+    from clip_ebc_b200 import ops
+
+    ops.set_ln_fold(request.param)
+    yield request.param
+    ops.set_ln_fold(False)
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_cuda_path_matches_reference_fixture(case):
+def test_cuda_path_matches_reference_fixture(case, ln_fold):
     from clip_ebc_b200 import sliding_window_predict
 
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
