@@ -67,6 +67,7 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -82,6 +83,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first_sample(self, timeout_s: float = 10.0):
+        """nvidia-smi takes a few hundred ms to initialise NVML, and while it does kernel launches of this process stall
+        (measured: a timed region that overlaps the start-up runs up to 2x slower). Start it before the warm-up and
+        enter the timed region only once it is polling; samples taken before mark() are dropped."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
@@ -91,7 +103,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -228,25 +240,47 @@ def main():
                     "(234 windows/image), images sharded round-robin over ranks, one count all-gather at the end")
         l2 = "each image touches > 1 GB of activations (>> 126 MB L2)"
 
+    sampler.start()
     for i in range(W):
-        step(i)
+        last = step(i)
+    if args.workload == "sliding":
+        # the collective is part of the warm-up too: its first call creates the NCCL communicator and loads torch's
+        # fill / index kernels (lazy module loading) -- 70-200 ms that belong to no step
+        gather_counts(last[1].reshape(1), world, rank, world)
     barrier()
+    sampler.wait_first_sample()
 
     # ---- timed region (device-resident inputs): CUDA events on the launching stream, max over ranks ---------------
-    sampler.start()
+    sampler.mark()
     l0 = lib.clipebc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     last = None
+    # bounded run-ahead: at most 2 steps in flight, so the host never sits on a full launch queue (with ~260 launches
+    # per image the queue fills after 4 images; a blocked launch thread next to the nvidia-smi sampler made the timed
+    # region vary by 2x between runs); the GPU still always has the next step queued
+    inflight, step_events = [], []
     for i in range(K):
+        if len(inflight) == 2:
+            inflight.pop(0).synchronize()
         last = step(i)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        inflight.append(ev)
+        step_events.append(ev)
     if args.workload == "sliding":
         # the path's only collective: all-gather of the per-image counts (here: of the last image of every rank)
         counts = gather_counts(last[1].reshape(1), world, rank, world)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("BENCH_DEBUG"):
+        prev, per = e0, []
+        for ev in step_events:
+            per.append(prev.elapsed_time(ev))
+            prev = ev
+        print("[bench] per-step ms: " + " ".join(f"{v:.1f}" for v in per), file=sys.stderr)
     launches = lib.clipebc_launch_count() - l0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -93,13 +93,20 @@ void set_launch_tag(const char* tag);  // nullptr clears
 
 // Launch with programmatic stream serialization (see common.cuh: pdl_wait) and an optional cluster width.
 bool pdl_enabled();  // false when CLIPEBC_NO_PDL is set (A/B experiments)
+// Persisting-L2 access-policy window attached to every launch of the calling thread while set (api.cu: L2Window), or nullptr
+const cudaAccessPolicyWindow* current_l2_window();
 template <class... KArgs, class... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
                        Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[3];
   unsigned n = 0;
+  if (const cudaAccessPolicyWindow* w = current_l2_window()) {
+    at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[n].val.accessPolicyWindow = *w;
+    ++n;
+  }
   if (cluster_x > 1) {
     at[n].id = cudaLaunchAttributeClusterDimension;
     at[n].val.clusterDim.x = static_cast<unsigned>(cluster_x); at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
