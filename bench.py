@@ -205,6 +205,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set in this image): keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     model, parts = build_model(dev)
@@ -406,7 +409,9 @@ def main():
         line = {
             "metric": "windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 operands on tcgen05 kind::f16 (bf16 selectable, same rate); fp32 accumulate / residual / LayerNorm / softmax / head",
+            "dtype": "fp16",
+            "dtype_note": "16-bit tensor-core operands on tcgen05 kind::f16: fp16 by default (11-bit mantissa; bf16 selectable, same "
+                          "rate); fp32 accumulate / residual stream / LayerNorm statistics / softmax / head",
             "data": "synthetic",
             "config": {"workload": workload, "l2": l2, "global_batch_windows": world * units_per_step,
                        "parallelism": f"dp{world} (independent windows/images per rank)",
