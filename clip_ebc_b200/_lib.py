@@ -28,6 +28,7 @@ class ClipEbcConfig(C.Structure):
         ("num_bins", C.c_int),
         ("window_chunk", C.c_int),
         ("operand_fp16", C.c_int),
+        ("patch", C.c_int),
     ]
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "clipebc_layernorm768": (_i, [_fp, _fp, _fp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_patchify": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
     "clipebc_ebc_head": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_fold_average": (_i, [_fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),

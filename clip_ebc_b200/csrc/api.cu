@@ -115,7 +115,7 @@ int fail_cuda(cudaError_t e, const char* what) {
     if (_m != nullptr) return fail(CLIPEBC_ECUDA, std::string(_m));        \
   } while (0)
 
-constexpr int kWidth = 768, kLayers = 12, kHeads = 12, kPatch = 16, kEmbed = 512, kHidden = 3072;
+constexpr int kWidth = 768, kLayers = 12, kHeads = 12, kEmbed = 512, kHidden = 3072;
 
 struct DevBuf {
   void* p = nullptr;
@@ -216,7 +216,7 @@ void cubic_coeffs(float t, float w[4]) {
 }
 
 int get_pos(clipebc_model* m, int hp, int wp, cudaStream_t stream, const float** out) {
-  const int g0 = m->cfg.input_size / kPatch;
+  const int g0 = m->cfg.input_size / m->cfg.patch;
   if (hp == g0 && wp == g0) { *out = raw_ptr(m, "image_encoder.positional_embedding"); return CLIPEBC_OK; }
   const int key = hp * 4096 + wp;
   auto it = m->pos_cache.find(key);
@@ -264,11 +264,12 @@ GemmParams plain(int fp16, int out16_fp16, int M, int N, int K, void* out, int l
   return p;
 }
 
-// patch embedding as a split-precision GEMM: rows [hi | lo] (2*768) x W3 = [Whi | Whi | Wlo] (3*768), segments hi, lo, hi
-GemmParams patch_embed_params(int fp16, int rows, void* out) {
-  GemmParams p = gemm_params_plain(rows, 768, 3 * 768);
-  p.n_seg = 3; p.seg_kblocks = 768 / 64;
-  p.seg_col_start[0] = 0; p.seg_col_start[1] = 768; p.seg_col_start[2] = 0;
+// patch embedding as a split-precision GEMM: rows [hi | lo] (2*KP) x W3 = [Whi | Whi | Wlo] (3*KP), segments hi, lo, hi;
+// KP = 3 * patch^2 (768 for ViT-B/16, 3072 for ViT-B/32)
+GemmParams patch_embed_params(int fp16, int rows, void* out, int kp) {
+  GemmParams p = gemm_params_plain(rows, 768, 3 * kp);
+  p.n_seg = 3; p.seg_kblocks = kp / 64;
+  p.seg_col_start[0] = 0; p.seg_col_start[1] = kp; p.seg_col_start[2] = 0;
   p.out = out; p.ldo = 768; p.bias = nullptr; p.ab_fp16 = fp16; p.out_fp16 = fp16;
   return p;
 }
@@ -326,7 +327,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   const int npatch = hp * wp;
   const int T = 1 + n_prompt_live + npatch;
   const int M = nw * T;
-  const int gh = hp * kPatch / c.reduction, gw = wp * kPatch / c.reduction;
+  const int gh = hp * c.patch / c.reduction, gw = wp * c.patch / c.reduction;
   const int Hp = gh + 1, Wp = gw + 1;  // shared-border decoder grid (kernels.h: resample_to_padded): 841 rows per r8
   const int Mp = nw * Hp * Wp;         // window instead of 900 on a grid bordered on all four sides
 
@@ -478,8 +479,9 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 int default_chunk(const clipebc_model* m) { return m->cfg.window_chunk > 0 ? m->cfg.window_chunk : 96; }
 
 int check_window_geometry(clipebc_model* m, int h, int w) {
+  const int kPatch = m->cfg.patch;
   if (h <= 0 || w <= 0 || h % kPatch != 0 || w % kPatch != 0)
-    return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of 16");
+    return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of the patch size");
   if ((h % m->cfg.reduction) != 0 || (w % m->cfg.reduction) != 0)
     return fail(CLIPEBC_EINVAL, "window height/width must be multiples of the reduction");
   const int T = 1 + m->cfg.num_vpt + (h / kPatch) * (w / kPatch);
@@ -553,12 +555,15 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (!cfg || !out) return fail(CLIPEBC_EINVAL, "null argument");
   if (cfg->reduction != 8 && cfg->reduction != 16 && cfg->reduction != 32)
     return fail(CLIPEBC_EINVAL, "reduction must be 8, 16 or 32");
-  if (cfg->input_size <= 0 || cfg->input_size % kPatch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of 16");
+  if (cfg->patch != 0 && cfg->patch != 16 && cfg->patch != 32) return fail(CLIPEBC_EINVAL, "patch must be 16 (ViT-B/16) or 32 (ViT-B/32)");
+  const int kPatch = cfg->patch ? cfg->patch : 16;
+  if (cfg->input_size <= 0 || cfg->input_size % kPatch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of the patch size");
   if (cfg->num_vpt < 0 || cfg->num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
   if (cfg->num_bins < 1 || cfg->num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
   if (cfg->operand_fp16 != 0 && cfg->operand_fp16 != 1) return fail(CLIPEBC_EINVAL, "operand_fp16 must be 0 (bf16) or 1 (fp16)");
   clipebc_model* m = new clipebc_model();
   m->cfg = *cfg;
+  m->cfg.patch = kPatch;
   *out = m;
   return CLIPEBC_OK;
 }
@@ -586,6 +591,7 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const clipebc_config& c = m->cfg;
   const int fp16 = c.operand_fp16 != 0;
+  const int kPatch = c.patch, kp = 3 * kPatch * kPatch;
   const int g0 = c.input_size / kPatch;
   std::string err;
   const int n_vpt_layers = c.deep_vpt ? kLayers : 1;
@@ -619,8 +625,8 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   if (!ok) return fail(CLIPEBC_ESTATE, "pack: " + err);
 
   int rc;
-  CUDA_TRY(m->w_patch.reserve(static_cast<size_t>(kWidth) * 3 * kWidth * 2));
-  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "image_encoder.conv1.weight"), kWidth, kWidth, m->w_patch.p, fp16));
+  CUDA_TRY(m->w_patch.reserve(static_cast<size_t>(kWidth) * 3 * kp * 2));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "image_encoder.conv1.weight"), kWidth, kp, m->w_patch.p, fp16));
   for (int l = 0; l < kLayers; ++l) {
     LayerPack& L = m->layer[l];
     if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * kWidth * kWidth, &L.w_qkv, fp16))) return rc;
@@ -678,6 +684,7 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   int rc;
   if ((rc = check_window_geometry(m, h, w))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
   const int hp = h / kPatch, wp = w / kPatch, npatch = hp * wp;
   const int gh = h / m->cfg.reduction, gw = w / m->cfg.reduction;
   const float* pos;
@@ -685,13 +692,13 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
 
   const int64_t rows = static_cast<int64_t>(B) * npatch;
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kWidth * 2));
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kp * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  K_TRY(patchify16(s, x_dev, B, h, w, 0, 0, hp, wp, m->ws_patch_rows.p, fp16));
+  K_TRY(patchify(s, x_dev, B, h, w, 0, 0, hp, wp, kPatch, m->ws_patch_rows.p, fp16));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kWidth, 2 * kWidth,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
-                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p), 0));
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
+                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p, kp), 0));
   set_launch_tag(nullptr);
   // window b reads patch rows [b * npatch, (b+1) * npatch)
   const std::string key = "fw:" + std::to_string(B) + ":" + std::to_string(npatch);
@@ -745,6 +752,7 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   std::vector<int> ro(nr), co(nc);
   clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, ro.data(), co.data());
   const int n_win = nr * nc;
+  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
   const int gh = wh / r, gw = ww / r;
   const float* pos;
@@ -794,14 +802,14 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   const int* d_cc = d_rc + nr;
 
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kWidth * 2));
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kp * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  if (on_grid) K_TRY(patchify16(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, m->ws_patch_rows.p, fp16));
-  else K_TRY(patchify16_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, m->ws_patch_rows.p, fp16));
+  if (on_grid) K_TRY(patchify(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, kPatch, m->ws_patch_rows.p, fp16));
+  else K_TRY(patchify_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, kPatch, m->ws_patch_rows.p, fp16));
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kWidth, 2 * kWidth,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
-                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p), 0));
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
+                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p, kp), 0));
   set_launch_tag(nullptr);
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
@@ -827,6 +835,7 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   if ((rc = check_window_geometry(m, wh, ww))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const int r = m->cfg.reduction;
+  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
   const int gh = wh / r, gw = ww / r;
   const float* pos;
@@ -889,18 +898,18 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
 
   // patch rows of all images, one patch-embedding GEMM over all of them
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(total_rows) * 2 * kWidth * 2));
+  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(total_rows) * 2 * kp * 2));
   CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(total_rows) * kWidth * 4));
   for (int i = 0; i < n_images; ++i) {
     const Geom& g = gs[i];
-    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * kWidth;
-    if (g.on_grid) K_TRY(patchify16(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, dst, fp16));
-    else K_TRY(patchify16_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, dst, fp16));
+    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * kp;
+    if (g.on_grid) K_TRY(patchify(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, kPatch, dst, fp16));
+    else K_TRY(patchify_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, kPatch, dst, fp16));
   }
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), total_rows, 2 * kWidth, 2 * kWidth,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kWidth,
-                      patch_embed_params(fp16, static_cast<int>(total_rows), m->ws_patch_embed.p), 0));
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), total_rows, 2 * kp, 2 * kp,
+                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
+                      patch_embed_params(fp16, static_cast<int>(total_rows), m->ws_patch_embed.p, kp), 0));
   set_launch_tag(nullptr);
 
   // the windows of all images share the passes of the ViT / decoder / head (chunks may span image boundaries)
@@ -1002,9 +1011,16 @@ int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_
   return CLIPEBC_OK;
 }
 
+int clipebc_patchify(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch, void* out,
+                     int fp16, void* stream) {
+  if (!image || !out) return fail(CLIPEBC_EINVAL, "null argument");
+  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, patch, out, fp16 != 0));
+  return CLIPEBC_OK;
+}
+
 int clipebc_patchify16(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, void* out, int fp16,
                        void* stream) {
-  K_TRY(patchify16(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, out, fp16 != 0));
+  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, 16, out, fp16 != 0));
   return CLIPEBC_OK;
 }
 

@@ -113,33 +113,36 @@ __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------ patchify -----------------------------------
-__device__ __forceinline__ void store_hi_lo(uint16_t* dst, const float4& v, int fp16) {
+// One thread per 4 horizontally adjacent pixels; consecutive threads walk along an image row (coalesced 16B reads),
+// each writes 4 bf16 (8 B) into its patch row; 4 consecutive threads fill one 32 B sector. P = patch size (16 or 32),
+// KP = 3 * P * P columns per half.
+// Rows are written as [hi(KP) | lo(KP)] with hi = round16(x), lo = round16(x - hi): the patch-embed GEMM multiplies
+// [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9 (the stem is 0.4 % of the FLOPs).
+__device__ __forceinline__ void store_hi_lo_p(uint16_t* dst, int kp, const float4& v, int fp16) {
   const float hx = round16(v.x, fp16), hy = round16(v.y, fp16), hz = round16(v.z, fp16), hw = round16(v.w, fp16);
   *reinterpret_cast<uint2*>(dst) = make_uint2(pack16x2(hx, hy, fp16), pack16x2(hz, hw, fp16));
-  *reinterpret_cast<uint2*>(dst + kD) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
+  *reinterpret_cast<uint2*>(dst + kp) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
 }
 
-// One thread per 4 horizontally adjacent pixels; consecutive threads walk along an image row (coalesced 16B reads),
-// each writes 4 bf16 (8 B) into its patch row; 4 consecutive threads fill one 32 B sector.
-// Rows are written as [hi(768) | lo(768)] with hi = round16(x), lo = round16(x - hi): the patch-embed GEMM multiplies
-// [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9 (the stem is 0.4 % of the FLOPs).
-__global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict__ image, int n_img, int H, int W,
-                                                         int y0, int x0, int gh, int gw, uint16_t* __restrict__ out,
-                                                         int fp16) {
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ image, int n_img, int H, int W,
+                                                       int y0, int x0, int gh, int gw, int P, uint16_t* __restrict__ out,
+                                                       int fp16) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t quads_per_row = static_cast<int64_t>(gw) * 4;            // 4 quads per patch row of 16 px
-  const int64_t per_img = static_cast<int64_t>(3) * gh * 16 * quads_per_row;
+  const int qpp = P >> 2;                                                  // quads per patch row
+  const int kp = 3 * P * P;
+  const int64_t quads_per_row = static_cast<int64_t>(gw) * qpp;
+  const int64_t per_img = static_cast<int64_t>(3) * gh * P * quads_per_row;
   const int64_t total = per_img * n_img;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int64_t t = idx;
     const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
-    const int yy = static_cast<int>(t % (gh * 16)); t /= (gh * 16);
+    const int yy = static_cast<int>(t % (gh * P)); t /= (gh * P);
     const int c = static_cast<int>(t % 3);
     const int img = static_cast<int>(t / 3);
-    const int gx = qx >> 2, px4 = qx & 3;
-    const int gy = yy >> 4, py = yy & 15;
+    const int gx = qx / qpp, px4 = qx - gx * qpp;
+    const int gy = yy / P, py = yy - gy * P;
     const float* src = image + ((static_cast<int64_t>(img) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * 4;
     float4 v;
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -148,32 +151,34 @@ __global__ void __launch_bounds__(256) patchify16_kernel(const float* __restrict
       v = make_float4(src[0], src[1], src[2], src[3]);
     }
     const int64_t patch = (static_cast<int64_t>(img) * gh + gy) * gw + gx;
-    store_hi_lo(out + patch * 2 * kD + c * 256 + py * 16 + px4 * 4, v, fp16);
+    store_hi_lo_p(out + patch * 2 * kp + c * P * P + py * P + px4 * 4, kp, v, fp16);
   }
 }
 
-__global__ void __launch_bounds__(256) patchify16_windows_kernel(const float* __restrict__ image, int H, int W,
-                                                                 const int* __restrict__ origins_yx, int n_win, int hp,
-                                                                 int wp, uint16_t* __restrict__ out, int fp16) {
+__global__ void __launch_bounds__(256) patchify_windows_kernel(const float* __restrict__ image, int H, int W,
+                                                               const int* __restrict__ origins_yx, int n_win, int hp,
+                                                               int wp, int P, uint16_t* __restrict__ out, int fp16) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t quads_per_row = static_cast<int64_t>(wp) * 4;
-  const int64_t per_win = static_cast<int64_t>(3) * hp * 16 * quads_per_row;
+  const int qpp = P >> 2;
+  const int kp = 3 * P * P;
+  const int64_t quads_per_row = static_cast<int64_t>(wp) * qpp;
+  const int64_t per_win = static_cast<int64_t>(3) * hp * P * quads_per_row;
   const int64_t total = per_win * n_win;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int64_t t = idx;
     const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
-    const int yy = static_cast<int>(t % (hp * 16)); t /= (hp * 16);
+    const int yy = static_cast<int>(t % (hp * P)); t /= (hp * P);
     const int c = static_cast<int>(t % 3);
     const int win = static_cast<int>(t / 3);
     const int oy = origins_yx[2 * win], ox = origins_yx[2 * win + 1];
-    const int gx = qx >> 2, px4 = qx & 3;
-    const int gy = yy >> 4, py = yy & 15;
+    const int gx = qx / qpp, px4 = qx - gx * qpp;
+    const int gy = yy / P, py = yy - gy * P;
     const float* src = image + (static_cast<int64_t>(c) * H + (oy + yy)) * W + ox + qx * 4;
     const float4 v = make_float4(src[0], src[1], src[2], src[3]);
     const int64_t patch = (static_cast<int64_t>(win) * hp + gy) * wp + gx;
-    store_hi_lo(out + patch * 2 * kD + c * 256 + py * 16 + px4 * 4, v, fp16);
+    store_hi_lo_p(out + patch * 2 * kp + c * P * P + py * P + px4 * 4, kp, v, fp16);
   }
 }
 
@@ -398,24 +403,26 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
-const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       void* out, int fp16) {
+const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
+                     int patch, void* out, int fp16) {
+  if (patch != 16 && patch != 32) return "patchify: patch size must be 16 or 32";
   if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
-  if (y0 < 0 || x0 < 0 || y0 + gh * 16 > H || x0 + gw * 16 > W) return "patchify: grid exceeds image";
-  const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * 16 * gw * 4;
+  if (y0 < 0 || x0 < 0 || y0 + gh * patch > H || x0 + gw * patch > W) return "patchify: grid exceeds image";
+  const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * patch * gw * (patch / 4);
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  cudaError_t e = launch_pdl(patchify16_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0, stream, 1,
-                             image, n_img, H, W, y0, x0, gh, gw, static_cast<uint16_t*>(out), fp16);
+  cudaError_t e = launch_pdl(patchify_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0, stream, 1,
+                             image, n_img, H, W, y0, x0, gh, gw, patch, static_cast<uint16_t*>(out), fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
-const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                               int n_win, int hp, int wp, void* out, int fp16) {
+const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
+                             int n_win, int hp, int wp, int patch, void* out, int fp16) {
+  if (patch != 16 && patch != 32) return "patchify: patch size must be 16 or 32";
   if (n_win <= 0) return "patchify: no windows";
-  const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * 16 * wp * 4;
+  const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * patch * wp * (patch / 4);
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  cudaError_t e = launch_pdl(patchify16_windows_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0,
-                             stream, 1, image, H, W, origins_yx_dev, n_win, hp, wp, static_cast<uint16_t*>(out), fp16);
+  cudaError_t e = launch_pdl(patchify_windows_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0,
+                             stream, 1, image, H, W, origins_yx_dev, n_win, hp, wp, patch, static_cast<uint16_t*>(out), fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 

@@ -130,13 +130,14 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
                          int in_row_offset);
 
 // ------------------------------------------------------------------ stem ---------------------------------------
-// image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * 768] = [hi | lo] split of the
-// pixels, k = c*256 + py*16 + px, on the grid whose (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches).
-const char* patchify16(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       void* out, int fp16);
-// per-window patchify when window origins are not on the 16-pixel grid: out rows [n_win * hp * wp, 2 * 768]
-const char* patchify16_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                               int n_win, int hp, int wp, void* out, int fp16);
+// image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * KP] = [hi | lo] split of the
+// pixels, KP = 3 * patch^2, k = c * patch^2 + py * patch + px (= conv1.weight.view(768, KP)), on the grid whose (0,0)
+// patch starts at pixel (y0, x0) of each image (gh, gw patches). patch = 16 (ViT-B/16) or 32 (ViT-B/32).
+const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
+                     int patch, void* out, int fp16);
+// per-window patchify when window origins are not on the patch grid: out rows [n_win * hp * wp, 2 * KP]
+const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
+                             int n_win, int hp, int wp, int patch, void* out, int fp16);
 
 // Assemble the residual stream X f32 [n_win * t_live, 768]:
 //   row 0            : LN_pre(class_emb + pos[0])

@@ -31,7 +31,10 @@ clip_names = ["resnet50", "resnet50x4", "resnet50x16", "resnet50x64", "resnet101
 resnet_backbones = ["resnet50", "resnet101", "resnet50x4", "resnet50x16", "resnet50x64"]
 vit_backbones = ["vit_b_16", "vit_b_32", "vit_l_14", "vit_l_14_336px"]
 
-_WIDTH, _LAYERS, _HEADS, _PATCH, _EMBED = 768, 12, 12, 16, 512
+_WIDTH, _LAYERS, _HEADS, _EMBED = 768, 12, 12, 512
+# the ViT-B backbones of the reference that share width 768 / 12 layers / 12 heads / embed 512 (models/clip/model.py:20-21):
+# backbone -> patch size (= encoder reduction)
+_VIT_B_PATCH = {"vit_b_16": 16, "vit_b_32": 32}
 
 
 class _Block(nn.Module):
@@ -55,10 +58,11 @@ class _Transformer(nn.Module):
 class _ImageEncoder(nn.Module):
     """Parameter names of VisionTransformer(features_only=True) (_clip/image_encoder.py:118-160)."""
 
-    def __init__(self, input_size: int) -> None:
+    def __init__(self, input_size: int, patch: int) -> None:
         super().__init__()
         scale = _WIDTH ** -0.5
-        g = input_size // _PATCH
+        g = input_size // patch
+        _PATCH = patch
         self.conv1 = nn.Conv2d(3, _WIDTH, kernel_size=_PATCH, stride=_PATCH, bias=False)
         self.class_embedding = nn.Parameter(scale * torch.randn(_WIDTH))
         self.positional_embedding = nn.Parameter(scale * torch.randn(g * g + 1, _WIDTH))
@@ -95,7 +99,7 @@ def _init_decoder(m: nn.Module) -> None:
 
 
 class CLIP_EBC(nn.Module):
-    """B200-native CLIP-EBC (ViT-B/16 + VPT). Constructor arguments as in models/clip/model.py:31-45."""
+    """B200-native CLIP-EBC (ViT-B/16 or ViT-B/32 + VPT). Constructor arguments as in models/clip/model.py:31-45."""
 
     def __init__(
         self,
@@ -118,10 +122,13 @@ class CLIP_EBC(nn.Module):
         super().__init__()
         assert backbone in resnet_backbones + vit_backbones, \
             f"Backbone should be in {resnet_backbones + vit_backbones}, got {backbone}"
-        if backbone != "vit_b_16":
+        if backbone not in _VIT_B_PATCH:
             raise NotImplementedError(
-                f"clip_ebc_b200 implements the hot path for backbone 'vit_b_16' only (got '{backbone}'); the other CLIP "
-                "backbones of the reference are outside the scope of this build (SURVEY.md section 8f).")
+                f"clip_ebc_b200 implements the hot path for the ViT-B backbones {sorted(_VIT_B_PATCH)} only (got "
+                f"'{backbone}'); the CLIP-ResNet and ViT-L/14 backbones of the reference are outside the scope of this "
+                "build (SURVEY.md section 8f).")
+        _PATCH = _VIT_B_PATCH[backbone]
+        self.patch = _PATCH
         assert input_size is not None, "Expected input_size to be an integer, got None."
         assert num_vpt is not None, "Expected num_vpt to be an integer, got None."
         assert deep_vpt is not None, "Expected deep_vpt to be a boolean, got None."
@@ -134,7 +141,7 @@ class CLIP_EBC(nn.Module):
         assert bins is not None and anchor_points is not None and len(bins) == len(anchor_points)
 
         self.backbone = backbone
-        self.image_encoder = _ImageEncoder(int(input_size))
+        self.image_encoder = _ImageEncoder(int(input_size), _PATCH)
         self.image_encoder_depth = _LAYERS
         for p in self.image_encoder.parameters():
             p.requires_grad = False
@@ -223,7 +230,7 @@ class CLIP_EBC(nn.Module):
         with torch.cuda.device(dev):
             if self._handle is None:
                 cfg = _lib.ClipEbcConfig(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt),
-                                         len(self.bins), self._window_chunk, int(self.operand_dtype == "fp16"))
+                                         len(self.bins), self._window_chunk, int(self.operand_dtype == "fp16"), self.patch)
                 h = C.c_void_p()
                 _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
                 self._handle = h

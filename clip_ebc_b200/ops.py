@@ -177,15 +177,15 @@ def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[tor
 
 
 def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = None,
-             gw: Optional[int] = None, fp16: bool = False) -> torch.Tensor:
-    """-> [n*gh*gw, 2*768]: columns [0, 768) = hi, [768, 1536) = lo of the hi/lo split of the pixels."""
+             gw: Optional[int] = None, fp16: bool = False, patch: int = 16) -> torch.Tensor:
+    """-> [n*gh*gw, 2*KP], KP = 3*patch^2: columns [0, KP) = hi, [KP, 2 KP) = lo of the hi/lo split of the pixels."""
     n, c, H, W = image.shape
     assert c == 3 and image.dtype == torch.float32
-    gh = (H - y0) // 16 if gh is None else gh
-    gw = (W - x0) // 16 if gw is None else gw
-    out = torch.empty((n * gh * gw, 2 * 768), dtype=_dt16(fp16), device=image.device)
-    _lib.check(_lib.load().clipebc_patchify16(_ptr(image), n, H, W, y0, x0, gh, gw, _ptr(out), int(fp16), _stream()),
-               "patchify")
+    gh = (H - y0) // patch if gh is None else gh
+    gw = (W - x0) // patch if gw is None else gw
+    out = torch.empty((n * gh * gw, 2 * 3 * patch * patch), dtype=_dt16(fp16), device=image.device)
+    _lib.check(_lib.load().clipebc_patchify(_ptr(image), n, H, W, y0, x0, gh, gw, int(patch), _ptr(out), int(fp16),
+                                            _stream()), "patchify")
     return out
 
 

@@ -30,15 +30,15 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 5
+#define CLIPEBC_ABI_VERSION 6
 
 typedef struct clipebc_model clipebc_model;
 
-/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16") -- models/clip/model.py:31-45, _clip_ebc :220-270.
- * Only width 768 / 12 heads / patch 16 / embed 512 (ViT-B/16) is implemented. */
+/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16" | "vit_b_32") -- models/clip/model.py:20-21,31-45, _clip_ebc :220-270.
+ * Width 768 / 12 layers / 12 heads / embed 512 with patch 16 (ViT-B/16) or patch 32 (ViT-B/32) are implemented. */
 typedef struct clipebc_config {
   int input_size;   /* side of the square the positional embedding was built for (224)        */
-  int reduction;    /* 8, 16 or 32 (model.reduction; encoder reduction is 16)                  */
+  int reduction;    /* 8, 16 or 32 (model.reduction; encoder reduction is the patch size)      */
   int num_vpt;      /* visual prompt tokens per layer (32)                                    */
   int deep_vpt;     /* 1: per-layer prompts vpt_0..vpt_11, 0: shallow (vpt_0 only, propagated) */
   int num_bins;     /* N = len(bins) = len(anchor_points), 1..32                              */
@@ -46,6 +46,8 @@ typedef struct clipebc_config {
   int operand_fp16; /* 16-bit tensor-core operand format: 1 = fp16 (11-bit mantissa; CLIP's released weights are fp16,
                        all operands are range-bounded and saturated), 0 = bf16. Accumulation, residual stream,
                        LayerNorm statistics, softmax and the head are fp32 either way.         */
+  int patch;        /* ViT patch size = encoder reduction: 16 (vit_b_16; also when 0) or 32 (vit_b_32)
+                       -- _clip/image_encoder.py:141, models/clip/model.py:78                  */
 } clipebc_config;
 
 const char* clipebc_last_error(void);
@@ -150,7 +152,10 @@ int clipebc_layernorm768(const float* in_dev, const float* gamma_dev, const floa
 /* q, k, v (and the constant keys/values) are bf16; the output is bf16 or fp16 (out_fp16) */
 int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
                       void* out_16_dev, int out_fp16, void* stream);
-/* out: [n_img*gh*gw, 2*768] = [hi | lo] split of the pixels in the 16-bit format */
+/* out: [n_img*gh*gw, 2*KP] = [hi | lo] split of the pixels in the 16-bit format, KP = 3 * patch^2, patch 16 or 32;
+ * clipebc_patchify16 is the patch-16 form kept from ABI v1 */
+int clipebc_patchify(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch,
+                     void* out_16_dev, int fp16, void* stream);
 int clipebc_patchify16(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw,
                        void* out_16_dev, int fp16, void* stream);
 /* Shared-border grid [n_win, gh+1, gw+1, 768]: cell (y, x) at row y*(gw+1)+x, column gw and row gh are zero; the zero

@@ -20,7 +20,13 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-WIDTH, LAYERS, HEADS, PATCH = 768, 12, 12, 16
+WIDTH, LAYERS, HEADS = 768, 12, 12
+
+
+def patch_size(sd: Dict[str, Tensor]) -> int:
+    """ViT patch size = encoder reduction (_clip/image_encoder.py:141, models/clip/model.py:78): 16 or 32, read off the
+    patch-embedding kernel."""
+    return int(sd["image_encoder.conv1.weight"].shape[-1])
 
 
 def _ln(x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
@@ -60,6 +66,7 @@ def forward_vpt(x: Tensor, sd: Dict[str, Tensor], num_vpt: int, deep_vpt: bool, 
                 taps: Optional[dict] = None) -> Tensor:
     """models/clip/model.py:142-189 (`_forward_vpt`). x: [B, 3, h, w] -> [B, 768, h/16, w/16]."""
     B, _, H, W = x.shape
+    PATCH = patch_size(sd)
     hp, wp = H // PATCH, W // PATCH
     f = F.conv2d(x, sd["image_encoder.conv1.weight"], stride=PATCH)  # :147, no bias
     f = f.reshape(B, WIDTH, -1).permute(0, 2, 1)  # :148-149
@@ -100,6 +107,7 @@ def clip_ebc_forward(x: Tensor, sd: Dict[str, Tensor], text_features: Tensor, an
                      reduction: int, num_vpt: int = 32, deep_vpt: bool = True, input_size: int = 224,
                      taps: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
     """models/clip/model.py:191-217 (`CLIP_EBC.forward`, ViT branch). Returns (logits [B,N,g,g], exp [B,1,g,g])."""
+    PATCH = patch_size(sd)
     with torch.no_grad():
         f = forward_vpt(x.float(), sd, num_vpt, deep_vpt, input_size, taps)
         if taps is not None:

@@ -32,14 +32,28 @@ CASES = [
     # non-224 windows: bicubic positional-embedding interpolation (_clip/image_encoder.py:183-198)
     dict(name="forward_r8_deep_160x192", kind="forward", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
          variant="stress", wseed=10, xseed=11, shape=(2, 3, 160, 192)),
+    # the ViT-B/32 backbone behind the same boundary (patch 32: 7x7 patches per 224 window, x4 bilinear
+    # resample to the reduction-8 grid, models/clip/model.py:20,195-196)
+    dict(name="b32_forward_r8_deep", kind="forward", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
+         variant="stress", wseed=12, xseed=13, shape=(4, 3, 224, 224), patch=32),
+    # overlapping stride 112 is off the 32-pixel patch grid (per-window unfold), 448 x 672 -> 15 windows
+    dict(name="b32_sliding_448x672_s112_r8_deep", kind="sliding", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
+         variant="default", wseed=14, xseed=15, shape=(1, 3, 448, 672), window=224, stride=112, patch=32),
+    # stride 224 keeps the origins on the patch grid (shared patch grid), reduction 16, shallow VPT
+    dict(name="b32_sliding_448x448_s224_r16_shallow", kind="sliding", bins="r16_t8_qnrf", deep_vpt=False, num_vpt=32,
+         variant="stress", wseed=16, xseed=17, shape=(1, 3, 448, 448), window=224, stride=224, patch=32),
 ]
+
+
+def backbone_of(case: dict) -> str:
+    return "vit_b_32" if case.get("patch", 16) == 32 else "vit_b_16"
 
 
 def case_inputs(case: dict):
     """-> (state_dict, text_features, bins, anchors, reduction, x) regenerated from the case's seeds."""
     reduction, bins, anchors = weights.bins_and_anchors(case["bins"])
     sd = weights.make_state_dict(case["wseed"], input_size=224, num_vpt=case["num_vpt"], deep_vpt=case["deep_vpt"],
-                                 variant=case["variant"])
+                                 variant=case["variant"], patch=case.get("patch", 16))
     tf = weights.make_text_features(len(bins), seed=100 + case["wseed"])
     x = weights.make_image(case["shape"], seed=case["xseed"])
     return sd, tf, bins, anchors, reduction, x

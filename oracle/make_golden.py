@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader, weights  # noqa: E402
-from oracle.golden_cases import CASES, case_inputs  # noqa: E402
+from oracle.golden_cases import CASES, backbone_of, case_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -28,7 +28,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 def run_case(case: dict) -> dict:
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
     model = ref_loader.build_reference_model(sd, tf, bins, anchors, reduction, num_vpt=case["num_vpt"],
-                                             deep_vpt=case["deep_vpt"], input_size=224)
+                                             deep_vpt=case["deep_vpt"], input_size=224, backbone=backbone_of(case))
     _, ev = ref_loader.load_reference()
     out = {}
     if case["kind"] == "forward":
@@ -62,7 +62,10 @@ def main() -> None:
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    only = sys.argv[1:]  # optional: names of the cases to (re)generate
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         res = run_case(case)
         path = os.path.join(OUT, case["name"] + ".npz")
         np.savez_compressed(path, **res)

@@ -66,6 +66,13 @@ def load_reference():
             m.adjust_pos_embed(input_size, input_size)
         return m
 
+    def vit_b_32_img(features_only=False, input_size=None, **kw):
+        m = ie.VisionTransformer(input_resolution=224, patch_size=32, output_dim=512, width=768, layers=12, heads=12,
+                                 features_only=features_only)
+        if input_size is not None:
+            m.adjust_pos_embed(input_size, input_size)
+        return m
+
     def vit_b_16_txt():
         m = te.CLIPTextEncoder(embed_dim=512, context_length=77, vocab_size=49408, transformer_width=512,
                                transformer_heads=8, transformer_layers=12)
@@ -82,6 +89,7 @@ def load_reference():
         return out
 
     clip_pkg.vit_b_16_img, clip_pkg.vit_b_16_txt, clip_pkg.tokenize = vit_b_16_img, vit_b_16_txt, tokenize
+    clip_pkg.vit_b_32_img, clip_pkg.vit_b_32_txt = vit_b_32_img, vit_b_16_txt  # same text tower (embed_dim 512)
     cm = _load("models.clip.model", f"{REF}/models/clip/model.py")
     ev = _load("ref_eval_utils", f"{REF}/utils/eval_utils.py")
     _cache["mods"] = (cm, ev)
@@ -89,7 +97,7 @@ def load_reference():
 
 
 def build_reference_model(sd, text_features, bins, anchor_points, reduction, num_vpt=32, deep_vpt=True,
-                          input_size=224):
+                          input_size=224, backbone="vit_b_16"):
     """The reference's own CLIP_EBC (via its `_clip_ebc` factory), loaded with `sd`; text features overridden by the
     supplied constant (a plain attribute of the module, models/clip/model.py:129)."""
     cm, _ = load_reference()
@@ -97,7 +105,7 @@ def build_reference_model(sd, text_features, bins, anchor_points, reduction, num
     import io
 
     with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints the prompts (model.py:122)
-        model = cm._clip_ebc(backbone="vit_b_16", input_size=input_size, reduction=reduction, bins=bins,
+        model = cm._clip_ebc(backbone=backbone, input_size=input_size, reduction=reduction, bins=bins,
                              anchor_points=anchor_points, prompt_type="word", num_vpt=num_vpt, vpt_drop=0.0,
                              deep_vpt=deep_vpt)
     missing, unexpected = model.load_state_dict(sd, strict=False)

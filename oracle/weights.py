@@ -48,9 +48,11 @@ def _n(rng, shape, std):
 
 
 def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, deep_vpt: bool = True,
-                    variant: str = "default") -> Dict[str, torch.Tensor]:
-    """Reference-keyed fp32 state_dict (without ``text_encoder.*``: the text tower is not on the hot path)."""
+                    variant: str = "default", patch: int = 16) -> Dict[str, torch.Tensor]:
+    """Reference-keyed fp32 state_dict (without ``text_encoder.*``: the text tower is not on the hot path).
+    patch = 16 (ViT-B/16) or 32 (ViT-B/32): the two differ in conv1 / positional-embedding shapes only."""
     assert variant in ("default", "stress")
+    PATCH = patch
     rng = np.random.default_rng(seed)
     stress = variant == "stress"
     sd: Dict[str, np.ndarray] = {}

@@ -44,7 +44,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.clipebc_abi_version() == 5
+    assert lib.clipebc_abi_version() == 6
     assert lib.clipebc_launch_count() == 0  # nothing ran on this CPU box
 
 
@@ -133,6 +133,18 @@ def test_python_host_mirrors_reference_interface():
     model.load_state_dict(sd, strict=True)
     with pytest.raises(RuntimeError, match="unexpected|Unexpected|Missing|missing"):
         model.load_state_dict({**sd, "bogus.weight": torch.zeros(1)}, strict=True)
+    # ViT-B/32 behind the same entry point: patch 32, 7 x 7 positional grid, same key names
+    b32 = get_model("clip_vit_b_32", input_size=224, reduction=8, bins=bins, anchor_points=anchors, prompt_type="word",
+                    num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=weights.make_text_features(5))
+    sd32 = weights.make_state_dict(0, patch=32)
+    assert set(sd32) == set(b32.state_dict())
+    assert tuple(sd32["image_encoder.conv1.weight"].shape) == (768, 3, 32, 32)
+    assert tuple(sd32["image_encoder.positional_embedding"].shape) == (50, 768)
+    b32.load_state_dict(sd32, strict=True)
+    assert b32.encoder_reduction == 32 and b32.reduction == 8
+    with pytest.raises(NotImplementedError):
+        get_model("clip_vit_l_14", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32, vpt_drop=0.0,
+                  deep_vpt=True)
     # text_encoder.* entries of a reference checkpoint are accepted and round-trip
     model.load_state_dict({**sd, "text_encoder.ln_final.weight": torch.ones(512)}, strict=True)
     assert "text_encoder.ln_final.weight" in model.state_dict()

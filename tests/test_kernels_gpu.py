@@ -368,15 +368,30 @@ def test_attention_large_scores(ops, impl):
 
 # ----------------------------------------------------------------------------------------------- stem / decoder
 @pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
-def test_patchify_matches_unfold(ops, dt):
+@pytest.mark.parametrize("patch", [16, 32])
+def test_patchify_matches_unfold(ops, dt, patch):
     img = _rand((2, 3, 64, 96), 40)
-    out = ops.patchify(img, fp16=dt == torch.float16).float().view(2, 4 * 6, 2, 768)
-    ref = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2)  # [n, L, c*256 + py*16 + px]
+    kp = 3 * patch * patch
+    out = ops.patchify(img, fp16=dt == torch.float16, patch=patch).float().view(2, (64 // patch) * (96 // patch), 2, kp)
+    ref = F.unfold(img, kernel_size=patch, stride=patch).transpose(1, 2)  # [n, L, c*P*P + py*P + px]
     hi = ref.to(dt).float()
     assert torch.equal(out[:, :, 0], hi)
     assert torch.equal(out[:, :, 1], (ref - hi).to(dt).float())
     # hi + lo carries the pixels to ~2 roundings of the 16-bit format
     assert (out[:, :, 0] + out[:, :, 1] - ref).abs().max().item() < 4 * ROUND16[dt] ** 2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("g", [28, 14, 7])
+def test_resample_from_the_7x7_grid_of_vit_b_32(ops, g):
+    """ViT-B/32 windows have 7 x 7 patches: x4 / x2 bilinear resample (or none) onto the reduction-8 / 16 / 32 grid."""
+    n = 3
+    Y = _rand((n * 49, 768), 42)
+    ub, uf = ops.resample_to_padded(Y, n, 7, 7, g, g, fp16=True)
+    x = Y.view(n, 7, 7, 768).permute(0, 3, 1, 2)
+    ref = x if g == 7 else F.interpolate(x, scale_factor=g / 7, mode="bilinear")
+    uf = uf.view(n, g + 1, g + 1, 768)
+    assert (uf[:, :-1, :-1].permute(0, 3, 1, 2) - ref).abs().max().item() < 1e-5
+    assert torch.equal(ub.view_as(uf), uf.to(torch.float16))
 
 
 @pytest.mark.parametrize("g", [28, 14, 7])

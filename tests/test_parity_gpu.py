@@ -19,7 +19,9 @@ pytestmark = pytest.mark.gpu
 def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0, operand_dtype="fp16"):
     from clip_ebc_b200 import get_model
 
-    model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+    from oracle.golden_cases import backbone_of
+
+    model = get_model("clip_" + backbone_of(case), input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
                       prompt_type="word", num_vpt=case["num_vpt"], vpt_drop=0.0, deep_vpt=case["deep_vpt"],
                       text_features=tf, window_chunk=window_chunk, operand_dtype=operand_dtype)
     model.load_state_dict(sd, strict=True)
