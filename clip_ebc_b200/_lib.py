@@ -46,6 +46,9 @@ SIGNATURES = {
     "clipebc_set_ln_fold": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
+    "clipebc_profile_enabled": (_i, []),
+    "clipebc_config_epoch": (_i64, []),
+    "clipebc_note_replayed_launches": (None, [_i64]),
     "clipebc_model_create": (_i, [C.POINTER(ClipEbcConfig), C.POINTER(_vp)]),
     "clipebc_model_destroy": (None, [_vp]),
     "clipebc_model_set_tensor": (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i64), _i]),

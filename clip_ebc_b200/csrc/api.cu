@@ -35,6 +35,7 @@ thread_local const char* g_tag = nullptr;
 }  // namespace
 
 void set_launch_tag(const char* tag) { g_tag = tag; }
+bool profiling_on() { return g_prof_on; }
 
 bool pdl_enabled() {
   static const bool on = std::getenv("CLIPEBC_NO_PDL") == nullptr;
@@ -498,18 +499,27 @@ const char* clipebc_last_error(void) { return g_err.c_str(); }
 int clipebc_abi_version(void) { return CLIPEBC_ABI_VERSION; }
 int64_t clipebc_launch_count(void) { return g_launches.load(); }
 
+// bumped by every clipebc_set_* switch: host layers that cache captured CUDA graphs key them on it
+static std::atomic<int64_t> g_config_epoch{0};
+int64_t clipebc_config_epoch(void) { return g_config_epoch.load(); }
+int clipebc_profile_enabled(void) { return cebc::profiling_on() ? 1 : 0; }
+void clipebc_note_replayed_launches(int64_t n) { if (n > 0) g_launches.fetch_add(n); }
+
 int clipebc_set_gemm_impl(int impl) {
+  g_config_epoch.fetch_add(1);
   if (impl != 1 && impl != 2) return fail(CLIPEBC_EINVAL, "gemm impl must be 1 (single CTA) or 2 (CTA pair)");
   g_gemm_impl.store(impl);
   return CLIPEBC_OK;
 }
 
 int clipebc_set_ln_fold(int on) {
+  g_config_epoch.fetch_add(1);
   g_ln_fold.store(on != 0);
   return CLIPEBC_OK;
 }
 
 int clipebc_set_attention_impl(int impl) {
+  g_config_epoch.fetch_add(1);
   if (impl < 1 || impl > 4) return fail(CLIPEBC_EINVAL, "attention impl must be 1 (mma.sync), 2, 3 or 4 (tcgen05)");
   g_attn_impl.store(impl);
   return CLIPEBC_OK;

@@ -90,6 +90,7 @@ struct LaunchScope {
   int slot_;
 };
 void set_launch_tag(const char* tag);  // nullptr clears
+bool profiling_on();
 
 // Launch with programmatic stream serialization (see common.cuh: pdl_wait) and an optional cluster width.
 bool pdl_enabled();  // false when CLIPEBC_NO_PDL is set (A/B experiments)

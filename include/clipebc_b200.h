@@ -30,7 +30,7 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 6
+#define CLIPEBC_ABI_VERSION 7
 
 typedef struct clipebc_model clipebc_model;
 
@@ -72,6 +72,12 @@ int clipebc_set_ln_fold(int on);
  * "flops", "bytes"}} (algorithmic work of the launches, summed since enable) into buf. Enabling clears the records. */
 int clipebc_profile_enable(int on);
 int clipebc_profile_dump(char* buf, int cap);
+int clipebc_profile_enabled(void);
+/* For host layers that replay captured CUDA graphs of this library's launches (clip_ebc_b200/model.py): the epoch
+ * changes whenever a clipebc_set_* switch is called (a captured graph holds the kernels chosen at capture time), and a
+ * replay reports the launches it contains so that clipebc_launch_count stays the number of kernels actually run. */
+int64_t clipebc_config_epoch(void);
+void clipebc_note_replayed_launches(int64_t n);
 
 /* ---- model lifetime: mirrors get_model() + load_state_dict() + .eval() ---------------------------------------- */
 int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out);
