@@ -80,6 +80,8 @@ static std::atomic<int> g_ln_fold{0};
 const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                                int n_win, int t_live, void* out, int out_fp16) {
   const int impl = g_attn_impl.load();
+  // windows with more than 256 tokens (e.g. 448 x 448): streamed-K/V kernel, the tcgen05 kernels hold one 256-key tile
+  if (t_live + n_const > 256) return attention_h64_long(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   if (impl == 4 && n_const % 8 == 0) return attention_h64_pp(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   if (impl == 3 && n_const % 8 == 0) return attention_h64_fa(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
   if (impl == 2 && n_const % 8 == 0) return attention_h64_tc(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
@@ -477,7 +479,14 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   return CLIPEBC_OK;
 }
 
-int default_chunk(const clipebc_model* m) { return m->cfg.window_chunk > 0 ? m->cfg.window_chunk : 96; }
+// windows per internal pass: 96 windows of 229 tokens (148 x 128 rows) by default; windows with more tokens get
+// proportionally fewer per pass so that the workspaces (4 MB per 229-token window) stay the same size
+int default_chunk(const clipebc_model* m, int hp = 14, int wp = 14) {
+  if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
+  const int64_t tokens = 1 + m->cfg.num_vpt + static_cast<int64_t>(hp) * wp;
+  if (tokens <= 256) return 96;
+  return static_cast<int>(std::max<int64_t>(1, 96 * 229 / tokens));
+}
 
 int check_window_geometry(clipebc_model* m, int h, int w) {
   const int kPatch = m->cfg.patch;
@@ -485,8 +494,8 @@ int check_window_geometry(clipebc_model* m, int h, int w) {
     return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of the patch size");
   if ((h % m->cfg.reduction) != 0 || (w % m->cfg.reduction) != 0)
     return fail(CLIPEBC_EINVAL, "window height/width must be multiples of the reduction");
-  const int T = 1 + m->cfg.num_vpt + (h / kPatch) * (w / kPatch);
-  if (T > 256) return fail(CLIPEBC_EINVAL, "window too large: 1 + num_vpt + patches must be <= 256 tokens");
+  const int64_t T = 1 + m->cfg.num_vpt + static_cast<int64_t>(h / kPatch) * (w / kPatch);
+  if (T > 16384) return fail(CLIPEBC_EINVAL, "window too large: 1 + num_vpt + patches must be <= 16384 tokens");
   return CLIPEBC_OK;
 }
 
@@ -723,7 +732,7 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   }
   const int* d_win_base = cached->second.as<int>();
 
-  const int chunk = default_chunk(m);
+  const int chunk = default_chunk(m, hp, wp);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nw = std::min(chunk, B - b0);
     float* lo = logits_out_dev ? logits_out_dev + static_cast<int64_t>(b0) * m->cfg.num_bins * gh * gw : nullptr;
@@ -824,7 +833,7 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
   float* preds = m->ws_preds.as<float>();
-  const int chunk = default_chunk(m);
+  const int chunk = default_chunk(m, hp, wp);
   for (int b0 = 0; b0 < n_win; b0 += chunk) {
     const int nw = std::min(chunk, n_win - b0);
     if ((rc = run_windows(m, s, d_base + b0, src_pitch, nw, hp, wp, pos, preds + static_cast<int64_t>(b0) * gh * gw, nullptr)))
@@ -925,7 +934,7 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   // the windows of all images share the passes of the ViT / decoder / head (chunks may span image boundaries)
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(total_win) * gh * gw * 4));
   float* preds = m->ws_preds.as<float>();
-  const int chunk = default_chunk(m);
+  const int chunk = default_chunk(m, hp, wp);
   for (int b0 = 0; b0 < total_win; b0 += chunk) {
     const int nw = std::min(chunk, total_win - b0);
     if ((rc = run_windows(m, s, d_base + b0, 0, nw, hp, wp, pos, preds + static_cast<int64_t>(b0) * gh * gw, nullptr, d_pitch + b0)))

@@ -163,6 +163,11 @@ const char* rowstats768(cudaStream_t stream, const float* in, int64_t n_rows, vo
 const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                           int n_win, int t_live, void* out, int out_fp16);
 
+// Same contract without the 256-key limit (attention.cu): 64-query chunks, K / V streamed in 64-key blocks, online softmax.
+// Used for windows with more than 256 tokens.
+const char* attention_h64_long(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                               int n_win, int t_live, void* out, int out_fp16);
+
 // tcgen05 / TMEM implementation of the same contract (attention_tc.cu); needs n_const % 8 == 0.
 const char* attention_h64_tc(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                              int n_win, int t_live, void* out, int out_fp16);

@@ -45,6 +45,18 @@ CASES = [
 ]
 
 
+# Windows with more than 256 tokens (the tcgen05 attention tile): 320 x 320 windows have 400 patches (433 tokens with
+# cls + prompts, positional embedding resized 14 -> 20), 448 x 448 windows have 784 (817 tokens)
+CASES += [
+    dict(name="forward_r8_deep_320x320", kind="forward", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
+         variant="stress", wseed=18, xseed=19, shape=(2, 3, 320, 320)),
+    dict(name="sliding_448x896_w448_r8_deep", kind="sliding", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
+         variant="default", wseed=20, xseed=21, shape=(1, 3, 448, 896), window=448, stride=448),
+    dict(name="sliding_448x672_w448_s224_r16_shallow", kind="sliding", bins="r16_t8_qnrf", deep_vpt=False, num_vpt=32,
+         variant="stress", wseed=22, xseed=23, shape=(1, 3, 448, 672), window=448, stride=224),
+]
+
+
 def backbone_of(case: dict) -> str:
     return "vit_b_32" if case.get("patch", 16) == 32 else "vit_b_16"
 

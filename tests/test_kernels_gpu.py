@@ -348,6 +348,25 @@ def test_attention(ops, n_win, t_live, n_const, impl, out_fp16):
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("n_win,t_live,n_const", [(2, 401, 32), (1, 785, 32), (2, 817, 0), (3, 257, 0), (1, 300, 7)])
+def test_attention_beyond_256_tokens(n_win, t_live, n_const):
+    """Windows with more than 256 tokens (320 x 320: 401 live + 32 prompt keys; 448 x 448: 785 + 32; shallow VPT: all 817
+    live) go through the streamed-K/V kernel (64-query chunks, 64-key blocks, online softmax)."""
+    from clip_ebc_b200 import ops as _ops
+
+    qkv = _bf(_rand((n_win * t_live, 2304), 34, 1.5))
+    ckv = _bf(_rand((n_const, 2304), 35, 1.5)) if n_const else None
+    out = _ops.attention(qkv, n_win, t_live, ckv, out_fp16=True).float().view(n_win, t_live, 12, 64)
+    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
+    if n_const:
+        ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
+        k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
+        v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()  # P rounded to bf16, 16-bit output
+
+
 @pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["mma_sync", "tcgen05", "tcgen05_persistent", "tcgen05_two_chains"])
 def test_attention_large_scores(ops, impl):
     """Peaky softmax (|score| up to ~40): the single-pass reference-max scheme must stay exact up to bf16 rounding."""
