@@ -183,11 +183,34 @@ def run_reference(args, rank):
         "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line. Libraries write there too (NCCL prints its version banner to stdout at
+    NCCL_DEBUG=VERSION, which the GPU boxes set), so file descriptor 1 is pointed at stderr for the life of the process
+    and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,9 +228,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set in this image): keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     model, parts = build_model(dev)
@@ -423,7 +443,7 @@ def main():
             if args.workload == "windows64" else None,
             "kernels": kernels,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
