@@ -317,6 +317,25 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   // everything above overlapped the tail of the previous kernel; its results (A, the residual) are needed from here on
   if (warp == 3) CEBC_TRACE(1);
   pdl_launch_dependents();
+  // The weights do not depend on the previous kernel: the producer requests the weight half-tiles of the first k-blocks
+  // of its first tile BEFORE the dependency wait, so that only the activation loads are exposed after it.
+  int pre_kb = 0;
+  if constexpr (MC == 1) {
+    if (warp == 0 && !(p.dbg & (8 | 16 | 2048)) && cluster_id < num_tiles) {
+      pre_kb = num_kb < STAGES ? num_kb : STAGES;
+      if (lane == 0) {
+        const int n_blk = cluster_id % n_tiles;
+        const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
+        for (int kb = 0; kb < pre_kb; ++kb) {  // fresh barriers: every slot is free
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[kb]), leader_crank);
+          if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2u * Cfg::kABytes + 2u * Cfg::kBBytes);
+          else mbar_arrive_cluster(leader_full);
+          tma_load_2d_pair(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tma_b, leader_full, kb * kBlockK, n0);
+        }
+      }
+      __syncwarp();
+    }
+  }
   pdl_wait();
   if (warp == 3) CEBC_TRACE(2);
   long long dbg_c0 = 0;
@@ -336,6 +355,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       int seg = 0, kk = 0;
       CEBC_TRACE(16 + 4 * ((t - cluster_id) / num_clusters));
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (t == cluster_id && kb < pre_kb) {
+          // barrier armed and weights requested before the dependency wait: only the activations are left
+          if (lane == 0) {
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), leader_crank);
+            tma_load_2d_pair(smem + stage * Cfg::kStageBytes, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK,
+                             m0 + p.seg_row_shift[seg]);
+          }
+          __syncwarp();
+          if (++kk == p.seg_kblocks) { kk = 0; ++seg; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         // slot free in every CTA of the cluster (each pair leader's commit is multicast to all of them), so multicast
         // writes into the other pair's slot are safe too
         mbar_wait(&empty_bar[stage], phase ^ 1);
