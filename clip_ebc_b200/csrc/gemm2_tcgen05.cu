@@ -88,7 +88,7 @@ constexpr bool has_resid() {
 template <int EPI>
 __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* stg, const float* bias_s, int lane, int row0,
                                                  int n, const uint32_t (&r)[32], const float* cs_s = nullptr, float ra = 1.f,
-                                                 float rc = 0.f) {
+                                                 float rc = 0.f, int tma_half = -1) {
   const int row = row0 + lane;
   bool border = false;
   if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
@@ -129,10 +129,14 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
     }
-    *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) =
-        make_uint4(pack16x2(v[0], v[1], p.out_fp16), pack16x2(v[2], v[3], p.out_fp16), pack16x2(v[4], v[5], p.out_fp16),
-                   pack16x2(v[6], v[7], p.out_fp16));
+    const uint4 pk = make_uint4(pack16x2(v[0], v[1], p.out_fp16), pack16x2(v[2], v[3], p.out_fp16),
+                                pack16x2(v[4], v[5], p.out_fp16), pack16x2(v[6], v[7], p.out_fp16));
+    if (tma_half >= 0)  // row `lane` of a 32 x 64 box in the 128B-swizzled layout a bulk tensor store reads
+      *reinterpret_cast<uint4*>(stg + lane * 128 + (((tma_half * 4 + j) ^ (lane & 7)) << 4)) = pk;
+    else
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) = pk;
   }
+  if (tma_half >= 0) return;
   __syncwarp();
   const int slot = lane & 3, rsub = lane >> 2;
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
@@ -603,6 +607,32 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         else if (p.head_bins <= 16) head_partial_tile<16>(p, t_addr, tm_s, BLOCK_N, bs + cbase, HALF_N, row, part);
         else head_partial_tile<32>(p, t_addr, tm_s, BLOCK_N, bs + cbase, HALF_N, row, part);
       } else if constexpr (out_is_bf16<EPI>()) {
+        if (HALF_N % 64 == 0 && p.tma_out) {
+          // 16-bit outputs through bulk tensor stores: thread = accumulator row writes its 64 columns into a 32 x 64
+          // box (128B-swizzled, conflict-free 16 B stores), lane 0 sends the box; no read-back of the staging tile, no
+          // per-lane global stores, full 128 B lines per row; rows >= M are clipped by the hardware
+#pragma unroll 1
+          for (int b = 0; b < HALF_N / 64; ++b) {
+            if (lane == 0) bulk_wait_group_read0();  // the previous box has left the staging tile
+            __syncwarp();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * b + cc;
+              uint32_t r[32];
+              if (!(p.dbg & 4)) tmem_ld_32x32b_x32(t_addr + c * 32, r);
+              tmem_ld_wait();
+              if (!(p.dbg & 2))
+                epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cs + cbase + c * 32, ln_a,
+                                      ln_c, cc);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 1)) {
+              tma_store_2d(&tma_o, stg, n0 + cbase + b * 64, row0);
+              bulk_commit_group();
+            }
+          }
+        } else
 #pragma unroll 1
         for (int c = 0; c < HALF_N / 32; ++c) {
           uint32_t r[32];
@@ -637,6 +667,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
   }
 
+  if constexpr (out_is_bf16<EPI>()) {
+    if (warp >= 4 && lane == 0 && p.tma_out) bulk_wait_group0();  // this warp's bulk stores are complete
+  }
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal its barriers / read its smem
   if (warp == 3) CEBC_TRACE(3);
@@ -720,6 +753,13 @@ cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtens
                         int num_sms) {
   using Cfg = Cfg2<BLOCK_N, tma_resid<BLOCK_N, EPI>()>;
   CUtensorMap tr = ta, to = ta;  // placeholders for the kernels that do not use them
+  GemmParams pl = p;
+  if constexpr (out_is_bf16<EPI>() && (BLOCK_N / 2) % 64 == 0) {
+    static const bool tma_out_env = getenv("CLIPEBC_GEMM_NO_TMA_OUT") == nullptr;  // A/B knob
+    if (tma_out_env && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0 &&
+        make_tmap2(&to, p.out, p.M, p.N, p.ldo, 32))
+      pl.tma_out = 1;
+  }
   if constexpr (tma_resid<BLOCK_N, EPI>()) {
     if ((reinterpret_cast<uintptr_t>(p.resid) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldr % 4) || (p.ldo % 4))
       return cudaErrorMisalignedAddress;
@@ -736,7 +776,7 @@ cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtens
     LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
                       2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
                           4.0 * p.M * static_cast<double>(p.N));
-    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, tr, to, p);
+    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, tr, to, pl);
   }
   return e != cudaSuccess ? e : cudaGetLastError();
 }

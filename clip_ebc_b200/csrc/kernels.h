@@ -59,6 +59,7 @@ struct GemmParams {
   const float2* ln_stats;             // EPI_LN_*: [M, kLnStatSlots]; ln_parts = 8: eight partials of 96 columns,
   int ln_parts;                       //           ln_parts = 1: slot 0 holds (mean, M2) of the whole row
   const float* ln_colsum;             // EPI_LN_*: [N]
+  int tma_out;                        // set by the launcher: 16-bit outputs leave through bulk tensor stores (gemm2)
   int dbg;                            // experiment knob (profiles/): 0 in production
   long long* trace;                   // experiment: clock64 time line of CTA 0 (profiles/gemm_trace.py), nullptr in production
 };
