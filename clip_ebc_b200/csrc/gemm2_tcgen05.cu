@@ -595,7 +595,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       named_bar_sync(1, kEpiWarps * 32);
       const int cbase = half * HALF_N;
       float4 xa[8], xb[8];
-      if constexpr (!out_is_bf16<EPI>()) load_resid32<EPI>(p, lane, row0, n0 + cbase, xa);
+      if constexpr (!out_is_bf16<EPI>()) {
+        if (!(EPI == EPI_BIAS_RESID_F32 && p.tma_out)) load_resid32<EPI>(p, lane, row0, n0 + cbase, xa);
+      }
       mbar_wait(&tmem_full_bar[as], aphase);
       if (ew == 0) CEBC_TRACE(19 + 4 * ((t - cluster_id) / num_clusters));
       tc_fence_after();
@@ -641,6 +643,35 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           if (!(p.dbg & 2))
             epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cs + cbase + c * 32, ln_a, ln_c);
         }
+      } else if (EPI == EPI_BIAS_RESID_F32 && p.tma_out) {
+        // In-place residual update as a memory-side reduction: thread = accumulator row stages acc + bias (fp32) in a
+        // 128B-swizzled 32 x 32 box and lane 0 issues cp.reduce.async.bulk.tensor .add -- X += tile happens in L2. The
+        // SM never reads the old rows (38.7 MB per launch at 64 windows), there are no per-lane global accesses and no
+        // read-back of the staging tile; x + (acc + bias) has the bits of (acc + bias) + x, and every element receives
+        // exactly one addition per launch, so the result is the same, deterministically.
+        constexpr int NC = HALF_N / 32;
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          if (lane == 0) bulk_wait_group_read0();  // the previous box has left the staging tile
+          __syncwarp();
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bs + cbase + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
+                            __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tma_o, stg, n0 + cbase + c * 32, row0);
+            bulk_commit_group();
+          }
+        }
       } else {
         constexpr int NC = HALF_N / 32;
 #pragma unroll 1
@@ -667,8 +698,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
   }
 
-  if constexpr (out_is_bf16<EPI>()) {
-    if (warp >= 4 && lane == 0 && p.tma_out) bulk_wait_group0();  // this warp's bulk stores are complete
+  if constexpr (out_is_bf16<EPI>() || EPI == EPI_BIAS_RESID_F32) {
+    if (warp >= 4 && lane == 0 && p.tma_out) bulk_wait_group0();  // this warp's bulk stores / reductions are complete
   }
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal its barriers / read its smem
@@ -758,6 +789,13 @@ cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtens
     static const bool tma_out_env = getenv("CLIPEBC_GEMM_NO_TMA_OUT") == nullptr;  // A/B knob
     if (tma_out_env && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0 &&
         make_tmap2(&to, p.out, p.M, p.N, p.ldo, 32))
+      pl.tma_out = 1;
+  }
+  if constexpr (EPI == EPI_BIAS_RESID_F32 && !tma_resid<BLOCK_N, EPI>()) {
+    // in place (out == resid): the residual add becomes a bulk tensor reduction
+    static const bool red_env = getenv("CLIPEBC_GEMM_NO_TMA_RED") == nullptr;  // A/B knob
+    if (red_env && p.out == static_cast<const void*>(p.resid) && p.ldo == p.ldr && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+        p.ldo % 4 == 0 && make_tmap2_f32(&to, p.out, p.M, p.N, p.ldo))
       pl.tma_out = 1;
   }
   if constexpr (tma_resid<BLOCK_N, EPI>()) {
