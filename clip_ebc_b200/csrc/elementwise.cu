@@ -2,6 +2,7 @@
 // + VPT splice), bilinear resample onto the zero-bordered decoder grid, and the pack-time weight transforms.
 // All are one-warp-per-row (768 channels = 6 x 128-bit per lane) or one-thread-per-vector kernels with coalesced,
 // vectorised global accesses and warp-shuffle reductions.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -109,6 +110,96 @@ __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __res
       store_row_16(static_cast<uint16_t*>(out) + r * kD, x, lane, fp16);
     else
       store_row_f32(static_cast<float*>(out) + r * kD, x, lane);
+  }
+}
+
+// LayerNorm over contiguous rows with the loads taken off the warps: the warp-per-row kernel above is bound by the latency
+// of its row loads (ncu: long-scoreboard stalls, 7 of 16 warps per scheduler active, no pipe above 35 %) and can only
+// keep 32 warps x 3 KB in flight per SM. Here every CTA streams blocks of 8 rows (24 KB) through a 3-stage shared-memory
+// ring with bulk async copies (2 CTAs per SM: 144 KB in flight whatever the warps are doing), warp w normalises row w of
+// a block from shared memory, and gamma / beta live in registers for the whole kernel (they are loaded before the
+// dependency wait -- they do not depend on the previous kernel).
+constexpr int kLnRows = 8, kLnStages = 3;
+constexpr int kLnStageBytes = kLnRows * kD * 4;                                   // 24 KB
+constexpr int kLnSmem = kLnStages * kLnStageBytes + 2 * kLnStages * 8 + 128;      // ring + barriers + alignment slack
+
+__global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, uint16_t* __restrict__ out,
+                                                                  int64_t n_rows, int fp16) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes);
+  uint64_t* empty_bar = full_bar + kLnStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLnRows); }
+    fence_mbar_init();
+  }
+  // gamma / beta in registers (constants of the model)
+  float4 g[kVecPerLane], b[kVecPerLane];
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    b[i] = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int64_t n_blocks = (n_rows + kLnRows - 1) / kLnRows;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  auto request = [&](int64_t blk, int s) {  // thread 0: rows [blk * 8, ...) -> stage s
+    const int64_t r0 = blk * kLnRows;
+    const int nr = static_cast<int>(n_rows - r0 < kLnRows ? n_rows - r0 : kLnRows);
+    const uint32_t bytes = static_cast<uint32_t>(nr) * kD * 4;
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_load_1d(smem + s * kLnStageBytes, in + r0 * kD, bytes, &full_bar[s]);
+  };
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int64_t blk = first; blk < n_blocks && s < kLnStages; blk += step, ++s) request(blk, s);
+  }
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t blk = first; blk < n_blocks; blk += step) {
+    mbar_wait(&full_bar[s], phase);
+    const int64_t r = blk * kLnRows + warp;
+    if (r < n_rows) {
+      Row768 x;
+      const float4* p4 = reinterpret_cast<const float4*>(smem + s * kLnStageBytes + warp * kD * 4);
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) x.v[i] = p4[i * 32 + lane];
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) sm += (x.v[i].x + x.v[i].y) + (x.v[i].z + x.v[i].w);
+      const float mean = warp_sum(sm) * (1.0f / kD);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) {
+        const float a = x.v[i].x - mean, bb = x.v[i].y - mean, c = x.v[i].z - mean, d = x.v[i].w - mean;
+        q += (a * a + bb * bb) + (c * c + d * d);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) {
+        x.v[i].x = (x.v[i].x - mean) * rstd * g[i].x + b[i].x;
+        x.v[i].y = (x.v[i].y - mean) * rstd * g[i].y + b[i].y;
+        x.v[i].z = (x.v[i].z - mean) * rstd * g[i].z + b[i].z;
+        x.v[i].w = (x.v[i].w - mean) * rstd * g[i].w + b[i].w;
+      }
+      store_row_16(out + r * kD, x, lane, fp16);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage (its row is in registers / stored)
+    // thread 0 refills the stage with the block kLnStages ahead once all eight warps have released it
+    if (threadIdx.x == 0) {
+      const int64_t nxt = blk + static_cast<int64_t>(kLnStages) * step;
+      if (nxt < n_blocks) {
+        mbar_wait(&empty_bar[s], phase);
+        request(nxt, s);
+      }
+    }
+    if (++s == kLnStages) { s = 0; phase ^= 1; }
   }
 }
 
@@ -394,8 +485,23 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
                          int in_row_offset) {
   if (n_rows_out <= 0) return nullptr;
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
-  const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
   LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_kind ? 2.0 : 4.0)));
+  // contiguous rows to a 16-bit output (the 24 LayerNorms inside the blocks): streaming kernel
+  static const bool stream_env = getenv("CLIPEBC_LN_NO_STREAM") == nullptr;  // A/B knob
+  if (stream_env && out_kind != 0 && rows_out_per_group == rows_in_per_group && in_row_offset == 0 && n_rows_out >= 64 &&
+      (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t ea = cudaFuncSetAttribute(layernorm768_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem);
+      if (ea != cudaSuccess) return cudaGetErrorString(ea);
+      attr_set = true;
+    }
+    const int blocks_s = grid_for(n_rows_out, kLnRows, device_num_sms() * 2);
+    cudaError_t es = launch_pdl(layernorm768_stream_kernel, dim3(blocks_s), dim3(256), kLnSmem, stream, 1, in, gamma, beta,
+                                static_cast<uint16_t*>(out), n_rows_out, out_kind == 2);
+    return es != cudaSuccess ? cudaGetErrorString(es) : last_err();
+  }
+  const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
   cudaError_t e = out_kind ? launch_pdl(layernorm768_kernel<true>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
                                         n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, out_kind == 2)
                            : launch_pdl(layernorm768_kernel<false>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
