@@ -44,6 +44,7 @@ SIGNATURES = {
     "clipebc_set_gemm_impl": (_i, [_i]),
     "clipebc_set_attention_impl": (_i, [_i]),
     "clipebc_set_ln_fold": (_i, [_i]),
+    "clipebc_set_conv1_coarse": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_profile_enabled": (_i, []),

@@ -76,6 +76,10 @@ static std::atomic<int> g_attn_impl{4};
 // LayerNorm folded into the GEMMs either side of it (run_windows): off by default -- measured on B200 it removes the 24
 // LayerNorm launches of a pass (-0.33 ms per 64 windows) but the heavier GEMM epilogues give 0.30 ms back
 static std::atomic<int> g_ln_fold{0};
+// conv1 of the decoder computed from the coarse patch grid (one GEMM with hp*wp rows per window + a gather kernel) when
+// the decoder grid is finer than the patch grid (reduction 8 with ViT-B/16, reductions 8 / 16 with ViT-B/32); 0 = the
+// implicit GEMM on the fine grid
+static std::atomic<int> g_conv1_coarse{std::getenv("CLIPEBC_CONV1_FINE") ? 0 : 1};  // env: A/B knob for bench runs
 
 const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                                int n_win, int t_live, void* out, int out_fp16) {
@@ -165,6 +169,9 @@ struct clipebc_model {
   // packed
   LayerPack layer[kLayers];
   DevBuf w_patch;           // bf16 [768, 768]
+  DevBuf w_c1z;             // 16-bit [9*768, 768]: conv1 with the tap on the output side (coarse-grid form)
+  DevBuf zero_bias;         // f32 [9*768] zeros
+  DevBuf ws_Y16, ws_Z;      // coarse-grid conv1: 16-bit ln_post rows, per-tap products [n * hp * wp, 9*768]
   DevBuf w_c1, w_c2;        // bf16 [768, 9*768]
   DevBuf b_c1, b_c2;        // f32 [768]
   DevBuf w_p3;              // bf16 [512, 3*768] = hi|hi|lo
@@ -424,11 +431,16 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 
   // ln_post on the patch rows only (cls / prompt rows are dropped, model.py:185-188), fp32 out
   float* Y = m->ws_Y.as<float>();
+  // conv1 from the coarse grid (elementwise.cu: conv1_from_coarse_kernel) whenever the decoder grid is at least twice as
+  // fine as the patch grid: ln_post then also leaves the 16-bit rows its GEMM reads
+  const bool coarse1 = g_conv1_coarse.load() != 0 && g_gemm_impl.load() == 2 && gh >= 2 * hp && gw >= 2 * wp;
+  if (coarse1) CUDA_TRY(m->ws_Y16.reserve(static_cast<size_t>(nw) * npatch * kWidth * 2));
   K_TRY(layernorm768(s, X, raw_ptr(m, "image_encoder.ln_post.weight"), raw_ptr(m, "image_encoder.ln_post.bias"), Y, 0,
-                     static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch));
+                     static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch, coarse1 ? m->ws_Y16.p : nullptr, fp16));
   __nv_bfloat16* Ub = m->ws_Ub.as<__nv_bfloat16>();
   float* Uf = m->ws_Uf.as<float>();
-  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf, fp16));
+  // coarse-grid conv1: the 16-bit fine-grid map is not needed, only the fp32 one for the BasicBlock skip
+  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, coarse1 ? nullptr : Ub, Uf, fp16));
 
   // decoder BasicBlock as two implicit GEMMs over the zero-bordered grid: 9 taps = 9 row-shifted K-segments
   GemmParams pc = gemm_params_plain(Mp, kWidth, 9 * kWidth);
@@ -444,6 +456,15 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   GemmParams p1 = pc;
   p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp; p1.mask_lead = 0;
   set_launch_tag("dec_conv1");
+  if (coarse1) {
+    const int64_t rows_c = static_cast<int64_t>(nw) * npatch;
+    CUDA_TRY(m->ws_Z.reserve(static_cast<size_t>(rows_c) * 9 * kWidth * 2));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->ws_Y16.as<__nv_bfloat16>(), rows_c, kWidth, kWidth, m->w_c1z.as<__nv_bfloat16>(), kWidth,
+                        plain(fp16, fp16, static_cast<int>(rows_c), 9 * kWidth, kWidth, m->ws_Z.p, 9 * kWidth,
+                              m->zero_bias.as<float>()), 0));
+    set_launch_tag(nullptr);
+    K_TRY(conv1_from_coarse(s, m->ws_Z.p, m->b_c1.as<float>(), nw, hp, wp, gh, gw, D1, fp16));
+  } else
   K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
   GemmParams p2 = pc;
   p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
@@ -518,6 +539,12 @@ int clipebc_set_gemm_impl(int impl) {
   g_config_epoch.fetch_add(1);
   if (impl != 1 && impl != 2) return fail(CLIPEBC_EINVAL, "gemm impl must be 1 (single CTA) or 2 (CTA pair)");
   g_gemm_impl.store(impl);
+  return CLIPEBC_OK;
+}
+
+int clipebc_set_conv1_coarse(int on) {
+  g_config_epoch.fetch_add(1);
+  g_conv1_coarse.store(on != 0);
   return CLIPEBC_OK;
 }
 
@@ -684,6 +711,13 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
     CUDA_TRY(B.reserve(kWidth * 4));
     K_TRY(fold_conv3x3_bn(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".bias"), raw_ptr(m, bn + ".running_mean"),
                           raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth, kWidth, W.p, B.as<float>(), fp16));
+    if (k == 1) {
+      CUDA_TRY(m->w_c1z.reserve(static_cast<size_t>(9) * kWidth * kWidth * 2));
+      K_TRY(fold_conv3x3_bn_tapout(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth,
+                                   kWidth, m->w_c1z.p, fp16));
+      CUDA_TRY(m->zero_bias.reserve(static_cast<size_t>(9) * kWidth * 4));
+      CUDA_TRY(cudaMemsetAsync(m->zero_bias.p, 0, static_cast<size_t>(9) * kWidth * 4, s));
+    }
   }
   CUDA_TRY(m->w_p3.reserve(static_cast<size_t>(kEmbed) * 3 * kWidth * 2));
   K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), kEmbed, kWidth, m->w_p3.p, fp16));

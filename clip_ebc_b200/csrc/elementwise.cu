@@ -95,7 +95,8 @@ template <bool OUT_16>
 __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, void* __restrict__ out,
                                                            int64_t n_rows_out, int rows_out_per_group,
-                                                           int rows_in_per_group, int in_row_offset, int fp16) {
+                                                           int rows_in_per_group, int in_row_offset, int fp16,
+                                                           uint16_t* __restrict__ out16_extra) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -106,10 +107,12 @@ __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __res
     const int64_t in_row = g * rows_in_per_group + in_row_offset + (r - g * rows_out_per_group);
     Row768 x = load_row(in + in_row * kD, lane);
     layernorm_row(x, gamma, beta, lane);
-    if constexpr (OUT_16)
+    if constexpr (OUT_16) {
       store_row_16(static_cast<uint16_t*>(out) + r * kD, x, lane, fp16);
-    else
+    } else {
       store_row_f32(static_cast<float*>(out) + r * kD, x, lane);
+      if (out16_extra != nullptr) store_row_16(out16_extra + r * kD, x, lane, fp16);  // ln_post: + the 16-bit GEMM operand
+    }
   }
 }
 
@@ -385,8 +388,137 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
         o.v[i].w = w00 * a.v[i].w + w01 * b.v[i].w + w10 * c.v[i].w + w11 * d.v[i].w;
       }
     }
-    store_row_16(U_16 + r * kD, o, lane, fp16);
+    if (U_16 != nullptr) store_row_16(U_16 + r * kD, o, lane, fp16);
     store_row_f32(U_f32 + r * kD, o, lane);
+  }
+}
+
+// ------------------------------------------------------------------ conv1 of the decoder from the coarse grid ------
+// conv3x3(bilinear_up(Y)) = sum over the 9 taps of bilinear_up(W_tap Y) shifted by the tap: the channel contraction
+// commutes with the (linear, per-channel) resampling, so it runs ONCE per tap on the coarse patch grid -- Z[src, tap, o] =
+// sum_c W'[o, c, tap] Y[src, c], a GEMM with hp*wp rows per window instead of (g+1)^2 (196 instead of 841 at reduction 8:
+// 2.08 instead of 8.9 GFLOP per window) -- and this kernel gathers, per output cell and tap, the four bilinear neighbours
+// of the shifted position: 36 multiply-adds per output value instead of 6912. Zero padding of the conv applies to the
+// FINE grid (taps that leave the window are skipped), the bilinear source clamps at the window edge, exactly as
+// F.interpolate followed by conv2d(padding=1) (models/clip/model.py:195-197, models/utils.py:290-296).
+// Thread = (cell of the shared-border grid, 8 output channels); ReLU and the zero border rows as in the GEMM epilogue it
+// replaces. Z: 16-bit [n_win * hp * wp, 9 * 768] (column = tap * 768 + o), bias f32 [768], D1: 16-bit [.., 768].
+__device__ __forceinline__ void fma8_16(float2 (&acc)[4], const uint4& z, float w, int fp16) {
+  const uint32_t u[4] = {z.x, z.y, z.z, z.w};
+  const float2 w2 = make_float2(w, w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f;
+    if (fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+    else f = make_float2(__uint_as_float(u[k] << 16), __uint_as_float(u[k] & 0xFFFF0000u));
+    acc[k] = __ffma2_rn(w2, f, acc[k]);  // packed fp32 FMA (sm_100): two multiply-adds per instruction
+  }
+}
+
+// Tiling: one CTA = (window, band of `bh` fine rows, tile of `bw` fine columns, slice of CS output channels); the coarse
+// positions the tile can touch are staged once in shared memory for all 9 taps (cp.async), thread item = (cell, 8
+// channels of the slice). Two shapes are used: the whole window with 16-channel slices when its patch grid fits
+// (hp * wp * 9 * 32 B <= 56 KB: no position is fetched twice), else bands of 4 x 32 cells with 32-channel slices (<= 5 x
+// 19 coarse positions, 54 KB). What bounds it: 36 16-byte shared-memory reads per 8 outputs (no reuse between cells:
+// neighbouring cells read the same positions under different taps) -- 3 GB per 64 windows.
+constexpr int kC1Smem = 5 * 19 * 9 * 32 * 2;  // 54720 B: the band shape; the whole-window shape is checked against it too
+
+template <int CS>
+__global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* __restrict__ Z, const float* __restrict__ bias,
+                                                                int n_win, int hp, int wp, int gh, int gw, int bh, int bw,
+                                                                int n_bands, int n_ctiles, uint16_t* __restrict__ D1, int fp16) {
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int kSlices = kD / CS;
+  constexpr int kG = CS / 8;          // 8-channel groups per cell
+  constexpr int kRowB = CS * 2;       // bytes per (position, tap)
+  constexpr int kPosB = 9 * kRowB;    // bytes per position
+  const int Hp = gh + 1, Wp = gw + 1;
+  const float inv_sy = static_cast<float>(hp) / static_cast<float>(gh), inv_sx = static_cast<float>(wp) / static_cast<float>(gw);
+  int b = blockIdx.x;
+  const int slice = b % kSlices; b /= kSlices;
+  const int ct = b % n_ctiles; b /= n_ctiles;
+  const int band = b % n_bands;
+  const int win = b / n_bands;
+  const int y_lo = band * bh, x_lo = ct * bw;
+  const int y_hi = min(y_lo + bh, Hp), x_hi = min(x_lo + bw, Wp);  // cells [y_lo, y_hi) x [x_lo, x_hi) incl. border
+  // coarse range touched by the fine positions [y_lo - 1, y_hi] x [x_lo - 1, x_hi] clipped to the window
+  int i_lo, i_hi, j_lo, j_hi, t0, t1;
+  float lam;
+  bilinear_src(max(y_lo - 1, 0), inv_sy, hp, i_lo, t1, lam);
+  bilinear_src(min(y_hi, gh - 1), inv_sy, hp, t0, i_hi, lam);
+  bilinear_src(max(x_lo - 1, 0), inv_sx, wp, j_lo, t1, lam);
+  bilinear_src(min(x_hi, gw - 1), inv_sx, wp, t0, j_hi, lam);
+  const int nr = i_hi - i_lo + 1, nc = j_hi - j_lo + 1;
+  // ---- stage Z[i_lo..i_hi, j_lo..j_hi, all taps, slice] ----
+  const int64_t ldz = 9 * kD;
+  const uint16_t* zw = Z + static_cast<int64_t>(win) * hp * wp * ldz + slice * CS;
+  const int n_chunks = nr * nc * 9 * kG;
+  for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+    const int ch = i % kG, pt = i / kG;
+    const int tap = pt % 9, pos = pt / 9;
+    const int rr = pos / nc, cc = pos - rr * nc;
+    // asynchronous copies: all of a thread's chunks are in flight at once (a load -> store loop waits for every load)
+    cp_async_16(smem_u32(c1_smem + pt * kRowB + (ch << 4)),
+                zw + (static_cast<int64_t>(i_lo + rr) * wp + (j_lo + cc)) * ldz + tap * kD + ch * 8, true);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- compute ----
+  const int tw = x_hi - x_lo, th = y_hi - y_lo;
+  const int n_items = th * tw * kG;
+  for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+    const int g = it % kG, cell = it / kG;
+    const int cy = cell / tw, cx = cell - cy * tw;
+    const int py = y_lo + cy, px = x_lo + cx;
+    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+    if (py < gh && px < gw) {
+      float2 acc[4];
+      const float* bp = bias + slice * CS + g * 8;
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+      acc[0] = make_float2(b0.x, b0.y); acc[1] = make_float2(b0.z, b0.w); acc[2] = make_float2(b1.x, b1.y); acc[3] = make_float2(b1.z, b1.w);
+      // column sources of the three horizontal taps, once per cell
+      int xo0[3], xo1[3];
+      float lxs[3];
+      bool xok[3];
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = px + dx;
+        xok[dx + 1] = xx >= 0 && xx < gw;
+        int x0, x1;
+        bilinear_src(xok[dx + 1] ? xx : px, inv_sx, wp, x0, x1, lxs[dx + 1]);
+        xo0[dx + 1] = (x0 - j_lo) * kPosB; xo1[dx + 1] = (x1 - j_lo) * kPosB;
+      }
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = py + dy;
+        if (yy < 0 || yy >= gh) continue;
+        int y0, y1;
+        float ly;
+        bilinear_src(yy, inv_sy, hp, y0, y1, ly);
+        const int yo0 = (y0 - i_lo) * nc * kPosB, yo1 = (y1 - i_lo) * nc * kPosB;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          if (!xok[dx + 1]) continue;
+          const float lx = lxs[dx + 1];
+          const uint8_t* zt = c1_smem + ((dy + 1) * 3 + (dx + 1)) * kRowB + (g << 4);
+          const uint4 a = *reinterpret_cast<const uint4*>(zt + yo0 + xo0[dx + 1]);
+          const uint4 bq = *reinterpret_cast<const uint4*>(zt + yo0 + xo1[dx + 1]);
+          const uint4 c = *reinterpret_cast<const uint4*>(zt + yo1 + xo0[dx + 1]);
+          const uint4 d = *reinterpret_cast<const uint4*>(zt + yo1 + xo1[dx + 1]);
+          fma8_16(acc, a, (1.f - ly) * (1.f - lx), fp16);
+          fma8_16(acc, bq, (1.f - ly) * lx, fp16);
+          fma8_16(acc, c, ly * (1.f - lx), fp16);
+          fma8_16(acc, d, ly * lx, fp16);
+        }
+      }
+      outv = make_uint4(pack16x2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f), fp16), pack16x2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f), fp16),
+                        pack16x2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f), fp16), pack16x2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f), fp16));
+    }
+    const int64_t r = (static_cast<int64_t>(win) * Hp + py) * Wp + px;
+    *reinterpret_cast<uint4*>(D1 + r * kD + slice * CS + g * 8) = outv;
   }
 }
 
@@ -413,6 +545,22 @@ __global__ void fold_conv3x3_bn_kernel(const float* __restrict__ W, const float*
     const float s = gamma[o] / sqrtf(var[o] + eps);
     Wp[idx] = cvt16(W[(static_cast<int64_t>(o) * I + i) * 9 + tap] * s, fp16);
     if (i == 0 && tap == 0) bias[o] = beta[o] - mean[o] * s;
+  }
+}
+
+// The same fold with the TAP on the output side: Wz[(tap * O + o), i] = W[o, i, tap] * g / sqrt(var + eps) -- the weight
+// of the coarse-grid form of conv1 (conv1_from_coarse_kernel): one [O, I] matrix per tap, stacked along N
+__global__ void fold_conv3x3_bn_tapout_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                              const float* __restrict__ var, float eps, int O, int I,
+                                              uint16_t* __restrict__ Wz, int fp16) {
+  const int64_t total = static_cast<int64_t>(O) * I * 9;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // idx enumerates the destination [tap][O][I]
+    const int i = static_cast<int>(idx % I);
+    const int o = static_cast<int>((idx / I) % O);
+    const int tap = static_cast<int>(idx / (static_cast<int64_t>(I) * O));
+    Wz[idx] = cvt16(W[(static_cast<int64_t>(o) * I + i) * 9 + tap] * (gamma[o] / sqrtf(var[o] + eps)), fp16);
   }
 }
 
@@ -482,7 +630,7 @@ inline const char* last_err() {
 
 const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
                          int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
-                         int in_row_offset) {
+                         int in_row_offset, void* out16_extra, int fp16_extra) {
   if (n_rows_out <= 0) return nullptr;
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
   LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_kind ? 2.0 : 4.0)));
@@ -503,9 +651,11 @@ const char* layernorm768(cudaStream_t stream, const float* in, const float* gamm
   }
   const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
   cudaError_t e = out_kind ? launch_pdl(layernorm768_kernel<true>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
-                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, out_kind == 2)
+                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, out_kind == 2,
+                                        static_cast<uint16_t*>(nullptr))
                            : launch_pdl(layernorm768_kernel<false>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
-                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, 0);
+                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, fp16_extra,
+                                        static_cast<uint16_t*>(out16_extra));
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
@@ -564,6 +714,45 @@ const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, i
   cudaError_t e = launch_pdl(resample_to_padded_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
                              Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+
+const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* bias, int n_win, int hp, int wp, int gh, int gw,
+                              void* D1, int fp16) {
+  if (n_win <= 0) return "conv1_from_coarse: no windows";
+  if (gh < 2 * hp || gw < 2 * wp) return "conv1_from_coarse: the decoder grid must be at least twice as fine as the patch grid";
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
+    if (ea != cudaSuccess) return cudaGetErrorString(ea);
+    attr_set = true;
+  }
+  LaunchScope scope(stream, "conv1_interp", 0.0,
+                    static_cast<double>(n_win) * hp * wp * 9 * kD * 2.0 + static_cast<double>(n_win) * (gh + 1) * (gw + 1) * kD * 2.0);
+  cudaError_t e;
+  const int whole = hp * wp * 9 * 16 * 2;  // the window's patch grid, all taps, 16 channels
+  if (whole <= 57344) {
+    const int64_t blocks = static_cast<int64_t>(n_win) * (kD / 16);
+    e = launch_pdl(conv1_from_coarse_kernel<16>, dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(whole), stream, 1,
+                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, gh + 1, gw + 1, 1, 1, static_cast<uint16_t*>(D1), fp16);
+  } else {
+    const int bh = 4, bw = 32;
+    const int n_bands = (gh + 1 + bh - 1) / bh, n_ctiles = (gw + 1 + bw - 1) / bw;
+    const int64_t blocks = static_cast<int64_t>(n_win) * n_bands * n_ctiles * (kD / 32);
+    if (blocks > 0x7fffffff) return "conv1_from_coarse: grid too large";
+    e = launch_pdl(conv1_from_coarse_kernel<32>, dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(kC1Smem), stream, 1,
+                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, bh, bw, n_bands, n_ctiles,
+                   static_cast<uint16_t*>(D1), fp16);
+  }
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+
+const char* fold_conv3x3_bn_tapout(cudaStream_t stream, const float* W, const float* gamma, const float* var, float eps, int O,
+                                   int I, void* Wz, int fp16) {
+  LaunchScope scope(stream, "pack");
+  fold_conv3x3_bn_tapout_kernel<<<grid_for(static_cast<int64_t>(O) * I * 9, 256, 4096), 256, 0, stream>>>(
+      W, gamma, var, eps, O, I, static_cast<uint16_t*>(Wz), fp16);
+  return last_err();
 }
 
 const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n, int fp16) {

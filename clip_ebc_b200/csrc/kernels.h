@@ -127,9 +127,10 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 // out[r] = LN(in[map(r)]) * gamma + beta, eps 1e-5, fp32 statistics (two-pass, in registers). D = 768 only.
 // out_kind: 0 = f32, 1 = bf16, 2 = fp16.
 // Row map: in_row = (r / rows_out_per_group) * rows_in_per_group + in_row_offset + r % rows_out_per_group.
+// out16_extra (f32 output only, nullable): also the 16-bit rounding of the rows, in the format fp16_extra selects.
 const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
                          int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
-                         int in_row_offset);
+                         int in_row_offset, void* out16_extra = nullptr, int fp16_extra = 0);
 
 // ------------------------------------------------------------------ stem ---------------------------------------
 // image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * KP] = [hi | lo] split of the
@@ -189,7 +190,15 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
 // that ends one window is the top border of the next (rows before the buffer are zero-filled by TMA): every 3x3 tap
 // r + dy * (gw + 1) + dx of an interior cell lands on the right neighbour or on a zero  (model.py:195-196).
 const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
-                               void* U_16, float* U_f32, int fp16);
+                               void* U_16, float* U_f32, int fp16);  // U_16 may be null (coarse-grid conv1)
+
+// conv1 of the decoder from the coarse patch grid (elementwise.cu: conv1_from_coarse_kernel): Z 16-bit
+// [n_win * hp * wp, 9 * 768] = Y_16 x Wz^T (Wz from fold_conv3x3_bn_tapout, column = tap * 768 + o) ->
+// D1 16-bit [n_win * (gh+1) * (gw+1), 768] = relu(conv3x3(bilinear_up(Y)) + bias) on the shared-border grid (border rows 0)
+const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* bias, int n_win, int hp, int wp, int gh, int gw,
+                              void* D1, int fp16);
+const char* fold_conv3x3_bn_tapout(cudaStream_t stream, const float* W, const float* gamma, const float* var, float eps, int O,
+                                   int I, void* Wz, int fp16);
 
 // F f32 [n_win * (gh+1) * (gw+1), 512] projected features on the shared-border grid -> EBC head on interior cells:
 // normalise, logits against tmat f32 [n_bins, 512] (= logit_scale * normalised text features), softmax, expectation

@@ -25,6 +25,11 @@ def set_ln_fold(on: bool) -> None:
     _lib.check(_lib.load().clipebc_set_ln_fold(int(bool(on))), "set_ln_fold")
 
 
+def set_conv1_coarse(on: bool) -> None:
+    """Decoder conv1 from the coarse patch grid (default on; see clipebc_set_conv1_coarse)."""
+    _lib.check(_lib.load().clipebc_set_conv1_coarse(int(bool(on))), "set_conv1_coarse")
+
+
 def set_attention_impl(impl: int) -> None:
     """1 = mma.sync attention, 2 = tcgen05 / TMEM attention (default)."""
     _lib.check(_lib.load().clipebc_set_attention_impl(int(impl)), "set_attention_impl")

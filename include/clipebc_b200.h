@@ -30,7 +30,7 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 7
+#define CLIPEBC_ABI_VERSION 8
 
 typedef struct clipebc_model clipebc_model;
 
@@ -66,6 +66,10 @@ int clipebc_set_attention_impl(int impl);
  * below) instead of separate LayerNorm launches; 0 (default): separate launches. Same results to a few 16-bit roundings
  * (both are checked against the oracle); measured speed on B200 is the same within 1 %. CTA-pair GEMM only. */
 int clipebc_set_ln_fold(int on);
+/* 1 (default): conv1 of the decoder is computed from the coarse patch grid whenever the decoder grid is finer
+ * (conv3x3(bilinear_up(Y)) = the 9 per-tap channel contractions on the patch grid, then a bilinear gather; DESIGN.md
+ * section 2 rewrite 8); 0: implicit GEMM on the fine grid. Same result to a few 16-bit roundings. */
+int clipebc_set_conv1_coarse(int on);
 
 /* Optional per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
  * clipebc_profile_dump synchronises the device and writes a JSON object {"<kernel>[:<use>]": {"ms", "launches",

@@ -44,7 +44,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.clipebc_abi_version() == 7
+    assert lib.clipebc_abi_version() == 8
     assert lib.clipebc_launch_count() == 0  # nothing ran on this CPU box
 
 

@@ -28,14 +28,17 @@ def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0, operand_
     return model.to("cuda").eval()
 
 
-@pytest.fixture(params=[False, True], ids=["ln_kernels", "ln_folded"])
+@pytest.fixture(params=["default", "ln_folded", "conv1_fine"])
 def ln_fold(request):
-    """Both forms of the LayerNorms inside the blocks: separate kernels (default) and folded into the GEMMs."""
+    """The optional forms of the path: LayerNorms folded into the GEMMs (default: separate kernels) and decoder conv1 as
+    an implicit GEMM on the fine grid (default: from the coarse patch grid). Every form meets the same gates."""
     from clip_ebc_b200 import ops
 
-    ops.set_ln_fold(request.param)
+    ops.set_ln_fold(request.param == "ln_folded")
+    ops.set_conv1_coarse(request.param != "conv1_fine")
     yield request.param
     ops.set_ln_fold(False)
+    ops.set_conv1_coarse(True)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
