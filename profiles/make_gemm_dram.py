@@ -6,8 +6,9 @@ step) -> profiles/rNN_gemm_dram.json, the per-use DRAM traffic bench.py reports 
   python profiles/make_gemm_dram.py gpurun_out/gemm_dram.csv profiles/r01i_gemm_dram.json
 
 Launch order of a step (api.cu run_windows): patch_embed <256,0>, 12 x [qkv <256,2>, out_proj <192,4>, c_fc <256,3>,
-c_proj <192,4>], dec_conv1 <256,5>, dec_conv2 <256,6>, projection+head <256,7>. Pack-time launches (the constant prompt
-K/V rows: <128,2> with M = 32) are skipped.
+c_proj <192,4>], dec_conv1 (coarse-grid form: <256,2> with N = 6912, the 13th <*,2> launch of a step; fine-grid form:
+<256,5>), dec_conv2 <256,6>, projection+head <256,7>. Pack-time launches (the constant prompt K/V rows: <128,2> with
+M = 32) are skipped.
 """
 import collections
 import csv
@@ -31,6 +32,7 @@ for row in csv.DictReader(lines):
     d[name] = v
 per_tag = collections.OrderedDict()
 n_resid = 0
+n_epi2 = 0
 for d in launches.values():
     m = re.search(r"gemm2_tcgen05_kernel<(\d+), (\d+), (\d+)>", d["kernel"])
     if not m:
@@ -41,8 +43,11 @@ for d in launches.values():
     if epi in (4, 8):
         tag = "out_proj" if n_resid % 2 == 0 else "c_proj"
         n_resid += 1
+    elif epi == 2:
+        tag = "dec_conv1" if n_epi2 % 13 == 12 else "qkv"
+        n_epi2 += 1
     else:
-        tag = {0: "patch_embed", 2: "qkv", 9: "qkv", 3: "c_fc", 10: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 7: "projection+head",
+        tag = {0: "patch_embed", 9: "qkv", 3: "c_fc", 10: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 7: "projection+head",
                1: "projection"}.get(epi)
     if tag is None:
         continue
