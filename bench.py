@@ -391,7 +391,7 @@ def main():
     # DRAM traffic per launch of the same kernel family from the committed ncu capture (dram__bytes_read + write per
     # launch, weighted by how often each GEMM of the step is launched); cold-L2 figures, so an upper bound in-step.
     traffic, traffic_note = None, "no ncu capture committed"
-    tpath = os.path.join(ROOT, "profiles", "r01i_gemm_dram.json")
+    tpath = os.path.join(ROOT, "profiles", "r01k_gemm_dram.json")
     if args.workload == "windows64" and os.path.exists(tpath):
         per_tag = json.load(open(tpath))["per_tag"]
         num = den = 0.0
@@ -403,7 +403,7 @@ def main():
                 den += n
         if den > 0:
             traffic = num / den
-            traffic_note = ("bytes per launch, launch-weighted mean over the GEMMs of a step, from profiles/r01i_gemm_dram.json "
+            traffic_note = ("bytes per launch, launch-weighted mean over the GEMMs of a step, from profiles/r01k_gemm_dram.json "
                             "(ncu dram__bytes_read.sum + dram__bytes_write.sum, cold L2 per launch)")
     roofline = {
         "bound": "tensor", "kernel": "gemm2_tcgen05_kernel (all epilogues)", "achieved": achieved, "peak": peak,

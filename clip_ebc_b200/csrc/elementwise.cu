@@ -403,13 +403,14 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
 // F.interpolate followed by conv2d(padding=1) (models/clip/model.py:195-197, models/utils.py:290-296).
 // Thread = (cell of the shared-border grid, 8 output channels); ReLU and the zero border rows as in the GEMM epilogue it
 // replaces. Z: 16-bit [n_win * hp * wp, 9 * 768] (column = tap * 768 + o), bias f32 [768], D1: 16-bit [.., 768].
-__device__ __forceinline__ void fma8_16(float2 (&acc)[4], const uint4& z, float w, int fp16) {
+template <bool FP16>
+__device__ __forceinline__ void fma8_16(float2 (&acc)[4], const uint4& z, float w) {
   const uint32_t u[4] = {z.x, z.y, z.z, z.w};
   const float2 w2 = make_float2(w, w);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float2 f;
-    if (fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+    if constexpr (FP16) f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
     else f = make_float2(__uint_as_float(u[k] << 16), __uint_as_float(u[k] & 0xFFFF0000u));
     acc[k] = __ffma2_rn(w2, f, acc[k]);  // packed fp32 FMA (sm_100): two multiply-adds per instruction
   }
@@ -423,10 +424,11 @@ __device__ __forceinline__ void fma8_16(float2 (&acc)[4], const uint4& z, float 
 // neighbouring cells read the same positions under different taps) -- 3 GB per 64 windows.
 constexpr int kC1Smem = 5 * 19 * 9 * 32 * 2;  // 54720 B: the band shape; the whole-window shape is checked against it too
 
-template <int CS>
+template <int CS, bool FP16>
 __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* __restrict__ Z, const float* __restrict__ bias,
                                                                 int n_win, int hp, int wp, int gh, int gw, int bh, int bw,
-                                                                int n_bands, int n_ctiles, uint16_t* __restrict__ D1, int fp16) {
+                                                                int n_bands, int n_ctiles, uint16_t* __restrict__ D1) {
+  constexpr int fp16 = FP16 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t c1_smem[];
   pdl_launch_dependents();
   pdl_wait();
@@ -508,10 +510,10 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
           const uint4 bq = *reinterpret_cast<const uint4*>(zt + yo0 + xo1[dx + 1]);
           const uint4 c = *reinterpret_cast<const uint4*>(zt + yo1 + xo0[dx + 1]);
           const uint4 d = *reinterpret_cast<const uint4*>(zt + yo1 + xo1[dx + 1]);
-          fma8_16(acc, a, (1.f - ly) * (1.f - lx), fp16);
-          fma8_16(acc, bq, (1.f - ly) * lx, fp16);
-          fma8_16(acc, c, ly * (1.f - lx), fp16);
-          fma8_16(acc, d, ly * lx, fp16);
+          fma8_16<FP16>(acc, a, (1.f - ly) * (1.f - lx));
+          fma8_16<FP16>(acc, bq, (1.f - ly) * lx);
+          fma8_16<FP16>(acc, c, ly * (1.f - lx));
+          fma8_16<FP16>(acc, d, ly * lx);
         }
       }
       outv = make_uint4(pack16x2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f), fp16), pack16x2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f), fp16),
@@ -722,8 +724,10 @@ const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* b
   if (gh < 2 * hp || gw < 2 * wp) return "conv1_from_coarse: the decoder grid must be at least twice as fine as the patch grid";
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
+    cudaError_t ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
     if (ea != cudaSuccess) return cudaGetErrorString(ea);
     attr_set = true;
   }
@@ -733,16 +737,17 @@ const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* b
   const int whole = hp * wp * 9 * 16 * 2;  // the window's patch grid, all taps, 16 channels
   if (whole <= 57344) {
     const int64_t blocks = static_cast<int64_t>(n_win) * (kD / 16);
-    e = launch_pdl(conv1_from_coarse_kernel<16>, dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(whole), stream, 1,
-                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, gh + 1, gw + 1, 1, 1, static_cast<uint16_t*>(D1), fp16);
+    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<16, true> : conv1_from_coarse_kernel<16, false>, dim3(static_cast<unsigned>(blocks)),
+                   dim3(256), static_cast<size_t>(whole), stream, 1, static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw,
+                   gh + 1, gw + 1, 1, 1, static_cast<uint16_t*>(D1));
   } else {
     const int bh = 4, bw = 32;
     const int n_bands = (gh + 1 + bh - 1) / bh, n_ctiles = (gw + 1 + bw - 1) / bw;
     const int64_t blocks = static_cast<int64_t>(n_win) * n_bands * n_ctiles * (kD / 32);
     if (blocks > 0x7fffffff) return "conv1_from_coarse: grid too large";
-    e = launch_pdl(conv1_from_coarse_kernel<32>, dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(kC1Smem), stream, 1,
-                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, bh, bw, n_bands, n_ctiles,
-                   static_cast<uint16_t*>(D1), fp16);
+    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<32, true> : conv1_from_coarse_kernel<32, false>, dim3(static_cast<unsigned>(blocks)),
+                   dim3(256), static_cast<size_t>(kC1Smem), stream, 1, static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw,
+                   bh, bw, n_bands, n_ctiles, static_cast<uint16_t*>(D1));
   }
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
