@@ -439,8 +439,9 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
                      static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch, coarse1 ? m->ws_Y16.p : nullptr, fp16));
   __nv_bfloat16* Ub = m->ws_Ub.as<__nv_bfloat16>();
   float* Uf = m->ws_Uf.as<float>();
-  // coarse-grid conv1: the 16-bit fine-grid map is not needed, only the fp32 one for the BasicBlock skip
-  K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, coarse1 ? nullptr : Ub, Uf, fp16));
+  // coarse-grid conv1: the fine-grid map is never materialised -- conv1 reads the per-tap products on the patch grid and
+  // conv2's epilogue evaluates the BasicBlock skip (bilinear_up(Y)) on the fly (EPI_BIAS_UPSKIP_RELU_SPLIT)
+  if (!coarse1) K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf, fp16));
 
   // decoder BasicBlock as two implicit GEMMs over the zero-bordered grid: 9 taps = 9 row-shifted K-segments
   GemmParams pc = gemm_params_plain(Mp, kWidth, 9 * kWidth);
@@ -468,8 +469,10 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
   GemmParams p2 = pc;
   p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
+  if (coarse1) { p2.resid = Y; p2.mask_hp = Hp; p2.mask_wp = Wp; p2.up_hp = hp; p2.up_wp = wp; }
   set_launch_tag("dec_conv2");
-  K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth, m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
+  K_TRY(gemm_dispatch(s, coarse1 ? EPI_BIAS_UPSKIP_RELU_SPLIT : EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth,
+                      m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
 
   // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
   GemmParams pp = gemm_params_plain(Mp, kEmbed, 3 * kWidth);

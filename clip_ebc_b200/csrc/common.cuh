@@ -81,6 +81,16 @@ __device__ __forceinline__ uint16_t cvt16(float x, int fp16) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// PyTorch upsample_bilinear2d, align_corners=False, scale_factor given: src = (dst + 0.5) / scale - 0.5, clamped at 0.
+__device__ __forceinline__ void bilinear_src(int dst, float inv_scale, int in_size, int& i0, int& i1, float& lam) {
+  float s = (dst + 0.5f) * inv_scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = static_cast<int>(s);
+  i0 = i0 > in_size - 1 ? in_size - 1 : i0;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  lam = s - static_cast<float>(i0);
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -337,16 +337,6 @@ __global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ resample -----------------------------------
-// PyTorch upsample_bilinear2d, align_corners=False, scale_factor given: src = (dst + 0.5) / scale - 0.5, clamped at 0.
-__device__ __forceinline__ void bilinear_src(int dst, float inv_scale, int in_size, int& i0, int& i1, float& lam) {
-  float s = (dst + 0.5f) * inv_scale - 0.5f;
-  s = s < 0.f ? 0.f : s;
-  i0 = static_cast<int>(s);
-  i0 = i0 > in_size - 1 ? in_size - 1 : i0;
-  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
-  lam = s - static_cast<float>(i0);
-}
-
 __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __restrict__ Y, int n_win, int hp, int wp,
                                                                  int gh, int gw, uint16_t* __restrict__ U_16,
                                                                  float* __restrict__ U_f32, int fp16) {

@@ -78,8 +78,11 @@ constexpr bool out_is_bf16() {
 }
 template <int EPI>
 constexpr bool has_resid() {
-  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_RESID_STATS;
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_RESID_STATS ||
+         EPI == EPI_BIAS_UPSKIP_RELU_SPLIT;
 }
+template <int EPI>
+constexpr bool is_relu_split() { return EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_UPSKIP_RELU_SPLIT; }
 
 // ---- bf16-output epilogues, 32 accumulator columns per pass -------------------------------------------------------
 // phase 1: thread = output row (as tcgen05.ld delivers it): bias (smem broadcast) + activation, pack, 4 x 16 B into the
@@ -152,7 +155,39 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
 // ---- fp32-finishing epilogues, 32 columns per pass (128 B rows, slot ^= row & 7) ----------------------------------
 template <int EPI>
 __device__ __forceinline__ void load_resid32(const GemmParams& p, int lane, int row0, int n, float4 (&x)[8]) {
-  if constexpr (has_resid<EPI>()) {
+  if constexpr (EPI == EPI_BIAS_UPSKIP_RELU_SPLIT) {
+    // residual = bilinear_up(Y)[cell of the row] (F.interpolate, align_corners = False; models/clip/model.py:195-196),
+    // four coarse rows per fine cell, weights as in resample_to_padded_kernel; border rows of the grid add nothing
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int gh = p.mask_hp - 1, gw = p.mask_wp - 1, rpi = p.mask_hp * p.mask_wp;
+    const float inv_sy = static_cast<float>(p.up_hp) / static_cast<float>(gh), inv_sx = static_cast<float>(p.up_wp) / static_cast<float>(gw);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row0 + it * 4 + rsub;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < p.M) {
+        const int win = grow / rpi, q = grow - win * rpi;
+        const int py = q / p.mask_wp, px = q - py * p.mask_wp;
+        if (py < gh && px < gw) {
+          int y0, y1, x0, x1;
+          float ly, lx;
+          bilinear_src(py, inv_sy, p.up_hp, y0, y1, ly);
+          bilinear_src(px, inv_sx, p.up_wp, x0, x1, lx);
+          const float* base = p.resid + static_cast<size_t>(win) * p.up_hp * p.up_wp * p.ldr + n + c4;
+          const float4 a = *reinterpret_cast<const float4*>(base + static_cast<size_t>(y0 * p.up_wp + x0) * p.ldr);
+          const float4 b = *reinterpret_cast<const float4*>(base + static_cast<size_t>(y0 * p.up_wp + x1) * p.ldr);
+          const float4 c = *reinterpret_cast<const float4*>(base + static_cast<size_t>(y1 * p.up_wp + x0) * p.ldr);
+          const float4 d = *reinterpret_cast<const float4*>(base + static_cast<size_t>(y1 * p.up_wp + x1) * p.ldr);
+          const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+          v.x = w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+          v.y = w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+          v.z = w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+          v.w = w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+        }
+      }
+      x[it] = v;
+    }
+  } else if constexpr (has_resid<EPI>()) {
     const int c4 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -181,7 +216,7 @@ __device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* st
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     if constexpr (has_resid<EPI>()) { v.x += x[it].x; v.y += x[it].y; v.z += x[it].z; v.w += x[it].w; }
     if (grow < p.M) {
-      if constexpr (EPI == EPI_BIAS_RESID_RELU_SPLIT) {
+      if constexpr (is_relu_split<EPI>()) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         const float hx = round16(v.x, p.out_fp16), hy = round16(v.y, p.out_fp16);
         const float hz = round16(v.z, p.out_fp16), hw = round16(v.w, p.out_fp16);
@@ -830,6 +865,9 @@ cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, con
     case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16, MC>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT, MC>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_UPSKIP_RELU_SPLIT:
+      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_BIAS_UPSKIP_RELU_SPLIT, 1>(stream, ta, tb, p, num_sms);
+      else return cudaErrorInvalidValue;
     case EPI_BIAS_RESID_STATS:
       if constexpr (MC == 1 && BLOCK_N == 192) return launch_one2<192, EPI_BIAS_RESID_STATS, 1>(stream, ta, tb, p, num_sms);
       else return cudaErrorInvalidValue;
@@ -885,8 +923,11 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if (block_n != 128 && block_n != 192 && block_n != 256) return "gemm: block_n must be 128, 192 or 256";
   if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
-  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT || epi == EPI_BIAS_RESID_STATS) && p.resid == nullptr)
+  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT || epi == EPI_BIAS_RESID_STATS ||
+       epi == EPI_BIAS_UPSKIP_RELU_SPLIT) && p.resid == nullptr)
     return "gemm: epilogue needs a residual";
+  if (epi == EPI_BIAS_UPSKIP_RELU_SPLIT && (p.mask_hp < 2 || p.mask_wp < 2 || p.up_hp < 1 || p.up_wp < 1))
+    return "gemm: upsampled-skip epilogue needs the grid (mask_hp, mask_wp) and the patch grid (up_hp, up_wp)";
   if (epi == EPI_BIAS_RESID_STATS) {
     if (p.x16_out == nullptr || p.stats_out == nullptr) return "gemm: statistics epilogue needs x16_out and stats_out";
     if (p.N != 2 * kLnPartCols * (kLnStatSlots / 2)) return "gemm: statistics epilogue: N must be 768";

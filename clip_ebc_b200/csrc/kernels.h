@@ -28,7 +28,11 @@ enum GemmEpilogue : int {
   EPI_LN_BIAS_BF16 = 9,         // out bf16 = rstd[row] * (acc - mean[row] * ln_colsum[n]) + bias[n]: A holds the RAW rows,
                                 // W = W * diag(gamma), bias = b + W beta, ln_colsum[n] = sum_k W'[n, k]; (mean, rstd) merged
                                 // per row in the epilogue from the ln_parts (1 or 8) partials of ln_stats (K = 768)
-  EPI_LN_BIAS_GELU_BF16 = 10    // quickgelu of the same
+  EPI_LN_BIAS_GELU_BF16 = 10,   // quickgelu of the same
+  EPI_BIAS_UPSKIP_RELU_SPLIT = 11  // EPI_BIAS_RESID_RELU_SPLIT whose residual is the bilinear upsample of the coarse map,
+                                // evaluated on the fly: resid = Y f32 [n_win * up_hp * up_wp, ldr] (ln_post rows), the row's
+                                // cell comes from the shared-border grid (mask_hp x mask_wp rows per window); border rows add 0.
+                                // The BasicBlock skip of the decoder without materialising the fine-grid map (CTA-pair kernel)
 };
 
 constexpr int kLnStatSlots = 8;   // float2 slots per row of a LayerNorm statistics buffer
@@ -47,6 +51,7 @@ struct GemmParams {
   const float* resid;                 // f32 [M, ldr]
   int ldr;
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
+  int up_hp, up_wp;                   // EPI_BIAS_UPSKIP_RELU_SPLIT: patch grid of the coarse map
   int mask_lead;                      // 1: first AND last row / column of the grid are border; 0: only the last ones
                                       // (shared-border grid: the trailing zero column / row of one line / image is the
                                       // leading border of the next)
