@@ -47,7 +47,7 @@ for d in launches.values():
         tag = "dec_conv1" if n_epi2 % 13 == 12 else "qkv"
         n_epi2 += 1
     else:
-        tag = {0: "patch_embed", 9: "qkv", 3: "c_fc", 10: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 7: "projection+head",
+        tag = {0: "patch_embed", 9: "qkv", 3: "c_fc", 10: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 11: "dec_conv2", 7: "projection+head",
                1: "projection"}.get(epi)
     if tag is None:
         continue
