@@ -176,8 +176,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "windows_per_sec", "value": wps, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CLIP-EBC ViT-B/16 deep-VPT(32) forward + EBC head, 224x224 windows, reduction 8, "
-                               f"CPU fp32; each step = {sample} windows sampled from the 64-window batch"},
+        # the same workload as the GPU arm (BASELINE.json configs[1]); the CPU arm times a bounded sample of it per step
+        "config": {"workload": "configs[1]: ViT-B/16 deep-VPT(32) forward + decoder + EBC head, batch 64 synthetic 224x224 "
+                               "windows, reduction 8 (5 bins)",
+                   "arm": f"reference algorithm on the host cores (CPU fp32 port, oracle/clip_ebc_oracle.py); each step = "
+                          f"{sample} windows sampled from the 64-window batch",
+                   "weights": "seeded random init with the reference's init distributions (oracle/weights.py)"},
         "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps x {sample} windows (oracle/clip_ebc_oracle.py, torch {torch.__version__} fp32)"},
         "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
