@@ -321,13 +321,22 @@ class CLIP_EBC(nn.Module):
                 self._graph_cache.pop(next(iter(self._graph_cache)))
             self._graph_cache[key] = {}
             return self._forward_eager(x.to(torch.float32).contiguous())
+        if entry.get("disabled"):
+            return self._forward_eager(x.to(torch.float32).contiguous())
         if "graph" not in entry:
             static_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)
             static_x.copy_(x)
             graph = torch.cuda.CUDAGraph()
             l0 = lib.clipebc_launch_count()
-            with torch.cuda.graph(graph):
-                outs = self._forward_eager(static_x)
+            try:
+                with torch.cuda.graph(graph):
+                    outs = self._forward_eager(static_x)
+            except Exception:
+                # a capture that cannot be completed (e.g. an allocation inside the library for a shape the eager call
+                # did not size) must not take the call down: this shape stays eager from now on
+                entry["disabled"] = True
+                torch.cuda.synchronize()
+                return self._forward_eager(static_x)
             entry.update(graph=graph, x=static_x, outs=outs, launches=int(lib.clipebc_launch_count() - l0))
         else:
             entry["x"].copy_(x)
