@@ -508,6 +508,7 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 int default_chunk(const clipebc_model* m, int hp = 14, int wp = 14) {
   if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
   const int64_t tokens = 1 + m->cfg.num_vpt + static_cast<int64_t>(hp) * wp;
+  if (tokens <= 128) return 256;  // ViT-B/32 windows (82 tokens): 256 windows give the GEMMs as many rows as 96 x 197
   if (tokens <= 256) return 96;
   return static_cast<int>(std::max<int64_t>(1, 96 * 229 / tokens));
 }

@@ -1,0 +1,32 @@
+"""Throughput of the ViT-B/32 backbone behind the same entry point: model(x) on 256 windows of 224x224 (python profiles/b32_bench.py)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from clip_ebc_b200 import get_model  # noqa: E402
+from oracle import weights  # noqa: E402
+
+dev = torch.device("cuda", 0)
+reduction, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
+for backbone, patch in (("clip_vit_b_32", 32), ("clip_vit_b_16", 16)):
+    sd = weights.make_state_dict(0, input_size=224, num_vpt=32, deep_vpt=True, variant="default", patch=patch)
+    model = get_model(backbone, input_size=224, reduction=reduction, bins=bins, anchor_points=anchors, prompt_type="word",
+                      num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=weights.make_text_features(len(bins), seed=100))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    B = 256
+    xs = [weights.make_image((B, 3, 224, 224), seed=70 + i).to(dev) for i in range(2)]
+    for i in range(6):
+        model(xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 10
+    for i in range(n):
+        model(xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"{backbone}: {B} windows in {ms:.2f} ms -> {B / ms * 1e3:.0f} windows/s")
