@@ -58,9 +58,10 @@ int64_t clipebc_launch_count(void);
 /* Selects the tcgen05 GEMM kernel used by the hot path and by clipebc_gemm_bf16: 1 = one CTA per 128-row tile,
  * 2 = CTA pair (cta_group::2, 256-row tiles; default). Both implement the same contract; tests run both. */
 int clipebc_set_gemm_impl(int impl);
-/* Selects the attention kernel: 1 = mma.sync (legacy tensor path), 2 = tcgen05 / TMEM, one CTA per 128-query tile,
- * 3 = tcgen05 persistent warp-specialised with P kept in TMEM (default). 2 and 3 fall back to 1 when the constant-key
- * count is not a multiple of 8. */
+/* Selects the attention kernel for windows of at most 256 tokens: 1 = mma.sync (legacy tensor path), 2 = tcgen05 / TMEM,
+ * one CTA per 128-query tile, 3 = tcgen05 persistent warp-specialised with P kept in TMEM, 4 = tcgen05 persistent with two
+ * independent chains per CTA (default). 2-4 fall back to 1 when the constant-key count is not a multiple of 8. Windows
+ * with more than 256 tokens always take the streamed-K/V kernel (any sequence length). */
 int clipebc_set_attention_impl(int impl);
 /* 1: run the ViT blocks with LayerNorm folded into the GEMMs either side of it (clipebc_gemm_resid_stats / clipebc_gemm_ln
  * below) instead of separate LayerNorm launches; 0 (default): separate launches. Same results to a few 16-bit roundings
