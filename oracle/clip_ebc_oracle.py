@@ -20,7 +20,14 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-WIDTH, LAYERS, HEADS = 768, 12, 12
+def dims(sd: Dict[str, Tensor]) -> Tuple[int, int, int]:
+    """(width, layers, heads) of the vision transformer, read off the state_dict: ViT-B (768, 12, 12) or ViT-L/14
+    (1024, 24, 16); heads = width // 64 (_clip/model.py:50)."""
+    width = int(sd["image_encoder.conv1.weight"].shape[0])
+    layers = 0
+    while f"image_encoder.transformer.resblocks.{layers}.ln_1.weight" in sd:
+        layers += 1
+    return width, layers, width // 64
 
 
 def patch_size(sd: Dict[str, Tensor]) -> int:
@@ -44,14 +51,15 @@ def interpolate_pos_embed(pos: Tensor, g0: int, h: int, w: int) -> Tensor:
 
 
 def residual_attention_block(z: Tensor, sd: Dict[str, Tensor], l: int) -> Tensor:
-    """_clip/blocks.py:22-42. z: [L, B, 768] (sequence first, as nn.MultiheadAttention(batch_first=False) sees it)."""
+    """_clip/blocks.py:22-42. z: [L, B, width] (sequence first, as nn.MultiheadAttention(batch_first=False) sees it)."""
     p = f"image_encoder.transformer.resblocks.{l}."
     L, B, D = z.shape
+    HEADS = D // 64
     a = _ln(z, sd, p + "ln_1")
     qkv = F.linear(a, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"])  # rows of W = [Wq; Wk; Wv]
     q, k, v = qkv.chunk(3, dim=-1)
 
-    def heads(t):  # [L, B, 768] -> [B, 12, L, 64]; head h = channels 64h..64h+63
+    def heads(t):  # [L, B, width] -> [B, heads, L, 64]; head h = channels 64h..64h+63
         return t.reshape(L, B, HEADS, D // HEADS).permute(1, 2, 0, 3)
 
     o = F.scaled_dot_product_attention(heads(q), heads(k), heads(v))  # scale 1/sqrt(64), no mask, no dropout
@@ -67,6 +75,7 @@ def forward_vpt(x: Tensor, sd: Dict[str, Tensor], num_vpt: int, deep_vpt: bool, 
     """models/clip/model.py:142-189 (`_forward_vpt`). x: [B, 3, h, w] -> [B, 768, h/16, w/16]."""
     B, _, H, W = x.shape
     PATCH = patch_size(sd)
+    WIDTH, LAYERS, _ = dims(sd)
     hp, wp = H // PATCH, W // PATCH
     f = F.conv2d(x, sd["image_encoder.conv1.weight"], stride=PATCH)  # :147, no bias
     f = f.reshape(B, WIDTH, -1).permute(0, 2, 1)  # :148-149

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader, weights  # noqa: E402
-from oracle.golden_cases import CASES, backbone_of, case_inputs  # noqa: E402
+from oracle.golden_cases import CASES, ORACLE_ONLY_CASES, backbone_of, case_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -63,7 +63,7 @@ def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     only = sys.argv[1:]  # optional: names of the cases to (re)generate
-    for case in CASES:
+    for case in CASES + ORACLE_ONLY_CASES:
         if only and case["name"] not in only:
             continue
         res = run_case(case)

@@ -73,6 +73,20 @@ def load_reference():
             m.adjust_pos_embed(input_size, input_size)
         return m
 
+    def vit_l_14_img(features_only=False, input_size=None, **kw):
+        m = ie.VisionTransformer(input_resolution=224, patch_size=14, output_dim=768, width=1024, layers=24, heads=16,
+                                 features_only=features_only)
+        if input_size is not None:
+            m.adjust_pos_embed(input_size, input_size)
+        return m
+
+    def vit_l_14_txt():
+        m = te.CLIPTextEncoder(embed_dim=768, context_length=77, vocab_size=49408, transformer_width=768,
+                               transformer_heads=12, transformer_layers=12)
+        torch.nn.init.normal_(m.positional_embedding, std=0.01)
+        torch.nn.init.normal_(m.text_projection, std=768 ** -0.5)
+        return m
+
     def vit_b_16_txt():
         m = te.CLIPTextEncoder(embed_dim=512, context_length=77, vocab_size=49408, transformer_width=512,
                                transformer_heads=8, transformer_layers=12)
@@ -90,6 +104,7 @@ def load_reference():
 
     clip_pkg.vit_b_16_img, clip_pkg.vit_b_16_txt, clip_pkg.tokenize = vit_b_16_img, vit_b_16_txt, tokenize
     clip_pkg.vit_b_32_img, clip_pkg.vit_b_32_txt = vit_b_32_img, vit_b_16_txt  # same text tower (embed_dim 512)
+    clip_pkg.vit_l_14_img, clip_pkg.vit_l_14_txt = vit_l_14_img, vit_l_14_txt
     cm = _load("models.clip.model", f"{REF}/models/clip/model.py")
     ev = _load("ref_eval_utils", f"{REF}/utils/eval_utils.py")
     _cache["mods"] = (cm, ev)

@@ -53,6 +53,10 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
     patch = 16 (ViT-B/16) or 32 (ViT-B/32): the two differ in conv1 / positional-embedding shapes only."""
     assert variant in ("default", "stress")
     PATCH = patch
+    # ViT-B/16 and ViT-B/32: width 768, 12 layers, embed 512; ViT-L/14 (patch 14): width 1024, 24 layers, embed 768
+    # (models/clip/model.py:16-24); hidden = 4 * width, heads = width // 64
+    WIDTH, LAYERS, EMBED = (1024, 24, 768) if patch == 14 else (768, 12, 512)
+    HIDDEN = 4 * WIDTH
     rng = np.random.default_rng(seed)
     stress = variant == "stress"
     sd: Dict[str, np.ndarray] = {}
@@ -109,10 +113,10 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
-def make_text_features(n_bins: int, seed: int = 100) -> torch.Tensor:
+def make_text_features(n_bins: int, seed: int = 100, embed: int = EMBED) -> torch.Tensor:
     """Stand-in for ``text_encoder(prompts)`` ([N, 512]); a constant input of the hot path (model.py:127-129)."""
     rng = np.random.default_rng(seed)
-    return torch.from_numpy(_n(rng, (n_bins, EMBED), 1.0))
+    return torch.from_numpy(_n(rng, (n_bins, embed), 1.0))
 
 
 def make_image(shape: Tuple[int, ...], seed: int = 1) -> torch.Tensor:

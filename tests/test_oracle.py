@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import clip_ebc_oracle as O
-from oracle.golden_cases import CASES, case_inputs
+from oracle.golden_cases import CASES, ORACLE_ONLY_CASES, case_inputs
 
 from . import parity
 
@@ -13,7 +13,7 @@ from . import parity
 ATOL = 2e-4
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("case", CASES + ORACLE_ONLY_CASES, ids=[c["name"] for c in CASES + ORACLE_ONLY_CASES])
 def test_oracle_matches_reference_fixture(case):
     torch.manual_seed(0)
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
