@@ -114,6 +114,23 @@ def test_model_create_validates_config(lib):
     lib.clipebc_model_destroy(h)
 
 
+def test_window_origins_bit_exact_randomised(lib):
+    """2000 seeded random geometries (including strides that do not divide anything and H == window): the C-ABI window
+    enumeration equals the reference formula int(np.ceil((H - h) / s) + 1) with clamped last origins, bit for bit."""
+    from clip_ebc_b200 import ops
+    from oracle import clip_ebc_oracle as O
+
+    rng = np.random.default_rng(123)
+    for _ in range(2000):
+        win_h, win_w = int(rng.integers(16, 513)), int(rng.integers(16, 513))
+        sh, sw = int(rng.integers(1, win_h + 1)), int(rng.integers(1, win_w + 1))
+        H, W = win_h + int(rng.integers(0, 4000)), win_w + int(rng.integers(0, 4000))
+        ro, co = ops.window_origins(H, W, (win_h, win_w), (sh, sw))
+        ref_r, ref_c = O.window_origins(H, W, (win_h, win_w), (sh, sw))
+        assert (ro, co) == (ref_r, ref_c), (H, W, win_h, win_w, sh, sw)
+        assert ro[-1] + win_h <= H and co[-1] + win_w <= W and ro[0] == 0 and co[0] == 0
+
+
 def test_python_host_mirrors_reference_interface():
     from clip_ebc_b200 import get_model, sliding_window_predict
     from oracle import weights
