@@ -124,10 +124,15 @@ int fail_cuda(cudaError_t e, const char* what) {
 
 constexpr int kWidth = 768, kLayers = 12, kHeads = 12, kEmbed = 512, kHidden = 3072;
 
+// Bumped by every clipebc_set_* switch AND by every (re)allocation or release of a device buffer of this library: host
+// layers that cache captured CUDA graphs of the library's launches key them on it (a graph holds the kernels chosen and
+// the buffer addresses used at capture time -- replaying it after a workspace has moved would write to freed memory).
+std::atomic<int64_t> g_config_epoch{0};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) { cudaFree(p); g_config_epoch.fetch_add(1); } }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -136,6 +141,7 @@ struct DevBuf {
     if (p) { cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t e = cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n;
+    g_config_epoch.fetch_add(1);
     return e;
   }
   template <class T> T* as() const { return static_cast<T*>(p); }
@@ -533,8 +539,6 @@ const char* clipebc_last_error(void) { return g_err.c_str(); }
 int clipebc_abi_version(void) { return CLIPEBC_ABI_VERSION; }
 int64_t clipebc_launch_count(void) { return g_launches.load(); }
 
-// bumped by every clipebc_set_* switch: host layers that cache captured CUDA graphs key them on it
-static std::atomic<int64_t> g_config_epoch{0};
 int64_t clipebc_config_epoch(void) { return g_config_epoch.load(); }
 int clipebc_profile_enabled(void) { return cebc::profiling_on() ? 1 : 0; }
 void clipebc_note_replayed_launches(int64_t n) { if (n > 0) g_launches.fetch_add(n); }

@@ -79,8 +79,9 @@ int clipebc_profile_enable(int on);
 int clipebc_profile_dump(char* buf, int cap);
 int clipebc_profile_enabled(void);
 /* For host layers that replay captured CUDA graphs of this library's launches (clip_ebc_b200/model.py): the epoch
- * changes whenever a clipebc_set_* switch is called (a captured graph holds the kernels chosen at capture time), and a
- * replay reports the launches it contains so that clipebc_launch_count stays the number of kernels actually run. */
+ * changes whenever a clipebc_set_* switch is called or a device buffer of the library is (re)allocated or released (a
+ * captured graph holds the kernels chosen and the workspace addresses used at capture time), and a replay reports the
+ * launches it contains so that clipebc_launch_count stays the number of kernels actually run. */
 int64_t clipebc_config_epoch(void);
 void clipebc_note_replayed_launches(int64_t n);
 

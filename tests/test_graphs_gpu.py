@@ -49,8 +49,9 @@ def test_graph_replay_is_bit_identical_to_eager_and_counts_its_launches():
     assert second.data_ptr() != third.data_ptr()  # results are copies, not views of the graph's static buffer
     # another batch size gets its own graph; train mode (logits, exp) too
     x8 = weights.make_image((8, 3, 224, 224), seed=210).cuda()
-    a, b, c = model(x8), model(x8), model(x8)
-    assert torch.equal(a, b) and torch.equal(b, c) and len(model._graph_cache) == 2
+    a, b, c, d = model(x8), model(x8), model(x8), model(x8)  # the first call grows the workspaces (new library epoch)
+    assert torch.equal(a, b) and torch.equal(b, c) and torch.equal(c, d)
+    assert any("graph" in e and tuple(e["x"].shape) == (8, 3, 224, 224) for e in model._graph_cache.values())
     model.training = True
     outs = [model(xs[0]) for _ in range(3)]
     model.training = False
@@ -80,6 +81,22 @@ def test_graph_cache_follows_library_switches_and_weights():
     outs = [model(x) for _ in range(3)]
     model.use_cuda_graphs = False
     assert torch.equal(outs[-1], model(x)) and not torch.equal(outs[-1], base)
+
+
+def test_graphs_do_not_outlive_a_workspace_reallocation():
+    """A larger batch grows the library's workspaces (free + malloc): graphs captured before hold the old addresses and
+    must not be replayed -- the cache key carries the library's epoch, which every (re)allocation bumps."""
+    case = [c for c in CASES if c["name"] == "c1_forward_r8_deep"][0]
+    model = _model(case)
+    x_small = weights.make_image((2, 3, 224, 224), seed=240).cuda()
+    small = [model(x_small) for _ in range(3)][-1]            # eager, capture, replay
+    assert any("graph" in e for e in model._graph_cache.values())
+    x_big = weights.make_image((40, 3, 224, 224), seed=241).cuda()
+    big = [model(x_big) for _ in range(4)][-1]                # grows every workspace, then captures its own graph
+    again = [model(x_small) for _ in range(3)]
+    model.use_cuda_graphs = False
+    assert torch.equal(model(x_small), small) and torch.equal(model(x_big), big)
+    assert all(torch.equal(a, small) for a in again)
 
 
 def test_graph_path_steps_aside_for_profiling_and_outer_captures():
