@@ -18,9 +18,10 @@ _lib: Optional[C.CDLL] = None
 
 
 class ClipEbcConfig(C.Structure):
-    """``clipebc_config`` of the header."""
+    """``clipebc_config`` of the header (ABI v9). Build it with :func:`make_config`, which fills ``struct_size``."""
 
     _fields_ = [
+        ("struct_size", C.c_uint32),
         ("input_size", C.c_int),
         ("reduction", C.c_int),
         ("num_vpt", C.c_int),
@@ -29,7 +30,19 @@ class ClipEbcConfig(C.Structure):
         ("window_chunk", C.c_int),
         ("operand_fp16", C.c_int),
         ("patch", C.c_int),
+        ("width", C.c_int),
+        ("layers", C.c_int),
+        ("embed_dim", C.c_int),
+        ("decoder_conv1_fine", C.c_int),
     ]
+
+
+def make_config(input_size: int, reduction: int, num_vpt: int, deep_vpt: int, num_bins: int, window_chunk: int = 0,
+                operand_fp16: int = 1, patch: int = 16, width: int = 768, layers: int = 12, embed_dim: int = 512,
+                decoder_conv1_fine: int = 0) -> ClipEbcConfig:
+    return ClipEbcConfig(C.sizeof(ClipEbcConfig), int(input_size), int(reduction), int(num_vpt), int(deep_vpt), int(num_bins),
+                         int(window_chunk), int(operand_fp16), int(patch), int(width), int(layers), int(embed_dim),
+                         int(decoder_conv1_fine))
 
 
 _vp, _i, _i64, _fp = C.c_void_p, C.c_int, C.c_int64, C.c_void_p  # float* passed as raw addresses
@@ -41,10 +54,6 @@ SIGNATURES = {
     "clipebc_last_error": (C.c_char_p, []),
     "clipebc_abi_version": (_i, []),
     "clipebc_launch_count": (_i64, []),
-    "clipebc_set_gemm_impl": (_i, [_i]),
-    "clipebc_set_attention_impl": (_i, [_i]),
-    "clipebc_set_ln_fold": (_i, [_i]),
-    "clipebc_set_conv1_coarse": (_i, [_i]),
     "clipebc_profile_enable": (_i, [_i]),
     "clipebc_profile_dump": (_i, [C.c_char_p, _i]),
     "clipebc_profile_enabled": (_i, []),
@@ -61,16 +70,10 @@ SIGNATURES = {
     "clipebc_f32_to_16": (_i, [_fp, _vp, _i64, _i, _vp]),
     "clipebc_gemm_bf16": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _ip, _ip, _vp, _i, _fp, _fp, _i,
                                _i, _i, _i, _i, _i, _i, _vp]),
-    "clipebc_gemm_resid_stats": (_i, [_vp, _i64, _i64, _vp, _i64, _i, _i, _i, _fp, _fp, _vp, _vp, _i, _i, _i, _vp]),
-    "clipebc_gemm_ln": (_i, [_i, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _fp, _vp, _i, _fp, _i, _i, _i, _vp]),
-    "clipebc_rowstats768": (_i, [_fp, _i64, _vp, _vp, _i, _vp]),
-    "clipebc_fold_ln_linear": (_i, [_fp, _fp, _fp, _fp, _i, _vp, _fp, _fp, _i, _vp]),
-    "clipebc_layernorm768": (_i, [_fp, _fp, _fp, _vp, _i, _i64, _i, _i, _i, _vp]),
-    "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
-    "clipebc_patchify16": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "clipebc_patchify": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
-    "clipebc_ebc_head": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "clipebc_layernorm": (_i, [_fp, _fp, _fp, _i, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_patchify": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
     "clipebc_fold_average": (_i, [_fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_resize_bicubic_aa": (_i, [_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _cfp, _cfp, _vp]),
     "clipebc_pad_normalize": (_i, [_vp, _i, _i, _i, _i, _fp, _i, _i, _cfp, _cfp, _vp]),

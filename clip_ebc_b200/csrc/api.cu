@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -60,36 +61,19 @@ LaunchScope::~LaunchScope() {
   if (slot_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot_].e1, stream_);
 }
 
-// which GEMM kernel serves the hot path: 1 = one CTA per 128-row tile, 2 = CTA pair (cta_group::2, 256-row tiles)
-static std::atomic<int> g_gemm_impl{2};
-
 const char* gemm_dispatch(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols, int64_t lda,
                           const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
-  return g_gemm_impl.load() == 2 ? gemm2_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n)
-                                 : gemm_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n);
+  return gemm2_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n);
 }
 
-// which attention kernel serves the hot path: 1 = mma.sync (legacy tensor path), 2 = tcgen05 one CTA per query tile,
-// 3 = tcgen05 persistent warp-specialised (P in TMEM, the softmax groups split the keys of a tile),
-// 4 = tcgen05 persistent, two independent chains (a thread owns a query row)
-static std::atomic<int> g_attn_impl{4};
-// LayerNorm folded into the GEMMs either side of it (run_windows): off by default -- measured on B200 it removes the 24
-// LayerNorm launches of a pass (-0.33 ms per 64 windows) but the heavier GEMM epilogues give 0.30 ms back
-static std::atomic<int> g_ln_fold{0};
-// conv1 of the decoder computed from the coarse patch grid (one GEMM with hp*wp rows per window + a gather kernel) when
-// the decoder grid is finer than the patch grid (reduction 8 with ViT-B/16, reductions 8 / 16 with ViT-B/32); 0 = the
-// implicit GEMM on the fine grid
-static std::atomic<int> g_conv1_coarse{std::getenv("CLIPEBC_CONV1_FINE") ? 0 : 1};  // env: A/B knob for bench runs
-
+// tcgen05 / TMEM kernel for windows of at most 256 keys whose constant-key count is a multiple of 8 (every stock
+// configuration of ViT-B/16 and ViT-B/32); the streamed-K/V kernel takes everything else (ViT-L/14: 289 keys per 224 window,
+// windows larger than 224 x 224, odd prompt counts)
 const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                               int n_win, int t_live, void* out, int out_fp16) {
-  const int impl = g_attn_impl.load();
-  // windows with more than 256 tokens (e.g. 448 x 448): streamed-K/V kernel, the tcgen05 kernels hold one 256-key tile
-  if (t_live + n_const > 256) return attention_h64_long(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
-  if (impl == 4 && n_const % 8 == 0) return attention_h64_pp(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
-  if (impl == 3 && n_const % 8 == 0) return attention_h64_fa(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
-  if (impl == 2 && n_const % 8 == 0) return attention_h64_tc(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
-  return attention_h64(stream, qkv, const_kv, n_const, n_win, t_live, out, out_fp16);
+                               int n_win, int t_live, int heads, void* out, int out_fp16) {
+  if (t_live + n_const <= 256 && n_const % 8 == 0)
+    return attention_h64_pp(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
+  return attention_h64_long(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
 }
 
 namespace {
@@ -122,11 +106,9 @@ int fail_cuda(cudaError_t e, const char* what) {
     if (_m != nullptr) return fail(CLIPEBC_ECUDA, std::string(_m));        \
   } while (0)
 
-constexpr int kWidth = 768, kLayers = 12, kHeads = 12, kEmbed = 512, kHidden = 3072;
-
-// Bumped by every clipebc_set_* switch AND by every (re)allocation or release of a device buffer of this library: host
-// layers that cache captured CUDA graphs of the library's launches key them on it (a graph holds the kernels chosen and
-// the buffer addresses used at capture time -- replaying it after a workspace has moved would write to freed memory).
+// Bumped by every (re)allocation or release of a device buffer of this library: host layers that cache captured CUDA
+// graphs of the library's launches key them on it (a graph holds the buffer addresses used at capture time -- replaying
+// it after a workspace has moved would write to freed memory).
 std::atomic<int64_t> g_config_epoch{0};
 
 struct DevBuf {
@@ -154,12 +136,8 @@ struct RawTensor {
 };
 
 struct LayerPack {
-  DevBuf w_qkv, w_out, w_fc, w_proj;  // bf16
-  DevBuf const_kv;                    // bf16 [num_vpt, 2304] (deep VPT)
-  // LayerNorm folded into the Linear behind it (rewrite 7): W * diag(gamma) in 16 bits, the column
-  // sums of the rounded weights and b + W beta
-  DevBuf wf_qkv, wf_fc;               // 16-bit [2304, 768], [3072, 768]
-  DevBuf ln_aux;                      // f32: colsum_qkv [2304] | bias_qkv [2304] | colsum_fc [3072] | bias_fc [3072]
+  DevBuf w_qkv, w_out, w_fc, w_proj;  // 16-bit, nn.Linear layout [N, K]
+  DevBuf const_kv;                    // bf16 [num_vpt, 3 * width] (deep VPT): in_proj(LN1_l(vpt_l)), input-independent
   const float *b_qkv, *b_out, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
 };
 
@@ -169,33 +147,45 @@ struct LayerPack {
 using namespace cebc;
 
 struct clipebc_model {
-  clipebc_config cfg;
+  clipebc_config cfg;       // normalised: patch / width / layers / embed_dim filled in
+  int device = 0;           // the CUDA device the handle was created on: every buffer below lives there
+  int kp_pad = 0;           // patch row length 3 * patch^2 rounded up to the GEMM's K granularity (64)
   std::map<std::string, RawTensor> raw;
   bool packed = false;
   // packed
-  LayerPack layer[kLayers];
-  DevBuf w_patch;           // bf16 [768, 768]
-  DevBuf w_c1z;             // 16-bit [9*768, 768]: conv1 with the tap on the output side (coarse-grid form)
-  DevBuf zero_bias;         // f32 [9*768] zeros
-  DevBuf ws_Y16, ws_Z;      // coarse-grid conv1: 16-bit ln_post rows, per-tap products [n * hp * wp, 9*768]
-  DevBuf w_c1, w_c2;        // bf16 [768, 9*768]
-  DevBuf b_c1, b_c2;        // f32 [768]
-  DevBuf w_p3;              // bf16 [512, 3*768] = hi|hi|lo
-  DevBuf tmat;              // f32 [N, 512]
-  DevBuf pack_tmp_f32, pack_tmp_bf16;
-  std::map<int, DevBuf> pos_cache;  // key hp * 4096 + wp -> f32 [1 + hp*wp, 768]
+  std::unique_ptr<LayerPack[]> layer;  // [cfg.layers]
+  DevBuf w_patch;           // 16-bit [width, 3 * kp_pad] = hi | hi | lo
+  DevBuf w_c1z;             // 16-bit [9 * width, width]: conv1 with the tap on the output side (coarse-grid form)
+  DevBuf zero_bias;         // f32 [9 * width] zeros
+  DevBuf ws_Y16, ws_Z;      // coarse-grid conv1: 16-bit ln_post rows, per-tap products [n * hp * wp, 9 * width]
+  DevBuf w_c1, w_c2;        // 16-bit [width, 9 * width]
+  DevBuf b_c1, b_c2;        // f32 [width]
+  DevBuf w_p3;              // 16-bit [embed, 3 * width] = hi | hi | lo
+  DevBuf tmat;              // f32 [N, embed]
+  DevBuf pack_tmp_16;
+  std::map<int, DevBuf> pos_cache;  // key hp * 4096 + wp -> f32 [1 + hp*wp, width]; bounded (kMaxPosCache)
   // workspace
-  DevBuf ws_stats;          // float2 [M, kLnStatSlots]: per-row LayerNorm partials between a residual GEMM and its consumer
   DevBuf ws_patch_rows, ws_patch_embed, ws_X, ws_Xn, ws_QKV, ws_AO, ws_Hid, ws_Y, ws_Ub, ws_Uf, ws_D1, ws_D2, ws_F,
       ws_preds;
   // device-resident index tables (window -> patch-grid row, window origins, fold cell origins), cached per geometry so
-  // the steady state has no host->device upload and no host synchronisation
+  // the steady state has no host->device upload and no host synchronisation; bounded (kMaxIdxCache)
   std::map<std::string, DevBuf> idx_cache;
 };
 
 namespace {
 
-const float* raw_ptr(clipebc_model* m, const std::string& name) { return m->raw.at(name).buf.as<float>(); }
+constexpr size_t kMaxPosCache = 16, kMaxIdxCache = 64;
+
+// Tensor by its state_dict key, or nullptr: pack() has checked every key the path reads, so a miss can only be a tensor
+// the configuration does not need (never throws across the C ABI)
+const float* raw_ptr(clipebc_model* m, const std::string& name) {
+  auto it = m->raw.find(name);
+  return it == m->raw.end() ? nullptr : it->second.buf.as<float>();
+}
+
+// Every entry point that touches a handle: the handle's buffers live on the device it was created on, and the kernels'
+// per-device attributes are keyed on the current device, so the two must agree.
+int check_device(const clipebc_model* m);
 
 bool check_shape(clipebc_model* m, const std::string& name, std::initializer_list<int64_t> want, std::string* err) {
   auto it = m->raw.find(name);
@@ -232,15 +222,15 @@ void cubic_coeffs(float t, float w[4]) {
 }
 
 int get_pos(clipebc_model* m, int hp, int wp, cudaStream_t stream, const float** out) {
-  const int g0 = m->cfg.input_size / m->cfg.patch;
+  const int g0 = m->cfg.input_size / m->cfg.patch, D = m->cfg.width;
   if (hp == g0 && wp == g0) { *out = raw_ptr(m, "image_encoder.positional_embedding"); return CLIPEBC_OK; }
   const int key = hp * 4096 + wp;
   auto it = m->pos_cache.find(key);
   if (it != m->pos_cache.end()) { *out = it->second.as<float>(); return CLIPEBC_OK; }
-  std::vector<float> src(static_cast<size_t>(1 + g0 * g0) * kWidth);
+  std::vector<float> src(static_cast<size_t>(1 + g0 * g0) * D);
   CUDA_TRY(cudaMemcpy(src.data(), raw_ptr(m, "image_encoder.positional_embedding"), src.size() * 4, cudaMemcpyDeviceToHost));
-  std::vector<float> dst(static_cast<size_t>(1 + hp * wp) * kWidth);
-  std::memcpy(dst.data(), src.data(), kWidth * 4);
+  std::vector<float> dst(static_cast<size_t>(1 + hp * wp) * D);
+  std::memcpy(dst.data(), src.data(), static_cast<size_t>(D) * 4);
   const float sy = static_cast<float>(g0) / hp, sx = static_cast<float>(g0) / wp;
   for (int oy = 0; oy < hp; ++oy) {
     const float fy = (oy + 0.5f) * sy - 0.5f;
@@ -250,18 +240,24 @@ int get_pos(clipebc_model* m, int hp, int wp, cudaStream_t stream, const float**
       const float fx = (ox + 0.5f) * sx - 0.5f;
       const int ix = static_cast<int>(std::floor(fx));
       float wx[4]; cubic_coeffs(fx - ix, wx);
-      float* o = &dst[static_cast<size_t>(1 + oy * wp + ox) * kWidth];
-      for (int c = 0; c < kWidth; ++c) o[c] = 0.f;
+      float* o = &dst[static_cast<size_t>(1 + oy * wp + ox) * D];
+      for (int c = 0; c < D; ++c) o[c] = 0.f;
       for (int a = 0; a < 4; ++a) {
         const int yy = std::min(std::max(iy - 1 + a, 0), g0 - 1);
         for (int b = 0; b < 4; ++b) {
           const int xx = std::min(std::max(ix - 1 + b, 0), g0 - 1);
           const float wgt = wy[a] * wx[b];
-          const float* s = &src[static_cast<size_t>(1 + yy * g0 + xx) * kWidth];
-          for (int c = 0; c < kWidth; ++c) o[c] += wgt * s[c];
+          const float* sp = &src[static_cast<size_t>(1 + yy * g0 + xx) * D];
+          for (int c = 0; c < D; ++c) o[c] += wgt * sp[c];
         }
       }
     }
+  }
+  // bounded: a stream of differently sized windows must not grow the cache without limit. Entries are only dropped
+  // between calls that use them (the stream is synchronised below), never while a launch may still read one.
+  if (m->pos_cache.size() >= kMaxPosCache) {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    m->pos_cache.clear();
   }
   DevBuf& buf = m->pos_cache[key];
   CUDA_TRY(buf.reserve(dst.size() * 4));
@@ -280,18 +276,18 @@ GemmParams plain(int fp16, int out16_fp16, int M, int N, int K, void* out, int l
   return p;
 }
 
-// patch embedding as a split-precision GEMM: rows [hi | lo] (2*KP) x W3 = [Whi | Whi | Wlo] (3*KP), segments hi, lo, hi;
-// KP = 3 * patch^2 (768 for ViT-B/16, 3072 for ViT-B/32)
-GemmParams patch_embed_params(int fp16, int rows, void* out, int kp) {
-  GemmParams p = gemm_params_plain(rows, 768, 3 * kp);
+// patch embedding as a split-precision GEMM: rows [hi | lo] (2 * kp) x W3 = [Whi | Whi | Wlo] (3 * kp), segments hi, lo,
+// hi; kp = 3 * patch^2 rounded up to 64 (768 for ViT-B/16, 3072 for ViT-B/32, 640 for ViT-L/14)
+GemmParams patch_embed_params(int fp16, int rows, int width, void* out, int kp) {
+  GemmParams p = gemm_params_plain(rows, width, 3 * kp);
   p.n_seg = 3; p.seg_kblocks = kp / 64;
   p.seg_col_start[0] = 0; p.seg_col_start[1] = kp; p.seg_col_start[2] = 0;
-  p.out = out; p.ldo = 768; p.bias = nullptr; p.ab_fp16 = fp16; p.out_fp16 = fp16;
+  p.out = out; p.ldo = width; p.bias = nullptr; p.ab_fp16 = fp16; p.out_fp16 = fp16;
   return p;
 }
 
 // RAII: persisting-L2 access-policy window over [ptr, ptr + bytes), attached as a LAUNCH attribute to every kernel this
-// thread launches while it lives (the caller's stream state is not touched). The device-wide carve-out
+// thread launches while it lives (the caller's stream state is not touched). The per-device carve-out
 // (cudaLimitPersistingL2CacheSize) only ever grows, up to kL2PersistCapMB / the device maximum.
 constexpr int kL2PersistCapMB = 60;
 struct L2Window {
@@ -300,23 +296,25 @@ struct L2Window {
   L2Window(const void* ptr, size_t bytes) {
     static const int env_mb = std::getenv("CLIPEBC_L2_PERSIST") ? std::atoi(std::getenv("CLIPEBC_L2_PERSIST")) : -1;
     if (env_mb == 0 || bytes == 0 || cebc::current_l2_window() != nullptr) return;
-    static size_t max_persist = [] {
-      int dev = 0, v = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) v = 0;
-      cudaGetLastError();
-      return static_cast<size_t>(v > 0 ? v : 0);
-    }();
-    size_t carve = std::min(bytes, static_cast<size_t>(env_mb > 0 ? env_mb : kL2PersistCapMB) << 20);
-    carve = std::min(carve, max_persist);
-    if (carve == 0) return;
+    // the carve-out limit and its maximum are per device
+    constexpr int kMaxDev = 64;
     static std::mutex mu;
-    static size_t limit_now = 0;
-    {
-      std::lock_guard<std::mutex> lock(mu);
-      if (carve > limit_now) {
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
-        limit_now = carve;
-      }
+    static long long max_persist[kMaxDev];  // 0 = not queried yet, -1 = none
+    static size_t limit_now[kMaxDev];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { cudaGetLastError(); return; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (max_persist[dev] == 0) {
+      int v = 0;
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) { cudaGetLastError(); v = 0; }
+      max_persist[dev] = v > 0 ? v : -1;
+    }
+    size_t carve = std::min(bytes, static_cast<size_t>(env_mb > 0 ? env_mb : kL2PersistCapMB) << 20);
+    carve = std::min(carve, static_cast<size_t>(std::max(0ll, max_persist[dev])));
+    if (carve == 0) return;
+    if (carve > limit_now[dev]) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+      limit_now[dev] = carve;
     }
     win_.base_ptr = const_cast<void*>(ptr);
     win_.num_bytes = bytes;
@@ -335,9 +333,10 @@ struct L2Window {
 int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int src_pitch, int nw, int hp, int wp,
                 const float* pos, float* exp_out, float* logits_out, const int* win_pitch_dev = nullptr) {
   const clipebc_config& c = m->cfg;
+  const int D = c.width, heads = D / 64, hidden = 4 * D, E = c.embed_dim;
   const bool deep = c.deep_vpt != 0;
   const int fp16 = c.operand_fp16 != 0;   // 16-bit operand format of every GEMM of the path
-  const int ln16 = fp16 ? 2 : 1;          // layernorm768 out_kind
+  const int ln16 = fp16 ? 2 : 1;          // layernorm_rows out_kind
   const int n_prompt_live = deep ? 0 : c.num_vpt;
   const int n_const = deep ? c.num_vpt : 0;
   const int npatch = hp * wp;
@@ -346,113 +345,81 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   const int gh = hp * c.patch / c.reduction, gw = wp * c.patch / c.reduction;
   const int Hp = gh + 1, Wp = gw + 1;  // shared-border decoder grid (kernels.h: resample_to_padded): 841 rows per r8
   const int Mp = nw * Hp * Wp;         // window instead of 900 on a grid bordered on all four sides
+  // conv1 from the coarse grid (elementwise.cu: conv1_from_coarse_kernel) whenever the decoder grid is at least twice as
+  // fine as the patch grid (reduction 8 with ViT-B/16; 8 / 16 with ViT-B/32); else the implicit GEMM on the fine grid
+  const bool coarse1 = c.decoder_conv1_fine == 0 && gh >= 2 * hp && gw >= 2 * wp;
 
-  CUDA_TRY(m->ws_X.reserve(static_cast<size_t>(M) * kWidth * 4));
-  CUDA_TRY(m->ws_Xn.reserve(static_cast<size_t>(M) * kWidth * 2));
-  CUDA_TRY(m->ws_QKV.reserve(static_cast<size_t>(M) * 3 * kWidth * 2));
-  CUDA_TRY(m->ws_AO.reserve(static_cast<size_t>(M) * kWidth * 2));
-  CUDA_TRY(m->ws_Hid.reserve(static_cast<size_t>(M) * kHidden * 2));
-  CUDA_TRY(m->ws_Y.reserve(static_cast<size_t>(nw) * npatch * kWidth * 4));
-  CUDA_TRY(m->ws_Ub.reserve(static_cast<size_t>(Mp) * kWidth * 2));
-  CUDA_TRY(m->ws_Uf.reserve(static_cast<size_t>(Mp) * kWidth * 4));
-  CUDA_TRY(m->ws_D1.reserve(static_cast<size_t>(Mp) * kWidth * 2));
-  CUDA_TRY(m->ws_D2.reserve(static_cast<size_t>(Mp) * 2 * kWidth * 2));
-  CUDA_TRY(m->ws_F.reserve(static_cast<size_t>(Mp) * kEmbed * 4));
+  CUDA_TRY(m->ws_X.reserve(static_cast<size_t>(M) * D * 4));
+  CUDA_TRY(m->ws_Xn.reserve(static_cast<size_t>(M) * D * 2));
+  CUDA_TRY(m->ws_QKV.reserve(static_cast<size_t>(M) * 3 * D * 2));
+  CUDA_TRY(m->ws_AO.reserve(static_cast<size_t>(M) * D * 2));
+  CUDA_TRY(m->ws_Hid.reserve(static_cast<size_t>(M) * hidden * 2));
+  CUDA_TRY(m->ws_Y.reserve(static_cast<size_t>(nw) * npatch * D * 4));
+  if (coarse1) {
+    CUDA_TRY(m->ws_Y16.reserve(static_cast<size_t>(nw) * npatch * D * 2));
+    CUDA_TRY(m->ws_Z.reserve(static_cast<size_t>(nw) * npatch * 9 * D * 2));
+  } else {
+    CUDA_TRY(m->ws_Ub.reserve(static_cast<size_t>(Mp) * D * 2));
+    CUDA_TRY(m->ws_Uf.reserve(static_cast<size_t>(Mp) * D * 4));
+  }
+  CUDA_TRY(m->ws_D1.reserve(static_cast<size_t>(Mp) * D * 2));
+  CUDA_TRY(m->ws_D2.reserve(static_cast<size_t>(Mp) * 2 * D * 2));
+  const int kParts = 2 * (E / 256);  // head partials per cell: one per half of a 256-wide projection tile
+  CUDA_TRY(m->ws_F.reserve(static_cast<size_t>(Mp) * kParts * (1 + c.num_bins) * 4));
 
   float* X = m->ws_X.as<float>();
   // The fp32 residual stream is read / updated four times per block while QKV (58 MB at 64 windows) and Hid (77 MB)
   // stream through L2 once: an access-policy window on the launching stream keeps X in the persisting carve-out of L2
   // for the duration of the pass (measured on B200: +4 % on 2048x1536 images, +0.3..1.3 % at 64 windows;
   // profiles/r01i_l2_persist.txt). CLIPEBC_L2_PERSIST=<MB> overrides the carve-out (0 = off).
-  const L2Window l2win(X, static_cast<size_t>(M) * kWidth * 4);
+  const L2Window l2win(X, static_cast<size_t>(M) * D * 4);
   __nv_bfloat16* Xn = m->ws_Xn.as<__nv_bfloat16>();
   __nv_bfloat16* QKV = m->ws_QKV.as<__nv_bfloat16>();
   __nv_bfloat16* AO = m->ws_AO.as<__nv_bfloat16>();
   __nv_bfloat16* Hid = m->ws_Hid.as<__nv_bfloat16>();
 
-  // Optional (clipebc_set_ln_fold): LayerNorm folded into the GEMMs either side of it (CTA-pair GEMM only): the residual
-  // GEMMs leave a 16-bit copy of the new rows and per-row (mean, M2) partials, QKV / c_fc read the raw rows and normalise
-  // in their epilogue -- no LayerNorm launch and no second pass over X inside the blocks.
-  const bool ln_fold = g_gemm_impl.load() == 2 && g_ln_fold.load() != 0;
-  float2* stats = nullptr;
-  if (ln_fold) {
-    CUDA_TRY(m->ws_stats.reserve(static_cast<size_t>(M) * kLnStatSlots * sizeof(float2)));
-    stats = m->ws_stats.as<float2>();
-  }
-
-  K_TRY(assemble_tokens(s, m->ws_patch_embed.as<float>(), win_base_dev, src_pitch, win_pitch_dev,
+  K_TRY(assemble_tokens(s, D, m->ws_patch_embed.as<float>(), win_base_dev, src_pitch, win_pitch_dev,
                         raw_ptr(m, "image_encoder.class_embedding"), pos, raw_ptr(m, "image_encoder.ln_pre.weight"),
-                        raw_ptr(m, "image_encoder.ln_pre.bias"), deep ? nullptr : raw_ptr(m, "vpt_0"), n_prompt_live, nw,
-                        hp, wp, X, ln_fold ? Xn : nullptr, stats, fp16));
+                        raw_ptr(m, "image_encoder.ln_pre.bias"), n_prompt_live > 0 ? raw_ptr(m, "vpt_0") : nullptr,
+                        n_prompt_live, nw, hp, wp, X));
 
-  for (int l = 0; l < kLayers && ln_fold; ++l) {
+  for (int l = 0; l < c.layers; ++l) {
     const LayerPack& L = m->layer[l];
-    const float* aux = L.ln_aux.as<float>();
-    // ln_1 + in_proj: the rows come from assemble_tokens (whole-row statistics) or from the previous c_proj (8 partials)
-    GemmParams pq = plain(fp16, 0, M, 3 * kWidth, kWidth, QKV, 3 * kWidth, aux + 3 * kWidth);
-    pq.ln_stats = stats; pq.ln_colsum = aux; pq.ln_parts = (l == 0) ? 1 : kLnStatSlots;
+    K_TRY(layernorm_rows(s, D, X, L.ln1_g, L.ln1_b, Xn, ln16, M, 1, 1, 0));
     set_launch_tag("qkv");
-    K_TRY(gemm_dispatch(s, EPI_LN_BIAS_BF16, Xn, M, kWidth, kWidth, L.wf_qkv.as<__nv_bfloat16>(), kWidth, pq, 0));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, Xn, M, D, D, L.w_qkv.as<__nv_bfloat16>(), D,
+                        plain(fp16, 0, M, 3 * D, D, QKV, 3 * D, L.b_qkv), 0));
     set_launch_tag(nullptr);
-    K_TRY(attention_dispatch(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO, fp16));
-    GemmParams po = plain(fp16, fp16, M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth);
-    po.x16_out = Xn; po.stats_out = stats;
+    K_TRY(attention_dispatch(s, QKV, n_const > 0 ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, heads, AO, fp16));
     set_launch_tag("out_proj");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_STATS, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth, po, 192));
-    // ln_2 + c_fc + QuickGELU
-    GemmParams pf = plain(fp16, fp16, M, kHidden, kWidth, Hid, kHidden, aux + 6 * kWidth + kHidden);
-    pf.ln_stats = stats; pf.ln_colsum = aux + 6 * kWidth; pf.ln_parts = kLnStatSlots;
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, AO, M, D, D, L.w_out.as<__nv_bfloat16>(), D,
+                        plain(fp16, fp16, M, D, D, X, D, L.b_out, X, D), 0));
+    set_launch_tag(nullptr);
+    K_TRY(layernorm_rows(s, D, X, L.ln2_g, L.ln2_b, Xn, ln16, M, 1, 1, 0));
     set_launch_tag("c_fc");
-    K_TRY(gemm_dispatch(s, EPI_LN_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.wf_fc.as<__nv_bfloat16>(), kWidth, pf, 0));
-    GemmParams pj = plain(fp16, fp16, M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth);
-    pj.x16_out = Xn; pj.stats_out = stats;
+    K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, D, D, L.w_fc.as<__nv_bfloat16>(), D,
+                        plain(fp16, fp16, M, hidden, D, Hid, hidden, L.b_fc), 0));
     set_launch_tag("c_proj");
-    // the last block feeds ln_post (fp32 rows only)
-    K_TRY(gemm_dispatch(s, l + 1 < kLayers ? EPI_BIAS_RESID_STATS : EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden,
-                        L.w_proj.as<__nv_bfloat16>(), kHidden, pj, 192));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, hidden, hidden, L.w_proj.as<__nv_bfloat16>(), hidden,
+                        plain(fp16, fp16, M, D, hidden, X, D, L.b_proj, X, D), 0));
     set_launch_tag(nullptr);
   }
 
-  for (int l = 0; l < kLayers && !ln_fold; ++l) {
-    const LayerPack& L = m->layer[l];
-    K_TRY(layernorm768(s, X, L.ln1_g, L.ln1_b, Xn, ln16, M, 1, 1, 0));
-    set_launch_tag("qkv");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, Xn, M, kWidth, kWidth, L.w_qkv.as<__nv_bfloat16>(), kWidth,
-                       plain(fp16, 0, M, 3 * kWidth, kWidth, QKV, 3 * kWidth, L.b_qkv), 0));
-    set_launch_tag(nullptr);
-    K_TRY(attention_dispatch(s, QKV, deep ? L.const_kv.as<__nv_bfloat16>() : nullptr, n_const, nw, T, AO, fp16));
-    set_launch_tag("out_proj");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, AO, M, kWidth, kWidth, L.w_out.as<__nv_bfloat16>(), kWidth,
-                       plain(fp16, fp16, M, kWidth, kWidth, X, kWidth, L.b_out, X, kWidth), 0));
-    set_launch_tag(nullptr);
-    K_TRY(layernorm768(s, X, L.ln2_g, L.ln2_b, Xn, ln16, M, 1, 1, 0));
-    set_launch_tag("c_fc");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, kWidth, kWidth, L.w_fc.as<__nv_bfloat16>(), kWidth,
-                       plain(fp16, fp16, M, kHidden, kWidth, Hid, kHidden, L.b_fc), 0));
-    set_launch_tag("c_proj");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, kHidden, kHidden, L.w_proj.as<__nv_bfloat16>(), kHidden,
-                       plain(fp16, fp16, M, kWidth, kHidden, X, kWidth, L.b_proj, X, kWidth), 0));
-    set_launch_tag(nullptr);
-  }
-
-  // ln_post on the patch rows only (cls / prompt rows are dropped, model.py:185-188), fp32 out
+  // ln_post on the patch rows only (cls / prompt rows are dropped, model.py:185-188), fp32 out; the coarse-grid conv1 also
+  // gets the 16-bit rows its GEMM reads
   float* Y = m->ws_Y.as<float>();
-  // conv1 from the coarse grid (elementwise.cu: conv1_from_coarse_kernel) whenever the decoder grid is at least twice as
-  // fine as the patch grid: ln_post then also leaves the 16-bit rows its GEMM reads
-  const bool coarse1 = g_conv1_coarse.load() != 0 && g_gemm_impl.load() == 2 && gh >= 2 * hp && gw >= 2 * wp;
-  if (coarse1) CUDA_TRY(m->ws_Y16.reserve(static_cast<size_t>(nw) * npatch * kWidth * 2));
-  K_TRY(layernorm768(s, X, raw_ptr(m, "image_encoder.ln_post.weight"), raw_ptr(m, "image_encoder.ln_post.bias"), Y, 0,
-                     static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch, coarse1 ? m->ws_Y16.p : nullptr, fp16));
+  K_TRY(layernorm_rows(s, D, X, raw_ptr(m, "image_encoder.ln_post.weight"), raw_ptr(m, "image_encoder.ln_post.bias"), Y, 0,
+                       static_cast<int64_t>(nw) * npatch, npatch, T, T - npatch, coarse1 ? m->ws_Y16.p : nullptr, fp16));
   __nv_bfloat16* Ub = m->ws_Ub.as<__nv_bfloat16>();
   float* Uf = m->ws_Uf.as<float>();
   // coarse-grid conv1: the fine-grid map is never materialised -- conv1 reads the per-tap products on the patch grid and
   // conv2's epilogue evaluates the BasicBlock skip (bilinear_up(Y)) on the fly (EPI_BIAS_UPSKIP_RELU_SPLIT)
-  if (!coarse1) K_TRY(resample_to_padded(s, Y, nw, hp, wp, gh, gw, Ub, Uf, fp16));
+  if (!coarse1) K_TRY(resample_to_padded(s, D, Y, nw, hp, wp, gh, gw, Ub, Uf, fp16));
 
   // decoder BasicBlock as two implicit GEMMs over the zero-bordered grid: 9 taps = 9 row-shifted K-segments
-  GemmParams pc = gemm_params_plain(Mp, kWidth, 9 * kWidth);
+  GemmParams pc = gemm_params_plain(Mp, D, 9 * D);
   pc.ab_fp16 = fp16; pc.out_fp16 = fp16;
-  pc.n_seg = 9; pc.seg_kblocks = kWidth / 64;
+  pc.n_seg = 9; pc.seg_kblocks = D / 64;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) {
       pc.seg_row_shift[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
@@ -460,63 +427,52 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
     }
   __nv_bfloat16* D1 = m->ws_D1.as<__nv_bfloat16>();
   __nv_bfloat16* D2 = m->ws_D2.as<__nv_bfloat16>();
-  GemmParams p1 = pc;
-  p1.out = D1; p1.ldo = kWidth; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp; p1.mask_lead = 0;
   set_launch_tag("dec_conv1");
   if (coarse1) {
     const int64_t rows_c = static_cast<int64_t>(nw) * npatch;
-    CUDA_TRY(m->ws_Z.reserve(static_cast<size_t>(rows_c) * 9 * kWidth * 2));
-    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->ws_Y16.as<__nv_bfloat16>(), rows_c, kWidth, kWidth, m->w_c1z.as<__nv_bfloat16>(), kWidth,
-                        plain(fp16, fp16, static_cast<int>(rows_c), 9 * kWidth, kWidth, m->ws_Z.p, 9 * kWidth,
-                              m->zero_bias.as<float>()), 0));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->ws_Y16.as<__nv_bfloat16>(), rows_c, D, D, m->w_c1z.as<__nv_bfloat16>(), D,
+                        plain(fp16, fp16, static_cast<int>(rows_c), 9 * D, D, m->ws_Z.p, 9 * D, m->zero_bias.as<float>()), 0));
     set_launch_tag(nullptr);
-    K_TRY(conv1_from_coarse(s, m->ws_Z.p, m->b_c1.as<float>(), nw, hp, wp, gh, gw, D1, fp16));
-  } else
-  K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, kWidth, kWidth, m->w_c1.as<__nv_bfloat16>(), 9 * kWidth, p1, 0));
+    K_TRY(conv1_from_coarse(s, D, m->ws_Z.p, m->b_c1.as<float>(), nw, hp, wp, gh, gw, D1, fp16));
+  } else {
+    GemmParams p1 = pc;
+    p1.out = D1; p1.ldo = D; p1.bias = m->b_c1.as<float>(); p1.mask_hp = Hp; p1.mask_wp = Wp; p1.mask_lead = 0;
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, D, D, m->w_c1.as<__nv_bfloat16>(), 9 * D, p1, 0));
+  }
   GemmParams p2 = pc;
-  p2.out = D2; p2.ldo = 2 * kWidth; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = kWidth;
+  p2.out = D2; p2.ldo = 2 * D; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = D;
   if (coarse1) { p2.resid = Y; p2.mask_hp = Hp; p2.mask_wp = Wp; p2.up_hp = hp; p2.up_wp = wp; }
   set_launch_tag("dec_conv2");
-  K_TRY(gemm_dispatch(s, coarse1 ? EPI_BIAS_UPSKIP_RELU_SPLIT : EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, kWidth, kWidth,
-                      m->w_c2.as<__nv_bfloat16>(), 9 * kWidth, p2, 0));
+  K_TRY(gemm_dispatch(s, coarse1 ? EPI_BIAS_UPSKIP_RELU_SPLIT : EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, D, D,
+                      m->w_c2.as<__nv_bfloat16>(), 9 * D, p2, 0));
 
-  // projection 1x1 in split precision: [hi | lo | hi] x [Whi | Whi | Wlo]  (A segments re-use the hi columns)
-  GemmParams pp = gemm_params_plain(Mp, kEmbed, 3 * kWidth);
+  // projection 1x1 in split precision, [hi | lo | hi] x [Whi | Whi | Wlo] (the A segments re-use the hi columns), fused
+  // with the head: the `embed` projected features of a cell are never written; the GEMM epilogue leaves ||f||^2 and the N
+  // bin dot products per half tile (kParts partials per row), ebc_head_finish does the rest
+  GemmParams pp = gemm_params_plain(Mp, E, 3 * D);
   pp.ab_fp16 = fp16; pp.out_fp16 = fp16;
-  pp.n_seg = 3; pp.seg_kblocks = kWidth / 64;
-  pp.seg_col_start[0] = 0; pp.seg_col_start[1] = kWidth; pp.seg_col_start[2] = 0;
+  pp.n_seg = 3; pp.seg_kblocks = D / 64;
+  pp.seg_col_start[0] = 0; pp.seg_col_start[1] = D; pp.seg_col_start[2] = 0;
   float* F = m->ws_F.as<float>();
   pp.bias = raw_ptr(m, "projection.bias");
-  static const bool unfused_head = std::getenv("CLIPEBC_HEAD_UNFUSED") != nullptr;  // A/B knob (profiles/)
-  if (g_gemm_impl.load() == 2 && !unfused_head) {
-    // projection fused with the head: the 512 projected features of a cell are never written; the GEMM epilogue
-    // leaves ||f||^2 and the N bin dot products per half tile (4 partials per row), ebc_head_finish does the rest
-    constexpr int kParts = 2 * (kEmbed / 256);
-    pp.out = F; pp.ldo = kParts * (1 + c.num_bins);
-    pp.head_tmat = m->tmat.as<float>(); pp.head_bins = c.num_bins;
-    set_launch_tag("projection+head");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_HEAD_PARTIAL, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 256));
-    set_launch_tag(nullptr);
-    K_TRY(ebc_head_finish(s, F, kParts, raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
-    return CLIPEBC_OK;
-  }
-  pp.out = F; pp.ldo = kEmbed;
-  set_launch_tag("projection");
-  K_TRY(gemm_dispatch(s, EPI_BIAS_F32, D2, Mp, 2 * kWidth, 2 * kWidth, m->w_p3.as<__nv_bfloat16>(), 3 * kWidth, pp, 0));
-
+  pp.out = F; pp.ldo = kParts * (1 + c.num_bins);
+  pp.head_tmat = m->tmat.as<float>(); pp.head_bins = c.num_bins;
+  set_launch_tag("projection+head");
+  K_TRY(gemm_dispatch(s, EPI_BIAS_HEAD_PARTIAL, D2, Mp, 2 * D, 2 * D, m->w_p3.as<__nv_bfloat16>(), 3 * D, pp, 256));
   set_launch_tag(nullptr);
-  K_TRY(ebc_head(s, F, m->tmat.as<float>(), raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
+  K_TRY(ebc_head_finish(s, F, kParts, raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
   return CLIPEBC_OK;
 }
 
-// windows per internal pass: 96 windows of 229 tokens (148 x 128 rows) by default; windows with more tokens get
-// proportionally fewer per pass so that the workspaces (4 MB per 229-token window) stay the same size
-int default_chunk(const clipebc_model* m, int hp = 14, int wp = 14) {
+// windows per internal pass: 96 windows of 197 / 229 tokens (~148 x 128 rows) by default; windows with more tokens (or the
+// wider ViT-L/14 rows) get proportionally fewer per pass so that the workspaces stay the same size
+int default_chunk(const clipebc_model* m, int hp, int wp) {
   if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
   const int64_t tokens = 1 + m->cfg.num_vpt + static_cast<int64_t>(hp) * wp;
-  if (tokens <= 128) return 256;  // ViT-B/32 windows (82 tokens): 256 windows give the GEMMs as many rows as 96 x 197
-  if (tokens <= 256) return 96;
-  return static_cast<int>(std::max<int64_t>(1, 96 * 229 / tokens));
+  const int64_t wide = m->cfg.width > 768 ? 2 : 1;
+  if (tokens <= 128) return static_cast<int>(256 / wide);  // ViT-B/32 windows (82 tokens): as many GEMM rows as 96 x 197
+  if (tokens <= 256) return static_cast<int>(96 / wide);
+  return static_cast<int>(std::max<int64_t>(1, 96 * 229 / tokens / wide));
 }
 
 int check_window_geometry(clipebc_model* m, int h, int w) {
@@ -527,6 +483,54 @@ int check_window_geometry(clipebc_model* m, int h, int w) {
     return fail(CLIPEBC_EINVAL, "window height/width must be multiples of the reduction");
   const int64_t T = 1 + m->cfg.num_vpt + static_cast<int64_t>(h / kPatch) * (w / kPatch);
   if (T > 16384) return fail(CLIPEBC_EINVAL, "window too large: 1 + num_vpt + patches must be <= 16384 tokens");
+  return CLIPEBC_OK;
+}
+
+int check_device(const clipebc_model* m) {
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != m->device)
+    return fail(CLIPEBC_ESTATE, "the model handle lives on CUDA device " + std::to_string(m->device) + " but the current device is " +
+                                    std::to_string(dev) + ": make its device current, or create a new handle on this one");
+  return CLIPEBC_OK;
+}
+
+// patch rows of a call: [rows, 2 * kp_pad] 16-bit; when 3 * patch^2 is not a multiple of 64 (ViT-L/14: 588 -> 640) the
+// pad columns must be zero, and since patchify never writes them they are cleared whenever the buffer is (re)allocated
+int reserve_patch_rows(clipebc_model* m, int64_t rows, cudaStream_t s) {
+  const size_t bytes = static_cast<size_t>(rows) * 2 * m->kp_pad * 2;
+  const void* before = m->ws_patch_rows.p;
+  CUDA_TRY(m->ws_patch_rows.reserve(bytes));
+  if (m->ws_patch_rows.p != before && m->kp_pad != 3 * m->cfg.patch * m->cfg.patch)
+    CUDA_TRY(cudaMemsetAsync(m->ws_patch_rows.p, 0, m->ws_patch_rows.bytes, s));
+  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * m->cfg.width * 4));
+  return CLIPEBC_OK;
+}
+
+// stem of a call: patch rows are in ws_patch_rows -> patch embeddings f32 [rows, width] in ws_patch_embed
+int patch_embed(clipebc_model* m, cudaStream_t s, int64_t rows) {
+  const int fp16 = m->cfg.operand_fp16 != 0, kp = m->kp_pad;
+  set_launch_tag("patch_embed");
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp, m->w_patch.as<__nv_bfloat16>(),
+                      3 * kp, patch_embed_params(fp16, static_cast<int>(rows), m->cfg.width, m->ws_patch_embed.p, kp), 0));
+  set_launch_tag(nullptr);
+  return CLIPEBC_OK;
+}
+
+// device copy of a host index table, cached under `key`
+int cached_table(clipebc_model* m, const std::string& key, const std::vector<int>& tab, cudaStream_t s, const int** out) {
+  auto it = m->idx_cache.find(key);
+  if (it == m->idx_cache.end()) {
+    if (m->idx_cache.size() >= kMaxIdxCache) {  // bound the cache for streams of differently sized images / batches
+      CUDA_TRY(cudaStreamSynchronize(s));      // no launch may still be reading an entry
+      m->idx_cache.clear();
+    }
+    DevBuf& buf = m->idx_cache[key];
+    CUDA_TRY(buf.reserve(tab.size() * 4));
+    CUDA_TRY(cudaMemcpy(buf.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    it = m->idx_cache.find(key);
+  }
+  *out = it->second.as<int>();
   return CLIPEBC_OK;
 }
 
@@ -542,32 +546,6 @@ int64_t clipebc_launch_count(void) { return g_launches.load(); }
 int64_t clipebc_config_epoch(void) { return g_config_epoch.load(); }
 int clipebc_profile_enabled(void) { return cebc::profiling_on() ? 1 : 0; }
 void clipebc_note_replayed_launches(int64_t n) { if (n > 0) g_launches.fetch_add(n); }
-
-int clipebc_set_gemm_impl(int impl) {
-  g_config_epoch.fetch_add(1);
-  if (impl != 1 && impl != 2) return fail(CLIPEBC_EINVAL, "gemm impl must be 1 (single CTA) or 2 (CTA pair)");
-  g_gemm_impl.store(impl);
-  return CLIPEBC_OK;
-}
-
-int clipebc_set_conv1_coarse(int on) {
-  g_config_epoch.fetch_add(1);
-  g_conv1_coarse.store(on != 0);
-  return CLIPEBC_OK;
-}
-
-int clipebc_set_ln_fold(int on) {
-  g_config_epoch.fetch_add(1);
-  g_ln_fold.store(on != 0);
-  return CLIPEBC_OK;
-}
-
-int clipebc_set_attention_impl(int impl) {
-  g_config_epoch.fetch_add(1);
-  if (impl < 1 || impl > 4) return fail(CLIPEBC_EINVAL, "attention impl must be 1 (mma.sync), 2, 3 or 4 (tcgen05)");
-  g_attn_impl.store(impl);
-  return CLIPEBC_OK;
-}
 
 int clipebc_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -607,25 +585,51 @@ int clipebc_profile_dump(char* buf, int cap) {
 
 int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (!cfg || !out) return fail(CLIPEBC_EINVAL, "null argument");
-  if (cfg->reduction != 8 && cfg->reduction != 16 && cfg->reduction != 32)
-    return fail(CLIPEBC_EINVAL, "reduction must be 8, 16 or 32");
-  if (cfg->patch != 0 && cfg->patch != 16 && cfg->patch != 32) return fail(CLIPEBC_EINVAL, "patch must be 16 (ViT-B/16) or 32 (ViT-B/32)");
-  const int kPatch = cfg->patch ? cfg->patch : 16;
-  if (cfg->input_size <= 0 || cfg->input_size % kPatch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of the patch size");
-  if (cfg->num_vpt < 0 || cfg->num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
-  if (cfg->num_bins < 1 || cfg->num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
-  if (cfg->operand_fp16 != 0 && cfg->operand_fp16 != 1) return fail(CLIPEBC_EINVAL, "operand_fp16 must be 0 (bf16) or 1 (fp16)");
+  if (cfg->struct_size != sizeof(clipebc_config))
+    return fail(CLIPEBC_EINVAL, "clipebc_config.struct_size is " + std::to_string(cfg->struct_size) + " but this library's "
+                "clipebc_config has " + std::to_string(sizeof(clipebc_config)) + " bytes (ABI v" +
+                std::to_string(CLIPEBC_ABI_VERSION) + "): the caller was built against another header");
+  clipebc_config c = *cfg;
+  if (c.patch == 0) c.patch = 16;
+  if (c.width == 0) c.width = 768;
+  if (c.layers == 0) c.layers = 12;
+  if (c.embed_dim == 0) c.embed_dim = 512;
+  if (c.reduction != 8 && c.reduction != 16 && c.reduction != 32) return fail(CLIPEBC_EINVAL, "reduction must be 8, 16 or 32");
+  if (c.patch != 14 && c.patch != 16 && c.patch != 32)
+    return fail(CLIPEBC_EINVAL, "patch must be 16 (ViT-B/16), 32 (ViT-B/32) or 14 (ViT-L/14)");
+  if (c.width != 768 && c.width != 1024) return fail(CLIPEBC_EINVAL, "width must be 768 (ViT-B) or 1024 (ViT-L)");
+  if (c.layers < 1 || c.layers > 48) return fail(CLIPEBC_EINVAL, "layers must be in 1..48");
+  if (c.embed_dim <= 0 || c.embed_dim % 256 != 0 || c.embed_dim > 1024)
+    return fail(CLIPEBC_EINVAL, "embed_dim must be 256, 512, 768 or 1024");
+  if (c.input_size <= 0 || c.input_size % c.patch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of the patch size");
+  if (c.num_vpt < 0 || c.num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
+  if (c.num_bins < 1 || c.num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
+  if (c.operand_fp16 != 0 && c.operand_fp16 != 1) return fail(CLIPEBC_EINVAL, "operand_fp16 must be 0 (bf16) or 1 (fp16)");
+  if (c.window_chunk < 0) return fail(CLIPEBC_EINVAL, "window_chunk must not be negative");
   clipebc_model* m = new clipebc_model();
-  m->cfg = *cfg;
-  m->cfg.patch = kPatch;
+  m->cfg = c;
+  m->kp_pad = (3 * c.patch * c.patch + 63) / 64 * 64;
+  m->layer.reset(new LayerPack[c.layers]);
+  // the device current at creation owns the handle (-1 on a host without a CUDA device: such a handle can be configured
+  // and inspected, every compute entry point then fails with CLIPEBC_ECUDA)
+  if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); m->device = -1; }
   *out = m;
   return CLIPEBC_OK;
 }
 
-void clipebc_model_destroy(clipebc_model* m) { delete m; }
+void clipebc_model_destroy(clipebc_model* m) {
+  if (!m) return;
+  int cur = -1;
+  const bool sw = m->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != m->device && cudaSetDevice(m->device) == cudaSuccess;
+  delete m;  // frees the device buffers on the device that owns them
+  if (sw) cudaSetDevice(cur);
+  cudaGetLastError();
+}
 
 int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim) {
   if (!m || !name || !data || ndim < 0 || (ndim > 0 && !shape)) return fail(CLIPEBC_EINVAL, "null argument");
+  int rc;
+  if ((rc = check_device(m))) return rc;
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) {
     if (shape[i] <= 0) return fail(CLIPEBC_EINVAL, std::string("empty tensor '") + name + "'");
@@ -642,95 +646,94 @@ int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* da
 
 int clipebc_model_pack(clipebc_model* m, void* stream_) {
   if (!m) return fail(CLIPEBC_EINVAL, "null model");
+  int rc;
+  if ((rc = check_device(m))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const clipebc_config& c = m->cfg;
   const int fp16 = c.operand_fp16 != 0;
+  const int D = c.width, hidden = 4 * D, E = c.embed_dim, nL = c.layers;
   const int kPatch = c.patch, kp = 3 * kPatch * kPatch;
   const int g0 = c.input_size / kPatch;
   std::string err;
-  const int n_vpt_layers = c.deep_vpt ? kLayers : 1;
+  const int n_vpt_layers = c.deep_vpt ? nL : 1;
   bool ok = true;
   if (c.num_vpt > 0)
-    for (int l = 0; l < n_vpt_layers && ok; ++l) ok = check_shape(m, "vpt_" + std::to_string(l), {c.num_vpt, kWidth}, &err);
+    for (int l = 0; l < n_vpt_layers && ok; ++l) ok = check_shape(m, "vpt_" + std::to_string(l), {c.num_vpt, D}, &err);
   ok = ok && check_shape(m, "logit_scale", {}, &err) &&
-       check_shape(m, "image_encoder.class_embedding", {kWidth}, &err) &&
-       check_shape(m, "image_encoder.positional_embedding", {1 + g0 * g0, kWidth}, &err) &&
-       check_shape(m, "image_encoder.conv1.weight", {kWidth, 3, kPatch, kPatch}, &err) &&
-       check_shape(m, "image_encoder.ln_pre.weight", {kWidth}, &err) && check_shape(m, "image_encoder.ln_pre.bias", {kWidth}, &err) &&
-       check_shape(m, "image_encoder.ln_post.weight", {kWidth}, &err) && check_shape(m, "image_encoder.ln_post.bias", {kWidth}, &err);
-  for (int l = 0; l < kLayers && ok; ++l) {
-    ok = check_shape(m, blk(l, "attn.in_proj_weight"), {3 * kWidth, kWidth}, &err) &&
-         check_shape(m, blk(l, "attn.in_proj_bias"), {3 * kWidth}, &err) &&
-         check_shape(m, blk(l, "attn.out_proj.weight"), {kWidth, kWidth}, &err) &&
-         check_shape(m, blk(l, "attn.out_proj.bias"), {kWidth}, &err) &&
-         check_shape(m, blk(l, "ln_1.weight"), {kWidth}, &err) && check_shape(m, blk(l, "ln_1.bias"), {kWidth}, &err) &&
-         check_shape(m, blk(l, "ln_2.weight"), {kWidth}, &err) && check_shape(m, blk(l, "ln_2.bias"), {kWidth}, &err) &&
-         check_shape(m, blk(l, "mlp.c_fc.weight"), {kHidden, kWidth}, &err) && check_shape(m, blk(l, "mlp.c_fc.bias"), {kHidden}, &err) &&
-         check_shape(m, blk(l, "mlp.c_proj.weight"), {kWidth, kHidden}, &err) && check_shape(m, blk(l, "mlp.c_proj.bias"), {kWidth}, &err);
+       check_shape(m, "image_encoder.class_embedding", {D}, &err) &&
+       check_shape(m, "image_encoder.positional_embedding", {1 + g0 * g0, D}, &err) &&
+       check_shape(m, "image_encoder.conv1.weight", {D, 3, kPatch, kPatch}, &err) &&
+       check_shape(m, "image_encoder.ln_pre.weight", {D}, &err) && check_shape(m, "image_encoder.ln_pre.bias", {D}, &err) &&
+       check_shape(m, "image_encoder.ln_post.weight", {D}, &err) && check_shape(m, "image_encoder.ln_post.bias", {D}, &err);
+  for (int l = 0; l < nL && ok; ++l) {
+    ok = check_shape(m, blk(l, "attn.in_proj_weight"), {3 * D, D}, &err) &&
+         check_shape(m, blk(l, "attn.in_proj_bias"), {3 * D}, &err) &&
+         check_shape(m, blk(l, "attn.out_proj.weight"), {D, D}, &err) &&
+         check_shape(m, blk(l, "attn.out_proj.bias"), {D}, &err) &&
+         check_shape(m, blk(l, "ln_1.weight"), {D}, &err) && check_shape(m, blk(l, "ln_1.bias"), {D}, &err) &&
+         check_shape(m, blk(l, "ln_2.weight"), {D}, &err) && check_shape(m, blk(l, "ln_2.bias"), {D}, &err) &&
+         check_shape(m, blk(l, "mlp.c_fc.weight"), {hidden, D}, &err) && check_shape(m, blk(l, "mlp.c_fc.bias"), {hidden}, &err) &&
+         check_shape(m, blk(l, "mlp.c_proj.weight"), {D, hidden}, &err) && check_shape(m, blk(l, "mlp.c_proj.bias"), {D}, &err);
   }
   for (int k = 1; k <= 2 && ok; ++k) {
     const std::string cv = "image_decoder.0.conv" + std::to_string(k) + ".weight", bn = "image_decoder.0.bn" + std::to_string(k);
-    ok = check_shape(m, cv, {kWidth, kWidth, 3, 3}, &err) && check_shape(m, bn + ".weight", {kWidth}, &err) &&
-         check_shape(m, bn + ".bias", {kWidth}, &err) && check_shape(m, bn + ".running_mean", {kWidth}, &err) &&
-         check_shape(m, bn + ".running_var", {kWidth}, &err);
+    ok = check_shape(m, cv, {D, D, 3, 3}, &err) && check_shape(m, bn + ".weight", {D}, &err) &&
+         check_shape(m, bn + ".bias", {D}, &err) && check_shape(m, bn + ".running_mean", {D}, &err) &&
+         check_shape(m, bn + ".running_var", {D}, &err);
   }
-  ok = ok && check_shape(m, "projection.weight", {kEmbed, kWidth, 1, 1}, &err) && check_shape(m, "projection.bias", {kEmbed}, &err) &&
-       check_shape(m, "text_features", {c.num_bins, kEmbed}, &err) && check_shape(m, "anchor_points", {c.num_bins}, &err);
+  ok = ok && check_shape(m, "projection.weight", {E, D, 1, 1}, &err) && check_shape(m, "projection.bias", {E}, &err) &&
+       check_shape(m, "text_features", {c.num_bins, E}, &err) && check_shape(m, "anchor_points", {c.num_bins}, &err);
   if (!ok) return fail(CLIPEBC_ESTATE, "pack: " + err);
 
-  int rc;
-  CUDA_TRY(m->w_patch.reserve(static_cast<size_t>(kWidth) * 3 * kp * 2));
-  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "image_encoder.conv1.weight"), kWidth, kp, m->w_patch.p, fp16));
-  for (int l = 0; l < kLayers; ++l) {
+  CUDA_TRY(m->w_patch.reserve(static_cast<size_t>(D) * 3 * m->kp_pad * 2));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "image_encoder.conv1.weight"), D, kp, m->kp_pad, m->w_patch.p, fp16));
+  for (int l = 0; l < nL; ++l) {
     LayerPack& L = m->layer[l];
-    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * kWidth * kWidth, &L.w_qkv, fp16))) return rc;
-    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.out_proj.weight")), static_cast<int64_t>(kWidth) * kWidth, &L.w_out, fp16))) return rc;
-    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), static_cast<int64_t>(kHidden) * kWidth, &L.w_fc, fp16))) return rc;
-    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_proj.weight")), static_cast<int64_t>(kWidth) * kHidden, &L.w_proj, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), static_cast<int64_t>(3) * D * D, &L.w_qkv, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "attn.out_proj.weight")), static_cast<int64_t>(D) * D, &L.w_out, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), static_cast<int64_t>(hidden) * D, &L.w_fc, fp16))) return rc;
+    if ((rc = to_16(s, raw_ptr(m, blk(l, "mlp.c_proj.weight")), static_cast<int64_t>(D) * hidden, &L.w_proj, fp16))) return rc;
     L.b_qkv = raw_ptr(m, blk(l, "attn.in_proj_bias"));
     L.b_out = raw_ptr(m, blk(l, "attn.out_proj.bias"));
     L.b_fc = raw_ptr(m, blk(l, "mlp.c_fc.bias"));
     L.b_proj = raw_ptr(m, blk(l, "mlp.c_proj.bias"));
     L.ln1_g = raw_ptr(m, blk(l, "ln_1.weight")); L.ln1_b = raw_ptr(m, blk(l, "ln_1.bias"));
     L.ln2_g = raw_ptr(m, blk(l, "ln_2.weight")); L.ln2_b = raw_ptr(m, blk(l, "ln_2.bias"));
-    CUDA_TRY(L.wf_qkv.reserve(static_cast<size_t>(3) * kWidth * kWidth * 2));
-    CUDA_TRY(L.wf_fc.reserve(static_cast<size_t>(kHidden) * kWidth * 2));
-    CUDA_TRY(L.ln_aux.reserve(static_cast<size_t>(2) * (3 * kWidth + kHidden) * 4));
-    float* aux = L.ln_aux.as<float>();
-    K_TRY(fold_ln_linear(s, raw_ptr(m, blk(l, "attn.in_proj_weight")), L.b_qkv, L.ln1_g, L.ln1_b, 3 * kWidth, L.wf_qkv.p, aux,
-                         aux + 3 * kWidth, fp16));
-    K_TRY(fold_ln_linear(s, raw_ptr(m, blk(l, "mlp.c_fc.weight")), L.b_fc, L.ln2_g, L.ln2_b, kHidden, L.wf_fc.p,
-                         aux + 6 * kWidth, aux + 6 * kWidth + kHidden, fp16));
-    if (c.deep_vpt && c.num_vpt > 0) {
-      // constant prompt K/V of layer l: in_proj(LN1_l(vpt_l)) -- same kernels as the live path
-      CUDA_TRY(m->pack_tmp_bf16.reserve(static_cast<size_t>(c.num_vpt) * kWidth * 2));
-      CUDA_TRY(L.const_kv.reserve(static_cast<size_t>(c.num_vpt) * 3 * kWidth * 2));
-      K_TRY(layernorm768(s, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_bf16.p, fp16 ? 2 : 1, c.num_vpt, 1, 1, 0));
-      K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->pack_tmp_bf16.as<__nv_bfloat16>(), c.num_vpt, kWidth, kWidth,
-                         L.w_qkv.as<__nv_bfloat16>(), kWidth,
-                         plain(fp16, 0, c.num_vpt, 3 * kWidth, kWidth, L.const_kv.p, 3 * kWidth, L.b_qkv), 0));
+  }
+  if (c.deep_vpt && c.num_vpt > 0) {
+    // constant prompt K/V of every layer: in_proj(LN1_l(vpt_l)) with the kernels of the live path. These GEMMs read
+    // weights that the conversion kernels above have just written, so their weight tiles must not be requested ahead of
+    // the programmatic-dependency wait (GemmParams::w_prefetch = 0).
+    CUDA_TRY(m->pack_tmp_16.reserve(static_cast<size_t>(c.num_vpt) * D * 2));
+    for (int l = 0; l < nL; ++l) {
+      LayerPack& L = m->layer[l];
+      CUDA_TRY(L.const_kv.reserve(static_cast<size_t>(c.num_vpt) * 3 * D * 2));
+      K_TRY(layernorm_rows(s, D, raw_ptr(m, "vpt_" + std::to_string(l)), L.ln1_g, L.ln1_b, m->pack_tmp_16.p, fp16 ? 2 : 1, c.num_vpt, 1, 1, 0));
+      GemmParams pk = plain(fp16, 0, c.num_vpt, 3 * D, D, L.const_kv.p, 3 * D, L.b_qkv);
+      pk.w_prefetch = 0;
+      K_TRY(gemm_dispatch(s, EPI_BIAS_BF16, m->pack_tmp_16.as<__nv_bfloat16>(), c.num_vpt, D, D, L.w_qkv.as<__nv_bfloat16>(), D, pk, 0));
     }
   }
   for (int k = 1; k <= 2; ++k) {
     const std::string cv = "image_decoder.0.conv" + std::to_string(k) + ".weight", bn = "image_decoder.0.bn" + std::to_string(k);
     DevBuf& W = (k == 1) ? m->w_c1 : m->w_c2;
     DevBuf& B = (k == 1) ? m->b_c1 : m->b_c2;
-    CUDA_TRY(W.reserve(static_cast<size_t>(kWidth) * 9 * kWidth * 2));
-    CUDA_TRY(B.reserve(kWidth * 4));
+    CUDA_TRY(W.reserve(static_cast<size_t>(D) * 9 * D * 2));
+    CUDA_TRY(B.reserve(static_cast<size_t>(D) * 4));
     K_TRY(fold_conv3x3_bn(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".bias"), raw_ptr(m, bn + ".running_mean"),
-                          raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth, kWidth, W.p, B.as<float>(), fp16));
+                          raw_ptr(m, bn + ".running_var"), 1e-5f, D, D, W.p, B.as<float>(), fp16));
     if (k == 1) {
-      CUDA_TRY(m->w_c1z.reserve(static_cast<size_t>(9) * kWidth * kWidth * 2));
-      K_TRY(fold_conv3x3_bn_tapout(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".running_var"), 1e-5f, kWidth,
-                                   kWidth, m->w_c1z.p, fp16));
-      CUDA_TRY(m->zero_bias.reserve(static_cast<size_t>(9) * kWidth * 4));
-      CUDA_TRY(cudaMemsetAsync(m->zero_bias.p, 0, static_cast<size_t>(9) * kWidth * 4, s));
+      CUDA_TRY(m->w_c1z.reserve(static_cast<size_t>(9) * D * D * 2));
+      K_TRY(fold_conv3x3_bn_tapout(s, raw_ptr(m, cv), raw_ptr(m, bn + ".weight"), raw_ptr(m, bn + ".running_var"), 1e-5f, D, D,
+                                   m->w_c1z.p, fp16));
+      CUDA_TRY(m->zero_bias.reserve(static_cast<size_t>(9) * D * 4));
+      CUDA_TRY(cudaMemsetAsync(m->zero_bias.p, 0, static_cast<size_t>(9) * D * 4, s));
     }
   }
-  CUDA_TRY(m->w_p3.reserve(static_cast<size_t>(kEmbed) * 3 * kWidth * 2));
-  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), kEmbed, kWidth, m->w_p3.p, fp16));
-  CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * kEmbed * 4));
-  K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, kEmbed, m->tmat.as<float>()));
+  CUDA_TRY(m->w_p3.reserve(static_cast<size_t>(E) * 3 * D * 2));
+  K_TRY(split_weight_hi_hi_lo(s, raw_ptr(m, "projection.weight"), E, D, D, m->w_p3.p, fp16));
+  CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * E * 4));
+  K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, E, m->tmat.as<float>()));
   CUDA_TRY(cudaStreamSynchronize(s));
   m->pos_cache.clear();
   m->packed = true;
@@ -743,9 +746,10 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
   if (B <= 0) return fail(CLIPEBC_EINVAL, "batch must be positive");
   int rc;
+  if ((rc = check_device(m))) return rc;
   if ((rc = check_window_geometry(m, h, w))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
+  const int kPatch = m->cfg.patch;
   const int hp = h / kPatch, wp = w / kPatch, npatch = hp * wp;
   const int gh = h / m->cfg.reduction, gw = w / m->cfg.reduction;
   const float* pos;
@@ -753,26 +757,14 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
 
   const int64_t rows = static_cast<int64_t>(B) * npatch;
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kp * 2));
-  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  K_TRY(patchify(s, x_dev, B, h, w, 0, 0, hp, wp, kPatch, m->ws_patch_rows.p, fp16));
-  set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
-                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p, kp), 0));
-  set_launch_tag(nullptr);
+  if ((rc = reserve_patch_rows(m, rows, s))) return rc;
+  K_TRY(patchify(s, x_dev, B, h, w, 0, 0, hp, wp, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
+  if ((rc = patch_embed(m, s, rows))) return rc;
   // window b reads patch rows [b * npatch, (b+1) * npatch)
-  const std::string key = "fw:" + std::to_string(B) + ":" + std::to_string(npatch);
-  auto cached = m->idx_cache.find(key);
-  if (cached == m->idx_cache.end()) {
-    std::vector<int> base(B);
-    for (int b = 0; b < B; ++b) base[b] = b * npatch;
-    DevBuf& buf = m->idx_cache[key];
-    CUDA_TRY(buf.reserve(static_cast<size_t>(B) * 4));
-    CUDA_TRY(cudaMemcpy(buf.p, base.data(), static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice));
-    cached = m->idx_cache.find(key);
-  }
-  const int* d_win_base = cached->second.as<int>();
+  std::vector<int> base(B);
+  for (int b = 0; b < B; ++b) base[b] = b * npatch;
+  const int* d_win_base;
+  if ((rc = cached_table(m, "fw:" + std::to_string(B) + ":" + std::to_string(npatch), base, s, &d_win_base))) return rc;
 
   const int chunk = default_chunk(m, hp, wp);
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -806,6 +798,7 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   if (!m || !image_dev || !density_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
   int rc, nr = 0, nc = 0;
+  if ((rc = check_device(m))) return rc;
   if ((rc = clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, nullptr, nullptr))) return rc;
   if ((rc = check_window_geometry(m, wh, ww))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
@@ -813,26 +806,25 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   std::vector<int> ro(nr), co(nc);
   clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, ro.data(), co.data());
   const int n_win = nr * nc;
-  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
+  const int kPatch = m->cfg.patch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
   const int gh = wh / r, gw = ww / r;
   const float* pos;
   if ((rc = get_pos(m, hp, wp, s, &pos))) return rc;
 
-  bool on_grid = true;
+  // one patch grid per image, shared by all overlapping windows (the unfold never materialises windows), when every
+  // window origin is on it; else a per-window unfold
+  bool on_grid = H % kPatch == 0 && W % kPatch == 0;
   for (int v : ro) on_grid = on_grid && (v % kPatch == 0);
   for (int v : co) on_grid = on_grid && (v % kPatch == 0);
 
-  // host-side index tables: [0, n_win) win_base | [n_win, 3 n_win) origins (y, x) | row cells | col cells
+  // index tables: [0, n_win) win_base | [n_win, 3 n_win) origins (y, x) | row cells | col cells
   const std::string key = "sw:" + std::to_string(H) + ":" + std::to_string(W) + ":" + std::to_string(wh) + ":" +
                           std::to_string(ww) + ":" + std::to_string(sh) + ":" + std::to_string(sw);
-  auto cached = m->idx_cache.find(key);
-  const bool need_upload = cached == m->idx_cache.end();
   std::vector<int> tab(static_cast<size_t>(3) * n_win + nr + nc);
   int src_pitch;
   int64_t rows;
   if (on_grid) {
-    // one patch grid per image, shared by all overlapping windows (the unfold never materialises windows)
     const int GH = H / kPatch, GW = W / kPatch;
     rows = static_cast<int64_t>(GH) * GW;
     src_pitch = GW;
@@ -850,28 +842,17 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
     }
   for (int i = 0; i < nr; ++i) tab[3 * n_win + i] = ro[i] / r;       // x_start // reduction (eval_utils.py:90)
   for (int j = 0; j < nc; ++j) tab[3 * n_win + nr + j] = co[j] / r;
-  if (need_upload) {
-    if (m->idx_cache.size() > 64) m->idx_cache.clear();  // bound the cache for streams of differently sized images
-    DevBuf& buf = m->idx_cache[key];
-    CUDA_TRY(buf.reserve(tab.size() * 4));
-    CUDA_TRY(cudaMemcpy(buf.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-    cached = m->idx_cache.find(key);
-  }
-  const int* d_base = cached->second.as<int>();
+  const int* d_base;
+  if ((rc = cached_table(m, key, tab, s, &d_base))) return rc;
   const int* d_orig = d_base + n_win;
   const int* d_rc = d_base + 3 * n_win;
   const int* d_cc = d_rc + nr;
 
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(rows) * 2 * kp * 2));
-  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(rows) * kWidth * 4));
-  if (on_grid) K_TRY(patchify(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, kPatch, m->ws_patch_rows.p, fp16));
-  else K_TRY(patchify_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, kPatch, m->ws_patch_rows.p, fp16));
-  set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
-                      patch_embed_params(fp16, static_cast<int>(rows), m->ws_patch_embed.p, kp), 0));
-  set_launch_tag(nullptr);
+  if ((rc = reserve_patch_rows(m, rows, s))) return rc;
+  if (on_grid) K_TRY(patchify(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
+  else K_TRY(patchify_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
+  if ((rc = patch_embed(m, s, rows))) return rc;
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
   float* preds = m->ws_preds.as<float>();
@@ -893,10 +874,11 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   if (n_images <= 0) return fail(CLIPEBC_EINVAL, "batch must contain at least one image");
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
   int rc;
+  if ((rc = check_device(m))) return rc;
   if ((rc = check_window_geometry(m, wh, ww))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const int r = m->cfg.reduction;
-  const int kPatch = m->cfg.patch, kp = 3 * kPatch * kPatch;
+  const int kPatch = m->cfg.patch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
   const int gh = wh / r, gw = ww / r;
   const float* pos;
@@ -916,7 +898,7 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
     g.ro.resize(g.nr); g.co.resize(g.nc);
     clipebc_window_origins(g.H, g.W, wh, ww, sh, sw, &g.nr, &g.nc, g.ro.data(), g.co.data());
     g.n_win = g.nr * g.nc;
-    g.on_grid = true;
+    g.on_grid = g.H % kPatch == 0 && g.W % kPatch == 0;
     for (int v : g.ro) g.on_grid = g.on_grid && (v % kPatch == 0);
     for (int v : g.co) g.on_grid = g.on_grid && (v % kPatch == 0);
     g.rows = g.on_grid ? static_cast<int64_t>(g.H / kPatch) * (g.W / kPatch) : static_cast<int64_t>(g.n_win) * npatch;
@@ -930,9 +912,9 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   // index tables: win_base | win_pitch | origins (y, x) | per image: row cells, col cells
   size_t tab_len = static_cast<size_t>(4) * total_win;
   for (Geom& g : gs) { g.tab_off = static_cast<int>(tab_len); tab_len += g.nr + g.nc; }
-  auto cached = m->idx_cache.find(key);
-  if (cached == m->idx_cache.end()) {
-    std::vector<int> tab(tab_len);
+  std::vector<int> tab;
+  if (m->idx_cache.find(key) == m->idx_cache.end()) {
+    tab.resize(tab_len);
     for (const Geom& g : gs) {
       for (int i = 0; i < g.nr; ++i)
         for (int j = 0; j < g.nc; ++j) {
@@ -946,32 +928,23 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
       for (int i = 0; i < g.nr; ++i) tab[g.tab_off + i] = g.ro[i] / r;
       for (int j = 0; j < g.nc; ++j) tab[g.tab_off + g.nr + j] = g.co[j] / r;
     }
-    if (m->idx_cache.size() > 64) m->idx_cache.clear();
-    DevBuf& buf = m->idx_cache[key];
-    CUDA_TRY(buf.reserve(tab.size() * 4));
-    CUDA_TRY(cudaMemcpy(buf.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-    cached = m->idx_cache.find(key);
   }
-  const int* d_tab = cached->second.as<int>();
+  const int* d_tab;
+  if ((rc = cached_table(m, key, tab, s, &d_tab))) return rc;
   const int* d_base = d_tab;
   const int* d_pitch = d_tab + total_win;
   const int* d_orig = d_tab + 2 * total_win;
 
   // patch rows of all images, one patch-embedding GEMM over all of them
   const int fp16 = m->cfg.operand_fp16 != 0;
-  CUDA_TRY(m->ws_patch_rows.reserve(static_cast<size_t>(total_rows) * 2 * kp * 2));
-  CUDA_TRY(m->ws_patch_embed.reserve(static_cast<size_t>(total_rows) * kWidth * 4));
+  if ((rc = reserve_patch_rows(m, total_rows, s))) return rc;
   for (int i = 0; i < n_images; ++i) {
     const Geom& g = gs[i];
-    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * kp;
-    if (g.on_grid) K_TRY(patchify(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, kPatch, dst, fp16));
-    else K_TRY(patchify_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, kPatch, dst, fp16));
+    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * m->kp_pad;
+    if (g.on_grid) K_TRY(patchify(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, kPatch, m->kp_pad, dst, fp16));
+    else K_TRY(patchify_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, kPatch, m->kp_pad, dst, fp16));
   }
-  set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), total_rows, 2 * kp, 2 * kp,
-                      m->w_patch.as<__nv_bfloat16>(), 3 * kp,
-                      patch_embed_params(fp16, static_cast<int>(total_rows), m->ws_patch_embed.p, kp), 0));
-  set_launch_tag(nullptr);
+  if ((rc = patch_embed(m, s, total_rows))) return rc;
 
   // the windows of all images share the passes of the ViT / decoder / head (chunks may span image boundaries)
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(total_win) * gh * gw * 4));
@@ -1018,82 +991,36 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
   return CLIPEBC_OK;
 }
 
-int clipebc_gemm_resid_stats(const void* A, int64_t a_rows, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
-                             float* X, const float* bias, void* x16_out, void* stats_out, int block_n, int ab_fp16,
-                             int out_fp16, void* stream) {
-  if (!A || !W || !X || !bias || !x16_out || !stats_out) return fail(CLIPEBC_EINVAL, "null argument");
-  if (g_gemm_impl.load() != 2) return fail(CLIPEBC_ESTATE, "the statistics epilogue exists in the CTA-pair GEMM only");
-  GemmParams p = gemm_params_plain(M, N, K);
-  p.out = X; p.ldo = N; p.bias = bias; p.resid = X; p.ldr = N; p.ab_fp16 = ab_fp16; p.out_fp16 = out_fp16;
-  p.x16_out = x16_out; p.stats_out = static_cast<float2*>(stats_out);
-  K_TRY(gemm2_bf16_tn(static_cast<cudaStream_t>(stream), EPI_BIAS_RESID_STATS, static_cast<const __nv_bfloat16*>(A), a_rows, K,
-                      lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n));
-  return CLIPEBC_OK;
-}
-
-int clipebc_gemm_ln(int gelu, const void* A, int64_t a_rows, int64_t lda, const void* Wf, int64_t ldw, int M, int N, int K,
-                    void* out, int ldo, const float* bias_f, const void* ln_stats, int ln_parts, const float* ln_colsum,
-                    int block_n, int ab_fp16, int out_fp16, void* stream) {
-  if (!A || !Wf || !out || !bias_f || !ln_stats || !ln_colsum) return fail(CLIPEBC_EINVAL, "null argument");
-  if (g_gemm_impl.load() != 2) return fail(CLIPEBC_ESTATE, "the LayerNorm epilogue exists in the CTA-pair GEMM only");
-  GemmParams p = gemm_params_plain(M, N, K);
-  p.out = out; p.ldo = ldo; p.bias = bias_f; p.ab_fp16 = ab_fp16; p.out_fp16 = out_fp16;
-  p.ln_stats = static_cast<const float2*>(ln_stats); p.ln_colsum = ln_colsum; p.ln_parts = ln_parts;
-  K_TRY(gemm2_bf16_tn(static_cast<cudaStream_t>(stream), gelu ? EPI_LN_BIAS_GELU_BF16 : EPI_LN_BIAS_BF16,
-                      static_cast<const __nv_bfloat16*>(A), a_rows, K, lda, static_cast<const __nv_bfloat16*>(Wf), ldw, p, block_n));
-  return CLIPEBC_OK;
-}
-
-int clipebc_rowstats768(const float* in, int64_t n_rows, void* x16_out, void* stats_out, int fp16, void* stream) {
-  if (!in || !x16_out || !stats_out) return fail(CLIPEBC_EINVAL, "null argument");
-  K_TRY(rowstats768(static_cast<cudaStream_t>(stream), in, n_rows, x16_out, static_cast<float2*>(stats_out), fp16));
-  return CLIPEBC_OK;
-}
-
-int clipebc_fold_ln_linear(const float* W, const float* b, const float* gamma, const float* beta, int O, void* Wf, float* colsum,
-                           float* bias_f, int fp16, void* stream) {
-  if (!W || !b || !gamma || !beta || !Wf || !colsum || !bias_f) return fail(CLIPEBC_EINVAL, "null argument");
-  K_TRY(fold_ln_linear(static_cast<cudaStream_t>(stream), W, b, gamma, beta, O, Wf, colsum, bias_f, fp16));
-  return CLIPEBC_OK;
-}
-
-int clipebc_layernorm768(const float* in, const float* g, const float* b, void* out, int out_kind, int64_t n_rows_out,
-                         int rows_out_per_group, int rows_in_per_group, int in_row_offset, void* stream) {
+int clipebc_layernorm(const float* in, const float* g, const float* b, int width, void* out, int out_kind, int64_t n_rows_out,
+                      int rows_out_per_group, int rows_in_per_group, int in_row_offset, void* stream) {
+  if (!in || !g || !b || !out) return fail(CLIPEBC_EINVAL, "null argument");
   if (out_kind < 0 || out_kind > 2) return fail(CLIPEBC_EINVAL, "layernorm: out_kind must be 0 (f32), 1 (bf16) or 2 (fp16)");
-  K_TRY(layernorm768(static_cast<cudaStream_t>(stream), in, g, b, out, out_kind, n_rows_out, rows_out_per_group,
-                     rows_in_per_group, in_row_offset));
+  if (width != 768 && width != 1024) return fail(CLIPEBC_EINVAL, "layernorm: width must be 768 or 1024");
+  K_TRY(layernorm_rows(static_cast<cudaStream_t>(stream), width, in, g, b, out, out_kind, n_rows_out, rows_out_per_group,
+                       rows_in_per_group, in_row_offset));
   return CLIPEBC_OK;
 }
 
-int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_win, int t_live, void* out, int out_fp16,
-                      void* stream) {
+int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_win, int t_live, int heads, void* out,
+                      int out_fp16, void* stream) {
+  if (!qkv || !out) return fail(CLIPEBC_EINVAL, "null argument");
+  if (heads < 1 || heads > 32) return fail(CLIPEBC_EINVAL, "attention: heads must be in 1..32");
   K_TRY(attention_dispatch(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
-                           static_cast<const __nv_bfloat16*>(const_kv), n_const, n_win, t_live, out, out_fp16 != 0));
+                           static_cast<const __nv_bfloat16*>(const_kv), n_const, n_win, t_live, heads, out, out_fp16 != 0));
   return CLIPEBC_OK;
 }
 
-int clipebc_patchify(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch, void* out,
-                     int fp16, void* stream) {
+int clipebc_patchify(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch, int kp_pad,
+                     void* out, int fp16, void* stream) {
   if (!image || !out) return fail(CLIPEBC_EINVAL, "null argument");
-  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, patch, out, fp16 != 0));
+  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, patch, kp_pad, out, fp16 != 0));
   return CLIPEBC_OK;
 }
 
-int clipebc_patchify16(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, void* out, int fp16,
-                       void* stream) {
-  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, 16, out, fp16 != 0));
-  return CLIPEBC_OK;
-}
-
-int clipebc_resample_to_padded(const float* Y, int n_win, int hp, int wp, int gh, int gw, void* Ub, float* Uf, int fp16,
-                               void* stream) {
-  K_TRY(resample_to_padded(static_cast<cudaStream_t>(stream), Y, n_win, hp, wp, gh, gw, Ub, Uf, fp16 != 0));
-  return CLIPEBC_OK;
-}
-
-int clipebc_ebc_head(const float* F, const float* tmat, const float* anchors, int n_bins, int n_win, int gh, int gw,
-                     float* exp_out, float* logits_out, void* stream) {
-  K_TRY(ebc_head(static_cast<cudaStream_t>(stream), F, tmat, anchors, n_bins, n_win, gh, gw, exp_out, logits_out));
+int clipebc_resample_to_padded(const float* Y, int n_win, int hp, int wp, int gh, int gw, int width, void* Ub, float* Uf,
+                               int fp16, void* stream) {
+  if (!Y || !Uf) return fail(CLIPEBC_EINVAL, "null argument");
+  K_TRY(resample_to_padded(static_cast<cudaStream_t>(stream), width, Y, n_win, hp, wp, gh, gw, Ub, Uf, fp16 != 0));
   return CLIPEBC_OK;
 }
 

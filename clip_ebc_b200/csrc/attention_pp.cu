@@ -3,11 +3,11 @@
 // Replaces nn.MultiheadAttention -> F.scaled_dot_product_attention (/root/reference/models/clip/_clip/blocks.py:25,35-37);
 // deep-VPT constant prompt keys/values are appended as in attention.cu (reference models/clip/model.py:164-183).
 //
-// Why another generation. In attention_fa.cu the two softmax groups split the keys of ONE tile, so both warps of every
-// SM sub-partition execute the same phase at the same time: the ALU part, the MUFU (exp2) part and the TMEM / epilogue
-// part of a tile add up instead of overlapping (measured with the parts switched off one at a time:
-// 17 + 10 + 13 us per layer at 64 windows, profiles/attn_knobs.sh). Here a CTA runs two independent chains, one per
-// TMEM buffer; chain b owns the 128-query tiles u = b, b + 2, ...:
+// Why two chains. With two softmax groups splitting the keys of ONE tile (the previous generation of this kernel, see
+// DESIGN.md 4.2) both warps of every SM sub-partition execute the same phase at the same time: the ALU part, the MUFU
+// (exp2) part and the TMEM / epilogue part of a tile add up instead of overlapping (measured with the parts switched off
+// one at a time: 17 + 10 + 13 us per layer at 64 windows). Here a CTA runs two independent chains, one per TMEM buffer;
+// chain b owns the 128-query tiles u = b, b + 2, ...:
 //
 //     S = Q_t K^T  ->  softmax (one thread = one query row, all keys)  ->  O = P V  ->  O / rowsum -> global
 //       MMA warp b          softmax group b (4 warps)                   MMA warp b      softmax group b
@@ -24,7 +24,6 @@
 //   warps 4-7     softmax + output of chain 0, warps 8-11 of chain 1 (thread = query row = TMEM lane)
 // TMEM buffer of a tile: S fp32 [0,256)  ->  P packed bf16 [0,128) | O fp32 [128,192)
 // Scores and probabilities never leave the SM: HBM traffic is Q, K, V in and O out.
-#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -39,7 +38,6 @@ constexpr int kKVBytesP = 256 * 128;       // 256 key rows x 64 dims, 16-bit
 constexpr int kStageBytesP = kQBytesP + 2 * kKVBytesP;  // 96 KB
 constexpr int kOutStageBytesP = 8 * 32 * 64;            // per softmax warp: 32 rows x 64 B, XOR-swizzled
 constexpr int kSmemP = 2 * kStageBytesP + kOutStageBytesP + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kQkvLdP = 3 * 768;
 
 __device__ __forceinline__ uint64_t desc_sw128_mn_p(uint32_t smem_addr_bytes) {
   // MN-major operand in 128B-swizzled rows; SBO = 1024 B between 8-key groups; LBO unused for N = 64.
@@ -112,10 +110,9 @@ __device__ __forceinline__ void chunk_exp_store_p(const uint32_t (&v)[32], int l
 
 __global__ void __launch_bounds__(kThreadsP, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                    const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items,
-                    uint16_t* __restrict__ out, int out_fp16, long long* trace) {
-  // experiment: time line of CTA 0 (profiles/attn_trace.py), slot <- clock64()
-#define PP_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && (slot) < 256) trace[(slot)] = clock64(); } while (0)
+                    const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items, int heads,
+                    uint16_t* __restrict__ out, int out_fp16) {
+  const int width = heads * 64;  // q | k | v thirds of a qkv row; row pitch of the output
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* out_stage = smem + 2 * kStageBytesP;  // [8 warps][32 rows][64 B]
@@ -163,14 +160,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
   pdl_wait();  // QKV of this layer comes from the previous kernel
-  if (warp == 2) PP_TRACE(0);
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     for (int it = 0; it < n_local; ++it) {
       const int item = item0 + it;
       const int s = it & 1, ph = (it >> 1) & 1;
-      const int head = item % 12, win = item / 12;
+      const int head = item % heads, win = item / heads;
       const int row_base = win * t_live;
       uint8_t* sQ = smem + s * kStageBytesP;
       uint8_t* sK = sQ + kQBytesP;
@@ -179,15 +175,15 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (lane == 0) {
         mbar_arrive_expect_tx(&qk_full[s], kQBytesP + kKVBytesP);
         tma_load_2d(sQ, &tm_q, &qk_full[s], head * 64, row_base);
-        if (n_const > 0) tma_load_2d(sK, &tm_const, &qk_full[s], 768 + head * 64, 0);
-        tma_load_2d(sK + n_const * 128, &tm_kv, &qk_full[s], 768 + head * 64, row_base);
+        if (n_const > 0) tma_load_2d(sK, &tm_const, &qk_full[s], width + head * 64, 0);
+        tma_load_2d(sK + n_const * 128, &tm_kv, &qk_full[s], width + head * 64, row_base);
       }
       __syncwarp();
       mbar_wait(&v_empty[s], ph ^ 1);
       if (lane == 0) {
         mbar_arrive_expect_tx(&v_full[s], kKVBytesP);
-        if (n_const > 0) tma_load_2d(sV, &tm_const, &v_full[s], 1536 + head * 64, 0);
-        tma_load_2d(sV + n_const * 128, &tm_kv, &v_full[s], 1536 + head * 64, row_base);
+        if (n_const > 0) tma_load_2d(sV, &tm_const, &v_full[s], 2 * width + head * 64, 0);
+        tma_load_2d(sV + n_const * 128, &tm_kv, &v_full[s], 2 * width + head * 64, row_base);
       }
       __syncwarp();
     }
@@ -219,7 +215,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // S = Q_t K^T once Q / K have landed and the previous tile of this chain has been written out
       mbar_wait(&qk_full[s], ph);
       mbar_wait(&buf_free[b], (k & 1) ^ 1);
-      PP_TRACE(8 + 8 * u + 0);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -234,7 +229,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // O = P V once the softmax group has written P
       mbar_wait(&v_full[s], ph);
       mbar_wait(&p_ready[b], k & 1);
-      PP_TRACE(8 + 8 * u + 1);
       tc_fence_after();
       if (lane == 0) {
         for (int ks = 0; ks < k_steps; ++ks)
@@ -258,12 +252,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int u = b; u < total_tiles; u += 2, ++k) {
       const int g = g0 + u;
       const int item = g / n_qt, t = g - item * n_qt;
-      const int head = item % 12, win = item / 12;
+      const int head = item % heads, win = item / heads;
       const int row0 = t * 128 + q * 32;          // first row of this warp inside the window
       const bool active = row0 < t_live;          // warps whose 32 rows are all padding only keep the protocol going
       float row_sum = 0.f;
       mbar_wait(&s_full[b], k & 1);
-      if (q == 0) PP_TRACE(8 + 8 * u + 2);
       tc_fence_after();
       if (active) {
         // Single pass over S. Softmax is shift invariant, so the reference maximum only has to keep exp2 in range: the
@@ -293,12 +286,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[b]);
-      if (q == 0) PP_TRACE(8 + 8 * u + 3);
 
       // O / rowsum -> 16-bit -> global, two halves of 32 dims through the warp's smem staging tile (thread = row holds
       // 64 B of its row; staged, one instruction writes 8 complete 64 B row segments)
       mbar_wait(&o_full[b], k & 1);
-      if (q == 0) PP_TRACE(8 + 8 * u + 4);
       tc_fence_after();
       if (active) {
         const float inv = 1.0f / row_sum;
@@ -323,12 +314,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                            pack16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, out_fp16),
                            pack16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, out_fp16));
           __syncwarp();
-          uint16_t* obase = out + (static_cast<int64_t>(win) * t_live + row0) * 768 + head * 64 + hh * 32 + slot * 8;
+          uint16_t* obase = out + (static_cast<int64_t>(win) * t_live + row0) * width + head * 64 + hh * 32 + slot * 8;
 #pragma unroll
           for (int it4 = 0; it4 < 4; ++it4) {
             const int rr = it4 * 8 + rsub;
             const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((slot ^ ((rr >> 1) & 3)) << 4));
-            if (row0 + rr < t_live) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(rr) * 768) = v;
+            if (row0 + rr < t_live) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(rr) * width) = v;
           }
           __syncwarp();
         }
@@ -337,7 +328,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&buf_free[b]);
       }
-      if (q == 0) PP_TRACE(8 + 8 * u + 5);
     }
   }
 
@@ -353,7 +343,7 @@ typedef CUresult (*PFN_encodeTiledP)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_tmap_rows_p(CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
+bool make_tmap_rows_p(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int ld) {
   static PFN_encodeTiledP enc = nullptr;
   if (!enc) {
     void* ptr = nullptr;
@@ -363,8 +353,8 @@ bool make_tmap_rows_p(CUtensorMap* map, const void* base, int64_t rows, int box_
       return false;
     enc = reinterpret_cast<PFN_encodeTiledP>(ptr);
   }
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kQkvLdP), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kQkvLdP) * 2};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -374,54 +364,35 @@ bool make_tmap_rows_p(CUtensorMap* map, const void* base, int64_t rows, int box_
 
 }  // namespace
 
-// Same contract as attention_h64 (kernels.h); additionally requires n_const to be a multiple of 8 (swizzle atom).
+// Contract: kernels.h. Needs t_live + n_const <= 256 and n_const % 8 == 0 (swizzle atom of the K / V tiles).
 const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                             int n_win, int t_live, void* out, int out_fp16) {
-  if (n_win <= 0 || t_live <= 0) return "attention: empty problem";
+                             int n_win, int t_live, int heads, void* out, int out_fp16) {
+  if (n_win <= 0 || t_live <= 0 || heads <= 0) return "attention: empty problem";
   if (n_const < 0 || (n_const > 0 && const_kv == nullptr)) return "attention: constant keys missing";
-  if (t_live + n_const > 256) return "attention: sequence longer than 256 keys is not supported";
+  if (t_live + n_const > 256) return "attention: sequence longer than 256 keys is not supported by the tcgen05 kernel";
   if (n_const % 8 != 0) return "attention(pp): constant key count must be a multiple of 8";
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemP);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  cudaError_t ea = ensure_dyn_smem(attention_pp_kernel, kSmemP, &attr_done);
+  if (ea != cudaSuccess) return cudaGetErrorString(ea);
   const int64_t rows = static_cast<int64_t>(n_win) * t_live;
+  const int ld = 3 * 64 * heads;
   CUtensorMap tq, tkv, tc;
-  if (!make_tmap_rows_p(&tq, qkv, rows, 256)) return "attention: cuTensorMapEncodeTiled(q) failed";
-  if (!make_tmap_rows_p(&tkv, qkv, rows, 256 - n_const)) return "attention: cuTensorMapEncodeTiled(kv) failed";
+  if (!make_tmap_rows_p(&tq, qkv, rows, 256, ld)) return "attention: cuTensorMapEncodeTiled(q) failed";
+  if (!make_tmap_rows_p(&tkv, qkv, rows, 256 - n_const, ld)) return "attention: cuTensorMapEncodeTiled(kv) failed";
   if (n_const > 0) {
-    if (!make_tmap_rows_p(&tc, const_kv, n_const, n_const)) return "attention: cuTensorMapEncodeTiled(const) failed";
+    if (!make_tmap_rows_p(&tc, const_kv, n_const, n_const, ld)) return "attention: cuTensorMapEncodeTiled(const) failed";
   } else {
     tc = tkv;
   }
-  const int n_items = n_win * 12;
+  const int n_items = n_win * heads;
   const int64_t n_tiles_all = static_cast<int64_t>(n_items) * ((t_live + 127) / 128);
   const int grid = n_tiles_all < device_num_sms() ? static_cast<int>(n_tiles_all) : device_num_sms();
   {
     const double tk = t_live + n_const;
-    LaunchScope scope(stream, "attention", 4.0 * n_win * 12.0 * t_live * tk * 64.0,
-                      2.0 * n_win * t_live * (2304.0 + 768.0));
-    static const bool trace_env = getenv("CLIPEBC_ATTN_TRACE") != nullptr;  // experiment: time line of CTA 0
-    static long long* trace_dev = nullptr;
-    if (trace_env) {
-      if (!trace_dev) cudaMalloc(&trace_dev, 256 * sizeof(long long));
-      cudaMemsetAsync(trace_dev, 0, 256 * sizeof(long long), stream);
-    }
+    LaunchScope scope(stream, "attention", 4.0 * n_items * t_live * tk * 64.0, 2.0 * n_win * t_live * 4.0 * 64.0 * heads);
     cudaError_t le = launch_pdl(attention_pp_kernel, dim3(grid), dim3(kThreadsP), kSmemP, stream, 1, tq, tkv, tc, n_const,
-                                t_live, n_items, static_cast<uint16_t*>(out), out_fp16, trace_env ? trace_dev : nullptr);
+                                t_live, n_items, heads, static_cast<uint16_t*>(out), out_fp16);
     if (le != cudaSuccess) return cudaGetErrorString(le);
-    if (trace_env) {
-      long long h[256];
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
-      const long long t0 = h[0];
-      printf("[attn pp trace] tile: S issued | s_full seen -> P done | PV issued | o_full seen -> output done\n");
-      for (int u = 0; u < 12 && h[8 + 8 * u + 2]; ++u)
-        printf("  tile%2d (chain %d): %6lld | %6lld -> %6lld | %6lld | %6lld -> %6lld\n", u, u & 1, h[8 + 8 * u] - t0,
-               h[8 + 8 * u + 2] - t0, h[8 + 8 * u + 3] - t0, h[8 + 8 * u + 1] - t0, h[8 + 8 * u + 4] - t0, h[8 + 8 * u + 5] - t0);
-    }
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -1,8 +1,8 @@
 // HBM-bound kernels of the CLIP-EBC hot path: LayerNorm, window unfold / patchify, token assembly (cls + pos + ln_pre
 // + VPT splice), bilinear resample onto the zero-bordered decoder grid, and the pack-time weight transforms.
-// All are one-warp-per-row (768 channels = 6 x 128-bit per lane) or one-thread-per-vector kernels with coalesced,
-// vectorised global accesses and warp-shuffle reductions.
-#include <cstdlib>
+// All are one-warp-per-row (D = 768 or 1024 channels = 6 or 8 x 128-bit per lane) or one-thread-per-vector kernels with
+// coalesced, vectorised global accesses and warp-shuffle reductions. D is a template parameter: 768 for the ViT-B
+// backbones, 1024 for ViT-L/14 (models/clip/model.py:16-24).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -10,50 +10,58 @@ namespace cebc {
 
 namespace {
 
-constexpr int kD = 768;
-constexpr int kVecPerLane = kD / 4 / 32;  // 6 float4 per lane
-
-struct Row768 {
-  float4 v[kVecPerLane];
+template <int D>
+struct Row {
+  static constexpr int kVec = D / 4 / 32;  // float4 per lane: 6 (768) or 8 (1024)
+  float4 v[kVec];
 };
 
-__device__ __forceinline__ Row768 load_row(const float* p, int lane) {
-  Row768 r;
+template <int D>
+__device__ __forceinline__ Row<D> load_row(const float* p, int lane) {
+  Row<D> r;
   const float4* p4 = reinterpret_cast<const float4*>(p);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) r.v[i] = p4[i * 32 + lane];
+  for (int i = 0; i < Row<D>::kVec; ++i) r.v[i] = p4[i * 32 + lane];
   return r;
 }
-__device__ __forceinline__ Row768 load_row_ldg(const float* p, int lane) {
-  Row768 r;
+template <int D>
+__device__ __forceinline__ Row<D> load_row_ldg(const float* p, int lane) {
+  Row<D> r;
   const float4* p4 = reinterpret_cast<const float4*>(p);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) r.v[i] = __ldg(p4 + i * 32 + lane);
+  for (int i = 0; i < Row<D>::kVec; ++i) r.v[i] = __ldg(p4 + i * 32 + lane);
   return r;
 }
-__device__ __forceinline__ void add_row(Row768& a, const Row768& b) {
+template <int D>
+__device__ __forceinline__ void add_row(Row<D>& a, const Row<D>& b) {
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
+  for (int i = 0; i < Row<D>::kVec; ++i) {
     a.v[i].x += b.v[i].x; a.v[i].y += b.v[i].y; a.v[i].z += b.v[i].z; a.v[i].w += b.v[i].w;
   }
 }
-// nn.LayerNorm(768, eps=1e-5) on one row held by a warp (reference: blocks.py:8-14); two-pass statistics in fp32.
-__device__ __forceinline__ void layernorm_row(Row768& r, const float* gamma, const float* beta, int lane) {
+// (mean, rstd) of one row held by a warp: nn.LayerNorm(D, eps=1e-5) statistics, two-pass in fp32 (blocks.py:8-14)
+template <int D>
+__device__ __forceinline__ void row_stats(const Row<D>& r, float& mean, float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
-  const float mean = warp_sum(s) * (1.0f / kD);
+  for (int i = 0; i < Row<D>::kVec; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
+  for (int i = 0; i < Row<D>::kVec; ++i) {
     const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + 1e-5f);
+  rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+}
+template <int D>
+__device__ __forceinline__ void layernorm_row(Row<D>& r, const float* gamma, const float* beta, int lane) {
+  float mean, rstd;
+  row_stats<D>(r, mean, rstd);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
+  for (int i = 0; i < Row<D>::kVec; ++i) {
     const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
     r.v[i].x = (r.v[i].x - mean) * rstd * g.x + b.x;
     r.v[i].y = (r.v[i].y - mean) * rstd * g.y + b.y;
@@ -61,42 +69,27 @@ __device__ __forceinline__ void layernorm_row(Row768& r, const float* gamma, con
     r.v[i].w = (r.v[i].w - mean) * rstd * g.w + b.w;
   }
 }
-__device__ __forceinline__ void store_row_f32(float* p, const Row768& r, int lane) {
+template <int D>
+__device__ __forceinline__ void store_row_f32(float* p, const Row<D>& r, int lane) {
   float4* p4 = reinterpret_cast<float4*>(p);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) p4[i * 32 + lane] = r.v[i];
+  for (int i = 0; i < Row<D>::kVec; ++i) p4[i * 32 + lane] = r.v[i];
 }
-__device__ __forceinline__ void store_row_16(void* p, const Row768& r, int lane, int fp16) {
+template <int D>
+__device__ __forceinline__ void store_row_16(void* p, const Row<D>& r, int lane, int fp16) {
   uint2* p2 = reinterpret_cast<uint2*>(p);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i)
+  for (int i = 0; i < Row<D>::kVec; ++i)
     p2[i * 32 + lane] = make_uint2(pack16x2(r.v[i].x, r.v[i].y, fp16), pack16x2(r.v[i].z, r.v[i].w, fp16));
 }
 
-// (mean, sum of squared deviations) of one row held by a warp, two-pass in registers -> slot 0 of its statistics row
-// (kernels.h: EPI_LN_* with ln_parts = 1)
-__device__ __forceinline__ void store_row_stats(const Row768& r, int lane, float2* stats) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
-  const float mean = warp_sum(s) * (1.0f / kD);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
-    const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  q = warp_sum(q);
-  if (lane == 0) stats[0] = make_float2(mean, q);
-}
-
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
-template <bool OUT_16>
-__global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, void* __restrict__ out,
-                                                           int64_t n_rows_out, int rows_out_per_group,
-                                                           int rows_in_per_group, int in_row_offset, int fp16,
-                                                           uint16_t* __restrict__ out16_extra) {
+template <int D, bool OUT_16>
+__global__ void __launch_bounds__(256, D == 768 ? 4 : 3) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, void* __restrict__ out,
+                                                         int64_t n_rows_out, int rows_out_per_group,
+                                                         int rows_in_per_group, int in_row_offset, int fp16,
+                                                         uint16_t* __restrict__ out16_extra) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -105,33 +98,39 @@ __global__ void __launch_bounds__(256, 4) layernorm768_kernel(const float* __res
        r += warps_total) {
     const int64_t g = r / rows_out_per_group;
     const int64_t in_row = g * rows_in_per_group + in_row_offset + (r - g * rows_out_per_group);
-    Row768 x = load_row(in + in_row * kD, lane);
-    layernorm_row(x, gamma, beta, lane);
+    Row<D> x = load_row<D>(in + in_row * D, lane);
+    layernorm_row<D>(x, gamma, beta, lane);
     if constexpr (OUT_16) {
-      store_row_16(static_cast<uint16_t*>(out) + r * kD, x, lane, fp16);
+      store_row_16<D>(static_cast<uint16_t*>(out) + r * D, x, lane, fp16);
     } else {
-      store_row_f32(static_cast<float*>(out) + r * kD, x, lane);
-      if (out16_extra != nullptr) store_row_16(out16_extra + r * kD, x, lane, fp16);  // ln_post: + the 16-bit GEMM operand
+      store_row_f32<D>(static_cast<float*>(out) + r * D, x, lane);
+      if (out16_extra != nullptr) store_row_16<D>(out16_extra + r * D, x, lane, fp16);  // ln_post: + the 16-bit GEMM operand
     }
   }
 }
 
 // LayerNorm over contiguous rows with the loads taken off the warps: the warp-per-row kernel above is bound by the latency
 // of its row loads (ncu: long-scoreboard stalls, 7 of 16 warps per scheduler active, no pipe above 35 %) and can only
-// keep 32 warps x 3 KB in flight per SM. Here every CTA streams blocks of 8 rows (24 KB) through a 3-stage shared-memory
-// ring with bulk async copies (2 CTAs per SM: 144 KB in flight whatever the warps are doing), warp w normalises row w of
-// a block from shared memory, and gamma / beta live in registers for the whole kernel (they are loaded before the
-// dependency wait -- they do not depend on the previous kernel).
+// keep 32 warps x 3 KB in flight per SM. Here every CTA streams blocks of 8 rows (24 KB at D = 768) through a 3-stage
+// shared-memory ring with bulk async copies (2 CTAs per SM: 144 KB in flight whatever the warps are doing), warp w
+// normalises row w of a block from shared memory, and gamma / beta live in registers for the whole kernel (they are
+// loaded before the dependency wait -- they do not depend on the previous kernel).
 constexpr int kLnRows = 8, kLnStages = 3;
-constexpr int kLnStageBytes = kLnRows * kD * 4;                                   // 24 KB
-constexpr int kLnSmem = kLnStages * kLnStageBytes + 2 * kLnStages * 8 + 128;      // ring + barriers + alignment slack
+template <int D>
+struct LnStream {
+  static constexpr int kStageBytes = kLnRows * D * 4;                                 // 24 KB / 32 KB
+  static constexpr int kSmem = kLnStages * kStageBytes + 2 * kLnStages * 8 + 128;     // ring + barriers + alignment slack
+};
 
-__global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta, uint16_t* __restrict__ out,
-                                                                  int64_t n_rows, int fp16) {
+template <int D>
+__global__ void __launch_bounds__(256, 2) layernorm_stream_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, uint16_t* __restrict__ out,
+                                                                int64_t n_rows, int fp16) {
+  constexpr int kVec = Row<D>::kVec;
+  constexpr int kStageBytes = LnStream<D>::kStageBytes;
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLnStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kLnStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -139,9 +138,9 @@ __global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float
     fence_mbar_init();
   }
   // gamma / beta in registers (constants of the model)
-  float4 g[kVecPerLane], b[kVecPerLane];
+  float4 g[kVec], b[kVec];
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     b[i] = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
   }
@@ -154,9 +153,9 @@ __global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float
   auto request = [&](int64_t blk, int s) {  // thread 0: rows [blk * 8, ...) -> stage s
     const int64_t r0 = blk * kLnRows;
     const int nr = static_cast<int>(n_rows - r0 < kLnRows ? n_rows - r0 : kLnRows);
-    const uint32_t bytes = static_cast<uint32_t>(nr) * kD * 4;
+    const uint32_t bytes = static_cast<uint32_t>(nr) * D * 4;
     mbar_arrive_expect_tx(&full_bar[s], bytes);
-    bulk_load_1d(smem + s * kLnStageBytes, in + r0 * kD, bytes, &full_bar[s]);
+    bulk_load_1d(smem + s * kStageBytes, in + r0 * D, bytes, &full_bar[s]);
   };
   if (threadIdx.x == 0) {
     int s = 0;
@@ -168,29 +167,20 @@ __global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float
     mbar_wait(&full_bar[s], phase);
     const int64_t r = blk * kLnRows + warp;
     if (r < n_rows) {
-      Row768 x;
-      const float4* p4 = reinterpret_cast<const float4*>(smem + s * kLnStageBytes + warp * kD * 4);
+      Row<D> x;
+      const float4* p4 = reinterpret_cast<const float4*>(smem + s * kStageBytes + warp * D * 4);
 #pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) x.v[i] = p4[i * 32 + lane];
-      float sm = 0.f;
+      for (int i = 0; i < kVec; ++i) x.v[i] = p4[i * 32 + lane];
+      float mean, rstd;
+      row_stats<D>(x, mean, rstd);
 #pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) sm += (x.v[i].x + x.v[i].y) + (x.v[i].z + x.v[i].w);
-      const float mean = warp_sum(sm) * (1.0f / kD);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) {
-        const float a = x.v[i].x - mean, bb = x.v[i].y - mean, c = x.v[i].z - mean, d = x.v[i].w - mean;
-        q += (a * a + bb * bb) + (c * c + d * d);
-      }
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) {
+      for (int i = 0; i < kVec; ++i) {
         x.v[i].x = (x.v[i].x - mean) * rstd * g[i].x + b[i].x;
         x.v[i].y = (x.v[i].y - mean) * rstd * g[i].y + b[i].y;
         x.v[i].z = (x.v[i].z - mean) * rstd * g[i].z + b[i].z;
         x.v[i].w = (x.v[i].w - mean) * rstd * g[i].w + b[i].w;
       }
-      store_row_16(out + r * kD, x, lane, fp16);
+      store_row_16<D>(out + r * D, x, lane, fp16);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage (its row is in registers / stored)
@@ -207,76 +197,61 @@ __global__ void __launch_bounds__(256, 2) layernorm768_stream_kernel(const float
 }
 
 // ------------------------------------------------------------------ patchify -----------------------------------
-// One thread per 4 horizontally adjacent pixels; consecutive threads walk along an image row (coalesced 16B reads),
-// each writes 4 bf16 (8 B) into its patch row; 4 consecutive threads fill one 32 B sector. P = patch size (16 or 32),
-// KP = 3 * P * P columns per half.
+// One thread per VEC horizontally adjacent pixels of a patch row (VEC = 4 for patch 16 / 32, 2 for the 14-pixel patches of
+// ViT-L/14); consecutive threads walk along an image row (coalesced reads), each writes VEC 16-bit values into its patch
+// row. P = patch size, KP = columns per half (>= 3 * P * P; the columns beyond 3 * P * P are zeroed once by the caller).
 // Rows are written as [hi(KP) | lo(KP)] with hi = round16(x), lo = round16(x - hi): the patch-embed GEMM multiplies
 // [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9 (the stem is 0.4 % of the FLOPs).
-__device__ __forceinline__ void store_hi_lo_p(uint16_t* dst, int kp, const float4& v, int fp16) {
-  const float hx = round16(v.x, fp16), hy = round16(v.y, fp16), hz = round16(v.z, fp16), hw = round16(v.w, fp16);
-  *reinterpret_cast<uint2*>(dst) = make_uint2(pack16x2(hx, hy, fp16), pack16x2(hz, hw, fp16));
-  *reinterpret_cast<uint2*>(dst + kp) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
-}
-
-__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ image, int n_img, int H, int W,
-                                                       int y0, int x0, int gh, int gw, int P, uint16_t* __restrict__ out,
-                                                       int fp16) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int qpp = P >> 2;                                                  // quads per patch row
-  const int kp = 3 * P * P;
-  const int64_t quads_per_row = static_cast<int64_t>(gw) * qpp;
-  const int64_t per_img = static_cast<int64_t>(3) * gh * P * quads_per_row;
-  const int64_t total = per_img * n_img;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int64_t t = idx;
-    const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
-    const int yy = static_cast<int>(t % (gh * P)); t /= (gh * P);
-    const int c = static_cast<int>(t % 3);
-    const int img = static_cast<int>(t / 3);
-    const int gx = qx / qpp, px4 = qx - gx * qpp;
-    const int gy = yy / P, py = yy - gy * P;
-    const float* src = image + ((static_cast<int64_t>(img) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * 4;
+template <int VEC>
+__device__ __forceinline__ void load_store_hi_lo(const float* src, uint16_t* dst, int kp, int fp16) {
+  if constexpr (VEC == 4) {
     float4 v;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      v = *reinterpret_cast<const float4*>(src);
-    } else {
-      v = make_float4(src[0], src[1], src[2], src[3]);
-    }
-    const int64_t patch = (static_cast<int64_t>(img) * gh + gy) * gw + gx;
-    store_hi_lo_p(out + patch * 2 * kp + c * P * P + py * P + px4 * 4, kp, v, fp16);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) v = *reinterpret_cast<const float4*>(src);
+    else v = make_float4(src[0], src[1], src[2], src[3]);
+    const float hx = round16(v.x, fp16), hy = round16(v.y, fp16), hz = round16(v.z, fp16), hw = round16(v.w, fp16);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack16x2(hx, hy, fp16), pack16x2(hz, hw, fp16));
+    *reinterpret_cast<uint2*>(dst + kp) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
+  } else {
+    const float vx = src[0], vy = src[1];
+    const float hx = round16(vx, fp16), hy = round16(vy, fp16);
+    *reinterpret_cast<uint32_t*>(dst) = pack16x2(hx, hy, fp16);
+    *reinterpret_cast<uint32_t*>(dst + kp) = pack16x2(vx - hx, vy - hy, fp16);
   }
 }
 
-__global__ void __launch_bounds__(256) patchify_windows_kernel(const float* __restrict__ image, int H, int W,
-                                                               const int* __restrict__ origins_yx, int n_win, int hp,
-                                                               int wp, int P, uint16_t* __restrict__ out, int fp16) {
+// origins_yx == nullptr: n_units images [3, H, W], patch grid gh x gw starting at pixel (y0, x0) of every image;
+// else: n_units windows of ONE image, window u has its (0, 0) patch at pixel origins_yx[2u], origins_yx[2u + 1]
+template <int VEC>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ image, int n_units, int H, int W, int y0,
+                                                       int x0, const int* __restrict__ origins_yx, int gh, int gw, int P,
+                                                       int kp, uint16_t* __restrict__ out, int fp16) {
   pdl_launch_dependents();
   pdl_wait();
-  const int qpp = P >> 2;
-  const int kp = 3 * P * P;
-  const int64_t quads_per_row = static_cast<int64_t>(wp) * qpp;
-  const int64_t per_win = static_cast<int64_t>(3) * hp * P * quads_per_row;
-  const int64_t total = per_win * n_win;
+  const int vpp = P / VEC;                                                 // vectors per patch row
+  const int64_t vec_per_row = static_cast<int64_t>(gw) * vpp;
+  const int64_t per_unit = static_cast<int64_t>(3) * gh * P * vec_per_row;
+  const int64_t total = per_unit * n_units;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int64_t t = idx;
-    const int qx = static_cast<int>(t % quads_per_row); t /= quads_per_row;
-    const int yy = static_cast<int>(t % (hp * P)); t /= (hp * P);
+    const int qx = static_cast<int>(t % vec_per_row); t /= vec_per_row;
+    const int yy = static_cast<int>(t % (gh * P)); t /= (gh * P);
     const int c = static_cast<int>(t % 3);
-    const int win = static_cast<int>(t / 3);
-    const int oy = origins_yx[2 * win], ox = origins_yx[2 * win + 1];
-    const int gx = qx / qpp, px4 = qx - gx * qpp;
+    const int unit = static_cast<int>(t / 3);
+    const int gx = qx / vpp, pxv = qx - gx * vpp;
     const int gy = yy / P, py = yy - gy * P;
-    const float* src = image + (static_cast<int64_t>(c) * H + (oy + yy)) * W + ox + qx * 4;
-    const float4 v = make_float4(src[0], src[1], src[2], src[3]);
-    const int64_t patch = (static_cast<int64_t>(win) * hp + gy) * wp + gx;
-    store_hi_lo_p(out + patch * 2 * kp + c * P * P + py * P + px4 * 4, kp, v, fp16);
+    const float* src;
+    if (origins_yx != nullptr)
+      src = image + (static_cast<int64_t>(c) * H + (origins_yx[2 * unit] + yy)) * W + origins_yx[2 * unit + 1] + qx * VEC;
+    else
+      src = image + ((static_cast<int64_t>(unit) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * VEC;
+    const int64_t patch = (static_cast<int64_t>(unit) * gh + gy) * gw + gx;
+    load_store_hi_lo<VEC>(src, out + patch * 2 * kp + c * P * P + py * P + pxv * VEC, kp, fp16);
   }
 }
 
 // ------------------------------------------------------------------ token assembly -----------------------------
+template <int D>
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch_embed,
                                                               const int* __restrict__ win_base, int src_pitch,
                                                               const int* __restrict__ win_pitch,
@@ -285,9 +260,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
                                                               const float* __restrict__ ln_g,
                                                               const float* __restrict__ ln_b,
                                                               const float* __restrict__ vpt0, int n_prompt, int n_win,
-                                                              int hp, int wp, float* __restrict__ X,
-                                                              uint16_t* __restrict__ X16, float2* __restrict__ stats,
-                                                              int fp16) {
+                                                              int hp, int wp, float* __restrict__ X) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -298,45 +271,28 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
        r += warps_total) {
     const int win = static_cast<int>(r / t_live);
     const int t = static_cast<int>(r - static_cast<int64_t>(win) * t_live);
-    Row768 x;
+    Row<D> x;
     if (t == 0) {
-      x = load_row_ldg(class_emb, lane);
-      add_row(x, load_row_ldg(pos, lane));
-      layernorm_row(x, ln_g, ln_b, lane);
+      x = load_row_ldg<D>(class_emb, lane);
+      add_row<D>(x, load_row_ldg<D>(pos, lane));
+      layernorm_row<D>(x, ln_g, ln_b, lane);
     } else if (t <= n_prompt) {
-      x = load_row_ldg(vpt0 + static_cast<int64_t>(t - 1) * kD, lane);  // prompts join after ln_pre (model.py:161-168)
+      x = load_row_ldg<D>(vpt0 + static_cast<int64_t>(t - 1) * D, lane);  // prompts join after ln_pre (model.py:161-168)
     } else {
       const int pidx = t - 1 - n_prompt;
       const int py = pidx / wp, px = pidx - py * wp;
       const int pitch = win_pitch != nullptr ? win_pitch[win] : src_pitch;  // windows of different images in one pass
       const int64_t src = static_cast<int64_t>(win_base[win]) + static_cast<int64_t>(py) * pitch + px;
-      x = load_row(patch_embed + src * kD, lane);
-      add_row(x, load_row_ldg(pos + static_cast<int64_t>(1 + pidx) * kD, lane));
-      layernorm_row(x, ln_g, ln_b, lane);
+      x = load_row<D>(patch_embed + src * D, lane);
+      add_row<D>(x, load_row_ldg<D>(pos + static_cast<int64_t>(1 + pidx) * D, lane));
+      layernorm_row<D>(x, ln_g, ln_b, lane);
     }
-    store_row_f32(X + r * kD, x, lane);
-    if (X16 != nullptr) {
-      store_row_16(X16 + r * kD, x, lane, fp16);
-      store_row_stats(x, lane, stats + r * kLnStatSlots);
-    }
-  }
-}
-
-// rows f32 -> 16-bit copy + (mean, M2): the inputs of an LN-folded GEMM for rows that no GEMM epilogue produced
-__global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restrict__ in, int64_t n_rows,
-                                                          uint16_t* __restrict__ X16, float2* __restrict__ stats, int fp16) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
-    const Row768 x = load_row(in + r * kD, lane);
-    store_row_16(X16 + r * kD, x, lane, fp16);
-    store_row_stats(x, lane, stats + r * kLnStatSlots);
+    store_row_f32<D>(X + r * D, x, lane);
   }
 }
 
 // ------------------------------------------------------------------ resample -----------------------------------
+template <int D>
 __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __restrict__ Y, int n_win, int hp, int wp,
                                                                  int gh, int gw, uint16_t* __restrict__ U_16,
                                                                  float* __restrict__ U_f32, int fp16) {
@@ -353,33 +309,33 @@ __global__ void __launch_bounds__(256) resample_to_padded_kernel(const float* __
     const int win = static_cast<int>(r / (Hp * Wp));
     const int q = static_cast<int>(r - static_cast<int64_t>(win) * Hp * Wp);
     const int py = q / Wp, px = q - py * Wp;
-    Row768 o;
+    Row<D> o;
     if (py == gh || px == gw) {
 #pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) o.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < Row<D>::kVec; ++i) o.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (gh == hp && gw == wp) {
-      o = load_row(Y + (static_cast<int64_t>(win) * hp * wp + static_cast<int64_t>(py) * wp + px) * kD, lane);
+      o = load_row<D>(Y + (static_cast<int64_t>(win) * hp * wp + static_cast<int64_t>(py) * wp + px) * D, lane);
     } else {
       int y0, y1, x0, x1;
       float ly, lx;
       bilinear_src(py, inv_sy, hp, y0, y1, ly);
       bilinear_src(px, inv_sx, wp, x0, x1, lx);
-      const float* base = Y + static_cast<int64_t>(win) * hp * wp * kD;
-      const Row768 a = load_row(base + (static_cast<int64_t>(y0) * wp + x0) * kD, lane);
-      const Row768 b = load_row(base + (static_cast<int64_t>(y0) * wp + x1) * kD, lane);
-      const Row768 c = load_row(base + (static_cast<int64_t>(y1) * wp + x0) * kD, lane);
-      const Row768 d = load_row(base + (static_cast<int64_t>(y1) * wp + x1) * kD, lane);
+      const float* base = Y + static_cast<int64_t>(win) * hp * wp * D;
+      const Row<D> a = load_row<D>(base + (static_cast<int64_t>(y0) * wp + x0) * D, lane);
+      const Row<D> b = load_row<D>(base + (static_cast<int64_t>(y0) * wp + x1) * D, lane);
+      const Row<D> c = load_row<D>(base + (static_cast<int64_t>(y1) * wp + x0) * D, lane);
+      const Row<D> d = load_row<D>(base + (static_cast<int64_t>(y1) * wp + x1) * D, lane);
       const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
 #pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) {
+      for (int i = 0; i < Row<D>::kVec; ++i) {
         o.v[i].x = w00 * a.v[i].x + w01 * b.v[i].x + w10 * c.v[i].x + w11 * d.v[i].x;
         o.v[i].y = w00 * a.v[i].y + w01 * b.v[i].y + w10 * c.v[i].y + w11 * d.v[i].y;
         o.v[i].z = w00 * a.v[i].z + w01 * b.v[i].z + w10 * c.v[i].z + w11 * d.v[i].z;
         o.v[i].w = w00 * a.v[i].w + w01 * b.v[i].w + w10 * c.v[i].w + w11 * d.v[i].w;
       }
     }
-    if (U_16 != nullptr) store_row_16(U_16 + r * kD, o, lane, fp16);
-    store_row_f32(U_f32 + r * kD, o, lane);
+    if (U_16 != nullptr) store_row_16<D>(U_16 + r * D, o, lane, fp16);
+    store_row_f32<D>(U_f32 + r * D, o, lane);
   }
 }
 
@@ -414,7 +370,7 @@ __device__ __forceinline__ void fma8_16(float2 (&acc)[4], const uint4& z, float 
 // neighbouring cells read the same positions under different taps) -- 3 GB per 64 windows.
 constexpr int kC1Smem = 5 * 19 * 9 * 32 * 2;  // 54720 B: the band shape; the whole-window shape is checked against it too
 
-template <int CS, bool FP16>
+template <int D, int CS, bool FP16>
 __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* __restrict__ Z, const float* __restrict__ bias,
                                                                 int n_win, int hp, int wp, int gh, int gw, int bh, int bw,
                                                                 int n_bands, int n_ctiles, uint16_t* __restrict__ D1) {
@@ -422,7 +378,7 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
   extern __shared__ __align__(16) uint8_t c1_smem[];
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int kSlices = kD / CS;
+  constexpr int kSlices = D / CS;
   constexpr int kG = CS / 8;          // 8-channel groups per cell
   constexpr int kRowB = CS * 2;       // bytes per (position, tap)
   constexpr int kPosB = 9 * kRowB;    // bytes per position
@@ -444,7 +400,7 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
   bilinear_src(min(x_hi, gw - 1), inv_sx, wp, t0, j_hi, lam);
   const int nr = i_hi - i_lo + 1, nc = j_hi - j_lo + 1;
   // ---- stage Z[i_lo..i_hi, j_lo..j_hi, all taps, slice] ----
-  const int64_t ldz = 9 * kD;
+  const int64_t ldz = 9 * D;
   const uint16_t* zw = Z + static_cast<int64_t>(win) * hp * wp * ldz + slice * CS;
   const int n_chunks = nr * nc * 9 * kG;
   for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
@@ -453,7 +409,7 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
     const int rr = pos / nc, cc = pos - rr * nc;
     // asynchronous copies: all of a thread's chunks are in flight at once (a load -> store loop waits for every load)
     cp_async_16(smem_u32(c1_smem + pt * kRowB + (ch << 4)),
-                zw + (static_cast<int64_t>(i_lo + rr) * wp + (j_lo + cc)) * ldz + tap * kD + ch * 8, true);
+                zw + (static_cast<int64_t>(i_lo + rr) * wp + (j_lo + cc)) * ldz + tap * D + ch * 8, true);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -510,7 +466,7 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
                         pack16x2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f), fp16), pack16x2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f), fp16));
     }
     const int64_t r = (static_cast<int64_t>(win) * Hp + py) * Wp + px;
-    *reinterpret_cast<uint4*>(D1 + r * kD + slice * CS + g * 8) = outv;
+    *reinterpret_cast<uint4*>(D1 + r * D + slice * CS + g * 8) = outv;
   }
 }
 
@@ -556,41 +512,21 @@ __global__ void fold_conv3x3_bn_tapout_kernel(const float* __restrict__ W, const
   }
 }
 
-__global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, uint16_t* __restrict__ out, int fp16) {
-  const int64_t total = static_cast<int64_t>(O) * I;
+__global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, int Ip, uint16_t* __restrict__ out, int fp16) {
+  const int64_t total = static_cast<int64_t>(O) * Ip;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int i = static_cast<int>(idx % I);
-    const int64_t o = idx / I;
-    const float w = W[idx];
+    const int i = static_cast<int>(idx % Ip);
+    const int64_t o = idx / Ip;
+    const float w = i < I ? W[o * I + i] : 0.0f;  // columns I .. Ip - 1: zero padding up to the GEMM's K granularity
     const float hf = round16(w, fp16);
     const uint16_t hi = cvt16(hf, fp16);
     const uint16_t lo = cvt16(w - hf, fp16);
-    uint16_t* row = out + o * 3 * I;
+    uint16_t* row = out + o * 3 * Ip;
     row[i] = hi;
-    row[I + i] = hi;
-    row[2 * I + i] = lo;
+    row[Ip + i] = hi;
+    row[2 * Ip + i] = lo;
   }
-}
-
-// LayerNorm folded into the following Linear (I = 768): one warp per output row
-__global__ void fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, int O, uint16_t* __restrict__ Wf,
-                                      float* __restrict__ colsum, float* __restrict__ bias_f, int fp16) {
-  const int lane = threadIdx.x & 31;
-  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= O) return;
-  float cs = 0.f, bb = 0.f;
-  for (int k = lane; k < kD; k += 32) {
-    const float w = W[static_cast<int64_t>(o) * kD + k];
-    const float wf = round16(w * gamma[k], fp16);
-    Wf[static_cast<int64_t>(o) * kD + k] = cvt16(wf, fp16);
-    cs += wf;
-    bb += w * beta[k];
-  }
-  cs = warp_sum(cs);
-  bb = warp_sum(bb);
-  if (lane == 0) { colsum[o] = cs; bias_f[o] = b[o] + bb; }
 }
 
 // F.normalize(text, p=2, dim=-1) (eps 1e-12) scaled by exp(logit_scale)  (model.py:204,207-208); one warp per bin
@@ -620,126 +556,150 @@ inline const char* last_err() {
 
 }  // namespace
 
-const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
-                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
-                         int in_row_offset, void* out16_extra, int fp16_extra) {
+const char* layernorm_rows(cudaStream_t stream, int width, const float* in, const float* gamma, const float* beta, void* out,
+                           int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                           int in_row_offset, void* out16_extra, int fp16_extra) {
   if (n_rows_out <= 0) return nullptr;
+  if (width != 768 && width != 1024) return "layernorm: width must be 768 or 1024";
   if (rows_out_per_group <= 0 || rows_in_per_group <= 0) return "layernorm: bad row map";
-  LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * kD * (4.0 + (out_kind ? 2.0 : 4.0)));
-  // contiguous rows to a 16-bit output (the 24 LayerNorms inside the blocks): streaming kernel
-  static const bool stream_env = getenv("CLIPEBC_LN_NO_STREAM") == nullptr;  // A/B knob
-  if (stream_env && out_kind != 0 && rows_out_per_group == rows_in_per_group && in_row_offset == 0 && n_rows_out >= 64 &&
+  LaunchScope scope(stream, "layernorm", 0.0, static_cast<double>(n_rows_out) * width * (4.0 + (out_kind ? 2.0 : 4.0)));
+  // contiguous rows to a 16-bit output (the LayerNorms inside the blocks): streaming kernel
+  if (out_kind != 0 && rows_out_per_group == rows_in_per_group && in_row_offset == 0 && n_rows_out >= 64 &&
       (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t ea = cudaFuncSetAttribute(layernorm768_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem);
-      if (ea != cudaSuccess) return cudaGetErrorString(ea);
-      attr_set = true;
-    }
+    static unsigned long long attr_done_768 = 0, attr_done_1024 = 0;
+    cudaError_t ea = width == 768 ? ensure_dyn_smem(layernorm_stream_kernel<768>, LnStream<768>::kSmem, &attr_done_768)
+                                  : ensure_dyn_smem(layernorm_stream_kernel<1024>, LnStream<1024>::kSmem, &attr_done_1024);
+    if (ea != cudaSuccess) return cudaGetErrorString(ea);
     const int blocks_s = grid_for(n_rows_out, kLnRows, device_num_sms() * 2);
-    cudaError_t es = launch_pdl(layernorm768_stream_kernel, dim3(blocks_s), dim3(256), kLnSmem, stream, 1, in, gamma, beta,
-                                static_cast<uint16_t*>(out), n_rows_out, out_kind == 2);
+    cudaError_t es = width == 768
+        ? launch_pdl(layernorm_stream_kernel<768>, dim3(blocks_s), dim3(256), LnStream<768>::kSmem, stream, 1, in, gamma, beta,
+                     static_cast<uint16_t*>(out), n_rows_out, out_kind == 2)
+        : launch_pdl(layernorm_stream_kernel<1024>, dim3(blocks_s), dim3(256), LnStream<1024>::kSmem, stream, 1, in, gamma, beta,
+                     static_cast<uint16_t*>(out), n_rows_out, out_kind == 2);
     return es != cudaSuccess ? cudaGetErrorString(es) : last_err();
   }
   const int blocks = grid_for(n_rows_out, 8, device_num_sms() * 8);
-  cudaError_t e = out_kind ? launch_pdl(layernorm768_kernel<true>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
-                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, out_kind == 2,
-                                        static_cast<uint16_t*>(nullptr))
-                           : launch_pdl(layernorm768_kernel<false>, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out,
-                                        n_rows_out, rows_out_per_group, rows_in_per_group, in_row_offset, fp16_extra,
-                                        static_cast<uint16_t*>(out16_extra));
+  auto go = [&](auto kern, int fp16, uint16_t* extra) {
+    return launch_pdl(kern, dim3(blocks), dim3(256), 0, stream, 1, in, gamma, beta, out, n_rows_out, rows_out_per_group,
+                      rows_in_per_group, in_row_offset, fp16, extra);
+  };
+  cudaError_t e;
+  if (out_kind) e = width == 768 ? go(layernorm_kernel<768, true>, out_kind == 2, static_cast<uint16_t*>(nullptr))
+                                 : go(layernorm_kernel<1024, true>, out_kind == 2, static_cast<uint16_t*>(nullptr));
+  else e = width == 768 ? go(layernorm_kernel<768, false>, fp16_extra, static_cast<uint16_t*>(out16_extra))
+                        : go(layernorm_kernel<1024, false>, fp16_extra, static_cast<uint16_t*>(out16_extra));
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
+namespace {
+const char* patchify_launch(cudaStream_t stream, const float* image, int n_units, int H, int W, int y0, int x0,
+                            const int* origins, int gh, int gw, int patch, int kp_pad, void* out, int fp16) {
+  if (patch != 14 && patch != 16 && patch != 32) return "patchify: patch size must be 14, 16 or 32";
+  if (kp_pad < 3 * patch * patch || kp_pad % 8 != 0) return "patchify: bad padded patch row length";
+  const int vec = patch % 4 == 0 ? 4 : 2;
+  const int64_t total = static_cast<int64_t>(n_units) * 3 * gh * patch * gw * (patch / vec);
+  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * vec * (4.0 + 4.0));
+  const dim3 grid(grid_for(total, 256, device_num_sms() * 16));
+  cudaError_t e = vec == 4 ? launch_pdl(patchify_kernel<4>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
+                                        gw, patch, kp_pad, static_cast<uint16_t*>(out), fp16)
+                           : launch_pdl(patchify_kernel<2>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
+                                        gw, patch, kp_pad, static_cast<uint16_t*>(out), fp16);
+  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+}  // namespace
+
 const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                     int patch, void* out, int fp16) {
-  if (patch != 16 && patch != 32) return "patchify: patch size must be 16 or 32";
+                     int patch, int kp_pad, void* out, int fp16) {
   if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
   if (y0 < 0 || x0 < 0 || y0 + gh * patch > H || x0 + gw * patch > W) return "patchify: grid exceeds image";
-  const int64_t total = static_cast<int64_t>(n_img) * 3 * gh * patch * gw * (patch / 4);
-  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  cudaError_t e = launch_pdl(patchify_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0, stream, 1,
-                             image, n_img, H, W, y0, x0, gh, gw, patch, static_cast<uint16_t*>(out), fp16);
-  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+  return patchify_launch(stream, image, n_img, H, W, y0, x0, nullptr, gh, gw, patch, kp_pad, out, fp16);
 }
 
 const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                             int n_win, int hp, int wp, int patch, void* out, int fp16) {
-  if (patch != 16 && patch != 32) return "patchify: patch size must be 16 or 32";
+                             int n_win, int hp, int wp, int patch, int kp_pad, void* out, int fp16) {
   if (n_win <= 0) return "patchify: no windows";
-  const int64_t total = static_cast<int64_t>(n_win) * 3 * hp * patch * wp * (patch / 4);
-  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * 4 * (4.0 + 2.0));
-  cudaError_t e = launch_pdl(patchify_windows_kernel, dim3(grid_for(total, 256, device_num_sms() * 16)), dim3(256), 0,
-                             stream, 1, image, H, W, origins_yx_dev, n_win, hp, wp, patch, static_cast<uint16_t*>(out), fp16);
-  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+  if (origins_yx_dev == nullptr) return "patchify: window origins missing";
+  return patchify_launch(stream, image, n_win, H, W, 0, 0, origins_yx_dev, hp, wp, patch, kp_pad, out, fp16);
 }
 
-const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
+const char* assemble_tokens(cudaStream_t stream, int width, const float* patch_embed, const int* win_base_dev, int src_pitch,
                             const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
-                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X, void* X16, float2* stats,
-                            int fp16) {
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X) {
   if (n_win <= 0) return "assemble_tokens: no windows";
+  if (width != 768 && width != 1024) return "assemble_tokens: width must be 768 or 1024";
   if (n_prompt > 0 && vpt0 == nullptr) return "assemble_tokens: prompts missing";
-  if ((X16 == nullptr) != (stats == nullptr)) return "assemble_tokens: X16 and stats go together";
   const int64_t rows = static_cast<int64_t>(n_win) * (1 + n_prompt + hp * wp);
-  LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * kD * 8.0);
-  cudaError_t e = launch_pdl(assemble_tokens_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
-                             patch_embed, win_base_dev, src_pitch, win_pitch_dev, class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp,
-                             wp, X, static_cast<uint16_t*>(X16), stats, fp16);
+  LaunchScope scope(stream, "assemble_tokens", 0.0, static_cast<double>(rows) * width * 8.0);
+  const dim3 grid(grid_for(rows, 8, device_num_sms() * 8));
+  cudaError_t e = width == 768
+      ? launch_pdl(assemble_tokens_kernel<768>, grid, dim3(256), 0, stream, 1, patch_embed, win_base_dev, src_pitch, win_pitch_dev,
+                   class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X)
+      : launch_pdl(assemble_tokens_kernel<1024>, grid, dim3(256), 0, stream, 1, patch_embed, win_base_dev, src_pitch, win_pitch_dev,
+                   class_emb, pos, ln_g, ln_b, vpt0, n_prompt, n_win, hp, wp, X);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
-const char* rowstats768(cudaStream_t stream, const float* in, int64_t n_rows, void* X16, float2* stats, int fp16) {
-  if (n_rows <= 0) return nullptr;
-  if (X16 == nullptr || stats == nullptr) return "rowstats: null output";
-  LaunchScope scope(stream, "rowstats", 0.0, static_cast<double>(n_rows) * kD * 6.0);
-  cudaError_t e = launch_pdl(rowstats768_kernel, dim3(grid_for(n_rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1, in,
-                             n_rows, static_cast<uint16_t*>(X16), stats, fp16);
-  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
-}
-
-const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
+const char* resample_to_padded(cudaStream_t stream, int width, const float* Y, int n_win, int hp, int wp, int gh, int gw,
                                void* U_16, float* U_f32, int fp16) {
   if (n_win <= 0) return "resample: no windows";
+  if (width != 768 && width != 1024) return "resample: width must be 768 or 1024";
   const int64_t rows = static_cast<int64_t>(n_win) * (gh + 1) * (gw + 1);
-  LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * kD * 4.0 + static_cast<double>(rows) * kD * 6.0);
-  cudaError_t e = launch_pdl(resample_to_padded_kernel, dim3(grid_for(rows, 8, device_num_sms() * 8)), dim3(256), 0, stream, 1,
-                             Y, n_win, hp, wp, gh, gw, static_cast<uint16_t*>(U_16), U_f32, fp16);
+  LaunchScope scope(stream, "resample", 0.0, static_cast<double>(n_win) * hp * wp * width * 4.0 + static_cast<double>(rows) * width * 6.0);
+  const dim3 grid(grid_for(rows, 8, device_num_sms() * 8));
+  cudaError_t e = width == 768 ? launch_pdl(resample_to_padded_kernel<768>, grid, dim3(256), 0, stream, 1, Y, n_win, hp, wp, gh, gw,
+                                            static_cast<uint16_t*>(U_16), U_f32, fp16)
+                               : launch_pdl(resample_to_padded_kernel<1024>, grid, dim3(256), 0, stream, 1, Y, n_win, hp, wp, gh, gw,
+                                            static_cast<uint16_t*>(U_16), U_f32, fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 
-const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* bias, int n_win, int hp, int wp, int gh, int gw,
-                              void* D1, int fp16) {
-  if (n_win <= 0) return "conv1_from_coarse: no windows";
-  if (gh < 2 * hp || gw < 2 * wp) return "conv1_from_coarse: the decoder grid must be at least twice as fine as the patch grid";
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(conv1_from_coarse_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
-    if (ea != cudaSuccess) return cudaGetErrorString(ea);
-    attr_set = true;
+namespace {
+template <int D>
+const char* conv1_from_coarse_t(cudaStream_t stream, const void* Z, const float* bias, int n_win, int hp, int wp, int gh, int gw,
+                                void* D1, int fp16) {
+  static unsigned long long attr_done = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done & (1ull << (dev & 63)))) {
+      unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+      cudaError_t ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 16, true>, 57344, &m0);
+      if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 16, false>, 57344, &m1);
+      if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 32, true>, kC1Smem, &m2);
+      if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 32, false>, kC1Smem, &m3);
+      if (ea != cudaSuccess) return cudaGetErrorString(ea);
+      attr_done |= 1ull << (dev & 63);
+    }
   }
   LaunchScope scope(stream, "conv1_interp", 0.0,
-                    static_cast<double>(n_win) * hp * wp * 9 * kD * 2.0 + static_cast<double>(n_win) * (gh + 1) * (gw + 1) * kD * 2.0);
+                    static_cast<double>(n_win) * hp * wp * 9 * D * 2.0 + static_cast<double>(n_win) * (gh + 1) * (gw + 1) * D * 2.0);
   cudaError_t e;
   const int whole = hp * wp * 9 * 16 * 2;  // the window's patch grid, all taps, 16 channels
   if (whole <= 57344) {
-    const int64_t blocks = static_cast<int64_t>(n_win) * (kD / 16);
-    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<16, true> : conv1_from_coarse_kernel<16, false>, dim3(static_cast<unsigned>(blocks)),
-                   dim3(256), static_cast<size_t>(whole), stream, 1, static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw,
-                   gh + 1, gw + 1, 1, 1, static_cast<uint16_t*>(D1));
+    const int64_t blocks = static_cast<int64_t>(n_win) * (D / 16);
+    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<D, 16, true> : conv1_from_coarse_kernel<D, 16, false>,
+                   dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(whole), stream, 1,
+                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, gh + 1, gw + 1, 1, 1, static_cast<uint16_t*>(D1));
   } else {
     const int bh = 4, bw = 32;
     const int n_bands = (gh + 1 + bh - 1) / bh, n_ctiles = (gw + 1 + bw - 1) / bw;
-    const int64_t blocks = static_cast<int64_t>(n_win) * n_bands * n_ctiles * (kD / 32);
+    const int64_t blocks = static_cast<int64_t>(n_win) * n_bands * n_ctiles * (D / 32);
     if (blocks > 0x7fffffff) return "conv1_from_coarse: grid too large";
-    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<32, true> : conv1_from_coarse_kernel<32, false>, dim3(static_cast<unsigned>(blocks)),
-                   dim3(256), static_cast<size_t>(kC1Smem), stream, 1, static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw,
-                   bh, bw, n_bands, n_ctiles, static_cast<uint16_t*>(D1));
+    e = launch_pdl(fp16 ? conv1_from_coarse_kernel<D, 32, true> : conv1_from_coarse_kernel<D, 32, false>,
+                   dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(kC1Smem), stream, 1,
+                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gh, gw, bh, bw, n_bands, n_ctiles, static_cast<uint16_t*>(D1));
   }
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
+}
+}  // namespace
+
+const char* conv1_from_coarse(cudaStream_t stream, int width, const void* Z, const float* bias, int n_win, int hp, int wp,
+                              int gh, int gw, void* D1, int fp16) {
+  if (n_win <= 0) return "conv1_from_coarse: no windows";
+  if (gh < 2 * hp || gw < 2 * wp) return "conv1_from_coarse: the decoder grid must be at least twice as fine as the patch grid";
+  if (width == 768) return conv1_from_coarse_t<768>(stream, Z, bias, n_win, hp, wp, gh, gw, D1, fp16);
+  if (width == 1024) return conv1_from_coarse_t<1024>(stream, Z, bias, n_win, hp, wp, gh, gw, D1, fp16);
+  return "conv1_from_coarse: width must be 768 or 1024";
 }
 
 const char* fold_conv3x3_bn_tapout(cudaStream_t stream, const float* W, const float* gamma, const float* var, float eps, int O,
@@ -765,18 +725,11 @@ const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* ga
   return last_err();
 }
 
-const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, void* out, int fp16) {
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, int Ip, void* out, int fp16) {
+  if (Ip < I) return "split_weight: padded length below the row length";
   LaunchScope scope(stream, "pack");
-  split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * I, 256, 4096), 256, 0, stream>>>(
-      W, O, I, static_cast<uint16_t*>(out), fp16);
-  return last_err();
-}
-
-const char* fold_ln_linear(cudaStream_t stream, const float* W, const float* b, const float* gamma, const float* beta, int O,
-                           void* Wf, float* colsum, float* bias_f, int fp16) {
-  if (O <= 0) return "fold_ln_linear: empty";
-  LaunchScope scope(stream, "pack");
-  fold_ln_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(W, b, gamma, beta, O, static_cast<uint16_t*>(Wf), colsum, bias_f, fp16);
+  split_weight_kernel<<<grid_for(static_cast<int64_t>(O) * Ip, 256, 4096), 256, 0, stream>>>(
+      W, O, I, Ip, static_cast<uint16_t*>(out), fp16);
   return last_err();
 }
 

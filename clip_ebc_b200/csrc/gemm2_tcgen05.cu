@@ -13,14 +13,12 @@
 //   warp 2      TMEM allocator (both CTAs, cta_group::2)
 //   warps 4-11  epilogue (both CTAs): 2 warps per TMEM lane quadrant, each owning half of the tile's columns;
 //               tcgen05.ld -> XOR-swizzled smem transpose -> coalesced global accesses; the tile's bias lives in smem
-// Same fused epilogues and K-segment addressing as gemm_tcgen05.cu (see kernels.h).
+// Fused epilogues and K-segment addressing: kernels.h.
 //
-// MC = 2 (cluster of 4 CTAs = two pairs working on vertically adjacent 256-row tiles of the same N-tile): at 32 KB of
-// operands per k-block and SM the pair kernel pulls ~10.6 TB/s out of L2, which is the chip's L2 slice throughput
-// (~6300 B/clk) -- the tensor pipe waits on it (~450 ns per k-block instead of 270). The two pairs need the same weight
-// tile, so each CTA fetches only a quarter of it (64 rows) and TMA-multicasts it to its counterpart in the other pair:
-// 24 KB per k-block and SM leave L2. The price is placement: only 33 clusters of 4 fit on the 148 SMs (132 SMs).
-#include <cstdlib>
+// Tried and not kept (measured on B200): clusters of two pairs sharing the weight tile by TMA multicast
+// (only 33 clusters of 4 fit on 148 SMs; chip rate unchanged), LayerNorm folded into the epilogues either side of it
+// (+0.6 % on the step for three more epilogues), a TMA round trip of the residual tile. Their code lives in the history
+// of this file (round 1).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -35,33 +33,20 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kStagingPerWarp = 32 * 128;  // 32 rows x 128 B, XOR-swizzled 16 B slots
 
-// The statistics epilogue moves the residual tile with TMA (see the TR branch of the epilogue). Measured on B200 the plain
-// residual epilogue is 2 us (out_proj) / 5 us (c_proj) per launch FASTER through registers (the TMA round trip doubles the
-// shared-memory traffic of the epilogue, and the shared-memory port is what the mainloop competes for), so only
-// EPI_BIAS_RESID_STATS -- which needs a thread to own its row -- takes this path.
-template <int BLOCK_N, int EPI>
-constexpr bool tma_resid() { return BLOCK_N == 192 && EPI == EPI_BIAS_RESID_STATS; }
-constexpr int kResidBoxBytes = 32 * 32 * 4;  // TMA box of the residual tile: 32 rows x 32 fp32 columns, 128B-swizzled
-
-template <int BLOCK_N, bool TR = false>
+template <int BLOCK_N>
 struct Cfg2 {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = TR ? 4 : ((BLOCK_N > 192) ? 5 : 6);
+  static constexpr int kStages = (BLOCK_N > 192) ? 5 : 6;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
-  // TR: every epilogue warp owns the residual of its 32 rows x BLOCK_N / 2 columns (BLOCK_N / 64 boxes of 4 KB)
-  static constexpr int kStagingBytes = TR ? kEpiWarps * (BLOCK_N / 64) * kResidBoxBytes : kEpiWarps * kStagingPerWarp;
-  static constexpr int kBiasBytes = 4 * BLOCK_N * 4;  // [2][BLOCK_N] bias + [2][BLOCK_N] LN column sums (EPI_LN_*)
+  static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // [2][BLOCK_N] bias, double-buffered by accumulator stage
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float quick_gelu2_exact(float x) {
-  // x * sigmoid(1.702 x)   (reference: blocks.py:17-19)
-  return __fdividef(x, 1.0f + __expf(-1.702f * x));
-}
-// Same function through sigmoid(z) = (1 + tanh(z / 2)) / 2: ONE special-function op (MUFU.TANH) per element instead of
-// two (EX2 + RCP). The c_fc epilogue is MUFU-bound (32768 elements per 128 x 256 tile and SM against a ~9.4k-cycle
+// QuickGELU x * sigmoid(1.702 x) (reference: blocks.py:17-19) through sigmoid(z) = (1 + tanh(z / 2)) / 2: ONE
+// special-function op (MUFU.TANH) per element instead of two (EX2 + RCP). The c_fc epilogue is MUFU-bound (32768 elements per 128 x 256 tile and SM against a ~9.4k-cycle
 // mainloop); tanh.approx has 2^-11 relative error, the size of the fp16 rounding that follows.
 __device__ __forceinline__ float quick_gelu2(float x) {
   float t;
@@ -71,15 +56,12 @@ __device__ __forceinline__ float quick_gelu2(float x) {
 }
 
 template <int EPI>
-constexpr bool is_ln() { return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16; }
-template <int EPI>
 constexpr bool out_is_bf16() {
-  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16 || is_ln<EPI>();
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16;
 }
 template <int EPI>
 constexpr bool has_resid() {
-  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_RESID_STATS ||
-         EPI == EPI_BIAS_UPSKIP_RELU_SPLIT;
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_UPSKIP_RELU_SPLIT;
 }
 template <int EPI>
 constexpr bool is_relu_split() { return EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI == EPI_BIAS_UPSKIP_RELU_SPLIT; }
@@ -90,8 +72,7 @@ constexpr bool is_relu_split() { return EPI == EPI_BIAS_RESID_RELU_SPLIT || EPI 
 // warp store writes 8 complete 64 B row segments.
 template <int EPI>
 __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* stg, const float* bias_s, int lane, int row0,
-                                                 int n, const uint32_t (&r)[32], const float* cs_s = nullptr, float ra = 1.f,
-                                                 float rc = 0.f, int tma_half = -1) {
+                                                 int n, const uint32_t (&r)[32], int tma_half = -1) {
   const int row = row0 + lane;
   bool border = false;
   if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
@@ -110,23 +91,9 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
     v[2] = __uint_as_float(r[8 * j + 2]) + ba.z; v[3] = __uint_as_float(r[8 * j + 3]) + ba.w;
     v[4] = __uint_as_float(r[8 * j + 4]) + bb.x; v[5] = __uint_as_float(r[8 * j + 5]) + bb.y;
     v[6] = __uint_as_float(r[8 * j + 6]) + bb.z; v[7] = __uint_as_float(r[8 * j + 7]) + bb.w;
-    if constexpr (is_ln<EPI>()) {
-      // LayerNorm applied after the contraction: rstd * (acc - mean * colsum[n]) + bias'[n]; ra = rstd, rc = -rstd * mean
-      const float4* c4p = reinterpret_cast<const float4*>(cs_s);
-      const float4 ca = c4p[2 * j], cb = c4p[2 * j + 1];
-      v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ra, fmaf(rc, ca.x, ba.x)); v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ra, fmaf(rc, ca.y, ba.y));
-      v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ra, fmaf(rc, ca.z, ba.z)); v[3] = fmaf(__uint_as_float(r[8 * j + 3]), ra, fmaf(rc, ca.w, ba.w));
-      v[4] = fmaf(__uint_as_float(r[8 * j + 4]), ra, fmaf(rc, cb.x, bb.x)); v[5] = fmaf(__uint_as_float(r[8 * j + 5]), ra, fmaf(rc, cb.y, bb.y));
-      v[6] = fmaf(__uint_as_float(r[8 * j + 6]), ra, fmaf(rc, cb.z, bb.z)); v[7] = fmaf(__uint_as_float(r[8 * j + 7]), ra, fmaf(rc, cb.w, bb.w));
-    }
-    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16) {
-      if (p.dbg & 64) {  // experiment: the two-MUFU form
+    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = quick_gelu2_exact(v[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
-      }
+      for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
     }
     if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
 #pragma unroll
@@ -147,7 +114,7 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
   for (int it = 0; it < 4; ++it) {
     const int rr = it * 8 + rsub;
     const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((slot ^ ((rr >> 1) & 3)) << 4));
-    if (row0 + rr < p.M && !(p.dbg & 1)) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + slot * 8) = u;
+    if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + rr) * p.ldo + n + slot * 8) = u;
   }
   __syncwarp();
 }
@@ -275,77 +242,50 @@ __device__ __forceinline__ void head_partial_tile(const GemmParams& p, uint32_t 
   }
 }
 
-// TMA load multicast to the CTAs of `cta_mask`; with cta_group::2 the transaction bytes of every destination CTA are
-// reported to the barrier of that CTA's pair leader (the peer bit, bit 24 of the shared address, is cleared).
-__device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
-                                                       int32_t c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
-        "h"(cta_mask)
-      : "memory");
-}
-
-// time line of CTA 0 (experiment): slot i <- clock64()
-#define CEBC_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (slot) < 256) p.trace[(slot)] = clock64(); } while (0)
-
-template <int BLOCK_N, int EPI, int MC>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                     const __grid_constant__ CUtensorMap tma_r, const __grid_constant__ CUtensorMap tma_o,
-                     const __grid_constant__ GemmParams p) {
-  constexpr bool TR = tma_resid<BLOCK_N, EPI>();
-  using Cfg = Cfg2<BLOCK_N, TR>;
+                     const __grid_constant__ CUtensorMap tma_o, const __grid_constant__ GemmParams p) {
+  using Cfg = Cfg2<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int HALF_N = BLOCK_N / 2;
-  constexpr int CL = 2 * MC;  // CTAs per cluster
-  static_assert(MC == 1 || MC == 2, "one or two CTA pairs per cluster");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BLOCK_N] bias, then [2][BLOCK_N] LN column sums
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BLOCK_N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;                         // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + STAGES;               // [STAGES]  one set per CTA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]       one set per CTA
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]       used in the leader CTA only
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint64_t* resid_bar = bars + 2 * STAGES + 5;       // [kEpiWarps]  TR: residual boxes of one epilogue warp have landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp == 3) CEBC_TRACE(0);
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1;          // rank inside the CTA pair
-  const uint32_t pr = crank >> 1;           // pair inside the cluster
-  const uint32_t leader_crank = crank & ~1u;
+  const uint32_t rank = cluster_ctarank();  // rank inside the CTA pair
   const bool leader = rank == 0;
 
   const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row pair tiles
   const int n_tiles = p.N / BLOCK_N;
-  const int num_tiles = ((m_tiles + MC - 1) / MC) * n_tiles;   // cluster tiles: MC vertically adjacent pair tiles
+  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / kBlockK;
-  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if constexpr (TR) { tma_prefetch_desc(&tma_r); tma_prefetch_desc(&tma_o); }
+    if (p.tma_out) tma_prefetch_desc(&tma_o);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
-      mbar_init(&empty_bar[s], MC);  // tcgen05.commit multicast from the leader of every pair of the cluster
+      mbar_init(&empty_bar[s], 1);  // tcgen05.commit multicast from the leader
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // every epilogue warp of both CTAs
     }
-    if constexpr (TR)
-      for (int s = 0; s < kEpiWarps; ++s) mbar_init(&resid_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -354,81 +294,47 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above overlapped the tail of the previous kernel; its results (A, the residual) are needed from here on
-  if (warp == 3) CEBC_TRACE(1);
   pdl_launch_dependents();
-  // The weights do not depend on the previous kernel: the producer requests the weight half-tiles of the first k-blocks
+  // The weights do not depend on the previous kernel of the stream (p.w_prefetch; pack-time launches whose weights were
+  // written by the kernel just before them clear it): the producer requests the weight half-tiles of the first k-blocks
   // of its first tile BEFORE the dependency wait, so that only the activation loads are exposed after it.
   int pre_kb = 0;
-  if constexpr (MC == 1) {
-    if (warp == 0 && !(p.dbg & (8 | 16 | 2048)) && cluster_id < num_tiles) {
-      pre_kb = num_kb < STAGES ? num_kb : STAGES;
-      if (lane == 0) {
-        const int n_blk = cluster_id % n_tiles;
-        const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
-        for (int kb = 0; kb < pre_kb; ++kb) {  // fresh barriers: every slot is free
-          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[kb]), leader_crank);
-          if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2u * Cfg::kABytes + 2u * Cfg::kBBytes);
-          else mbar_arrive_cluster(leader_full);
-          tma_load_2d_pair(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tma_b, leader_full, kb * kBlockK, n0);
-        }
+  if (warp == 0 && p.w_prefetch && pair_id < num_tiles) {
+    pre_kb = num_kb < STAGES ? num_kb : STAGES;
+    if (lane == 0) {
+      const int n_blk = pair_id % n_tiles;
+      const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
+      for (int kb = 0; kb < pre_kb; ++kb) {  // fresh barriers: every slot is free
+        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[kb]), 0);
+        if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2u * Cfg::kABytes + 2u * Cfg::kBBytes);
+        else mbar_arrive_cluster(leader_full);
+        tma_load_2d_pair(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tma_b, leader_full, kb * kBlockK, n0);
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
   pdl_wait();
-  if (warp == 3) CEBC_TRACE(2);
-  long long dbg_c0 = 0;
-  unsigned long long dbg_t0 = 0;
-  if ((p.dbg & 32) && blockIdx.x == 0 && threadIdx.x == 96) {  // experiment: effective SM clock during the kernel
-    dbg_c0 = clock64();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-  }
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
     uint32_t stage = 0, phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
-      const int m0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int m0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
       const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
       int seg = 0, kk = 0;
-      CEBC_TRACE(16 + 4 * ((t - cluster_id) / num_clusters));
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (t == cluster_id && kb < pre_kb) {
-          // barrier armed and weights requested before the dependency wait: only the activations are left
-          if (lane == 0) {
-            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), leader_crank);
-            tma_load_2d_pair(smem + stage * Cfg::kStageBytes, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK,
-                             m0 + p.seg_row_shift[seg]);
-          }
-          __syncwarp();
-          if (++kk == p.seg_kblocks) { kk = 0; ++seg; }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          continue;
-        }
-        // slot free in every CTA of the cluster (each pair leader's commit is multicast to all of them), so multicast
-        // writes into the other pair's slot are safe too
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool weights_done = t == pair_id && kb < pre_kb;  // barrier armed, weights requested before the wait
+        if (!weights_done) mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), leader_crank);
-          const uint32_t tx = ((p.dbg & 16) ? 0u : 2u * Cfg::kABytes) + ((p.dbg & 8) ? 0u : 2u * Cfg::kBBytes);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx);
-          else mbar_arrive_cluster(leader_full);
-          if (!(p.dbg & 16))
-            tma_load_2d_pair(sa, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK, m0 + p.seg_row_shift[seg]);
-          if (p.dbg & 8) {
-          } else if constexpr (MC == 1) {
-            tma_load_2d_pair(sb, &tma_b, leader_full, kb * kBlockK, n0);
-          } else {
-            // this CTA's share of the weight half-tile, delivered to the same slot of the CTA with the same pair rank in
-            // every pair of the cluster
-            constexpr int kShareRows = HALF_N / MC;
-            const uint16_t mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
-            tma_load_2d_pair_mcast(sb + pr * (Cfg::kBBytes / MC), &tma_b, &full_bar[stage], kb * kBlockK,
-                                   n0 + static_cast<int>(pr) * kShareRows, mask);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (!weights_done) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * Cfg::kABytes + 2u * Cfg::kBBytes);
+            else mbar_arrive_cluster(leader_full);
           }
+          tma_load_2d_pair(sa, &tma_a, leader_full, p.seg_col_start[seg] + kk * kBlockK, m0 + p.seg_row_shift[seg]);
+          if (!weights_done) tma_load_2d_pair(sa + Cfg::kABytes, &tma_b, leader_full, kb * kBlockK, n0);
         }
         __syncwarp();
         if (++kk == p.seg_kblocks) { kk = 0; ++seg; }
@@ -439,16 +345,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // ------------------------------- MMA issuer (leader CTA) -------------------------------
     const uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N, p.ab_fp16);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-    constexpr uint16_t kAllCtas = (1u << CL) - 1;
-    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pr));
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    constexpr uint16_t kBothCtas = 3;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      CEBC_TRACE(17 + 4 * ((t - cluster_id) / num_clusters));
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        if (kb == 0) CEBC_TRACE(18 + 4 * ((t - cluster_id) / num_clusters));
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -459,8 +362,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             const uint64_t db = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 2);
             umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_pair_mcast(&empty_bar[stage], kAllCtas);                           // this pair is done with the slot
-          if (kb == num_kb - 1) umma_commit_pair_mcast(&tmem_full_bar[as], pair_mask);  // accumulator ready in both CTAs
+          umma_commit_pair_mcast(&empty_bar[stage], kBothCtas);                          // the pair is done with the slot
+          if (kb == num_kb - 1) umma_commit_pair_mcast(&tmem_full_bar[as], kBothCtas);  // accumulator ready in both CTAs
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -475,110 +378,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int half = ew >> 2;    // which half of the tile's columns
     const int et = threadIdx.x - 128;
     uint8_t* stg = staging + ew * kStagingPerWarp;
-    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), leader_crank);
-    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), leader_crank);
+    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     uint32_t as = 0, aphase = 0;
-    if constexpr (TR) {
-      // ---- fp32 residual tiles through TMA ------------------------------------------------------------------------
-      // The register-staged epilogue below keeps only one 32-column chunk of the residual in flight per warp and is
-      // latency-bound (out_proj: ~10 us per tile against a 4.5 us mainloop). Here every epilogue warp owns the residual of
-      // its 32 rows x 96 columns as three 128B-swizzled 4 KB boxes in shared memory: the boxes of the NEXT tile are
-      // requested as soon as the store of the current one has been read out of shared memory, thread = accumulator row
-      // adds accumulator + bias in place (16 B accesses, conflict-free under the swizzle) and lane 0 sends the boxes
-      // back with a bulk tensor store; rows >= M are clipped by the hardware. No predicates, no staging transposes, and
-      // the row statistics of EPI_BIAS_RESID_STATS are plain per-thread sums (a thread owns its row).
-      constexpr int NB = HALF_N / 32;
-      uint8_t* Rw = staging + ew * (NB * kResidBoxBytes);
-      uint64_t* rbar = &resid_bar[ew];
-      uint32_t rphase = 0;
-      const int cbase = half * HALF_N;
-      auto request_resid = [&](int t) {
-        const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
-        const int r0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
-        mbar_arrive_expect_tx(rbar, NB * kResidBoxBytes);
-#pragma unroll
-        for (int c = 0; c < NB; ++c) tma_load_2d(Rw + c * kResidBoxBytes, &tma_r, rbar, n_blk * BLOCK_N + cbase + c * 32, r0);
-      };
-      if (lane == 0 && cluster_id < num_tiles) request_resid(cluster_id);
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
-        const int row0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
-        const int n0 = n_blk * BLOCK_N;
-        float* bs = bias_s + as * BLOCK_N;
-        if (et < BLOCK_N) bs[et] = __ldg(p.bias + n0 + et);
-        named_bar_sync(1, kEpiWarps * 32);
-        mbar_wait(rbar, rphase);
-        rphase ^= 1;
-        mbar_wait(&tmem_full_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
-        const int row = row0 + lane;
-        uint16_t* x16 = nullptr;
-        if constexpr (EPI == EPI_BIAS_RESID_STATS)
-          x16 = static_cast<uint16_t*>(p.x16_out) + static_cast<size_t>(row) * p.N + n0 + cbase;
-        float pivot = 0.f, sd = 0.f, sq = 0.f;   // sum (v - pivot), sum (v - pivot)^2 over the thread's 96 columns
-#pragma unroll 1
-        for (int c = 0; c < NB; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + c * 32, r);
-          tmem_ld_wait();
-          uint8_t* rowp = Rw + c * kResidBoxBytes + lane * 128;
-          const float4* b4 = reinterpret_cast<const float4*>(bs + cbase + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float4* s0 = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
-            float4* s1 = reinterpret_cast<float4*>(rowp + (((j + 1) ^ (lane & 7)) << 4));
-            float4 v0 = *s0, v1 = *s1;
-            const float4 ba = b4[j], bb = b4[j + 1];
-            v0.x += __uint_as_float(r[4 * j + 0]) + ba.x; v0.y += __uint_as_float(r[4 * j + 1]) + ba.y;
-            v0.z += __uint_as_float(r[4 * j + 2]) + ba.z; v0.w += __uint_as_float(r[4 * j + 3]) + ba.w;
-            v1.x += __uint_as_float(r[4 * j + 4]) + bb.x; v1.y += __uint_as_float(r[4 * j + 5]) + bb.y;
-            v1.z += __uint_as_float(r[4 * j + 6]) + bb.z; v1.w += __uint_as_float(r[4 * j + 7]) + bb.w;
-            *s0 = v0;
-            *s1 = v1;
-            if constexpr (EPI == EPI_BIAS_RESID_STATS) {
-              if (c == 0 && j == 0) pivot = v0.x;
-              const float d0 = v0.x - pivot, d1 = v0.y - pivot, d2 = v0.z - pivot, d3 = v0.w - pivot;
-              const float d4 = v1.x - pivot, d5 = v1.y - pivot, d6 = v1.z - pivot, d7 = v1.w - pivot;
-              sd += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
-              sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
-              sq = fmaf(d4, d4, sq); sq = fmaf(d5, d5, sq); sq = fmaf(d6, d6, sq); sq = fmaf(d7, d7, sq);
-              if (row < p.M)
-                *reinterpret_cast<uint4*>(x16 + c * 32 + 4 * j) =
-                    make_uint4(pack16x2(v0.x, v0.y, p.out_fp16), pack16x2(v0.z, v0.w, p.out_fp16),
-                               pack16x2(v1.x, v1.y, p.out_fp16), pack16x2(v1.z, v1.w, p.out_fp16));
-            }
-          }
-        }
-        // the accumulator has been read: hand the TMEM buffer back before the stores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
-        fence_proxy_async_smem();  // this thread's generic-proxy writes -> visible to the bulk store
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < NB; ++c) tma_store_2d(&tma_o, Rw + c * kResidBoxBytes, n0 + cbase + c * 32, row0);
-          bulk_commit_group();
-          bulk_wait_group_read0();  // the boxes have left shared memory: refill them with the next tile's residual
-          if (t + num_clusters < num_tiles) request_resid(t + num_clusters);
-        }
-        if constexpr (EPI == EPI_BIAS_RESID_STATS) {
-          if (row < p.M) {
-            const float mean_d = sd * (1.0f / HALF_N);
-            p.stats_out[static_cast<size_t>(row) * kLnStatSlots + 2 * n_blk + half] =
-                make_float2(pivot + mean_d, fmaxf(sq - sd * mean_d, 0.f));
-          }
-        }
-        __syncwarp();
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-      }
-      if (lane == 0) bulk_wait_group0();  // all stores complete before the CTA may exit
-    } else
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int ms_blk = t / n_tiles, n_blk = t - ms_blk * n_tiles;
-      const int row0 = (ms_blk * MC + static_cast<int>(pr)) * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int row0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
       const int n0 = n_blk * BLOCK_N;
       // the tile's bias -> smem (double-buffered by accumulator stage); overlaps the wait for the accumulator
       float* bs = bias_s + as * BLOCK_N;
@@ -594,39 +399,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         }
       }
       if (et < BLOCK_N) bs[et] = (EPI != EPI_F32 || p.bias != nullptr) ? __ldg(p.bias + n0 + et) : 0.0f;
-      float* cs = bias_s + (2 + as) * BLOCK_N;
-      float ln_a = 1.f, ln_c = 0.f;
-      if constexpr (is_ln<EPI>()) {
-        if (et < BLOCK_N) cs[et] = __ldg(p.ln_colsum + n0 + et);
-        // this thread's row: merge the partials (mean, M2) left by the producer of the rows -> rstd, -rstd * mean
-        const int row = row0 + lane;
-        if (row < p.M) {
-          const float4* st = reinterpret_cast<const float4*>(p.ln_stats + static_cast<size_t>(row) * kLnStatSlots);
-          float mean, m2;
-          if (p.ln_parts == 1) {
-            const float2 v = *reinterpret_cast<const float2*>(st);
-            mean = v.x; m2 = v.y;
-          } else {
-            float4 v[kLnStatSlots / 2];
-#pragma unroll
-            for (int j = 0; j < kLnStatSlots / 2; ++j) v[j] = st[j];  // two partials each; independent loads
-            float ms = 0.f;
-            m2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < kLnStatSlots / 2; ++j) { ms += v[j].x + v[j].z; m2 += v[j].y + v[j].w; }
-            mean = ms * (1.0f / kLnStatSlots);
-            float dv = 0.f;
-#pragma unroll
-            for (int j = 0; j < kLnStatSlots / 2; ++j) {
-              const float a = v[j].x - mean, b = v[j].z - mean;
-              dv += a * a + b * b;
-            }
-            m2 += static_cast<float>(kLnPartCols) * dv;
-          }
-          ln_a = rsqrtf(m2 * (1.0f / 768.0f) + 1e-5f);
-          ln_c = -ln_a * mean;
-        }
-      }
       named_bar_sync(1, kEpiWarps * 32);
       const int cbase = half * HALF_N;
       float4 xa[8], xb[8];
@@ -634,7 +406,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         if (!(EPI == EPI_BIAS_RESID_F32 && p.tma_out)) load_resid32<EPI>(p, lane, row0, n0 + cbase, xa);
       }
       mbar_wait(&tmem_full_bar[as], aphase);
-      if (ew == 0) CEBC_TRACE(19 + 4 * ((t - cluster_id) / num_clusters));
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cbase;
       if constexpr (EPI == EPI_BIAS_HEAD_PARTIAL) {
@@ -656,15 +427,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             for (int cc = 0; cc < 2; ++cc) {
               const int c = 2 * b + cc;
               uint32_t r[32];
-              if (!(p.dbg & 4)) tmem_ld_32x32b_x32(t_addr + c * 32, r);
+              tmem_ld_32x32b_x32(t_addr + c * 32, r);
               tmem_ld_wait();
-              if (!(p.dbg & 2))
-                epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cs + cbase + c * 32, ln_a,
-                                      ln_c, cc);
+              epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cc);
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 1)) {
+            if (lane == 0) {
               tma_store_2d(&tma_o, stg, n0 + cbase + b * 64, row0);
               bulk_commit_group();
             }
@@ -673,10 +442,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll 1
         for (int c = 0; c < HALF_N / 32; ++c) {
           uint32_t r[32];
-          if (!(p.dbg & 4)) tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
           tmem_ld_wait();
-          if (!(p.dbg & 2))
-            epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r, cs + cbase + c * 32, ln_a, ln_c);
+          epi_bf16_chunk32<EPI>(p, stg, bs + cbase + c * 32, lane, row0, n0 + cbase + c * 32, r);
         }
       } else if (EPI == EPI_BIAS_RESID_F32 && p.tma_out) {
         // In-place residual update as a memory-side reduction: thread = accumulator row stages acc + bias (fp32) in a
@@ -727,7 +495,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
-      if (ew == 0) CEBC_TRACE(8 + ((t - cluster_id) / num_clusters));  // epilogue of tile i done
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -738,13 +505,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   }
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal its barriers / read its smem
-  if (warp == 3) CEBC_TRACE(3);
-  if ((p.dbg & 32) && blockIdx.x == 0 && threadIdx.x == 96) {
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    const long long c1 = clock64();
-    printf("[gemm2] %lld cycles in %llu ns -> %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0, 1e3 * (c1 - dbg_c0) / (double)(t1 - dbg_t0));
-  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
@@ -781,7 +541,7 @@ bool make_tmap2(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// fp32 [rows, cols] pitch ld: 32 x 32 boxes, 128B-swizzled (the residual / output tile of the TR epilogue)
+// fp32 [rows, cols] pitch ld: 32 x 32 boxes, 128B-swizzled (the tile of the in-place residual reduction)
 bool make_tmap2_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
   PFN_encodeTiled enc = get_encode_fn2();
   if (!enc) return false;
@@ -794,91 +554,83 @@ bool make_tmap2_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t co
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// clusters of 2*MC CTAs (1 CTA per SM) that can be co-resident: 74 pairs, but only 33 clusters of 4 on B200
-template <int BLOCK_N, int EPI, int MC>
-int max_clusters2(int num_sms) {
-  static int cached = 0;
-  if (cached) return cached;
-  using Cfg = Cfg2<BLOCK_N, tma_resid<BLOCK_N, EPI>()>;
-  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
+// CTA pairs (1 CTA per SM) that can be co-resident on the current device: 74 on B200. Cached per device; the first call on
+// a device also sets the kernel's dynamic shared-memory attribute there (a per-device attribute).
+template <int BLOCK_N, int EPI>
+int max_pairs2(int num_sms) {
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev]) return cached[dev];
+  using Cfg = Cfg2<BLOCK_N>;
+  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * MC * 64); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.gridDim = dim3(2 * 64); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2 * MC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / (2 * MC); }
-  cached = n;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
+  cached[dev] = n;
   return n;
 }
 
-template <int BLOCK_N, int EPI, int MC>
+template <int BLOCK_N, int EPI>
 cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_sms) {
-  using Cfg = Cfg2<BLOCK_N, tma_resid<BLOCK_N, EPI>()>;
-  CUtensorMap tr = ta, to = ta;  // placeholders for the kernels that do not use them
+  using Cfg = Cfg2<BLOCK_N>;
+  CUtensorMap to = ta;  // placeholder for the epilogues that do not use it
   GemmParams pl = p;
+  pl.tma_out = 0;
   if constexpr (out_is_bf16<EPI>() && (BLOCK_N / 2) % 64 == 0) {
-    static const bool tma_out_env = getenv("CLIPEBC_GEMM_NO_TMA_OUT") == nullptr;  // A/B knob
-    if (tma_out_env && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0 &&
-        make_tmap2(&to, p.out, p.M, p.N, p.ldo, 32))
+    // 16-bit outputs leave through bulk tensor stores when the output allows it (else per-lane stores)
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0 && make_tmap2(&to, p.out, p.M, p.N, p.ldo, 32))
       pl.tma_out = 1;
   }
-  if constexpr (EPI == EPI_BIAS_RESID_F32 && !tma_resid<BLOCK_N, EPI>()) {
-    // in place (out == resid): the residual add becomes a bulk tensor reduction
-    static const bool red_env = getenv("CLIPEBC_GEMM_NO_TMA_RED") == nullptr;  // A/B knob
-    if (red_env && p.out == static_cast<const void*>(p.resid) && p.ldo == p.ldr && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+  if constexpr (EPI == EPI_BIAS_RESID_F32) {
+    // in place (out == resid): the residual add becomes a bulk tensor reduction (else the register path)
+    if (p.out == static_cast<const void*>(p.resid) && p.ldo == p.ldr && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
         p.ldo % 4 == 0 && make_tmap2_f32(&to, p.out, p.M, p.N, p.ldo))
       pl.tma_out = 1;
   }
-  if constexpr (tma_resid<BLOCK_N, EPI>()) {
-    if ((reinterpret_cast<uintptr_t>(p.resid) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldr % 4) || (p.ldo % 4))
-      return cudaErrorMisalignedAddress;
-    if (!make_tmap2_f32(&tr, p.resid, p.M, p.N, p.ldr) || !make_tmap2_f32(&to, p.out, p.M, p.N, p.ldo)) return cudaErrorInvalidValue;
-  }
-  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI, MC>;
-  const int max_cl = max_clusters2<BLOCK_N, EPI, MC>(num_sms);  // also sets the dynamic smem attribute (once)
-  if (max_cl <= 0) return cudaErrorInvalidConfiguration;
+  auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI>;
+  const int max_pairs = max_pairs2<BLOCK_N, EPI>(num_sms);  // also sets the dynamic smem attribute (once per device)
+  if (max_pairs <= 0) return cudaErrorInvalidConfiguration;
   const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
-  const int num_tiles = ((m_tiles + MC - 1) / MC) * (p.N / BLOCK_N);
-  const int clusters = num_tiles < max_cl ? num_tiles : max_cl;
+  const int num_tiles = m_tiles * (p.N / BLOCK_N);
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   cudaError_t e;
   {
     LaunchScope scope(stream, "gemm", 2.0 * p.M * static_cast<double>(p.N) * p.K,
                       2.0 * p.M * static_cast<double>(p.K) + 2.0 * p.N * static_cast<double>(p.K) +
                           4.0 * p.M * static_cast<double>(p.N));
-    e = launch_pdl(kern, dim3(2 * MC * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2 * MC, ta, tb, tr, to, pl);
+    e = launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), Cfg::kSmemBytes, stream, 2, ta, tb, to, pl);
   }
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <int BLOCK_N, int MC>
+template <int BLOCK_N>
 cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_sms) {
   switch (epi) {
-    case EPI_F32: return launch_one2<BLOCK_N, EPI_F32, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_F32: return launch_one2<BLOCK_N, EPI_BIAS_F32, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_BF16: return launch_one2<BLOCK_N, EPI_BIAS_BF16, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_GELU_BF16: return launch_one2<BLOCK_N, EPI_BIAS_GELU_BF16, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT, MC>(stream, ta, tb, p, num_sms);
-    case EPI_BIAS_UPSKIP_RELU_SPLIT:
-      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_BIAS_UPSKIP_RELU_SPLIT, 1>(stream, ta, tb, p, num_sms);
-      else return cudaErrorInvalidValue;
-    case EPI_BIAS_RESID_STATS:
-      if constexpr (MC == 1 && BLOCK_N == 192) return launch_one2<192, EPI_BIAS_RESID_STATS, 1>(stream, ta, tb, p, num_sms);
-      else return cudaErrorInvalidValue;
-    case EPI_LN_BIAS_BF16:
-      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_LN_BIAS_BF16, 1>(stream, ta, tb, p, num_sms);
-      else return cudaErrorInvalidValue;
-    case EPI_LN_BIAS_GELU_BF16:
-      if constexpr (MC == 1) return launch_one2<BLOCK_N, EPI_LN_BIAS_GELU_BF16, 1>(stream, ta, tb, p, num_sms);
-      else return cudaErrorInvalidValue;
+    case EPI_F32: return launch_one2<BLOCK_N, EPI_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_F32: return launch_one2<BLOCK_N, EPI_BIAS_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_BF16: return launch_one2<BLOCK_N, EPI_BIAS_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_GELU_BF16: return launch_one2<BLOCK_N, EPI_BIAS_GELU_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_F32: return launch_one2<BLOCK_N, EPI_BIAS_RESID_F32>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_UPSKIP_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_UPSKIP_RELU_SPLIT>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_HEAD_PARTIAL:
-      if constexpr (BLOCK_N == 256 && MC == 1) return launch_one2<256, EPI_BIAS_HEAD_PARTIAL, 1>(stream, ta, tb, p, num_sms);
+      if constexpr (BLOCK_N == 256) return launch_one2<256, EPI_BIAS_HEAD_PARTIAL>(stream, ta, tb, p, num_sms);
       else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
@@ -905,12 +657,21 @@ int pick_block_n2(int M, int N, int num_sms) {
 
 }  // namespace
 
+int device_num_sms() {
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 int gemm2_pick_block_n(int M, int N) { return pick_block_n2(M, N, device_num_sms()); }
 
 const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                           int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n) {
-  static const int dbg_env = getenv("CLIPEBC_GEMM_DBG") ? atoi(getenv("CLIPEBC_GEMM_DBG")) : 0;  // experiment knob
-  p.dbg = dbg_env;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
   if (p.K % kBlockK != 0) return "gemm: K must be a multiple of 64";
   if (p.n_seg < 1 || p.n_seg > kMaxGemmSegs) return "gemm: bad segment count";
@@ -919,25 +680,14 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   if ((lda * 2) % 16 != 0 || (ldw * 2) % 16 != 0) return "gemm: row pitch must be a multiple of 16 bytes";
   if (p.N % 64 != 0) return "gemm: N must be a multiple of 64";
   const int num_sms = device_num_sms();
-  if (block_n == 0) block_n = (epi == EPI_BIAS_RESID_STATS) ? 192 : pick_block_n2(p.M, p.N, num_sms);
+  if (block_n == 0) block_n = pick_block_n2(p.M, p.N, num_sms);
   if (block_n != 128 && block_n != 192 && block_n != 256) return "gemm: block_n must be 128, 192 or 256";
   if (p.N % block_n != 0) return "gemm: N must be a multiple of block_n";
   if (epi != EPI_F32 && p.bias == nullptr) return "gemm: epilogue needs a bias";
-  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT || epi == EPI_BIAS_RESID_STATS ||
-       epi == EPI_BIAS_UPSKIP_RELU_SPLIT) && p.resid == nullptr)
+  if ((epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_RESID_RELU_SPLIT || epi == EPI_BIAS_UPSKIP_RELU_SPLIT) && p.resid == nullptr)
     return "gemm: epilogue needs a residual";
   if (epi == EPI_BIAS_UPSKIP_RELU_SPLIT && (p.mask_hp < 2 || p.mask_wp < 2 || p.up_hp < 1 || p.up_wp < 1))
     return "gemm: upsampled-skip epilogue needs the grid (mask_hp, mask_wp) and the patch grid (up_hp, up_wp)";
-  if (epi == EPI_BIAS_RESID_STATS) {
-    if (p.x16_out == nullptr || p.stats_out == nullptr) return "gemm: statistics epilogue needs x16_out and stats_out";
-    if (p.N != 2 * kLnPartCols * (kLnStatSlots / 2)) return "gemm: statistics epilogue: N must be 768";
-    if (block_n != 192) return "gemm: statistics epilogue exists for 192-wide tiles only";
-  }
-  if (epi == EPI_LN_BIAS_BF16 || epi == EPI_LN_BIAS_GELU_BF16) {
-    if (p.ln_stats == nullptr || p.ln_colsum == nullptr) return "gemm: LayerNorm epilogue needs ln_stats and ln_colsum";
-    if (p.K != 768) return "gemm: LayerNorm epilogue: K must be 768";
-    if (p.ln_parts != 1 && p.ln_parts != kLnStatSlots) return "gemm: LayerNorm epilogue: ln_parts must be 1 or 8";
-  }
   if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 2 || p.mask_wp < 2)) return "gemm: mask grid missing";
   if (epi == EPI_BIAS_HEAD_PARTIAL) {
     if (p.head_tmat == nullptr || p.head_bins < 1 || p.head_bins > 32) return "gemm: head epilogue needs the text matrix and 1..32 bins";
@@ -945,40 +695,13 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
     block_n = 256;
   }
 
-  static const bool trace_env = getenv("CLIPEBC_GEMM_TRACE") != nullptr;  // experiment: print CTA 0's time line
-  static long long* trace_dev = nullptr;
-  if (trace_env) {
-    if (!trace_dev) cudaMalloc(&trace_dev, 256 * sizeof(long long));
-    cudaMemsetAsync(trace_dev, 0, 256 * sizeof(long long), stream);
-    p.trace = trace_dev;
-  }
-  static const int mc_env = getenv("CLIPEBC_GEMM_MC") ? atoi(getenv("CLIPEBC_GEMM_MC")) : 0;  // experiment knob
-  const int mc = (mc_env == 1 || mc_env == 2) ? mc_env : 1;  // measured on B200: no gain from the multicast variant (power-bound)
-
   CUtensorMap ta, tb;
   if (!make_tmap2(&ta, A, a_rows, a_cols, lda, kBlockM)) return "gemm: cuTensorMapEncodeTiled(A) failed";
-  if (!make_tmap2(&tb, W, p.N, p.K, ldw, block_n / 2 / mc)) return "gemm: cuTensorMapEncodeTiled(W) failed";
-  cudaError_t e;
-  if (mc == 2)
-    e = (block_n == 256)   ? launch_epi2<256, 2>(stream, epi, ta, tb, p, num_sms)
-        : (block_n == 192) ? launch_epi2<192, 2>(stream, epi, ta, tb, p, num_sms)
-                           : launch_epi2<128, 2>(stream, epi, ta, tb, p, num_sms);
-  else
-    e = (block_n == 256)   ? launch_epi2<256, 1>(stream, epi, ta, tb, p, num_sms)
-        : (block_n == 192) ? launch_epi2<192, 1>(stream, epi, ta, tb, p, num_sms)
-                           : launch_epi2<128, 1>(stream, epi, ta, tb, p, num_sms);
+  if (!make_tmap2(&tb, W, p.N, p.K, ldw, block_n / 2)) return "gemm: cuTensorMapEncodeTiled(W) failed";
+  const cudaError_t e = (block_n == 256)   ? launch_epi2<256>(stream, epi, ta, tb, p, num_sms)
+                        : (block_n == 192) ? launch_epi2<192>(stream, epi, ta, tb, p, num_sms)
+                                           : launch_epi2<128>(stream, epi, ta, tb, p, num_sms);
   if (e != cudaSuccess) return cudaGetErrorString(e);
-  if (trace_env) {
-    long long h[256];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
-    const long long t0 = h[0];
-    printf("[trace] setup %lld pdl %lld end %lld |", h[1] - t0, h[2] - t0, h[3] - t0);
-    for (int i = 0; i < 8 && h[16 + 4 * i]; ++i)
-      printf(" tile%d: tma %lld mma_free %lld first_full %lld acc_full %lld epi_done %lld |", i, h[16 + 4 * i] - t0,
-             h[17 + 4 * i] - t0, h[18 + 4 * i] - t0, h[19 + 4 * i] - t0, h[8 + i] - t0);
-    printf("\n");
-  }
   return nullptr;
 }
 

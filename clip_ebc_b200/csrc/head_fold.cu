@@ -1,64 +1,12 @@
-// EBC head (L2-normalise -> cosine logits against the fixed bin text embeddings -> softmax -> anchor expectation) and
-// the overlapping-window fold/average as an atomic-free gather, plus the per-image count reduction.
+// Second half of the EBC head (the first half -- ||f||^2 and the bin dot products -- is the epilogue of the projection GEMM,
+// gemm2_tcgen05.cu EPI_BIAS_HEAD_PARTIAL): L2-normalise -> cosine logits -> softmax -> anchor expectation; the
+// overlapping-window fold/average as an atomic-free gather; the per-image count reduction.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace cebc {
 
 namespace {
-
-constexpr int kE = 512;  // CLIP embed dim of ViT-B/16
-
-// One warp per interior cell of the shared-border decoder grid. Reference: models/clip/model.py:200-212
-//   f^ = f / max(||f||, 1e-12);  logits = (exp(logit_scale) * f^) @ t^T;  probs = softmax;  exp = sum probs * anchor
-// tmat already holds exp(logit_scale) * t^ (pack_text).
-__global__ void __launch_bounds__(256) ebc_head_kernel(const float* __restrict__ F, const float* __restrict__ tmat,
-                                                       const float* __restrict__ anchors, int n_bins, int n_win, int gh,
-                                                       int gw, float* __restrict__ exp_out,
-                                                       float* __restrict__ logits_out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int Hp = gh + 1, Wp = gw + 1;  // shared-border grid (kernels.h: resample_to_padded)
-  const int64_t n_cells = static_cast<int64_t>(n_win) * gh * gw;
-  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t cell = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < n_cells;
-       cell += warps_total) {
-    const int win = static_cast<int>(cell / (gh * gw));
-    const int q = static_cast<int>(cell - static_cast<int64_t>(win) * gh * gw);
-    const int y = q / gw, x = q - y * gw;
-    const int64_t row = (static_cast<int64_t>(win) * Hp + y) * Wp + x;
-    const float4* f4 = reinterpret_cast<const float4*>(F + row * kE);
-    float4 f[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f[i] = f4[i * 32 + lane];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ss += (f[i].x * f[i].x + f[i].y * f[i].y) + (f[i].z * f[i].z + f[i].w * f[i].w);
-    ss = warp_sum(ss);
-    const float inv_norm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-
-    float my_logit = -INFINITY;
-    for (int b = 0; b < n_bins; ++b) {
-      const float4* t4 = reinterpret_cast<const float4*>(tmat + static_cast<int64_t>(b) * kE);
-      float d = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = __ldg(t4 + i * 32 + lane);
-        d += (f[i].x * t.x + f[i].y * t.y) + (f[i].z * t.z + f[i].w * t.w);
-      }
-      d = warp_sum(d) * inv_norm;
-      if (lane == b) my_logit = d;
-    }
-    const float mx = warp_max(my_logit);
-    const float e = (lane < n_bins) ? __expf(my_logit - mx) : 0.f;
-    const float den = warp_sum(e);
-    const float num = warp_sum(lane < n_bins ? e * __ldg(anchors + lane) : 0.f);
-    if (lane == 0) exp_out[cell] = num / den;
-    if (logits_out != nullptr && lane < n_bins)
-      logits_out[((static_cast<int64_t>(win) * n_bins + lane) * gh + y) * gw + x] = my_logit;
-  }
-}
 
 // Second half of the fused head: one thread per interior cell sums the per-half-tile partials of the projection GEMM
 // (EPI_BIAS_HEAD_PARTIAL) in a fixed order and finishes normalise / softmax / expectation (models/clip/model.py:203-212).
@@ -152,20 +100,6 @@ inline const char* last_err() {
 }
 
 }  // namespace
-
-const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
-                     int n_win, int gh, int gw, float* exp_out, float* logits_out) {
-  if (n_bins < 1 || n_bins > 32) return "ebc_head: 1..32 bins supported";
-  if (n_win <= 0) return "ebc_head: no windows";
-  const int64_t cells = static_cast<int64_t>(n_win) * gh * gw;
-  int64_t blocks = (cells + 7) / 8;
-  const int64_t cap = static_cast<int64_t>(device_num_sms()) * 8;
-  if (blocks > cap) blocks = cap;
-  LaunchScope scope(stream, "ebc_head", 0.0, static_cast<double>(cells) * (kE * 4.0 + 4.0));
-  cudaError_t e = launch_pdl(ebc_head_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, F, tmat, anchors,
-                             n_bins, n_win, gh, gw, exp_out, logits_out);
-  return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
-}
 
 const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,
                             int gh, int gw, float* exp_out, float* logits_out) {

@@ -20,23 +20,11 @@ enum GemmEpilogue : int {
   EPI_BIAS_HEAD_PARTIAL = 7,    // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
                                 // tiles) out[row][2 * n_blk + half][0] = sum f^2, [1 + b] = sum f * head_tmat[b][n]
                                 // -- the projection fused with the first half of the EBC head (ebc_head_finish)
-  // LayerNorm folded into the GEMMs either side of it (CTA-pair kernel only; DESIGN.md section 2, rewrite 7):
-  EPI_BIAS_RESID_STATS = 8,     // EPI_BIAS_RESID_F32 + x16_out[row, n] = 16-bit copy of the new residual row and, per row and
-                                // half tile of 96 columns, stats_out[row][n / 96] = (mean, sum of squared deviations) of those
-                                // columns. 192-wide tiles only (N = 768 -> 8 partials per row), so the partition -- and with it
-                                // every bit of a row's statistics -- does not depend on the batch the row is part of
-  EPI_LN_BIAS_BF16 = 9,         // out bf16 = rstd[row] * (acc - mean[row] * ln_colsum[n]) + bias[n]: A holds the RAW rows,
-                                // W = W * diag(gamma), bias = b + W beta, ln_colsum[n] = sum_k W'[n, k]; (mean, rstd) merged
-                                // per row in the epilogue from the ln_parts (1 or 8) partials of ln_stats (K = 768)
-  EPI_LN_BIAS_GELU_BF16 = 10,   // quickgelu of the same
-  EPI_BIAS_UPSKIP_RELU_SPLIT = 11  // EPI_BIAS_RESID_RELU_SPLIT whose residual is the bilinear upsample of the coarse map,
+  EPI_BIAS_UPSKIP_RELU_SPLIT = 8  // EPI_BIAS_RESID_RELU_SPLIT whose residual is the bilinear upsample of the coarse map,
                                 // evaluated on the fly: resid = Y f32 [n_win * up_hp * up_wp, ldr] (ln_post rows), the row's
                                 // cell comes from the shared-border grid (mask_hp x mask_wp rows per window); border rows add 0.
                                 // The BasicBlock skip of the decoder without materialising the fine-grid map (CTA-pair kernel)
 };
-
-constexpr int kLnStatSlots = 8;   // float2 slots per row of a LayerNorm statistics buffer
-constexpr int kLnPartCols = 96;   // columns per partial written by EPI_BIAS_RESID_STATS (half of a 192-wide tile)
 
 constexpr int kMaxGemmSegs = 9;
 
@@ -59,31 +47,39 @@ struct GemmParams {
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
   const float* head_tmat;             // EPI_BIAS_HEAD_PARTIAL: f32 [head_bins, N] (logit_scale * normalised text features)
   int head_bins;                      // 1..32
-  void* x16_out;                      // EPI_BIAS_RESID_STATS: 16-bit [M, N] copy of the output rows (format out_fp16)
-  float2* stats_out;                  // EPI_BIAS_RESID_STATS: [M, kLnStatSlots] (mean, M2) per 96-column half tile
-  const float2* ln_stats;             // EPI_LN_*: [M, kLnStatSlots]; ln_parts = 8: eight partials of 96 columns,
-  int ln_parts;                       //           ln_parts = 1: slot 0 holds (mean, M2) of the whole row
-  const float* ln_colsum;             // EPI_LN_*: [N]
-  int tma_out;                        // set by the launcher: 16-bit outputs leave through bulk tensor stores (gemm2)
-  int dbg;                            // experiment knob (profiles/): 0 in production
-  long long* trace;                   // experiment: clock64 time line of CTA 0 (profiles/gemm_trace.py), nullptr in production
+  int w_prefetch;                     // 1 (gemm_params_plain default): W does not depend on the previous kernel of the
+                                      // stream, so its first tiles are requested BEFORE the programmatic-dependency wait.
+                                      // Must be 0 when the launch just before this one wrote W (weight packing).
+  int tma_out;                        // set by the launcher: outputs leave through bulk tensor stores / reductions
 };
 
 inline GemmParams gemm_params_plain(int M, int N, int K) {
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.n_seg = 1; p.seg_kblocks = K / 64;
+  p.w_prefetch = 1;
   return p;
 }
 
-// D[M,N] = A[M,K] * W[N,K]^T. A: bf16 [a_rows, a_cols] pitch lda; W: bf16 [N, K] pitch ldw. block_n: 0 = auto.
-const char* gemm_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
-                         int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
-// CTA-pair (cta_group::2) implementation of the same contract (gemm2_tcgen05.cu).
+// D[M,N] = A[M,K] * W[N,K]^T. A: 16-bit [a_rows, a_cols] pitch lda; W: 16-bit [N, K] pitch ldw. block_n: 0 = auto, else
+// 128 / 192 / 256. CTA-pair (cta_group::2) tcgen05 kernel, gemm2_tcgen05.cu.
 const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, int64_t a_rows, int64_t a_cols,
                           int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, int block_n);
 int gemm2_pick_block_n(int M, int N);  // the tile width gemm2_bf16_tn chooses for block_n = 0
-int device_num_sms();
+int device_num_sms();  // of the current device (cached per device)
+// Per-device, once: cudaFuncSetAttribute(MaxDynamicSharedMemorySize). The attribute is per device, so a process that
+// uses several GPUs must set it on each of them; `done_mask` is the caller's static bit mask of devices already served.
+template <class Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) *done_mask |= bit;
+  return e;
+}
 // Every kernel launch of this library goes through a LaunchScope: it counts the launch (clipebc_launch_count) and, when
 // profiling is enabled (clipebc_profile_enable), brackets it with CUDA events on the launching stream and books the
 // duration, algorithmic FLOPs and bytes under `tag` (the current tag set by api.cu, else `kind`).
@@ -129,91 +125,71 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 // ------------------------------------------------------------------ LayerNorm ----------------------------------
-// out[r] = LN(in[map(r)]) * gamma + beta, eps 1e-5, fp32 statistics (two-pass, in registers). D = 768 only.
-// out_kind: 0 = f32, 1 = bf16, 2 = fp16.
+// out[r] = LN(in[map(r)]) * gamma + beta over D = `width` channels (768: ViT-B, 1024: ViT-L/14), eps 1e-5, fp32 statistics
+// (two-pass, in registers). out_kind: 0 = f32, 1 = bf16, 2 = fp16.
 // Row map: in_row = (r / rows_out_per_group) * rows_in_per_group + in_row_offset + r % rows_out_per_group.
 // out16_extra (f32 output only, nullable): also the 16-bit rounding of the rows, in the format fp16_extra selects.
-const char* layernorm768(cudaStream_t stream, const float* in, const float* gamma, const float* beta, void* out,
-                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
-                         int in_row_offset, void* out16_extra = nullptr, int fp16_extra = 0);
+const char* layernorm_rows(cudaStream_t stream, int width, const float* in, const float* gamma, const float* beta, void* out,
+                           int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                           int in_row_offset, void* out16_extra = nullptr, int fp16_extra = 0);
 
 // ------------------------------------------------------------------ stem ---------------------------------------
 // image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * KP] = [hi | lo] split of the
-// pixels, KP = 3 * patch^2, k = c * patch^2 + py * patch + px (= conv1.weight.view(768, KP)), on the grid whose (0,0)
-// patch starts at pixel (y0, x0) of each image (gh, gw patches). patch = 16 (ViT-B/16) or 32 (ViT-B/32).
+// pixels, KP = kp_pad >= 3 * patch^2 (columns beyond 3 * patch^2 are zero: the GEMM needs K % 64 == 0, ViT-L/14 has
+// 3 * 14^2 = 588 -> 640), k = c * patch^2 + py * patch + px (= conv1.weight.view(width, 3 * patch^2)), on the grid whose
+// (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches). patch = 16 / 32 (ViT-B) or 14 (ViT-L/14).
 const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                     int patch, void* out, int fp16);
+                     int patch, int kp_pad, void* out, int fp16);
 // per-window patchify when window origins are not on the patch grid: out rows [n_win * hp * wp, 2 * KP]
 const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                             int n_win, int hp, int wp, int patch, void* out, int fp16);
+                             int n_win, int hp, int wp, int patch, int kp_pad, void* out, int fp16);
 
-// Assemble the residual stream X f32 [n_win * t_live, 768]:
+// Assemble the residual stream X f32 [n_win * t_live, width]:
 //   row 0            : LN_pre(class_emb + pos[0])
 //   rows 1..n_prompt : vpt0 rows (shallow VPT only; n_prompt = 0 for deep)            (model.py:161-168)
 //   remaining rows   : LN_pre(patch_embed[src_row(win, p)] + pos[1 + p])              (model.py:147-157)
 // src_row = win_base[win] + (p / wp) * pitch + p % wp  (gather from a shared per-image patch grid or per-window rows);
 // pitch = win_pitch_dev[win] when given (windows of several images in one pass), else src_pitch
-// X16 / stats (nullable together): 16-bit copy of the rows and their (mean, M2) in slot 0 of the statistics row -- what
-// the first LN-folded GEMM (EPI_LN_*, ln_parts = 1) consumes.
-const char* assemble_tokens(cudaStream_t stream, const float* patch_embed, const int* win_base_dev, int src_pitch,
+const char* assemble_tokens(cudaStream_t stream, int width, const float* patch_embed, const int* win_base_dev, int src_pitch,
                             const int* win_pitch_dev, const float* class_emb, const float* pos, const float* ln_g, const float* ln_b,
-                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X, void* X16 = nullptr,
-                            float2* stats = nullptr, int fp16 = 0);
-// rows f32 [n, 768] -> 16-bit copy + (mean, M2) in slot 0 (the same outputs for arbitrary rows)
-const char* rowstats768(cudaStream_t stream, const float* in, int64_t n_rows, void* X16, float2* stats, int fp16);
+                            const float* vpt0, int n_prompt, int n_win, int hp, int wp, float* X);
 
 // ------------------------------------------------------------------ attention ----------------------------------
-// qkv bf16 [n_win * t_live, 3*768] (q | k | v, head h at columns 64h..64h+63 of each third); const_kv bf16
-// [n_const, 3*768] rows appended as extra keys/values for every window (deep-VPT prompt tokens); out bf16
-// [n_win * t_live, 768] (bf16, or fp16 when out_fp16). softmax(q k^T / 8) v per (window, head), no mask.
-// t_live + n_const <= 256.
-const char* attention_h64(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                          int n_win, int t_live, void* out, int out_fp16);
-
-// Same contract without the 256-key limit (attention.cu): 64-query chunks, K / V streamed in 64-key blocks, online softmax.
-// Used for windows with more than 256 tokens.
-const char* attention_h64_long(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                               int n_win, int t_live, void* out, int out_fp16);
-
-// tcgen05 / TMEM implementation of the same contract (attention_tc.cu); needs n_const % 8 == 0.
-const char* attention_h64_tc(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                             int n_win, int t_live, void* out, int out_fp16);
-
-// persistent warp-specialised tcgen05 implementation (attention_fa.cu): P stays in TMEM, loads of the next item overlap
-const char* attention_h64_fa(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                             int n_win, int t_live, void* out, int out_fp16);
-
-// two independent chains per CTA, one per TMEM buffer (attention_pp.cu): a thread owns a whole query row, the softmax of
-// one chain overlaps the tensor work of the other
+// qkv bf16 [n_win * t_live, 3 * width] (q | k | v, head h at columns 64h..64h+63 of each third, width = 64 * heads);
+// const_kv bf16 [n_const, 3 * width] rows appended as extra keys/values for every window (deep-VPT prompt tokens); out
+// [n_win * t_live, width] (bf16, or fp16 when out_fp16). softmax(q k^T / 8) v per (window, head), no mask.
+//
+// attention_h64_pp (attention_pp.cu): tcgen05 / TMEM, persistent, two independent chains per CTA, one per TMEM buffer: a
+// thread owns a whole query row, the softmax of one chain overlaps the tensor work of the other. Needs
+// t_live + n_const <= 256 and n_const % 8 == 0.
 const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
-                             int n_win, int t_live, void* out, int out_fp16);
+                             int n_win, int t_live, int heads, void* out, int out_fp16);
+// attention_h64_long (attention.cu): any sequence length and any n_const -- 64-query chunks, K / V streamed in 64-key
+// blocks, online softmax, mma.sync. Windows with more than 256 tokens (ViT-L/14 224-windows: 289; 448 x 448 windows).
+const char* attention_h64_long(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                               int n_win, int t_live, int heads, void* out, int out_fp16);
 
 // ------------------------------------------------------------------ decoder / head -----------------------------
-// Y f32 [n_win * hp * wp, 768] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
-// shared-border NHWC grids U_16 / U_f32 [n_win, gh + 1, gw + 1, 768]: cell (y, x) of a window at row y * (gw + 1) + x,
+// Y f32 [n_win * hp * wp, width] (ln_post rows) -> bilinear resample (align_corners = False, scale = gh/hp) into the
+// shared-border NHWC grids U_16 / U_f32 [n_win, gh + 1, gw + 1, width]: cell (y, x) of a window at row y * (gw + 1) + x,
 // column gw and row gh are zero. The zero column that ends one line is the left border of the next line, the zero row
 // that ends one window is the top border of the next (rows before the buffer are zero-filled by TMA): every 3x3 tap
 // r + dy * (gw + 1) + dx of an interior cell lands on the right neighbour or on a zero  (model.py:195-196).
-const char* resample_to_padded(cudaStream_t stream, const float* Y, int n_win, int hp, int wp, int gh, int gw,
-                               void* U_16, float* U_f32, int fp16);  // U_16 may be null (coarse-grid conv1)
+const char* resample_to_padded(cudaStream_t stream, int width, const float* Y, int n_win, int hp, int wp, int gh, int gw,
+                               void* U_16, float* U_f32, int fp16);
 
 // conv1 of the decoder from the coarse patch grid (elementwise.cu: conv1_from_coarse_kernel): Z 16-bit
-// [n_win * hp * wp, 9 * 768] = Y_16 x Wz^T (Wz from fold_conv3x3_bn_tapout, column = tap * 768 + o) ->
-// D1 16-bit [n_win * (gh+1) * (gw+1), 768] = relu(conv3x3(bilinear_up(Y)) + bias) on the shared-border grid (border rows 0)
-const char* conv1_from_coarse(cudaStream_t stream, const void* Z, const float* bias, int n_win, int hp, int wp, int gh, int gw,
-                              void* D1, int fp16);
+// [n_win * hp * wp, 9 * width] = Y_16 x Wz^T (Wz from fold_conv3x3_bn_tapout, column = tap * width + o) ->
+// D1 16-bit [n_win * (gh+1) * (gw+1), width] = relu(conv3x3(bilinear_up(Y)) + bias) on the shared-border grid (border rows 0)
+const char* conv1_from_coarse(cudaStream_t stream, int width, const void* Z, const float* bias, int n_win, int hp, int wp,
+                              int gh, int gw, void* D1, int fp16);
 const char* fold_conv3x3_bn_tapout(cudaStream_t stream, const float* W, const float* gamma, const float* var, float eps, int O,
                                    int I, void* Wz, int fp16);
 
-// F f32 [n_win * (gh+1) * (gw+1), 512] projected features on the shared-border grid -> EBC head on interior cells:
-// normalise, logits against tmat f32 [n_bins, 512] (= logit_scale * normalised text features), softmax, expectation
-// over anchors. exp_out f32 [n_win, 1, gh, gw]; logits_out (nullable) f32 [n_win, n_bins, gh, gw]. (model.py:200-212)
-const char* ebc_head(cudaStream_t stream, const float* F, const float* tmat, const float* anchors, int n_bins,
-                     int n_win, int gh, int gw, float* exp_out, float* logits_out);
-
 // Second half of the fused head: partial f32 [n_win * (gh+1) * (gw+1), n_part, 1 + n_bins] written by the projection GEMM
 // with EPI_BIAS_HEAD_PARTIAL -> sums over the n_part partials in a fixed order, 1 / max(||f||, 1e-12), softmax over the
-// bins, anchor expectation on the interior cells. Same outputs as ebc_head.
+// bins, anchor expectation on the interior cells: exp_out f32 [n_win, 1, gh, gw]; logits_out (nullable) f32
+// [n_win, n_bins, gh, gw]  (model.py:200-212).
 const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,
                             int gh, int gw, float* exp_out, float* logits_out);
 
@@ -243,13 +219,8 @@ const char* f32_to_16(cudaStream_t stream, const float* in, void* out, int64_t n
 // W f32 [O, I, 3, 3] + BN(gamma, beta, mean, var, eps) -> Wp bf16 [O, 9*I] (tap-major K: k = (ky*3+kx)*I + i), bias f32 [O]
 const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
                             const float* var, float eps, int O, int I, void* Wp, float* bias, int fp16);
-// W f32 [O, I] -> bf16 [O, 3*I] = [hi | hi | lo]
-const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, void* out, int fp16);
-// LayerNorm folded into the Linear that follows it: W f32 [O, 768], b f32 [O], gamma / beta f32 [768] ->
-// Wf 16-bit [O, 768] = W * diag(gamma); colsum f32 [O] = sum_k Wf[o, k] (of the ROUNDED weights, what the MMA sees);
-// bias_f f32 [O] = b + W beta
-const char* fold_ln_linear(cudaStream_t stream, const float* W, const float* b, const float* gamma, const float* beta, int O,
-                           void* Wf, float* colsum, float* bias_f, int fp16);
+// W f32 [O, I] -> 16-bit [O, 3 * Ip] = [hi | hi | lo], every third zero-padded from I to Ip >= I columns
+const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, int Ip, void* out, int fp16);
 // text f32 [n, d] -> tmat = exp(logit_scale) * text / max(||text||, 1e-12)
 const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat);
 

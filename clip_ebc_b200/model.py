@@ -10,15 +10,20 @@ The module is a *parameter container* with the reference's ``state_dict`` keys (
 in PyTorch and there is no fallback: a CPU tensor or a missing ``libclipebc_b200.so`` raises.
 
 Out of scope here: the CLIP text tower and tokenizer. They run once at construction in the
-reference and produce the constant ``text_features`` [N, 512]; this module takes that matrix directly (``text_features=``
-kwarg, ``set_text_features()``, or the ``text_features`` attribute exactly as in the reference object), and keeps any
-``text_encoder.*`` checkpoint entries verbatim so a ``state_dict`` round-trips.
+reference (models/clip/model.py:97-129) and produce the constant ``text_features`` [N, embed_dim]; this module takes that
+matrix as a constructor argument (``text_features=``; construction FAILS without it, as the reference's would without its
+text tower) and keeps any ``text_encoder.*`` checkpoint entries verbatim so a ``state_dict`` round-trips.
+
+Train mode (``model.train()`` / ``model.training = True``) only switches the output signature to the reference's
+``(logits, exp)`` (models/clip/model.py:214-217): this is an inference build -- BatchNorm uses its running statistics,
+VPT dropout is not applied and no autograd graph is recorded (a warning says so once when gradients are enabled).
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
 import os
+import warnings
 from collections import OrderedDict
 from typing import Any, Dict, List, Optional, Tuple, Union
 
@@ -32,10 +37,9 @@ clip_names = ["resnet50", "resnet50x4", "resnet50x16", "resnet50x64", "resnet101
 resnet_backbones = ["resnet50", "resnet101", "resnet50x4", "resnet50x16", "resnet50x64"]
 vit_backbones = ["vit_b_16", "vit_b_32", "vit_l_14", "vit_l_14_336px"]
 
-_WIDTH, _LAYERS, _HEADS, _EMBED = 768, 12, 12, 512
-# the ViT-B backbones of the reference that share width 768 / 12 layers / 12 heads / embed 512 (models/clip/model.py:20-21):
-# backbone -> patch size (= encoder reduction)
-_VIT_B_PATCH = {"vit_b_16": 16, "vit_b_32": 32}
+# backbone -> (patch size = encoder reduction, width, layers, embed_dim); heads = width // 64 (_clip/model.py:50),
+# models/clip/model.py:16-24. The CLIP-ResNet backbones are not implemented.
+_VIT_DIMS = {"vit_b_16": (16, 768, 12, 512), "vit_b_32": (32, 768, 12, 512), "vit_l_14": (14, 1024, 24, 768)}
 
 
 class _Block(nn.Module):
@@ -59,21 +63,20 @@ class _Transformer(nn.Module):
 class _ImageEncoder(nn.Module):
     """Parameter names of VisionTransformer(features_only=True) (_clip/image_encoder.py:118-160)."""
 
-    def __init__(self, input_size: int, patch: int) -> None:
+    def __init__(self, input_size: int, patch: int, width: int, layers: int, embed: int) -> None:
         super().__init__()
-        scale = _WIDTH ** -0.5
+        scale = width ** -0.5
         g = input_size // patch
-        _PATCH = patch
-        self.conv1 = nn.Conv2d(3, _WIDTH, kernel_size=_PATCH, stride=_PATCH, bias=False)
-        self.class_embedding = nn.Parameter(scale * torch.randn(_WIDTH))
-        self.positional_embedding = nn.Parameter(scale * torch.randn(g * g + 1, _WIDTH))
-        self.ln_pre = nn.LayerNorm(_WIDTH)
-        self.transformer = _Transformer(_WIDTH, _LAYERS, _HEADS)
-        self.ln_post = nn.LayerNorm(_WIDTH)
-        self.patch_size = (_PATCH, _PATCH)
-        self.channels = _WIDTH
-        self.reduction = _PATCH
-        self.clip_embed_dim = _EMBED
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch, stride=patch, bias=False)
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(g * g + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = _Transformer(width, layers, width // 64)
+        self.ln_post = nn.LayerNorm(width)
+        self.patch_size = (patch, patch)
+        self.channels = width
+        self.reduction = patch
+        self.clip_embed_dim = embed
 
 
 class _BasicBlock(nn.Module):
@@ -100,7 +103,10 @@ def _init_decoder(m: nn.Module) -> None:
 
 
 class CLIP_EBC(nn.Module):
-    """B200-native CLIP-EBC (ViT-B/16 or ViT-B/32 + VPT). Constructor arguments as in models/clip/model.py:31-45."""
+    """B200-native CLIP-EBC (ViT-B/16, ViT-B/32 or ViT-L/14 + VPT). Constructor arguments as in models/clip/model.py:31-45,
+    plus: text_features (required, see the module docstring), window_chunk (windows per internal pass, 0 = default),
+    operand_dtype ("fp16" | "bf16": the 16-bit tensor-core operand format) and decoder_conv1_fine (A/B switch of the
+    decoder's conv1 form, see include/clipebc_b200.h)."""
 
     def __init__(
         self,
@@ -119,17 +125,17 @@ class CLIP_EBC(nn.Module):
         text_features: Optional[Tensor] = None,
         window_chunk: int = 0,
         operand_dtype: str = "fp16",
+        decoder_conv1_fine: bool = False,
     ) -> None:
         super().__init__()
         assert backbone in resnet_backbones + vit_backbones, \
             f"Backbone should be in {resnet_backbones + vit_backbones}, got {backbone}"
-        if backbone not in _VIT_B_PATCH:
+        if backbone not in _VIT_DIMS:
             raise NotImplementedError(
-                f"clip_ebc_b200 implements the hot path for the ViT-B backbones {sorted(_VIT_B_PATCH)} only (got "
-                f"'{backbone}'); the CLIP-ResNet and ViT-L/14 backbones of the reference are outside the scope of this "
-                "build (SURVEY.md section 8f).")
-        _PATCH = _VIT_B_PATCH[backbone]
-        self.patch = _PATCH
+                f"clip_ebc_b200 implements the hot path for the ViT backbones {sorted(_VIT_DIMS)} only (got '{backbone}'); the "
+                "CLIP-ResNet backbones of the reference are outside the scope of this build (SURVEY.md section 8f).")
+        patch, width, layers, embed = _VIT_DIMS[backbone]
+        self.patch, self.width, self.layers, self.embed_dim = patch, width, layers, embed
         assert input_size is not None, "Expected input_size to be an integer, got None."
         assert num_vpt is not None, "Expected num_vpt to be an integer, got None."
         assert deep_vpt is not None, "Expected deep_vpt to be a boolean, got None."
@@ -137,32 +143,40 @@ class CLIP_EBC(nn.Module):
         assert prompt_type in ["number", "word"], f"Expected prompt_type to be 'number' or 'word', got {prompt_type}"
         if not freeze_text_encoder:
             raise NotImplementedError("freeze_text_encoder=False (training the text tower) is outside the inference hot path")
-        if decoder_cfg is not None and list(decoder_cfg) != [768]:
-            raise NotImplementedError("only the reference default decoder_cfg=[768] (one BasicBlock) is implemented")
+        if decoder_cfg is not None and list(decoder_cfg) != [width]:
+            raise NotImplementedError(f"only the reference default decoder_cfg=[{width}] (one BasicBlock) is implemented")
         assert bins is not None and anchor_points is not None and len(bins) == len(anchor_points)
+        if text_features is None:
+            # the reference computes this matrix here, in __init__, with its CLIP text tower (models/clip/model.py:97-129);
+            # that tower is outside this build, so the matrix is an input -- and its absence is a construction error, not
+            # something to discover at the first forward
+            raise ValueError(
+                f"text_features is required: pass text_features=[{len(bins)}, {embed}] (the CLIP text-tower output for the "
+                "bin prompts; with the reference installed: reference_model.text_features). The text tower and tokenizer "
+                "are outside the scope of clip_ebc_b200.")
 
         self.backbone = backbone
-        self.image_encoder = _ImageEncoder(int(input_size), _PATCH)
-        self.image_encoder_depth = _LAYERS
+        self.image_encoder = _ImageEncoder(int(input_size), patch, width, layers, embed)
+        self.image_encoder_depth = layers
         for p in self.image_encoder.parameters():
             p.requires_grad = False
         self.num_vpt = int(num_vpt)
         self.deep_vpt = bool(deep_vpt)
         self.input_size = int(input_size)
-        val = math.sqrt(6.0 / float(3 * _PATCH + _WIDTH))  # model.py:70-75
-        for idx in range(_LAYERS if self.deep_vpt else 1):
-            p = nn.Parameter(torch.empty(self.num_vpt, _WIDTH))
+        val = math.sqrt(6.0 / float(3 * patch + width))  # model.py:70-75
+        for idx in range(layers if self.deep_vpt else 1):
+            p = nn.Parameter(torch.empty(self.num_vpt, width))
             nn.init.uniform_(p, -val, val)
             setattr(self, f"vpt_{idx}", p)
         self.vpt_drop = float(vpt_drop)  # identity in eval mode; the inference path has no dropout
 
-        self.encoder_reduction = _PATCH
+        self.encoder_reduction = patch
         self.reduction = self.encoder_reduction if reduction is None else int(reduction)
-        self.channels = _WIDTH
-        self.clip_embed_dim = _EMBED
-        self.image_decoder = nn.Sequential(_BasicBlock(_WIDTH))
+        self.channels = width
+        self.clip_embed_dim = embed
+        self.image_decoder = nn.Sequential(_BasicBlock(width))
         _init_decoder(self.image_decoder)
-        self.projection = nn.Conv2d(_WIDTH, _EMBED, kernel_size=1)
+        self.projection = nn.Conv2d(width, embed, kernel_size=1)
         _init_decoder(self.projection)
 
         self.prompt_type = prompt_type
@@ -170,25 +184,27 @@ class CLIP_EBC(nn.Module):
         self.bins = bins
         self.anchor_points = torch.tensor(anchor_points, dtype=torch.float32, requires_grad=False).view(1, -1, 1, 1)
         self.text_features: Optional[Tensor] = None
-        if text_features is not None:
-            self.set_text_features(text_features)
+        self.set_text_features(text_features)
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07), requires_grad=True)
 
         assert operand_dtype in ("fp16", "bf16"), f"operand_dtype must be 'fp16' or 'bf16', got {operand_dtype}"
         self.operand_dtype = operand_dtype  # 16-bit tensor-core operand format (accumulation / residual stay fp32)
+        self.decoder_conv1_fine = bool(decoder_conv1_fine)
         self._text_encoder_state: "OrderedDict[str, Tensor]" = OrderedDict()
         self._window_chunk = int(window_chunk)
         self._handle: Optional[C.c_void_p] = None
+        self._handle_device: Optional[int] = None
         self._packed_key = None
         self.use_cuda_graphs = True   # forward(): replay a captured CUDA graph per input shape (see _forward_graphed)
         self._graph_cache: dict = {}
+        self._warned_train = False
 
     # ------------------------------------------------------------------ text features (constant input of the head)
     def set_text_features(self, text_features: Tensor) -> None:
-        """[N, 512] output of the (out-of-scope) CLIP text tower for the bin prompts (model.py:127-129)."""
+        """[N, embed_dim] output of the (out-of-scope) CLIP text tower for the bin prompts (model.py:127-129)."""
         tf = torch.as_tensor(text_features, dtype=torch.float32).detach()
-        assert tf.dim() == 2 and tf.shape[0] == len(self.bins) and tf.shape[1] == _EMBED, \
-            f"Expected text_features of shape ({len(self.bins)}, {_EMBED}), got {tuple(tf.shape)}"
+        assert tf.dim() == 2 and tf.shape[0] == len(self.bins) and tf.shape[1] == self.embed_dim, \
+            f"Expected text_features of shape ({len(self.bins)}, {self.embed_dim}), got {tuple(tf.shape)}"
         self.text_features = tf
         self._packed_key = None
 
@@ -226,17 +242,22 @@ class CLIP_EBC(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("clip_ebc_b200.CLIP_EBC runs on a CUDA device only (no CPU fallback): call .to('cuda')")
         tensors = self._hot_path_tensors()
-        key = (dev.index, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()))
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        key = (dev_index, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()))
         if self._handle is not None and key == self._packed_key:
             return
         lib = _lib.load()
         with torch.cuda.device(dev):
+            if self._handle is not None and self._handle_device != dev_index:
+                # .to(another GPU): a native handle owns buffers on the device it was created on -- start over there
+                self._release_handle()
             if self._handle is None:
-                cfg = _lib.ClipEbcConfig(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt),
-                                         len(self.bins), self._window_chunk, int(self.operand_dtype == "fp16"), self.patch)
+                cfg = _lib.make_config(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt), len(self.bins),
+                                       self._window_chunk, int(self.operand_dtype == "fp16"), self.patch, self.width,
+                                       self.layers, self.embed_dim, int(self.decoder_conv1_fine))
                 h = C.c_void_p()
                 _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
-                self._handle = h
+                self._handle, self._handle_device = h, dev_index
             for name, t in tensors.items():
                 t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
                 shape = (C.c_int64 * t.dim())(*t.shape)
@@ -247,24 +268,24 @@ class CLIP_EBC(nn.Module):
         self._graph_cache.clear()  # captured graphs read the packed weights of the previous state
 
     def _hot_path_tensors(self) -> "OrderedDict[str, Tensor]":
-        if self.text_features is None:
-            raise RuntimeError(
-                "text_features is not set: pass text_features=[N,512] to get_model()/CLIP_EBC or call "
-                "set_text_features(); the CLIP text tower is outside this build's scope (see module docstring)")
         out = OrderedDict()
         for k, v in super().state_dict().items():
-            if k.endswith("num_batches_tracked"):
+            if k.endswith("num_batches_tracked") or v.numel() == 0:  # num_vpt == 0: the (0, width) prompts carry nothing
                 continue
             out[k] = v
         out["text_features"] = self.text_features
         out["anchor_points"] = self.anchor_points.reshape(-1)
         return out
 
+    def _release_handle(self) -> None:
+        if self._handle is not None:
+            self._graph_cache.clear()
+            _lib.load().clipebc_model_destroy(self._handle)
+            self._handle, self._handle_device, self._packed_key = None, None, None
+
     def __del__(self):
         try:
-            if self._handle is not None:
-                _lib.load().clipebc_model_destroy(self._handle)
-                self._handle = None
+            self._release_handle()
         except Exception:
             pass
 
@@ -276,6 +297,11 @@ class CLIP_EBC(nn.Module):
         dev = self._device()
         if x.device != dev:
             raise RuntimeError(f"input is on {x.device} but the model is on {dev}")
+        if self.training and torch.is_grad_enabled() and not self._warned_train:
+            self._warned_train = True
+            warnings.warn("clip_ebc_b200.CLIP_EBC is an inference build: in train mode forward() returns the reference's "
+                          "(logits, exp) pair, but with eval semantics (BatchNorm running statistics, no VPT dropout) and "
+                          "without an autograd graph -- the outputs carry no gradients.", stacklevel=2)
         x = x.detach()
         with torch.cuda.device(dev):
             if self._graphs_usable():
@@ -329,7 +355,10 @@ class CLIP_EBC(nn.Module):
             graph = torch.cuda.CUDAGraph()
             l0 = lib.clipebc_launch_count()
             try:
-                with torch.cuda.graph(graph):
+                # thread_local: only THIS thread's CUDA calls are checked during the capture. The default ("global") makes
+                # an unrelated cudaMalloc / event query of any other thread -- a DataLoader's pin-memory thread, another
+                # model -- fail with "operation not permitted when stream is capturing" while we capture.
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     outs = self._forward_eager(static_x)
             except Exception:
                 # a capture that cannot be completed (e.g. an allocation inside the library for a shape the eager call

@@ -15,26 +15,6 @@ EPI_F32, EPI_BIAS_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EP
     EPI_BIAS_RESID_RELU_SPLIT = range(7)
 
 
-def set_gemm_impl(impl: int) -> None:
-    """1 = single-CTA tcgen05 GEMM, 2 = CTA-pair (cta_group::2) GEMM (default)."""
-    _lib.check(_lib.load().clipebc_set_gemm_impl(int(impl)), "set_gemm_impl")
-
-
-def set_ln_fold(on: bool) -> None:
-    """LayerNorm folded into the GEMMs either side of it (default off; see clipebc_set_ln_fold)."""
-    _lib.check(_lib.load().clipebc_set_ln_fold(int(bool(on))), "set_ln_fold")
-
-
-def set_conv1_coarse(on: bool) -> None:
-    """Decoder conv1 from the coarse patch grid (default on; see clipebc_set_conv1_coarse)."""
-    _lib.check(_lib.load().clipebc_set_conv1_coarse(int(bool(on))), "set_conv1_coarse")
-
-
-def set_attention_impl(impl: int) -> None:
-    """1 = mma.sync attention, 2 = tcgen05 / TMEM attention (default)."""
-    _lib.check(_lib.load().clipebc_set_attention_impl(int(impl)), "set_attention_impl")
-
-
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -102,114 +82,54 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
     return out
 
 
-LN_STAT_SLOTS = 8  # float2 slots per row of a LayerNorm statistics buffer (kernels.h: kLnStatSlots)
-
-
-def rowstats(x: torch.Tensor, fp16: bool = False):
-    """rows f32 [n, 768] -> (16-bit copy, stats f32 [n, 8, 2]) with slot 0 = (mean, sum of squared deviations) of the row."""
-    assert x.dtype == torch.float32 and x.shape[-1] == 768
-    n = x.numel() // 768
-    x16 = torch.empty((n, 768), dtype=_dt16(fp16), device=x.device)
-    stats = torch.zeros((n, LN_STAT_SLOTS, 2), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().clipebc_rowstats768(_ptr(x), n, _ptr(x16), _ptr(stats), int(fp16), _stream()), "rowstats")
-    return x16, stats
-
-
-def fold_ln_linear(W: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, fp16: bool = False):
-    """LayerNorm(768) folded into the Linear behind it -> (W diag(gamma) in 16 bits, its column sums, b + W beta)."""
-    assert W.dtype == torch.float32 and W.shape[1] == 768
-    O = W.shape[0]
-    wf = torch.empty((O, 768), dtype=_dt16(fp16), device=W.device)
-    colsum = torch.empty((O,), dtype=torch.float32, device=W.device)
-    bias_f = torch.empty((O,), dtype=torch.float32, device=W.device)
-    _lib.check(_lib.load().clipebc_fold_ln_linear(_ptr(W), _ptr(b), _ptr(gamma), _ptr(beta), O, _ptr(wf), _ptr(colsum),
-                                                  _ptr(bias_f), int(fp16), _stream()), "fold_ln_linear")
-    return wf, colsum, bias_f
-
-
-def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias: torch.Tensor, block_n: int = 0,
-                     out_fp16: Optional[bool] = None):
-    """x f32 [M, 768] += a @ w^T + bias in place -> (x16, stats [M, 8, 2]): the residual GEMM of a block that also leaves
-    the 16-bit rows and the (mean, M2) partials of every 96 columns for the next LN-folded GEMM."""
-    assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16) and x.dtype == torch.float32
-    ab_fp16 = a.dtype == torch.float16
-    out_fp16 = ab_fp16 if out_fp16 is None else out_fp16
-    M, N = x.shape
-    x16 = torch.empty((M, N), dtype=_dt16(out_fp16), device=x.device)
-    stats = torch.zeros((M, LN_STAT_SLOTS, 2), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().clipebc_gemm_resid_stats(_ptr(a), a.shape[0], a.stride(0), _ptr(w), w.stride(0), M, N, w.shape[1],
-                                                    _ptr(x), _ptr(bias), _ptr(x16), _ptr(stats), block_n,
-                                                    int(ab_fp16), int(out_fp16), _stream()), "gemm_resid_stats")
-    return x16, stats
-
-
-def gemm_ln(a16: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, stats: torch.Tensor, colsum: torch.Tensor,
-            ln_parts: int, gelu: bool = False, block_n: int = 0, out_fp16: Optional[bool] = None) -> torch.Tensor:
-    """act(LayerNorm(rows) @ W^T + b) from the RAW 16-bit rows, the folded weights and the row statistics."""
-    assert a16.dtype == wf.dtype and a16.dtype in (torch.bfloat16, torch.float16)
-    ab_fp16 = a16.dtype == torch.float16
-    out_fp16 = ab_fp16 if out_fp16 is None else out_fp16
-    M, K = a16.shape
-    N = wf.shape[0]
-    out = torch.empty((M, N), dtype=_dt16(out_fp16), device=a16.device)
-    _lib.check(_lib.load().clipebc_gemm_ln(int(gelu), _ptr(a16), M, a16.stride(0), _ptr(wf), wf.stride(0), M, N, K, _ptr(out),
-                                           out.stride(0), _ptr(bias_f), _ptr(stats), int(ln_parts), _ptr(colsum), block_n,
-                                           int(ab_fp16), int(out_fp16), _stream()), "gemm_ln")
-    return out
-
-
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype = torch.bfloat16,
               n_rows_out: Optional[int] = None, rows_out_per_group: int = 1, rows_in_per_group: int = 1,
               in_row_offset: int = 0) -> torch.Tensor:
-    assert x.dtype == torch.float32 and x.shape[-1] == 768
-    n = x.numel() // 768 if n_rows_out is None else n_rows_out
+    """nn.LayerNorm over rows of 768 (ViT-B) or 1024 (ViT-L/14) channels."""
+    width = int(x.shape[-1])
+    assert x.dtype == torch.float32 and width in (768, 1024)
+    n = x.numel() // width if n_rows_out is None else n_rows_out
     kind = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out_dtype]
-    out = torch.empty((n, 768), dtype=out_dtype, device=x.device)
-    _lib.check(_lib.load().clipebc_layernorm768(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, n,
-                                                rows_out_per_group, rows_in_per_group, in_row_offset, _stream()),
+    out = torch.empty((n, width), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.load().clipebc_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), width, _ptr(out), kind, n,
+                                             rows_out_per_group, rows_in_per_group, in_row_offset, _stream()),
                "layernorm")
     return out
 
 
 def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[torch.Tensor] = None,
-              out_fp16: bool = False) -> torch.Tensor:
-    assert qkv.dtype == torch.bfloat16 and qkv.shape == (n_win * t_live, 2304)
+              out_fp16: bool = False, heads: int = 12) -> torch.Tensor:
+    width = 64 * heads
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (n_win * t_live, 3 * width)
     n_const = 0 if const_kv is None else const_kv.shape[0]
-    out = torch.empty((n_win * t_live, 768), dtype=_dt16(out_fp16), device=qkv.device)
-    _lib.check(_lib.load().clipebc_attention(_ptr(qkv), _ptr(const_kv), n_const, n_win, t_live, _ptr(out),
+    out = torch.empty((n_win * t_live, width), dtype=_dt16(out_fp16), device=qkv.device)
+    _lib.check(_lib.load().clipebc_attention(_ptr(qkv), _ptr(const_kv), n_const, n_win, t_live, heads, _ptr(out),
                                              int(out_fp16), _stream()), "attention")
     return out
 
 
 def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = None,
              gw: Optional[int] = None, fp16: bool = False, patch: int = 16) -> torch.Tensor:
-    """-> [n*gh*gw, 2*KP], KP = 3*patch^2: columns [0, KP) = hi, [KP, 2 KP) = lo of the hi/lo split of the pixels."""
+    """-> [n*gh*gw, 2*KP], KP = 3*patch^2 rounded up to 64: columns [0, KP) = hi, [KP, 2 KP) = lo of the hi/lo split of
+    the pixels (pad columns zero)."""
     n, c, H, W = image.shape
     assert c == 3 and image.dtype == torch.float32
     gh = (H - y0) // patch if gh is None else gh
     gw = (W - x0) // patch if gw is None else gw
-    out = torch.empty((n * gh * gw, 2 * 3 * patch * patch), dtype=_dt16(fp16), device=image.device)
-    _lib.check(_lib.load().clipebc_patchify(_ptr(image), n, H, W, y0, x0, gh, gw, int(patch), _ptr(out), int(fp16),
+    kp = (3 * patch * patch + 63) // 64 * 64
+    out = torch.zeros((n * gh * gw, 2 * kp), dtype=_dt16(fp16), device=image.device)
+    _lib.check(_lib.load().clipebc_patchify(_ptr(image), n, H, W, y0, x0, gh, gw, int(patch), kp, _ptr(out), int(fp16),
                                             _stream()), "patchify")
     return out
 
 
 def resample_to_padded(Y: torch.Tensor, n_win: int, hp: int, wp: int, gh: int, gw: int, fp16: bool = False):
-    ub = torch.empty((n_win * (gh + 1) * (gw + 1), 768), dtype=_dt16(fp16), device=Y.device)
-    uf = torch.empty((n_win * (gh + 1) * (gw + 1), 768), dtype=torch.float32, device=Y.device)
-    _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, _ptr(ub), _ptr(uf), int(fp16),
+    width = int(Y.shape[-1])
+    ub = torch.empty((n_win * (gh + 1) * (gw + 1), width), dtype=_dt16(fp16), device=Y.device)
+    uf = torch.empty((n_win * (gh + 1) * (gw + 1), width), dtype=torch.float32, device=Y.device)
+    _lib.check(_lib.load().clipebc_resample_to_padded(_ptr(Y), n_win, hp, wp, gh, gw, width, _ptr(ub), _ptr(uf), int(fp16),
                                                       _stream()), "resample")
     return ub, uf
-
-
-def ebc_head(F: torch.Tensor, tmat: torch.Tensor, anchors: torch.Tensor, n_win: int, gh: int, gw: int,
-             want_logits: bool = False):
-    n_bins = tmat.shape[0]
-    exp = torch.empty((n_win, 1, gh, gw), dtype=torch.float32, device=F.device)
-    logits = torch.empty((n_win, n_bins, gh, gw), dtype=torch.float32, device=F.device) if want_logits else None
-    _lib.check(_lib.load().clipebc_ebc_head(_ptr(F), _ptr(tmat), _ptr(anchors), n_bins, n_win, gh, gw, _ptr(exp),
-                                            _ptr(logits), _stream()), "ebc_head")
-    return (exp, logits) if want_logits else exp
 
 
 def fold_average(preds: torch.Tensor, row_cells: Sequence[int], col_cells: Sequence[int], Ho: int, Wo: int,

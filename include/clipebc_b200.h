@@ -30,47 +30,42 @@ extern "C" {
 #define CLIPEBC_ECUDA 2    /* CUDA runtime or driver error (message carries cudaGetErrorString) */
 #define CLIPEBC_ESTATE 3   /* call order: tensors missing, model not packed, ... */
 
-#define CLIPEBC_ABI_VERSION 8
+#define CLIPEBC_ABI_VERSION 9
 
 typedef struct clipebc_model clipebc_model;
 
-/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16" | "vit_b_32") -- models/clip/model.py:20-21,31-45, _clip_ebc :220-270.
- * Width 768 / 12 layers / 12 heads / embed 512 with patch 16 (ViT-B/16) or patch 32 (ViT-B/32) are implemented. */
+/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16" | "vit_b_32" | "vit_l_14") -- models/clip/model.py:16-24,31-45,
+ * _clip_ebc :220-270. The backbone is given by its dimensions:
+ *     vit_b_16: patch 16, width 768,  layers 12, embed_dim 512      vit_b_32: patch 32, width 768, layers 12, embed_dim 512
+ *     vit_l_14: patch 14, width 1024, layers 24, embed_dim 768      (heads = width / 64, hidden = 4 * width)
+ * `struct_size` MUST be set to sizeof(clipebc_config) by the caller: clipebc_model_create rejects any other value with
+ * CLIPEBC_EINVAL, so a binding written against an older (shorter) struct fails loudly instead of being read past its end. */
 typedef struct clipebc_config {
-  int input_size;   /* side of the square the positional embedding was built for (224)        */
-  int reduction;    /* 8, 16 or 32 (model.reduction; encoder reduction is the patch size)      */
-  int num_vpt;      /* visual prompt tokens per layer (32)                                    */
-  int deep_vpt;     /* 1: per-layer prompts vpt_0..vpt_11, 0: shallow (vpt_0 only, propagated) */
-  int num_bins;     /* N = len(bins) = len(anchor_points), 1..32                              */
-  int window_chunk; /* windows per internal pass (0 = library default)                         */
+  uint32_t struct_size; /* sizeof(clipebc_config) as the caller sees it                                              */
+  int input_size;   /* side of the square the positional embedding was built for (224)                              */
+  int reduction;    /* 8, 16 or 32 (model.reduction; encoder reduction is the patch size)                            */
+  int num_vpt;      /* visual prompt tokens per layer (32)                                                          */
+  int deep_vpt;     /* 1: per-layer prompts vpt_0..vpt_{layers-1}, 0: shallow (vpt_0 only, propagated)                */
+  int num_bins;     /* N = len(bins) = len(anchor_points), 1..32                                                    */
+  int window_chunk; /* windows per internal pass (0 = library default)                                               */
   int operand_fp16; /* 16-bit tensor-core operand format: 1 = fp16 (11-bit mantissa; CLIP's released weights are fp16,
                        all operands are range-bounded and saturated), 0 = bf16. Accumulation, residual stream,
-                       LayerNorm statistics, softmax and the head are fp32 either way.         */
-  int patch;        /* ViT patch size = encoder reduction: 16 (vit_b_16; also when 0) or 32 (vit_b_32)
-                       -- _clip/image_encoder.py:141, models/clip/model.py:78                  */
+                       LayerNorm statistics, softmax and the head are fp32 either way.                               */
+  int patch;        /* ViT patch size = encoder reduction: 16 (also when 0), 32 or 14
+                       -- _clip/image_encoder.py:141, models/clip/model.py:78                                        */
+  int width;        /* transformer width = decoder channels: 768 (also when 0) or 1024                               */
+  int layers;       /* transformer blocks: 12 (also when 0) or 24                                                    */
+  int embed_dim;    /* CLIP embedding = projection outputs = text feature length: 512 (also when 0) or 768             */
+  int decoder_conv1_fine; /* 0 (default): conv1 of the decoder is computed from the coarse patch grid whenever the decoder
+                       grid is at least twice as fine (conv3x3(bilinear_up(Y)) = 9 per-tap channel contractions on the patch
+                       grid + a bilinear gather; DESIGN.md section 2 rewrite 8); 1: always the implicit GEMM on the fine
+                       grid. Same result to a few 16-bit roundings; per model, for A/B measurements.                  */
 } clipebc_config;
 
 const char* clipebc_last_error(void);
 int clipebc_abi_version(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 int64_t clipebc_launch_count(void);
-
-/* Selects the tcgen05 GEMM kernel used by the hot path and by clipebc_gemm_bf16: 1 = one CTA per 128-row tile,
- * 2 = CTA pair (cta_group::2, 256-row tiles; default). Both implement the same contract; tests run both. */
-int clipebc_set_gemm_impl(int impl);
-/* Selects the attention kernel for windows of at most 256 tokens: 1 = mma.sync (legacy tensor path), 2 = tcgen05 / TMEM,
- * one CTA per 128-query tile, 3 = tcgen05 persistent warp-specialised with P kept in TMEM, 4 = tcgen05 persistent with two
- * independent chains per CTA (default). 2-4 fall back to 1 when the constant-key count is not a multiple of 8. Windows
- * with more than 256 tokens always take the streamed-K/V kernel (any sequence length). */
-int clipebc_set_attention_impl(int impl);
-/* 1: run the ViT blocks with LayerNorm folded into the GEMMs either side of it (clipebc_gemm_resid_stats / clipebc_gemm_ln
- * below) instead of separate LayerNorm launches; 0 (default): separate launches. Same results to a few 16-bit roundings
- * (both are checked against the oracle); measured speed on B200 is the same within 1 %. CTA-pair GEMM only. */
-int clipebc_set_ln_fold(int on);
-/* 1 (default): conv1 of the decoder is computed from the coarse patch grid whenever the decoder grid is finer
- * (conv3x3(bilinear_up(Y)) = the 9 per-tap channel contractions on the patch grid, then a bilinear gather; DESIGN.md
- * section 2 rewrite 8); 0: implicit GEMM on the fine grid. Same result to a few 16-bit roundings. */
-int clipebc_set_conv1_coarse(int on);
 
 /* Optional per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
  * clipebc_profile_dump synchronises the device and writes a JSON object {"<kernel>[:<use>]": {"ms", "launches",
@@ -79,20 +74,22 @@ int clipebc_profile_enable(int on);
 int clipebc_profile_dump(char* buf, int cap);
 int clipebc_profile_enabled(void);
 /* For host layers that replay captured CUDA graphs of this library's launches (clip_ebc_b200/model.py): the epoch
- * changes whenever a clipebc_set_* switch is called or a device buffer of the library is (re)allocated or released (a
- * captured graph holds the kernels chosen and the workspace addresses used at capture time), and a replay reports the
- * launches it contains so that clipebc_launch_count stays the number of kernels actually run. */
+ * changes whenever a device buffer of the library is (re)allocated or released (a captured graph holds the workspace
+ * addresses used at capture time), and a replay reports the launches it contains so that clipebc_launch_count stays the
+ * number of kernels actually run. */
 int64_t clipebc_config_epoch(void);
 void clipebc_note_replayed_launches(int64_t n);
 
 /* ---- model lifetime: mirrors get_model() + load_state_dict() + .eval() ---------------------------------------- */
+/* A handle belongs to the CUDA device that is current when it is created: its weights and workspaces live there, and every
+ * later call on it must be made with that device current (CLIPEBC_ESTATE otherwise). One handle per device. */
 int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out);
 void clipebc_model_destroy(clipebc_model* m);
 /* Upload one fp32 tensor under its reference state_dict key (models/clip/model.py state_dict):
- *   vpt_{l}, logit_scale, image_encoder.{class_embedding,positional_embedding,conv1.weight,ln_pre.*,ln_post.*,
+ *   vpt_{l} (only when num_vpt > 0), logit_scale, image_encoder.{class_embedding,positional_embedding,conv1.weight,ln_pre.*,ln_post.*,
  *   transformer.resblocks.{l}.{attn.in_proj_weight,attn.in_proj_bias,attn.out_proj.*,ln_1.*,ln_2.*,mlp.c_fc.*,
  *   mlp.c_proj.*}}, image_decoder.0.{conv1.weight,bn1.*,conv2.weight,bn2.*}, projection.{weight,bias}
- * plus the two plain attributes of the reference module: text_features [N,512] and anchor_points [N].
+ * plus the two plain attributes of the reference module: text_features [N, embed_dim] and anchor_points [N].
  * `data` may be a host or a device pointer (copied, caller keeps ownership). Invalidates a previous pack. */
 int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim);
 /* Build the device-resident packed form: bf16 GEMM layouts, BatchNorm folded into the decoder convs, hi/lo split of
@@ -128,55 +125,37 @@ int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_
 /* ---- single kernels (unit/parity tests and profiling; all pointers are device pointers) ------------------------ */
 /* "16" = a 16-bit floating format selected by an fp16 flag: 0 = bf16, 1 = fp16 (saturating). */
 int clipebc_f32_to_16(const float* in_dev, void* out_16_dev, int64_t n, int fp16, void* stream);
-/* epi: 0 f32, 1 bias f32, 2 bias ->16, 3 bias+quickgelu ->16, 4 bias+resid f32, 5 bias+relu+border-mask ->16,
+/* D[M,N] = A[M,K] W[N,K]^T on the CTA-pair tcgen05 kernel with a fused epilogue.
+ * epi: 0 f32, 1 bias f32, 2 bias ->16, 3 bias+quickgelu ->16, 4 bias+resid f32, 5 bias+relu+border-mask ->16,
  *      6 bias+resid+relu hi/lo split ->16. ab_fp16: format of A and W; out_fp16: format of a 16-bit output.
+ *      n_seg K-segments of A with per-segment row shift / column start (implicit-GEMM 3x3 taps, split precision).
  *      mask_hp x mask_wp: rows per image of the zero-bordered grid of epi 5; mask_lead 1: first and last row/column are
- *      border, 0: only the last ones (shared-border grid, see clipebc_resample_to_padded).
+ *      border, 0: only the last ones (shared-border grid, see clipebc_resample_to_padded). block_n: 0 (auto), 128, 192, 256.
  *      See clip_ebc_b200/csrc/kernels.h for the contract. */
 int clipebc_gemm_bf16(int epi, const void* A_16_dev, int64_t a_rows, int64_t a_cols, int64_t lda,
                       const void* W_16_dev, int64_t ldw, int M, int N, int K, int n_seg, const int* seg_row_shift,
                       const int* seg_col_start, void* out_dev, int ldo, const float* bias_dev, const float* resid_dev,
                       int ldr, int mask_hp, int mask_wp, int mask_lead, int block_n, int ab_fp16, int out_fp16,
                       void* stream);
-/* LayerNorm folded into the GEMMs either side of it (what the hot path runs between two residual updates; replaces
- * nn.LayerNorm + nn.Linear of _clip/blocks.py:28-42, see DESIGN.md section 2 rewrite 7). The statistics buffer is
- * float2 [M, 8]: per row (mean, sum of squared deviations) pairs.
- *   clipebc_gemm_resid_stats: X f32 [M, 768] += A W^T + bias in place; x16_out [M, 768] = 16-bit copy of the new rows;
- *     stats_out[row][n / 96] = partial of columns n .. n + 95 (192-wide tiles: block_n 0 or 192).
- *   clipebc_gemm_ln: out_16 [M, ldo] = act(rstd * (A W'^T - mean * colsum) + bias'), A = RAW 16-bit rows [M, 768],
- *     W' = W diag(gamma) (clipebc_fold_ln_linear), (mean, rstd) merged from ln_parts partials: 8 (as written by
- *     clipebc_gemm_resid_stats) or 1 (slot 0 = whole row, as written by clipebc_rowstats768); gelu 1 = QuickGELU.
- *   clipebc_rowstats768: rows f32 [n, 768] -> 16-bit copy + slot 0 = (mean, M2) of the row.
- *   clipebc_fold_ln_linear: W f32 [O, 768], b [O], gamma/beta [768] -> Wf 16-bit, colsum f32 [O], bias_f f32 [O]. */
-int clipebc_gemm_resid_stats(const void* A_16_dev, int64_t a_rows, int64_t lda, const void* W_16_dev, int64_t ldw, int M,
-                             int N, int K, float* X_inout_dev, const float* bias_dev, void* x16_out_dev, void* stats_out_dev,
-                             int block_n, int ab_fp16, int out_fp16, void* stream);
-int clipebc_gemm_ln(int gelu, const void* A_16_dev, int64_t a_rows, int64_t lda, const void* Wf_16_dev, int64_t ldw, int M,
-                    int N, int K, void* out_16_dev, int ldo, const float* bias_f_dev, const void* ln_stats_dev, int ln_parts,
-                    const float* ln_colsum_dev, int block_n, int ab_fp16, int out_fp16, void* stream);
-int clipebc_rowstats768(const float* in_dev, int64_t n_rows, void* x16_out_dev, void* stats_out_dev, int fp16, void* stream);
-int clipebc_fold_ln_linear(const float* W_dev, const float* b_dev, const float* gamma_dev, const float* beta_dev, int O,
-                           void* Wf_16_dev, float* colsum_dev, float* bias_f_dev, int fp16, void* stream);
-/* out_kind: 0 = f32, 1 = bf16, 2 = fp16 */
-int clipebc_layernorm768(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
-                         int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
-                         int in_row_offset, void* stream);
-/* q, k, v (and the constant keys/values) are bf16; the output is bf16 or fp16 (out_fp16) */
+/* nn.LayerNorm(width, eps 1e-5) over rows of `width` = 768 or 1024 channels; out_kind: 0 = f32, 1 = bf16, 2 = fp16.
+ * Row map: in_row = (r / rows_out_per_group) * rows_in_per_group + in_row_offset + r % rows_out_per_group. */
+int clipebc_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, int width, void* out_dev,
+                      int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
+                      int in_row_offset, void* stream);
+/* softmax(q k^T / 8) v per (window, head): qkv bf16 [n_win * t_live, 3 * 64 * heads], const_kv bf16 [n_const, 3 * 64 * heads]
+ * extra keys / values of every window (deep-VPT prompts), out 16-bit [n_win * t_live, 64 * heads]. tcgen05 kernel when
+ * t_live + n_const <= 256 and n_const % 8 == 0, streamed-K/V kernel otherwise. */
 int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
-                      void* out_16_dev, int out_fp16, void* stream);
-/* out: [n_img*gh*gw, 2*KP] = [hi | lo] split of the pixels in the 16-bit format, KP = 3 * patch^2, patch 16 or 32;
- * clipebc_patchify16 is the patch-16 form kept from ABI v1 */
+                      int heads, void* out_16_dev, int out_fp16, void* stream);
+/* out: [n_img*gh*gw, 2*kp_pad] = [hi | lo] split of the pixels in the 16-bit format; kp_pad >= 3 * patch^2 (a multiple of
+ * 8; pad columns are not written), patch 14, 16 or 32 */
 int clipebc_patchify(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch,
-                     void* out_16_dev, int fp16, void* stream);
-int clipebc_patchify16(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                       void* out_16_dev, int fp16, void* stream);
-/* Shared-border grid [n_win, gh+1, gw+1, 768]: cell (y, x) at row y*(gw+1)+x, column gw and row gh are zero; the zero
- * column ending a line is the left border of the next line, the zero row ending a window the top border of the next. */
-int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, void* U_16_dev,
+                     int kp_pad, void* out_16_dev, int fp16, void* stream);
+/* Shared-border grid [n_win, gh+1, gw+1, width]: cell (y, x) at row y*(gw+1)+x, column gw and row gh are zero; the zero
+ * column ending a line is the left border of the next line, the zero row ending a window the top border of the next.
+ * U_16_dev may be NULL. */
+int clipebc_resample_to_padded(const float* Y_dev, int n_win, int hp, int wp, int gh, int gw, int width, void* U_16_dev,
                                float* U_f32_dev, int fp16, void* stream);
-/* F_dev f32 [n_win*(gh+1)*(gw+1), 512] on the shared-border grid; evaluated on the gh x gw interior cells */
-int clipebc_ebc_head(const float* F_dev, const float* tmat_dev, const float* anchors_dev, int n_bins, int n_win, int gh,
-                     int gw, float* exp_out_dev, float* logits_out_dev, void* stream);
 /* preds_dev f32 [n_rows*n_cols, gh, gw]; row_cells/col_cells: HOST arrays of window origins // reduction. */
 int clipebc_fold_average(const float* preds_dev, const int* row_cells_host, const int* col_cells_host, int n_rows,
                          int n_cols, int gh, int gw, int Ho, int Wo, float* density_out_dev, float* count_out_dev,

@@ -79,7 +79,7 @@ def forward_vpt(x: Tensor, sd: Dict[str, Tensor], num_vpt: int, deep_vpt: bool, 
     hp, wp = H // PATCH, W // PATCH
     f = F.conv2d(x, sd["image_encoder.conv1.weight"], stride=PATCH)  # :147, no bias
     f = f.reshape(B, WIDTH, -1).permute(0, 2, 1)  # :148-149
-    cls = sd["image_encoder.class_embedding"] + torch.zeros(B, 1, WIDTH)
+    cls = sd["image_encoder.class_embedding"] + torch.zeros(B, 1, WIDTH, device=x.device)
     f = torch.cat([cls, f], dim=1)  # :150-153
     f = f + interpolate_pos_embed(sd["image_encoder.positional_embedding"], input_size // PATCH, hp, wp)  # :155-156
     f = _ln(f, sd, "image_encoder.ln_pre").permute(1, 0, 2)  # :157-158 -> [1 + L, B, 768]
@@ -132,7 +132,7 @@ def clip_ebc_forward(x: Tensor, sd: Dict[str, Tensor], text_features: Tensor, an
         logits = sd["logit_scale"].exp() * img @ txt.t()  # :207-208
         logits = logits.permute(0, 3, 1, 2)  # :209
         probs = logits.softmax(dim=1)  # :211
-        anchors = torch.tensor(list(anchor_points), dtype=torch.float32).view(1, -1, 1, 1)
+        anchors = torch.tensor(list(anchor_points), dtype=torch.float32, device=x.device).view(1, -1, 1, 1)
         exp = (probs * anchors).sum(dim=1, keepdim=True)  # :212
         return logits, exp
 

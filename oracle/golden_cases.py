@@ -56,16 +56,25 @@ CASES += [
          variant="stress", wseed=22, xseed=23, shape=(1, 3, 448, 672), window=448, stride=224),
 ]
 
+# trained-CLIP-like activation outliers (oracle/weights.py variant "outlier": MLP hidden activations ~1e4, one residual
+# channel carrying several hundred): the regime where fp16 (range) and bf16 (mantissa) operands differ in kind
+CASES += [
+    dict(name="forward_r8_deep_outlier", kind="forward", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
+         variant="outlier", wseed=30, xseed=31, shape=(4, 3, 224, 224)),
+]
+
 
 # ViT-L/14 (width 1024, 24 layers, 16 heads, patch 14, embed 768, decoder 1024 channels, x1.75 resample to the
-# reduction-8 grid): pinned for the ORACLE only -- the CUDA path does not implement this backbone yet (DESIGN.md
-# sections 8 and 11), so these cases are not in CASES and the GPU parity tests do not see them.
-ORACLE_ONLY_CASES = [
+# reduction-8 grid; 257 live tokens + 32 prompts = 289 keys per 224 x 224 window: the streamed-K/V attention kernel)
+CASES += [
     dict(name="l14_forward_r8_deep", kind="forward", bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32,
          variant="stress", wseed=24, xseed=25, shape=(1, 3, 224, 224), patch=14),
     dict(name="l14_sliding_224x448_s224_r8_shallow", kind="sliding", bins="r8_t4_nwpu", deep_vpt=False, num_vpt=32,
          variant="default", wseed=26, xseed=27, shape=(1, 3, 224, 448), window=224, stride=224, patch=14),
 ]
+
+# cases pinned for the oracle only (no CUDA implementation yet): none
+ORACLE_ONLY_CASES = []
 
 
 def backbone_of(case: dict) -> str:

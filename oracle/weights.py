@@ -14,6 +14,8 @@ Distributions follow the reference constructors (``variant="default"``):
   logit_scale                /root/reference/models/clip/model.py:117     ln(1/0.07)
 ``variant="stress"`` additionally randomises every bias, LayerNorm/BatchNorm affine + running statistics and uses a
 sharper logit_scale, so that bias / BN-fold / epsilon paths cannot cancel out in parity tests.
+``variant="outlier"`` is "stress" plus trained-CLIP-like activation outliers: MLP hidden activations of ~1e4 in two
+blocks and one residual channel that carries a few hundred from there on (see OUTLIER_* below).
 """
 from __future__ import annotations
 
@@ -39,6 +41,9 @@ BIN_CONFIGS = {
 }
 
 
+OUTLIER_LAYERS, OUTLIER_UNITS, OUTLIER_FC_SCALE, OUTLIER_PROJ_W = (2, 7), 6, 6000.0, 0.02
+
+
 def _u(rng, shape, bound):
     return rng.uniform(-bound, bound, size=shape).astype(np.float32)
 
@@ -51,14 +56,14 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
                     variant: str = "default", patch: int = 16) -> Dict[str, torch.Tensor]:
     """Reference-keyed fp32 state_dict (without ``text_encoder.*``: the text tower is not on the hot path).
     patch = 16 (ViT-B/16) or 32 (ViT-B/32): the two differ in conv1 / positional-embedding shapes only."""
-    assert variant in ("default", "stress")
+    assert variant in ("default", "stress", "outlier")
     PATCH = patch
     # ViT-B/16 and ViT-B/32: width 768, 12 layers, embed 512; ViT-L/14 (patch 14): width 1024, 24 layers, embed 768
     # (models/clip/model.py:16-24); hidden = 4 * width, heads = width // 64
     WIDTH, LAYERS, EMBED = (1024, 24, 768) if patch == 14 else (768, 12, 512)
     HIDDEN = 4 * WIDTH
     rng = np.random.default_rng(seed)
-    stress = variant == "stress"
+    stress = variant in ("stress", "outlier")
     sd: Dict[str, np.ndarray] = {}
     g0 = input_size // PATCH
 
@@ -110,6 +115,22 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
         sd[bn + "num_batches_tracked"] = np.array(0, dtype=np.int64)
     sd["projection.weight"] = _n(rng, (EMBED, WIDTH, 1, 1), math.sqrt(2.0 / EMBED))
     sd["projection.bias"] = _n(rng, (EMBED,), 0.1) if stress else np.zeros((EMBED,), np.float32)
+    if variant == "outlier":
+        # trained-CLIP-like activation outliers (applied after all draws, so the stream above is the "stress" one): in
+        # OUTLIER_LAYERS a handful of MLP hidden units get c_fc rows scaled up until QuickGELU(c_fc) reaches ~1e4 (the top
+        # of what a 16-bit operand with an fp16 exponent can hold is 65504), their c_proj columns are scaled down and routed
+        # into ONE residual channel, which therefore carries a "massive activation" of a few hundred through every later
+        # LayerNorm -- the regime in which fp16 and bf16 operands differ in kind (range vs mantissa)
+        orng = np.random.default_rng(seed + 7919)
+        for l in OUTLIER_LAYERS:
+            if l >= LAYERS:
+                continue
+            p = f"{ie}transformer.resblocks.{l}."
+            units = orng.choice(HIDDEN, size=OUTLIER_UNITS, replace=False)
+            chan = int(orng.integers(0, WIDTH))
+            sd[p + "mlp.c_fc.weight"][units, :] *= np.float32(OUTLIER_FC_SCALE)
+            sd[p + "mlp.c_proj.weight"][:, units] *= np.float32(0.02)
+            sd[p + "mlp.c_proj.weight"][chan, units] = np.float32(OUTLIER_PROJ_W)
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 

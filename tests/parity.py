@@ -20,6 +20,18 @@ def density_max_rel(d, ref):
     return float(np.abs(d - ref).max() / np.abs(ref).max())
 
 
+CELL_REL_FLOOR = 0.05     # per-cell check: cells whose reference value exceeds this fraction of the map maximum
+CELL_MAX_REL = 2e-2       # ... must each be within 2e-2 of their OWN reference value (not of the global maximum)
+
+
+def cell_max_rel(d, ref, floor=CELL_REL_FLOOR):
+    """max over cells with |ref| > floor * max|ref| of |d - ref| / |ref| -- a per-cell relative error, so that a large
+    global maximum cannot hide errors on small-valued cells (density_max_rel normalises by the global maximum)."""
+    d, ref = np.asarray(d, np.float64), np.asarray(ref, np.float64)
+    m = np.abs(ref) > floor * np.abs(ref).max()
+    return float((np.abs(d - ref)[m] / np.abs(ref)[m]).max()) if m.any() else 0.0
+
+
 def count_rel(d, ref):
     d, ref = np.asarray(d, np.float64), np.asarray(ref, np.float64)
     return float(abs(d.sum() - ref.sum()) / abs(ref.sum()))

@@ -44,7 +44,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.clipebc_abi_version() == 8
+    assert lib.clipebc_abi_version() == 9
     assert lib.clipebc_launch_count() == 0  # nothing ran on this CPU box
 
 
@@ -100,18 +100,51 @@ def test_model_create_validates_config(lib):
     from clip_ebc_b200 import _lib
 
     h = C.c_void_p()
-    bad = _lib.ClipEbcConfig(224, 12, 32, 1, 5, 0, 1)  # reduction 12
+    bad = _lib.make_config(224, 12, 32, 1, 5)  # reduction 12
     assert lib.clipebc_model_create(C.byref(bad), C.byref(h)) == 1
-    bad2 = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0, 7)  # operand format
+    bad2 = _lib.make_config(224, 8, 32, 1, 5, operand_fp16=7)  # operand format
     assert lib.clipebc_model_create(C.byref(bad2), C.byref(h)) == 1
-    ok = _lib.ClipEbcConfig(224, 8, 32, 1, 5, 0, 1)
-    assert lib.clipebc_model_create(C.byref(ok), C.byref(h)) == 0
-    # packing without tensors is a state error, reported by name
-    assert lib.clipebc_model_pack(h, None) == 3
-    assert b"missing tensor" in lib.clipebc_last_error()
-    # forward before pack is refused as well
-    assert lib.clipebc_forward_windows(h, C.c_void_p(16), 1, 224, 224, C.c_void_p(16), None, None) == 3
-    lib.clipebc_model_destroy(h)
+    bad3 = _lib.make_config(224, 8, 32, 1, 5, patch=14, width=1000)  # width
+    assert lib.clipebc_model_create(C.byref(bad3), C.byref(h)) == 1
+    bad4 = _lib.make_config(224, 8, 32, 1, 5, patch=14, width=1024, layers=24, embed_dim=700)
+    assert lib.clipebc_model_create(C.byref(bad4), C.byref(h)) == 1
+    for cfg in (_lib.make_config(224, 8, 32, 1, 5), _lib.make_config(224, 8, 32, 1, 5, patch=32),
+                _lib.make_config(224, 8, 32, 0, 5, patch=14, width=1024, layers=24, embed_dim=768),
+                _lib.make_config(224, 8, 0, 1, 5)):  # num_vpt = 0 is a valid reference configuration
+        assert lib.clipebc_model_create(C.byref(cfg), C.byref(h)) == 0, lib.clipebc_last_error()
+        # packing without tensors is a state error, reported by name (on a host without a GPU the device check comes first)
+        rc = lib.clipebc_model_pack(h, None)
+        assert rc in (2, 3) and (rc == 2 or b"missing tensor" in lib.clipebc_last_error())
+        # forward before pack is refused as well
+        assert lib.clipebc_forward_windows(h, C.c_void_p(16), 1, 224, 224, C.c_void_p(16), None, None) == 3
+        lib.clipebc_model_destroy(h)
+
+
+def test_model_create_rejects_a_struct_of_another_abi(lib):
+    """struct_size is the first field: a binding built against an older, shorter clipebc_config (INTEGRATION.md of ABI v8
+    listed 7 ints, the struct had 8) is rejected instead of being read past its end."""
+    from clip_ebc_b200 import _lib
+
+    class OldConfig(C.Structure):  # the ABI-v8 layout: no struct_size, 8 ints
+        _fields_ = [(n, C.c_int) for n in ("input_size", "reduction", "num_vpt", "deep_vpt", "num_bins", "window_chunk",
+                                           "operand_fp16", "patch")]
+
+    h = C.c_void_p()
+    raw = lib.clipebc_model_create
+    old_argtypes = raw.argtypes
+    raw.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    try:
+        old = OldConfig(224, 8, 32, 1, 5, 0, 1, 16)
+        assert raw(C.byref(old), C.byref(h)) == 1          # first word 224 != sizeof(clipebc_config)
+        assert b"struct_size" in lib.clipebc_last_error()
+        cfg = _lib.make_config(224, 8, 32, 1, 5)
+        cfg.struct_size = 0
+        assert raw(C.byref(cfg), C.byref(h)) == 1
+        cfg.struct_size = C.sizeof(_lib.ClipEbcConfig) + 4
+        assert raw(C.byref(cfg), C.byref(h)) == 1
+    finally:
+        raw.argtypes = old_argtypes
+    assert C.sizeof(_lib.ClipEbcConfig) == 52
 
 
 def test_window_origins_bit_exact_randomised(lib):
@@ -159,8 +192,22 @@ def test_python_host_mirrors_reference_interface():
     assert tuple(sd32["image_encoder.positional_embedding"].shape) == (50, 768)
     b32.load_state_dict(sd32, strict=True)
     assert b32.encoder_reduction == 32 and b32.reduction == 8
-    with pytest.raises(NotImplementedError):
+    # ViT-L/14: width 1024, 24 layers, patch 14 (16 x 16 positional grid), embed 768 -- same key names
+    l14 = get_model("clip_vit_l_14", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32, vpt_drop=0.0,
+                    deep_vpt=True, text_features=weights.make_text_features(5, embed=768))
+    sd14 = weights.make_state_dict(0, patch=14)
+    assert set(sd14) == set(l14.state_dict())
+    assert tuple(sd14["image_encoder.conv1.weight"].shape) == (1024, 3, 14, 14)
+    assert tuple(sd14["image_encoder.positional_embedding"].shape) == (257, 1024)
+    assert tuple(sd14["projection.weight"].shape) == (768, 1024, 1, 1)
+    l14.load_state_dict(sd14, strict=True)
+    assert l14.encoder_reduction == 14 and l14.image_encoder_depth == 24
+    with pytest.raises(AssertionError, match="text_features"):  # [N, 512] features do not fit a ViT-L/14 head
         get_model("clip_vit_l_14", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32, vpt_drop=0.0,
+                  deep_vpt=True, text_features=weights.make_text_features(5))
+    # the reference computes text_features in __init__ (models/clip/model.py:97-129): their absence is a construction error
+    with pytest.raises(ValueError, match="text_features is required"):
+        get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32, vpt_drop=0.0,
                   deep_vpt=True)
     # text_encoder.* entries of a reference checkpoint are accepted and round-trip
     model.load_state_dict({**sd, "text_encoder.ln_final.weight": torch.ones(512)}, strict=True)
@@ -173,7 +220,10 @@ def test_python_host_mirrors_reference_interface():
     with pytest.raises(RuntimeError, match="CUDA device only"):  # no CPU fallback
         sliding_window_predict(model, x, 224, 224)
     shallow = get_model("clip_vit_b_16", input_size=224, reduction=16, bins=bins, anchor_points=anchors, num_vpt=32,
-                        vpt_drop=0.0, deep_vpt=False)
+                        vpt_drop=0.0, deep_vpt=False, text_features=weights.make_text_features(5))
     assert [k for k in shallow.state_dict() if k.startswith("vpt_")] == ["vpt_0"]
-    with pytest.raises(RuntimeError, match="text_features"):
-        shallow._hot_path_tensors()
+    # num_vpt = 0 (accepted by the reference): the zero-sized prompt tensors are not part of what the native side loads
+    bare = get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=0, vpt_drop=0.0,
+                     deep_vpt=True, text_features=weights.make_text_features(5))
+    assert tuple(bare.vpt_0.shape) == (0, 768)
+    assert not any(k.startswith("vpt_") for k in bare._hot_path_tensors())

@@ -9,14 +9,11 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[1, 2], ids=["gemm1cta", "gemm2cta"])
-def ops(request):
-    """All kernel tests run once per GEMM implementation (single CTA / CTA pair with cta_group::2)."""
+@pytest.fixture(scope="module")
+def ops():
     from clip_ebc_b200 import ops as _ops
 
-    _ops.set_gemm_impl(request.param)
-    yield _ops
-    _ops.set_gemm_impl(2)
+    return _ops
 
 
 def _rand(shape, seed, scale=1.0, device="cuda"):
@@ -81,111 +78,6 @@ def test_gemm_bias_resid_inplace(ops, block_n):
 
 
 # ------------------------------------------------------------------- LayerNorm folded into the GEMMs either side of it
-def _ln_ref(x, gamma, beta):
-    """nn.LayerNorm(768, eps=1e-5) in float64 (reference: _clip/blocks.py:8-14)."""
-    xd = x.double()
-    mu = xd.mean(-1, keepdim=True)
-    var = ((xd - mu) ** 2).mean(-1, keepdim=True)
-    return ((xd - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()).float()
-
-
-def _merge_stats(stats, parts):
-    """Chan merge of the per-row partials (equal counts), in float64 -> (mean, variance)."""
-    st = stats[:, :parts].double()
-    n = 768 // parts
-    mean = st[..., 0].mean(1)
-    m2 = st[..., 1].sum(1) + n * ((st[..., 0] - mean[:, None]) ** 2).sum(1)
-    return mean, m2 / 768
-
-
-@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
-def test_rowstats_and_fold_ln_linear(dt):
-    from clip_ebc_b200 import ops as _ops
-
-    fp16 = dt == torch.float16
-    x = _rand((333, 768), 60, 2.0) + 3.0 * _rand((333, 1), 61)   # rows with a non-zero mean
-    x16, stats = _ops.rowstats(x, fp16=fp16)
-    assert torch.equal(x16, x.to(dt))
-    mean, var = _merge_stats(stats, 1)
-    assert (mean - x.double().mean(1)).abs().max().item() < 1e-5
-    assert ((var - x.double().var(1, unbiased=False)).abs() / x.double().var(1, unbiased=False)).max().item() < 1e-5
-    W, b = _rand((2304, 768), 62, 0.03), _rand((2304,), 63)
-    gamma, beta = 1.0 + 0.3 * _rand((768,), 64), 0.2 * _rand((768,), 65)
-    wf, colsum, bias_f = _ops.fold_ln_linear(W, b, gamma, beta, fp16=fp16)
-    assert torch.equal(wf, (W * gamma).to(dt))
-    assert (colsum - wf.double().sum(1)).abs().max().item() < 1e-4   # sums of the ROUNDED weights
-    assert (bias_f - (b.double() + W.double() @ beta.double())).abs().max().item() < 1e-4
-
-
-@pytest.mark.parametrize("block_n", [0, 192])
-@pytest.mark.parametrize("M,K", [(2000, 768), (777, 3072), (12608, 768), (31, 768)])
-def test_gemm_resid_stats(block_n, M, K):
-    """out_proj / c_proj with the statistics epilogue (residual tiles through TMA): same residual update as epilogue 4 plus
-    the 16-bit rows and the (mean, M2) partials of every 96 columns."""
-    from clip_ebc_b200 import ops as _ops
-
-    dt = torch.float16
-    a, w, b = _rand((M, K), 66).to(dt), _rand((768, K), 67, 0.02).to(dt), _rand((768,), 68)
-    x = _rand((M, 768), 69) + 2.0
-    ref = x + a.float() @ w.float().t() + b
-    x16, stats = _ops.gemm_resid_stats(a, w, x, b, block_n=block_n)
-    assert _rel(x, ref) < 2e-5                                   # in place, as EPI_BIAS_RESID_F32
-    assert torch.equal(x16, x.to(dt))                            # the 16-bit copy is the rounding of what was written
-    xc = x.double().view(M, 8, 96)
-    assert (stats[..., 0].double() - xc.mean(2)).abs().max().item() < 2e-5              # partial means
-    assert _rel(stats[..., 1], ((xc - xc.mean(2, keepdim=True)) ** 2).sum(2)) < 2e-5      # partial M2
-    mean, var = _merge_stats(stats, 8)
-    xd = x.double()
-    assert (mean - xd.mean(1)).abs().max().item() < 2e-5
-    assert ((var - xd.var(1, unbiased=False)).abs() / xd.var(1, unbiased=False)).max().item() < 2e-5
-
-
-@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
-@pytest.mark.parametrize("gelu", [False, True], ids=["qkv", "c_fc"])
-@pytest.mark.parametrize("M,N", [(1234, 2304), (12608, 3072), (50, 768)])
-def test_gemm_ln_matches_layernorm_linear(dt, gelu, M, N):
-    """LN folded into the GEMM (raw 16-bit rows, W diag(gamma), epilogue rstd * (acc - mean * colsum) + b') against
-    LayerNorm -> Linear (-> QuickGELU) in fp32/fp64 on the same rows. The only differences are one 16-bit rounding of the
-    raw rows (instead of the normalised ones) and of the folded weights: a few output roundings."""
-    from clip_ebc_b200 import ops as _ops
-
-    fp16 = dt == torch.float16
-    x = _rand((M, 768), 70, 1.5) + 2.0 * _rand((M, 1), 71) + 0.5 * _rand((1, 768), 72)
-    W, b = _rand((N, 768), 73, 0.03), _rand((N,), 74)
-    gamma, beta = 1.0 + 0.3 * _rand((768,), 75), 0.2 * _rand((768,), 76)
-    ref = _ln_ref(x, gamma, beta) @ W.t() + b
-    if gelu:
-        ref = ref * torch.sigmoid(1.702 * ref)
-    x16, stats = _ops.rowstats(x, fp16=fp16)
-    wf, colsum, bias_f = _ops.fold_ln_linear(W, b, gamma, beta, fp16=fp16)
-    out = _ops.gemm_ln(x16, wf, bias_f, stats, colsum, 1, gelu=gelu)
-    # what the separate-kernel path computes: 16-bit LN output x 16-bit weights
-    xn16 = _ln_ref(x, gamma, beta).to(dt).float()
-    unfused = xn16 @ W.to(dt).float().t() + b
-    if gelu:
-        unfused = unfused * torch.sigmoid(1.702 * unfused)
-    err, err_unfused = _rel(out, ref), _rel(unfused.to(dt), ref)
-    assert err < 4 * ROUND16[dt], (err, err_unfused)
-    assert err < 3 * err_unfused + 1e-4, (err, err_unfused)      # no worse than the path it replaces (same error class)
-
-
-def test_gemm_resid_stats_feeds_gemm_ln():
-    """The pair as the hot path chains it: residual GEMM -> (x16, chunk statistics) -> LN-folded GEMM."""
-    from clip_ebc_b200 import ops as _ops
-
-    dt = torch.float16
-    M = 3000
-    a, w, b = _rand((M, 768), 77).to(dt), _rand((768, 768), 78, 0.03).to(dt), _rand((768,), 79)
-    x = _rand((M, 768), 80)
-    W2, b2 = _rand((3072, 768), 81, 0.03), _rand((3072,), 82)
-    gamma, beta = 1.0 + 0.3 * _rand((768,), 83), 0.2 * _rand((768,), 84)
-    wf, colsum, bias_f = _ops.fold_ln_linear(W2, b2, gamma, beta, fp16=True)
-    xc = x.clone()
-    x16, stats = _ops.gemm_resid_stats(a, w, xc, b)
-    out = _ops.gemm_ln(x16, wf, bias_f, stats, colsum, 8, gelu=True)
-    r = _ln_ref(xc, gamma, beta) @ W2.t() + b2
-    r = r * torch.sigmoid(1.702 * r)
-    assert _rel(out, r) < 4 * ROUND16[dt]
 
 
 @pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
@@ -308,90 +200,88 @@ def test_gemm_rejects_bad_shapes(ops):
 
 
 # ----------------------------------------------------------------------------------------------- LayerNorm
-def test_layernorm(ops):
-    x = _rand((1000, 768), 20, 3.0) + 0.5
-    g, b = _rand((768,), 21) * 0.1 + 1.0, _rand((768,), 22) * 0.1
-    ref = F.layer_norm(x, (768,), g, b, 1e-5)
+@pytest.mark.parametrize("width", [768, 1024], ids=["vit_b", "vit_l"])
+def test_layernorm(ops, width):
+    x = _rand((1000, width), 20, 3.0) + 0.5
+    g, b = _rand((width,), 21) * 0.1 + 1.0, _rand((width,), 22) * 0.1
+    ref = F.layer_norm(x, (width,), g, b, 1e-5)
     out = ops.layernorm(x, g, b, out_dtype=torch.float32)
     assert (out - ref).abs().max().item() < 2e-5
     for dt in DT16:
-        out16 = ops.layernorm(x, g, b, out_dtype=dt)
+        out16 = ops.layernorm(x, g, b, out_dtype=dt)          # >= 64 contiguous rows: the streaming kernel
         assert torch.equal(out16, out.to(dt))
+        out16s = ops.layernorm(x[:40].contiguous(), g, b, out_dtype=dt)  # short input: the warp-per-row kernel
+        assert torch.equal(out16s, out[:40].to(dt))
     # row map: take the last 196 rows of every group of 229 (ln_post on the patch rows)
-    x = _rand((3 * 229, 768), 23)
+    x = _rand((3 * 229, width), 23)
     out = ops.layernorm(x, g, b, out_dtype=torch.float32, n_rows_out=3 * 196, rows_out_per_group=196, rows_in_per_group=229,
                         in_row_offset=33)
-    ref = F.layer_norm(x.view(3, 229, 768)[:, 33:], (768,), g, b, 1e-5).reshape(-1, 768)
+    ref = F.layer_norm(x.view(3, 229, width)[:, 33:], (width,), g, b, 1e-5).reshape(-1, width)
     assert (out - ref).abs().max().item() < 2e-5
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["mma_sync", "tcgen05", "tcgen05_persistent", "tcgen05_two_chains"])
+def _attention_ref(qkv, ckv, n_win, t_live, n_const, heads):
+    q, k, v = qkv.float().view(n_win, t_live, 3, heads, 64).unbind(2)
+    if n_const:
+        ck, cv = ckv.float().view(n_const, 3, heads, 64)[:, 1], ckv.float().view(n_const, 3, heads, 64)[:, 2]
+        k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
+        v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
+    return F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+
+
+# (2, 17, 5) and (1, 300, 7): constant-key counts that are not multiples of 8 take the streamed-K/V kernel
+@pytest.mark.parametrize("heads", [12, 16], ids=["h12", "h16"])
 @pytest.mark.parametrize("n_win,t_live,n_const", [(2, 197, 32), (3, 229, 0), (1, 50, 0), (2, 17, 5), (1, 256, 0),
                                                   (5, 197, 32), (2, 128, 8), (1, 129, 0), (40, 197, 32)])
 @pytest.mark.parametrize("out_fp16", [False, True], ids=["out_bf16", "out_fp16"])
-def test_attention(ops, n_win, t_live, n_const, impl, out_fp16):
-    ops.set_attention_impl(impl)  # impl 2 falls back to 1 when n_const % 8 != 0
-    qkv = _bf(_rand((n_win * t_live, 2304), 30))
-    ckv = _bf(_rand((n_const, 2304), 31)) if n_const else None
-    out = ops.attention(qkv, n_win, t_live, ckv, out_fp16=out_fp16)
+def test_attention(ops, n_win, t_live, n_const, out_fp16, heads):
+    qkv = _bf(_rand((n_win * t_live, 3 * 64 * heads), 30))
+    ckv = _bf(_rand((n_const, 3 * 64 * heads), 31)) if n_const else None
+    out = ops.attention(qkv, n_win, t_live, ckv, out_fp16=out_fp16, heads=heads)
     assert out.dtype == (torch.float16 if out_fp16 else torch.bfloat16)
-    out = out.float().view(n_win, t_live, 12, 64)
-    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
-    if n_const:
-        ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
-        k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
-        v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
-    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
-    ops.set_attention_impl(4)
+    out = out.float().view(n_win, t_live, heads, 64)
+    ref = _attention_ref(qkv, ckv, n_win, t_live, n_const, heads)
     # P is rounded to bf16 before P@V and the output is bf16: 2^-8 relative
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("n_win,t_live,n_const", [(2, 401, 32), (1, 785, 32), (2, 817, 0), (3, 257, 0), (1, 300, 7)])
-def test_attention_beyond_256_tokens(n_win, t_live, n_const):
-    """Windows with more than 256 tokens (320 x 320: 401 live + 32 prompt keys; 448 x 448: 785 + 32; shallow VPT: all 817
-    live) go through the streamed-K/V kernel (64-query chunks, 64-key blocks, online softmax)."""
-    from clip_ebc_b200 import ops as _ops
-
-    qkv = _bf(_rand((n_win * t_live, 2304), 34, 1.5))
-    ckv = _bf(_rand((n_const, 2304), 35, 1.5)) if n_const else None
-    out = _ops.attention(qkv, n_win, t_live, ckv, out_fp16=True).float().view(n_win, t_live, 12, 64)
-    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
-    if n_const:
-        ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
-        k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
-        v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
-    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+@pytest.mark.parametrize("n_win,t_live,n_const,heads", [(2, 401, 32, 12), (1, 785, 32, 12), (2, 817, 0, 12), (3, 257, 0, 12),
+                                                        (1, 300, 7, 12), (3, 257, 32, 16), (2, 289, 0, 16)])
+def test_attention_beyond_256_tokens(ops, n_win, t_live, n_const, heads):
+    """Windows with more than 256 keys (ViT-B/16 320 x 320: 401 live + 32 prompt keys; 448 x 448: 785 + 32; shallow VPT: all
+    817 live; ViT-L/14 224 x 224: 257 + 32 deep, 289 shallow) go through the streamed-K/V kernel (64-query chunks, 64-key
+    blocks, online softmax)."""
+    qkv = _bf(_rand((n_win * t_live, 3 * 64 * heads), 34, 1.5))
+    ckv = _bf(_rand((n_const, 3 * 64 * heads), 35, 1.5)) if n_const else None
+    out = ops.attention(qkv, n_win, t_live, ckv, out_fp16=True, heads=heads).float().view(n_win, t_live, heads, 64)
+    ref = _attention_ref(qkv, ckv, n_win, t_live, n_const, heads)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()  # P rounded to bf16, 16-bit output
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["mma_sync", "tcgen05", "tcgen05_persistent", "tcgen05_two_chains"])
-def test_attention_large_scores(ops, impl):
+def test_attention_large_scores(ops):
     """Peaky softmax (|score| up to ~40): the single-pass reference-max scheme must stay exact up to bf16 rounding."""
-    ops.set_attention_impl(impl)
     n_win, t_live, n_const = 3, 197, 32
     qkv = _bf(_rand((n_win * t_live, 2304), 32, 3.0))
     ckv = _bf(_rand((n_const, 2304), 33, 3.0))
     out = ops.attention(qkv, n_win, t_live, ckv).float().view(n_win, t_live, 12, 64)
-    ops.set_attention_impl(4)
-    q, k, v = qkv.float().view(n_win, t_live, 3, 12, 64).unbind(2)
-    ck, cv = ckv.float().view(n_const, 3, 12, 64)[:, 1], ckv.float().view(n_const, 3, 12, 64)[:, 2]
-    k = torch.cat([k, ck.expand(n_win, -1, -1, -1)], 1)
-    v = torch.cat([v, cv.expand(n_win, -1, -1, -1)], 1)
-    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+    ref = _attention_ref(qkv, ckv, n_win, t_live, n_const, 12)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
 # ----------------------------------------------------------------------------------------------- stem / decoder
 @pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
-@pytest.mark.parametrize("patch", [16, 32])
+@pytest.mark.parametrize("patch", [16, 32, 14])
 def test_patchify_matches_unfold(ops, dt, patch):
-    img = _rand((2, 3, 64, 96), 40)
-    kp = 3 * patch * patch
-    out = ops.patchify(img, fp16=dt == torch.float16, patch=patch).float().view(2, (64 // patch) * (96 // patch), 2, kp)
+    H, W = (64, 96) if patch != 14 else (56, 98)
+    img = _rand((2, 3, H, W), 40)
+    k = 3 * patch * patch
+    kp = (k + 63) // 64 * 64   # ViT-L/14: 588 real columns padded to 640 (the GEMM's K granularity), pad columns zero
+    out = ops.patchify(img, fp16=dt == torch.float16, patch=patch).float().view(2, (H // patch) * (W // patch), 2, kp)
+    assert out[..., k:].abs().max().item() == 0.0 if kp > k else True
+    out = out[..., :k]
     ref = F.unfold(img, kernel_size=patch, stride=patch).transpose(1, 2)  # [n, L, c*P*P + py*P + px]
     hi = ref.to(dt).float()
     assert torch.equal(out[:, :, 0], hi)
@@ -413,6 +303,19 @@ def test_resample_from_the_7x7_grid_of_vit_b_32(ops, g):
     assert torch.equal(ub.view_as(uf), uf.to(torch.float16))
 
 
+def test_resample_x1_75_of_vit_l_14(ops):
+    """ViT-L/14: 16 x 16 patches of 1024 channels -> the 28 x 28 reduction-8 grid, scale_factor 14 / 8 = 1.75."""
+    n = 2
+    Y = _rand((n * 256, 1024), 43)
+    ub, uf = ops.resample_to_padded(Y, n, 16, 16, 28, 28, fp16=True)
+    x = Y.view(n, 16, 16, 1024).permute(0, 3, 1, 2)
+    ref = F.interpolate(x, scale_factor=14 / 8, mode="bilinear")
+    assert ref.shape[-2:] == (28, 28)
+    uf = uf.view(n, 29, 29, 1024)
+    assert (uf[:, :-1, :-1].permute(0, 3, 1, 2) - ref).abs().max().item() < 1e-5
+    assert torch.equal(ub.view_as(uf), uf.to(torch.float16))
+
+
 @pytest.mark.parametrize("g", [28, 14, 7])
 @pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
 def test_resample_matches_interpolate(ops, g, dt):
@@ -427,23 +330,6 @@ def test_resample_matches_interpolate(ops, g, dt):
     border[:, :-1, :-1] = 0
     assert border.abs().max().item() == 0.0
     assert torch.equal(ub.view_as(uf), uf.to(dt))
-
-
-@pytest.mark.parametrize("n_bins", [3, 5, 20])
-def test_ebc_head(ops, n_bins):
-    n, g = 2, 7
-    Fm = _rand((n * (g + 1) * (g + 1), 512), 50)
-    text = _rand((n_bins, 512), 51)
-    anchors = torch.arange(n_bins, dtype=torch.float32, device="cuda") * 1.25
-    scale = math.log(1 / 0.07)
-    tmat = math.exp(scale) * F.normalize(text, dim=-1)
-    exp, logits = ops.ebc_head(Fm, tmat.contiguous(), anchors, n, g, g, want_logits=True)
-    f = Fm.view(n, g + 1, g + 1, 512)[:, :-1, :-1]
-    ref_logits = (math.exp(scale) * F.normalize(f, dim=-1)) @ F.normalize(text, dim=-1).t()
-    ref_logits = ref_logits.permute(0, 3, 1, 2)
-    ref_exp = (ref_logits.softmax(1) * anchors.view(1, -1, 1, 1)).sum(1, keepdim=True)
-    assert (logits - ref_logits).abs().max().item() < 1e-4
-    assert (exp - ref_exp).abs().max().item() < 1e-4
 
 
 # ----------------------------------------------------------------------------------------------- fold

@@ -4,6 +4,8 @@
 Gates are BASELINE.json's north_star tolerances (tests/parity.py): density max-rel-err <= 2e-2, count rel-err <= 0.5 %,
 bin-argmax agreement >= 99.5 %, window/fold indexing bit-exact (tests/test_kernels_gpu.py::test_fold_bit_exact).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -16,38 +18,37 @@ from . import parity
 pytestmark = pytest.mark.gpu
 
 
-def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0, operand_dtype="fp16"):
+def build_model(case, sd, tf, bins, anchors, reduction, window_chunk=0, operand_dtype="fp16", decoder_conv1_fine=False):
     from clip_ebc_b200 import get_model
 
     from oracle.golden_cases import backbone_of
 
     model = get_model("clip_" + backbone_of(case), input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
                       prompt_type="word", num_vpt=case["num_vpt"], vpt_drop=0.0, deep_vpt=case["deep_vpt"],
-                      text_features=tf, window_chunk=window_chunk, operand_dtype=operand_dtype)
+                      text_features=tf, window_chunk=window_chunk, operand_dtype=operand_dtype,
+                      decoder_conv1_fine=decoder_conv1_fine)
     model.load_state_dict(sd, strict=True)
     return model.to("cuda").eval()
 
 
-@pytest.fixture(params=["default", "ln_folded", "conv1_fine"])
-def ln_fold(request):
-    """The optional forms of the path: LayerNorms folded into the GEMMs (default: separate kernels) and decoder conv1 as
-    an implicit GEMM on the fine grid (default: from the coarse patch grid). Every form meets the same gates."""
-    from clip_ebc_b200 import ops
-
-    ops.set_ln_fold(request.param == "ln_folded")
-    ops.set_conv1_coarse(request.param != "conv1_fine")
-    yield request.param
-    ops.set_ln_fold(False)
-    ops.set_conv1_coarse(True)
+def _coarse_conv1_applies(case):
+    """Decoder conv1 has two forms (DESIGN.md section 2 rewrite 8); the coarse-grid one is the default wherever the decoder
+    grid is at least twice as fine as the patch grid. Only there does decoder_conv1_fine=True select different kernels."""
+    reduction = {"r8_t4_nwpu": 8, "r16_t8_qnrf": 16, "r32_t19_qnrf": 32}[case["bins"]]
+    return case.get("patch", 16) // reduction >= 2
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_cuda_path_matches_reference_fixture(case, ln_fold):
+PATH_FORMS = [(c, False) for c in CASES] + [(c, True) for c in CASES if _coarse_conv1_applies(c)]
+
+
+@pytest.mark.parametrize("case,conv1_fine", PATH_FORMS,
+                         ids=[c["name"] + ("-conv1_fine" if f else "") for c, f in PATH_FORMS])
+def test_cuda_path_matches_reference_fixture(case, conv1_fine):
     from clip_ebc_b200 import sliding_window_predict
 
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
     gold = parity.load_golden(case["name"])
-    model = build_model(case, sd, tf, bins, anchors, reduction)
+    model = build_model(case, sd, tf, bins, anchors, reduction, decoder_conv1_fine=conv1_fine)
     if case["kind"] == "forward":
         model.training = True  # like the reference: train-mode forward returns (logits, exp)
         logits, exp = model(x.cuda())
@@ -62,6 +63,7 @@ def test_cuda_path_matches_reference_fixture(case, ln_fold):
         print(f"\n[{case['name']}] exp max-rel {rel:.3e}  count-rel {parity.count_rel(exp, gold['exp']):.3e}  "
               f"argmax {agree:.4f} (margin>0.05: {agree_m:.4f})  logits max-abs {np.abs(logits - gold['logits']).max():.3e}")
         assert rel <= parity.DENSITY_MAX_REL
+        assert parity.cell_max_rel(exp, gold["exp"]) <= parity.CELL_MAX_REL
         assert parity.count_rel(exp, gold["exp"]) <= parity.COUNT_REL
         assert agree >= parity.ARGMAX_AGREE
     else:
@@ -74,15 +76,21 @@ def test_cuda_path_matches_reference_fixture(case, ln_fold):
         crel = parity.count_rel(dens.numpy(), gold["density"])
         print(f"\n[{case['name']}] density max-rel {rel:.3e}  count-rel {crel:.3e}")
         assert rel <= parity.DENSITY_MAX_REL
+        assert parity.cell_max_rel(dens.numpy(), gold["density"]) <= parity.CELL_MAX_REL
         assert crel <= parity.COUNT_REL
         assert abs(cnt.item() - float(gold["count"])) <= parity.COUNT_REL * abs(float(gold["count"]))
 
 
+# bf16 operands (the precision BASELINE.json configs[1] names): every forward fixture must meet ALL north_star gates,
+# including bin-argmax agreement >= 99.5 %. A case listed here is a measured, stated shortfall (value = the floor it is
+# held to instead); an empty dict means bf16 meets the full gate everywhere.
+BF16_ARGMAX_SHORTFALL = {}
+
+
 @pytest.mark.parametrize("case", [c for c in CASES if c["kind"] == "forward"],
                          ids=[c["name"] for c in CASES if c["kind"] == "forward"])
-def test_bf16_operands_stay_inside_density_and_count_gates(case):
-    """operand_dtype="bf16" (3 mantissa bits fewer): density / count gates hold; the argmax agreement is reported only
-    (on near-flat random-init logits it sits at 99.5 +- 0.2 %, which is why fp16 operands are the default)."""
+def test_bf16_operands_meet_the_north_star_gates(case):
+    """operand_dtype="bf16" (8-bit mantissa instead of fp16's 11): density, per-cell, count AND argmax gates."""
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
     gold = parity.load_golden(case["name"])
     model = build_model(case, sd, tf, bins, anchors, reduction, operand_dtype="bf16")
@@ -90,11 +98,14 @@ def test_bf16_operands_stay_inside_density_and_count_gates(case):
     logits, exp = model(x.cuda())
     model.training = False
     logits, exp = logits.cpu().numpy(), exp.cpu().numpy()
-    print(f"\n[bf16 {case['name']}] exp max-rel {parity.density_max_rel(exp, gold['exp']):.3e}  argmax "
-          f"{parity.argmax_agreement(logits, gold['logits']):.4f}")
+    agree = parity.argmax_agreement(logits, gold["logits"])
+    floor = BF16_ARGMAX_SHORTFALL.get(case["name"], parity.ARGMAX_AGREE)
+    print(f"\n[bf16 {case['name']}] exp max-rel {parity.density_max_rel(exp, gold['exp']):.3e}  cell-rel "
+          f"{parity.cell_max_rel(exp, gold['exp']):.3e}  argmax {agree:.4f} (gate {floor})")
     assert parity.density_max_rel(exp, gold["exp"]) <= parity.DENSITY_MAX_REL
+    assert parity.cell_max_rel(exp, gold["exp"]) <= parity.CELL_MAX_REL
     assert parity.count_rel(exp, gold["exp"]) <= parity.COUNT_REL
-    assert parity.argmax_agreement(logits, gold["logits"]) >= 0.99
+    assert agree >= floor
 
 
 def test_batch64_against_oracle():
@@ -142,6 +153,35 @@ def test_large_image_properties():
     assert torch.isfinite(dens).all()
     assert dens.min().item() >= min(anchors) - 1e-5 and dens.max().item() <= max(anchors) + 1e-5
     assert abs(cnt.item() - dens.double().sum().item()) <= 1e-4 * dens.double().sum().item()
+
+
+@pytest.mark.parametrize("H,W,stride,n_win", [(1536, 2048, 112, 234), (3072, 4096, 224, 266), (3072, 4096, 112, 972)],
+                         ids=["configs2_2048x1536_s112", "configs4_4096x3072_s224", "configs4_4096x3072_s112"])
+def test_full_size_image_against_oracle(H, W, stride, n_win):
+    """BASELINE.json configs[2] (2048x1536, stride 112: 234 windows) and configs[4] (4096x3072, strides 224 / 112: 266 /
+    972 windows) at FULL size against the CPU oracle's sliding_window_predict (utils/eval_utils.py:26-96 restated; the
+    model call is chunked 64 windows at a time, which does not change per-window results): north_star gates on the whole
+    density map and on the per-image count, plus the fused device-side count against the oracle's sum."""
+    from clip_ebc_b200 import ops, sliding_window_predict
+
+    case = dict(bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32, variant="stress", wseed=3, xseed=61 + stride,
+                shape=(1, 3, H, W))
+    sd, tf, bins, anchors, reduction, img = case_inputs(case)
+    ro, co = ops.window_origins(H, W, (224, 224), (stride, stride))
+    assert len(ro) * len(co) == n_win
+    model = build_model(case, sd, tf, bins, anchors, reduction)
+    dens, cnt = sliding_window_predict(model, img, 224, stride, return_count=True)  # CPU in, CPU out like the reference
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    ref = O.sliding_window_predict(img, sd, tf, anchors, reduction, 224, stride, 32, True, 224, max_batch=64)
+    assert tuple(dens.shape) == tuple(ref.shape) == (1, 1, H // 8, W // 8)
+    d, r = dens.numpy(), ref.numpy()
+    rel, cell, crel = parity.density_max_rel(d, r), parity.cell_max_rel(d, r), parity.count_rel(d, r)
+    print(f"\n[{H}x{W} s{stride}: {n_win} windows] density max-rel {rel:.3e}  cell-rel {cell:.3e}  count {d.sum():.3f} vs "
+          f"oracle {r.sum():.3f} (rel {crel:.3e})")
+    assert rel <= parity.DENSITY_MAX_REL
+    assert cell <= parity.CELL_MAX_REL
+    assert crel <= parity.COUNT_REL
+    assert abs(cnt.item() - float(r.astype(np.float64).sum())) <= parity.COUNT_REL * abs(float(r.astype(np.float64).sum()))
 
 
 @pytest.mark.parametrize("bins_key,g", [("r16_t8_qnrf", 14), ("r32_t19_qnrf", 7)])
@@ -200,6 +240,9 @@ def test_errors_follow_the_reference_convention():
         get_model("clip_vit_b_99", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
     with pytest.raises(AssertionError):  # ViT needs num_vpt / deep_vpt / vpt_drop (models/clip/model.py:55-58)
         get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    with pytest.raises(ValueError, match="text_features is required"):  # the reference computes them in __init__
+        get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32,
+                  vpt_drop=0.0, deep_vpt=True)
     model = build_model(case, sd, tf, bins, anchors, reduction)
     with pytest.raises(AssertionError):
         sliding_window_predict(model, x[0], 224, 224)  # not 4-D
