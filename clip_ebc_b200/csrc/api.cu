@@ -659,8 +659,12 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   bool ok = true;
   if (c.num_vpt > 0)
     for (int l = 0; l < n_vpt_layers && ok; ++l) ok = check_shape(m, "vpt_" + std::to_string(l), {c.num_vpt, D}, &err);
-  ok = ok && check_shape(m, "logit_scale", {}, &err) &&
-       check_shape(m, "image_encoder.class_embedding", {D}, &err) &&
+  if (ok) {  // a scalar: 0-dim as in the reference state_dict, or one element
+    auto ls = m->raw.find("logit_scale");
+    if (ls == m->raw.end()) { err = "missing tensor 'logit_scale'"; ok = false; }
+    else if (ls->second.numel != 1) { err = "tensor 'logit_scale' must hold one element"; ok = false; }
+  }
+  ok = ok && check_shape(m, "image_encoder.class_embedding", {D}, &err) &&
        check_shape(m, "image_encoder.positional_embedding", {1 + g0 * g0, D}, &err) &&
        check_shape(m, "image_encoder.conv1.weight", {D, 3, kPatch, kPatch}, &err) &&
        check_shape(m, "image_encoder.ln_pre.weight", {D}, &err) && check_shape(m, "image_encoder.ln_pre.bias", {D}, &err) &&

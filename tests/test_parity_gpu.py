@@ -84,7 +84,12 @@ def test_cuda_path_matches_reference_fixture(case, conv1_fine):
 # bf16 operands (the precision BASELINE.json configs[1] names): every forward fixture must meet ALL north_star gates,
 # including bin-argmax agreement >= 99.5 %. A case listed here is a measured, stated shortfall (value = the floor it is
 # held to instead); an empty dict means bf16 meets the full gate everywhere.
-BF16_ARGMAX_SHORTFALL = {}
+BF16_ARGMAX_SHORTFALL = {
+    # measured on B200 (profiles/r02/parity_prints.txt): 779 of 784 cells agree (99.36 %). 20 bins with near-flat random-init logits and
+    # 229 live rows of bf16 (8-bit mantissa) operands through 12 blocks; every other gate of the case holds with > 5x margin, fp16
+    # operands (the default) reach 99.9 %, and the reference's own bf16 autocast reaches 99.06-99.39 %
+    "forward_r32_shallow_stress": 0.99,
+}
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c["kind"] == "forward"],
