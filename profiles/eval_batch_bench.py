@@ -17,7 +17,7 @@ W = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 stride = int(sys.argv[3]) if len(sys.argv) > 3 else 224
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 16
 dev = torch.device("cuda", 0)
-model, _ = build_model(dev)
+model, _ = build_model(dev, "r8_deep")
 images = [weights.make_image((1, 3, H, W), seed=70 + i).to(dev) for i in range(n)]
 
 

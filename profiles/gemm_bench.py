@@ -31,10 +31,9 @@ for name, m, n, k, epi in shapes:
     resid = torch.randn(m, n, device=dev) if epi == ops.EPI_BIAS_RESID_F32 else None
     out = resid if resid is not None else None
     res = []
-    for impl, bn in [(i, b) for i in (1, 2) for b in (128, 192, 256, 0)]:
+    for bn in (128, 192, 256, 0):
         if bn and n % bn:
             continue
-        ops.set_gemm_impl(impl)
         o = ops.gemm(a, w, epi, bias=bias, resid=resid, out=out, block_n=bn)
         for _ in range(3):
             ops.gemm(a, w, epi, bias=bias, resid=resid, out=o, block_n=bn)
@@ -47,5 +46,5 @@ for name, m, n, k, epi in shapes:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        res.append(f"{impl}cta bn={bn or 'auto':>4}: {ms * 1e3:6.1f} us {2.0 * m * n * k / ms / 1e9:5.0f} TF/s")
+        res.append(f"bn={bn or 'auto':>4}: {ms * 1e3:6.1f} us {2.0 * m * n * k / ms / 1e9:5.0f} TF/s")
     print(f"{name:11s} M={m} N={n} K={k}\n   " + "\n   ".join(res))

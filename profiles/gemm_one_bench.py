@@ -1,4 +1,4 @@
-"""Time one GEMM shape/impl/tile (CUDA events, 50 reps): python profiles/gemm_one_bench.py impl M N K epi block_n"""
+"""Time one GEMM shape/impl/tile (CUDA events, 50 reps): python profiles/gemm_one_bench.py M N K epi block_n"""
 import os
 import sys
 
@@ -7,8 +7,7 @@ import torch  # noqa: E402
 
 from clip_ebc_b200 import ops  # noqa: E402
 
-impl, m, n, k, epi, bn = [int(v) for v in sys.argv[1:7]]
-ops.set_gemm_impl(impl)
+m, n, k, epi, bn = [int(v) for v in sys.argv[1:6]]
 a = torch.randn(m, k, device="cuda").to(torch.float16)
 w = (torch.randn(n, k, device="cuda") * 0.03).to(torch.float16)
 bias = torch.randn(n, device="cuda")
@@ -24,4 +23,4 @@ for _ in range(50):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 50
-print(f"impl={impl} M={m} N={n} K={k} epi={epi} bn={bn}: {ms * 1e3:.1f} us  {2.0 * m * n * k / ms / 1e9:.0f} TF/s")
+print(f"M={m} N={n} K={k} epi={epi} bn={bn}: {ms * 1e3:.1f} us  {2.0 * m * n * k / ms / 1e9:.0f} TF/s")

@@ -10,7 +10,7 @@ from bench import build_model  # noqa: E402
 from oracle import weights  # noqa: E402
 
 dev = torch.device("cuda", 0)
-model, _ = build_model(dev)
+model, _ = build_model(dev, "r8_deep")
 for B in (1, 4, 16, 64):
     x = weights.make_image((B, 3, 224, 224), seed=50).to(dev)
     for _ in range(5):

@@ -5,10 +5,10 @@ step) -> profiles/rNN_gemm_dram.json, the per-use DRAM traffic bench.py reports 
       -k regex:gemm2_tcgen05 --csv --log-file gpurun_out/gemm_dram.csv python profiles/prof_step.py 1
   python profiles/make_gemm_dram.py gpurun_out/gemm_dram.csv profiles/r01i_gemm_dram.json
 
-Launch order of a step (api.cu run_windows): patch_embed <256,0>, 12 x [qkv <256,2>, out_proj <192,4>, c_fc <256,3>,
-c_proj <192,4>], dec_conv1 (coarse-grid form: <256,2> with N = 6912, the 13th <*,2> launch of a step; fine-grid form:
-<256,5>), dec_conv2 <256,6>, projection+head <256,7>. Pack-time launches (the constant prompt K/V rows: <128,2> with
-M = 32) are skipped.
+Launch order of a step (api.cu run_windows), kernel = gemm2_tcgen05_kernel<BLOCK_N, EPI>: patch_embed <256,0>, 12 x [qkv
+<256,2>, out_proj <192,4>, c_fc <256,3>, c_proj <192,4>], dec_conv1 (coarse-grid form: <256,2> with N = 6912, the 13th
+<*,2> launch of a step; fine-grid form: <256,5>), dec_conv2 <256,8> (upsampled-skip epilogue; fine-grid form <256,6>),
+projection+head <256,7>. Pack-time launches (the constant prompt K/V rows: <128,2> with M = 32) are skipped.
 """
 import collections
 import csv
@@ -34,24 +34,23 @@ per_tag = collections.OrderedDict()
 n_resid = 0
 n_epi2 = 0
 for d in launches.values():
-    m = re.search(r"gemm2_tcgen05_kernel<(\d+), (\d+), (\d+)>", d["kernel"])
+    m = re.search(r"gemm2_tcgen05_kernel<(\d+), (\d+)>", d["kernel"])
     if not m:
         continue
     bn, epi = int(m.group(1)), int(m.group(2))
     if epi == 2 and bn == 128:
         continue  # pack time: constant prompt K/V rows
-    if epi in (4, 8):
+    if epi == 4:
         tag = "out_proj" if n_resid % 2 == 0 else "c_proj"
         n_resid += 1
     elif epi == 2:
         tag = "dec_conv1" if n_epi2 % 13 == 12 else "qkv"
         n_epi2 += 1
     else:
-        tag = {0: "patch_embed", 9: "qkv", 3: "c_fc", 10: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 11: "dec_conv2", 7: "projection+head",
-               1: "projection"}.get(epi)
+        tag = {0: "patch_embed", 3: "c_fc", 5: "dec_conv1", 6: "dec_conv2", 8: "dec_conv2", 7: "projection+head"}.get(epi)
     if tag is None:
         continue
-    t = per_tag.setdefault(tag, {"kernel": f"gemm2_tcgen05_kernel<{bn}, {epi}, 1>", "captured_launches": 0, "r": 0.0, "w": 0.0, "t": 0.0})
+    t = per_tag.setdefault(tag, {"kernel": f"gemm2_tcgen05_kernel<{bn}, {epi}>", "captured_launches": 0, "r": 0.0, "w": 0.0, "t": 0.0})
     t["captured_launches"] += 1
     t["r"] += d.get("dram__bytes_read.sum", 0.0)
     t["w"] += d.get("dram__bytes_write.sum", 0.0)

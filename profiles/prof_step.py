@@ -15,8 +15,9 @@ from oracle import weights  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 dev = torch.device("cuda", 0)
-model, _ = build_model(dev)
+model, _ = build_model(dev, "r8_deep")
 x = weights.make_image((batch, 3, 224, 224), seed=50).to(dev)
+model.use_cuda_graphs = False  # ncu must see the individual launches
 for _ in range(steps):
     out = model(x)
 torch.cuda.synchronize()

@@ -13,7 +13,7 @@ from oracle import weights  # noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 dev = torch.device("cuda", 0)
-model, _ = build_model(dev)
+model, _ = build_model(dev, "r8_deep")
 imgs = [weights.make_image((1, 3, 1536, 2048), seed=60 + i).to(dev) for i in range(2)]
 for i in range(5):
     sliding_window_predict(model, imgs[i % 2], 224, 112, return_device=True, return_count=True)
