@@ -578,8 +578,8 @@ class Runner:
                         out = model(dev_in[b])
                         consumed[b].record(comp_s)
                         host_out[b].copy_(out, non_blocking=True)
-                    if i >= 4 and i % 2 == 0:
-                        consumed[b].synchronize()  # bounded run-ahead of the host
+                    if i >= 1:
+                        consumed[1 - b].synchronize()  # bounded run-ahead of the host: at most 2 steps in flight
 
             e2e_loop(W)
             self.barrier()
@@ -673,27 +673,48 @@ class Runner:
             rec["roofline"] = self.roofline(prof, n_prof, n_win, spec["model"], region_s)
             rec["kernels"] = kernel_table(prof, n_prof)
         if with_e2e:
-            # the reference's own call: CPU image in, CPU density map out (utils/eval_utils.py:26-96), one image at a time
+            # (1) the evaluation loop of the reference (test_nwpu.py:89-106 / eval.py:25-35) through its mirror in this package,
+            # clip_ebc_b200.predict_counts: pinned HOST images in, per-image counts on the HOST out; the H2D copy of every
+            # image and the one D2H of the counts are inside the timed region, the host only enqueues (no sync per image)
+            from clip_ebc_b200 import predict_counts as loop_predict_counts
+
             host_img = [weights.make_image((1, 3, H, Wd), seed=600 + i + 10 * rank).pin_memory() for i in range(2)]
-            for i in range(2):
-                sliding_window_predict(model, host_img[i % 2], WINDOW, stride)
             n_e2e = max(2, n_local // 2)
+            loop_predict_counts(model, [host_img[i % 2] for i in range(3)], dev, True, WINDOW, stride)
             self.barrier()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.barrier()
             self.sampler.region_begin()
             s0.record()
-            for i in range(n_e2e):
+            got = loop_predict_counts(model, (host_img[i % 2] for i in range(n_e2e)), dev, True, WINDOW, stride)
+            s1.record()
+            self.barrier()
+            self.sampler.region_end()
+            assert len(got) == n_e2e
+            t2 = self.max_over_ranks(s0.elapsed_time(s1))
+            rec["e2e"] = {"value": world * n_win * n_e2e / (t2 / 1000.0), "unit": "windows/s",
+                          "h2d_bytes_per_step": 3 * H * Wd * 4, "d2h_bytes_per_step": 4,
+                          "ms_per_step": t2 / n_e2e, "timed_region_s": t2 / 1000.0, "images_per_sec": world * n_e2e / (t2 / 1000.0),
+                          "note": "clip_ebc_b200.predict_counts(model, pinned_host_images, device, sliding_window=True, 224, stride) -> "
+                                  "host counts: the loop of test_nwpu.py; images are copied H2D one by one inside the region"}
+            # (2) the reference's single call, synchronous per image: CPU image in, CPU density map out (utils/eval_utils.py:26-96)
+            for i in range(2):
+                sliding_window_predict(model, host_img[i % 2], WINDOW, stride)
+            n_call = max(2, n_local // 4)
+            self.barrier()
+            self.sampler.region_begin()
+            s0.record()
+            for i in range(n_call):
                 sliding_window_predict(model, host_img[i % 2], WINDOW, stride)
             s1.record()
             self.barrier()
             self.sampler.region_end()
-            t2 = self.max_over_ranks(s0.elapsed_time(s1))
-            rec["e2e"] = {"value": world * n_win * n_e2e / (t2 / 1000.0), "unit": "windows/s",
-                          "h2d_bytes_per_step": 3 * H * Wd * 4, "d2h_bytes_per_step": (H // r) * (Wd // r) * 4,
-                          "ms_per_step": t2 / n_e2e, "timed_region_s": t2 / 1000.0, "images_per_sec": world * n_e2e / (t2 / 1000.0),
-                          "note": "sliding_window_predict(model, cpu_image, 224, stride) -> CPU density map, synchronous per image as in "
-                                  "the reference API (pinned host image)"}
+            t3 = self.max_over_ranks(s0.elapsed_time(s1))
+            rec["e2e_per_call"] = {"value": world * n_win * n_call / (t3 / 1000.0), "unit": "windows/s",
+                                   "h2d_bytes_per_step": 3 * H * Wd * 4, "d2h_bytes_per_step": (H // r) * (Wd // r) * 4,
+                                   "ms_per_step": t3 / n_call, "images_per_sec": world * n_call / (t3 / 1000.0),
+                                   "note": "sliding_window_predict(model, cpu_image, 224, stride) -> CPU density map, synchronous per "
+                                           "image exactly as the reference call"}
         del mine_distinct
         torch.cuda.empty_cache()
         return rec
