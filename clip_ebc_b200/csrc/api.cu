@@ -167,7 +167,6 @@ struct clipebc_model {
   // workspace
   DevBuf ws_patch_rows, ws_patch_embed, ws_X, ws_Xn, ws_QKV, ws_AO, ws_Hid, ws_Y, ws_Ub, ws_Uf, ws_D1, ws_D2, ws_F,
       ws_preds;
-  DevBuf ws_flags;          // int [layers, ceil(M / 256)]: per-row-tile completion counters of c_fc (tile-level dependencies)
   // device-resident index tables (window -> patch-grid row, window origins, fold cell origins), cached per geometry so
   // the steady state has no host->device upload and no host synchronisation; bounded (kMaxIdxCache)
   std::map<std::string, DevBuf> idx_cache;
@@ -368,17 +367,6 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   const int kParts = 2 * (E / 256);  // head partials per cell: one per half of a 256-wide projection tile
   CUDA_TRY(m->ws_F.reserve(static_cast<size_t>(Mp) * kParts * (1 + c.num_bins) * 4));
 
-  // c_fc -> c_proj by row tile instead of by grid (kernels.h: rows_done / a_ready): one counter per 256-row tile and layer,
-  // cleared at the start of the pass (stream order: after every kernel of the previous pass)
-  const bool tile_deps = c.grid_level_deps == 0;
-  const int m_tiles = (M + 255) / 256;
-  int* flags = nullptr;
-  if (tile_deps) {
-    CUDA_TRY(m->ws_flags.reserve(static_cast<size_t>(c.layers) * m_tiles * sizeof(int)));
-    flags = m->ws_flags.as<int>();
-    CUDA_TRY(cudaMemsetAsync(flags, 0, static_cast<size_t>(c.layers) * m_tiles * sizeof(int), s));
-  }
-
   float* X = m->ws_X.as<float>();
   // The fp32 residual stream is read / updated four times per block while QKV (58 MB at 64 windows) and Hid (77 MB)
   // stream through L2 once: an access-policy window on the launching stream keeps X in the persisting carve-out of L2
@@ -408,17 +396,12 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
                         plain(fp16, fp16, M, D, D, X, D, L.b_out, X, D), 0));
     set_launch_tag(nullptr);
     K_TRY(layernorm_rows(s, D, X, L.ln2_g, L.ln2_b, Xn, ln16, M, 1, 1, 0));
-    GemmParams pf = plain(fp16, fp16, M, hidden, D, Hid, hidden, L.b_fc);
-    GemmParams pj = plain(fp16, fp16, M, D, hidden, X, D, L.b_proj, X, D);
-    if (tile_deps) {
-      pf.rows_done = flags + static_cast<size_t>(l) * m_tiles;
-      pj.a_ready = pf.rows_done;
-      pj.a_ready_target = 16 * (hidden / 256);  // 2 CTAs x 8 epilogue warps per 256-wide tile of c_fc
-    }
     set_launch_tag("c_fc");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, D, D, L.w_fc.as<__nv_bfloat16>(), D, pf, tile_deps ? 256 : 0));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_GELU_BF16, Xn, M, D, D, L.w_fc.as<__nv_bfloat16>(), D,
+                        plain(fp16, fp16, M, hidden, D, Hid, hidden, L.b_fc), 0));
     set_launch_tag("c_proj");
-    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, hidden, hidden, L.w_proj.as<__nv_bfloat16>(), hidden, pj, 0));
+    K_TRY(gemm_dispatch(s, EPI_BIAS_RESID_F32, Hid, M, hidden, hidden, L.w_proj.as<__nv_bfloat16>(), hidden,
+                        plain(fp16, fp16, M, D, hidden, X, D, L.b_proj, X, D), 0));
     set_launch_tag(nullptr);
   }
 
@@ -623,7 +606,6 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (c.num_bins < 1 || c.num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
   if (c.operand_fp16 != 0 && c.operand_fp16 != 1) return fail(CLIPEBC_EINVAL, "operand_fp16 must be 0 (bf16) or 1 (fp16)");
   if (c.window_chunk < 0) return fail(CLIPEBC_EINVAL, "window_chunk must not be negative");
-  if ((c.decoder_conv1_fine | c.grid_level_deps) & ~1) return fail(CLIPEBC_EINVAL, "decoder_conv1_fine / grid_level_deps must be 0 or 1");
   clipebc_model* m = new clipebc_model();
   m->cfg = c;
   m->kp_pad = (3 * c.patch * c.patch + 63) / 64 * 64;

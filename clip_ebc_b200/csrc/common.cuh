@@ -140,32 +140,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// inter-CTA flags in global memory (tile-level dependencies between kernels)
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flag_add_release(int* flag, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
-}
-__device__ __forceinline__ int flag_load_acquire(const int* flag) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-  return v;
-}
-// orders this thread's prior generic-proxy accesses (the acquire above) before its later async-proxy accesses (TMA loads)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Bounded spin: a protocol bug must trap instead of hanging the GPU box.
-__device__ __forceinline__ void flag_wait_ge(const int* flag, int target) {
-  if (flag_load_acquire(flag) >= target) return;
-  const long long t0 = clock64();
-  while (flag_load_acquire(flag) < target) {
-    __nanosleep(100);
-    if (clock64() - t0 > 4000000000ll) {
-      printf("[clipebc] flag timeout block=%d thread=%d target=%d\n", (int)blockIdx.x, (int)threadIdx.x, target);
-      __trap();
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -213,9 +187,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// all committed bulk groups but the N newest are complete
-template <int N>
-__device__ __forceinline__ void bulk_wait_group_n() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // all committed bulk stores are complete
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

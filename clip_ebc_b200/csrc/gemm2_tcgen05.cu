@@ -313,10 +313,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
     __syncwarp();
   }
-  // grid-level dependency on the previous kernel -- unless this launch consumes its A operand tile by tile (a_ready): then
-  // nothing here may wait for the whole producer grid (the producer warps wait per tile instead; the weights, the bias and
-  // the in-place reduction target do not depend on the producer)
-  if (p.a_ready == nullptr) pdl_wait();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
@@ -326,13 +323,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int m0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
       const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * HALF_N;
       int seg = 0, kk = 0;
-      if (p.a_ready != nullptr) {  // rows of this tile written (and visible) by the producer GEMM?
-        if (lane == 0) {
-          flag_wait_ge(p.a_ready + m_blk, p.a_ready_target);
-          fence_proxy_async_all();
-        }
-        __syncwarp();
-      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const bool weights_done = t == pair_id && kb < pre_kb;  // barrier armed, weights requested before the wait
         if (!weights_done) mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -391,7 +381,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     uint32_t as = 0, aphase = 0;
-    int prev_m_blk = -1;  // rows_done: the tile whose stores are still in flight
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
       const int row0 = m_blk * 2 * kBlockM + static_cast<int>(rank) * kBlockM + q * 32;
@@ -448,16 +437,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
               tma_store_2d(&tma_o, stg, n0 + cbase + b * 64, row0);
               bulk_commit_group();
             }
-          }
-          if (p.rows_done != nullptr && lane == 0) {
-            // Count this warp's part of a tile for the consumer GEMM once it is in global memory. Waiting for the stores just
-            // issued would put their latency into every tile of the epilogue, so the count lags one tile: the stores of
-            // the PREVIOUS tile (all bulk groups but the HALF_N / 64 newest) are complete by now, or nearly so.
-            if (prev_m_blk >= 0) {
-              bulk_wait_group_n<HALF_N / 64>();
-              flag_add_release(p.rows_done + prev_m_blk, 1);
-            }
-            prev_m_blk = m_blk;
           }
         } else
 #pragma unroll 1
@@ -518,10 +497,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       if (lane == 0) mbar_arrive_cluster(as == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
       as ^= 1;
       if (as == 0) aphase ^= 1;
-    }
-    if (p.rows_done != nullptr && lane == 0 && prev_m_blk >= 0) {  // the last tile of this warp
-      bulk_wait_group0();
-      flag_add_release(p.rows_done + prev_m_blk, 1);
     }
   }
 
@@ -626,9 +601,6 @@ cudaError_t launch_one2(cudaStream_t stream, const CUtensorMap& ta, const CUtens
         p.ldo % 4 == 0 && make_tmap2_f32(&to, p.out, p.M, p.N, p.ldo))
       pl.tma_out = 1;
   }
-  // tile-level dependencies: the producer counts completed bulk stores, the consumer needs the launch to be PDL-chained
-  if (p.rows_done != nullptr && !(out_is_bf16<EPI>() && pl.tma_out)) return cudaErrorInvalidValue;
-  if (p.a_ready != nullptr && !pdl_enabled()) pl.a_ready = nullptr;  // no early launch without PDL: plain stream order
   auto kern = gemm2_tcgen05_kernel<BLOCK_N, EPI>;
   const int max_pairs = max_pairs2<BLOCK_N, EPI>(num_sms);  // also sets the dynamic smem attribute (once per device)
   if (max_pairs <= 0) return cudaErrorInvalidConfiguration;

@@ -51,15 +51,6 @@ struct GemmParams {
                                       // stream, so its first tiles are requested BEFORE the programmatic-dependency wait.
                                       // Must be 0 when the launch just before this one wrote W (weight packing).
   int tma_out;                        // set by the launcher: outputs leave through bulk tensor stores / reductions
-  // Tile-level dependencies between two GEMMs of a stream instead of a grid-level one. The producer GEMM
-  // (16-bit output through bulk tensor stores) counts, per 256-row tile of its output, the epilogue warps whose stores have
-  // completed: rows_done[m_tile] reaches 16 * (N / block_n). The consumer GEMM (A = that output) is launched with
-  // programmatic stream serialization, never executes griddepcontrol.wait, and its producer warps wait for
-  // a_ready[m_tile] >= a_ready_target before the first A load of a tile: its CTAs start on the SMs the producer's last,
-  // partial round leaves idle. Both nullptr = plain grid-level dependency.
-  int* rows_done;                     // producer side: [ceil(M / 256)] counters, zeroed by the caller before the launch
-  const int* a_ready;                 // consumer side: the producer's rows_done
-  int a_ready_target;
 };
 
 inline GemmParams gemm_params_plain(int M, int N, int K) {

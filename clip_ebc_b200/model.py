@@ -105,8 +105,8 @@ def _init_decoder(m: nn.Module) -> None:
 class CLIP_EBC(nn.Module):
     """B200-native CLIP-EBC (ViT-B/16, ViT-B/32 or ViT-L/14 + VPT). Constructor arguments as in models/clip/model.py:31-45,
     plus: text_features (required, see the module docstring), window_chunk (windows per internal pass, 0 = default),
-    operand_dtype ("fp16" | "bf16": the 16-bit tensor-core operand format), decoder_conv1_fine and grid_level_deps (A/B
-    switches of the decoder's conv1 form and of the tile-level GEMM dependencies, see include/clipebc_b200.h)."""
+    operand_dtype ("fp16" | "bf16": the 16-bit tensor-core operand format) and decoder_conv1_fine (A/B switch of the
+    decoder's conv1 form, see include/clipebc_b200.h)."""
 
     def __init__(
         self,
@@ -126,7 +126,6 @@ class CLIP_EBC(nn.Module):
         window_chunk: int = 0,
         operand_dtype: str = "fp16",
         decoder_conv1_fine: bool = False,
-        grid_level_deps: bool = False,
     ) -> None:
         super().__init__()
         assert backbone in resnet_backbones + vit_backbones, \
@@ -191,7 +190,6 @@ class CLIP_EBC(nn.Module):
         assert operand_dtype in ("fp16", "bf16"), f"operand_dtype must be 'fp16' or 'bf16', got {operand_dtype}"
         self.operand_dtype = operand_dtype  # 16-bit tensor-core operand format (accumulation / residual stay fp32)
         self.decoder_conv1_fine = bool(decoder_conv1_fine)
-        self.grid_level_deps = bool(grid_level_deps)
         self._text_encoder_state: "OrderedDict[str, Tensor]" = OrderedDict()
         self._window_chunk = int(window_chunk)
         self._handle: Optional[C.c_void_p] = None
@@ -256,7 +254,7 @@ class CLIP_EBC(nn.Module):
             if self._handle is None:
                 cfg = _lib.make_config(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt), len(self.bins),
                                        self._window_chunk, int(self.operand_dtype == "fp16"), self.patch, self.width,
-                                       self.layers, self.embed_dim, int(self.decoder_conv1_fine), int(self.grid_level_deps))
+                                       self.layers, self.embed_dim, int(self.decoder_conv1_fine))
                 h = C.c_void_p()
                 _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
                 self._handle, self._handle_device = h, dev_index

@@ -60,10 +60,6 @@ typedef struct clipebc_config {
                        grid is at least twice as fine (conv3x3(bilinear_up(Y)) = 9 per-tap channel contractions on the patch
                        grid + a bilinear gather; DESIGN.md section 2 rewrite 8); 1: always the implicit GEMM on the fine
                        grid. Same result to a few 16-bit roundings; per model, for A/B measurements.                  */
-  int grid_level_deps; /* 0 (default): c_proj of a block consumes the output of c_fc tile by tile (per-row-tile completion
-                       counters in global memory) and starts on the SMs c_fc's last partial round leaves idle;
-                       1: every kernel waits for the whole previous kernel (plain programmatic dependent launch). Same
-                       results bit for bit; per model, for A/B measurements.                                          */
 } clipebc_config;
 
 const char* clipebc_last_error(void);

@@ -144,7 +144,7 @@ def test_model_create_rejects_a_struct_of_another_abi(lib):
         assert raw(C.byref(cfg), C.byref(h)) == 1
     finally:
         raw.argtypes = old_argtypes
-    assert C.sizeof(_lib.ClipEbcConfig) == 56
+    assert C.sizeof(_lib.ClipEbcConfig) == 52
 
 
 def test_window_origins_bit_exact_randomised(lib):

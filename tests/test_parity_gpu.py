@@ -259,31 +259,3 @@ def test_errors_follow_the_reference_convention():
                           num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
     with pytest.raises(RuntimeError):
         cpu_model(x[:, :, :224, :224])  # no CPU fallback
-
-
-@pytest.mark.parametrize("batch", [64, 7, 100])
-def test_tile_level_dependencies_do_not_change_a_bit(batch):
-    """c_proj consumes c_fc's output tile by tile (per-row-tile completion counters) instead of waiting for the
-    whole c_fc grid. It is the same arithmetic in the same order, so the results must equal the plain grid-level form bit
-    for bit -- on every one of many back-to-back calls (a missed dependency would show up as a stale read in some of them),
-    eager and through the captured CUDA graph, for one and for two internal passes (100 windows = 96 + 4)."""
-    case = dict(bins="r8_t4_nwpu", deep_vpt=True, num_vpt=32, variant="stress", wseed=3, xseed=71, shape=(batch, 3, 224, 224))
-    sd, tf, bins, anchors, reduction, x = case_inputs(case)
-    from clip_ebc_b200 import get_model
-
-    def build(grid_level):
-        m = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors, prompt_type="word",
-                      num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf, grid_level_deps=grid_level)
-        m.load_state_dict(sd, strict=True)
-        return m.to("cuda").eval()
-
-    plain, tiled = build(True), build(False)
-    xs = [x.cuda(), (x * 0.5 + 0.1).cuda()]
-    plain.use_cuda_graphs = False
-    refs = [plain(v) for v in xs]
-    tiled.use_cuda_graphs = False
-    for i in range(12):
-        assert torch.equal(tiled(xs[i % 2]), refs[i % 2]), f"eager call {i}"
-    tiled.use_cuda_graphs = True
-    for i in range(12):
-        assert torch.equal(tiled(xs[i % 2]), refs[i % 2]), f"graph call {i}"
