@@ -22,7 +22,8 @@ over ranks; inputs rotate over a ring larger than L2; nvidia-smi clocks are samp
 buffers (H2D of every step's input and D2H of its result inside the timed region).
 `roofline`: the tcgen05 GEMM kernel family (CUDA events around every launch in an instrumented pass that directly follows the
 timed region): executed 2*M*N*K / duration against BOTH measured peaks (burst, sustained); `frac` uses the peak of the regime
-the region ran in. `flops_executed` counts what the kernels multiply (split-precision segments, padded rows included),
+the region ran in. `flops_executed` counts what the kernels multiply (padded rows, and with bf16 operands the split-precision
+segments, included),
 `flops_algorithmic` what SURVEY.md section 8(d) credits (never more than what was run).
 `--impl reference` times the CPU restatement of the reference (oracle port; the reference is pure Python and /root/reference
 does not exist on the GPU box) on the host cores for the headline metric. `--impl torch_gpu` (also embedded in the main line
@@ -98,12 +99,12 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ FLOP accounting
-def flops_per_window(model_key: str) -> dict:
+def flops_per_window(model_key: str, split_precision: bool = False) -> dict:
     """FLOPs (2 * MAC) per 224x224 window of ViT-B/16 at the given configuration, per stage:
     (algorithmic, executed). `algorithmic` is SURVEY's figure, capped by what this implementation runs (deep VPT: the 32
     prompt rows are dead -> 197 live rows; conv1 from the coarse grid); `executed` is what the tensor cores multiply,
-    including the 2 extra segments of the split-precision patch-embed / projection GEMMs and the border rows of the
-    shared-border decoder grid."""
+    including the border rows of the shared-border decoder grid and -- with bf16 operands only (`split_precision`) -- the 2
+    extra segments of the split-precision patch-embed / projection GEMMs."""
     deep = MODELS[model_key]["deep"]
     red = {"r8_deep": 8, "r16_shallow": 16, "r32_shallow": 32}[model_key]
     D, L, Hd, P, E = 768, 12, 3072, 196, 512
@@ -112,7 +113,8 @@ def flops_per_window(model_key: str) -> dict:
     g = WINDOW // red
     Mp = (g + 1) * (g + 1)              # rows of the shared-border decoder grid
     st = {}
-    st["patch_embed"] = (2.0 * P * D * D, 2.0 * P * D * 3 * D)
+    seg = 3 if split_precision else 1
+    st["patch_embed"] = (2.0 * P * D * D, 2.0 * P * D * seg * D)
     gemm_layer = 2.0 * T * D * (3 * D + D + Hd + Hd)
     attn_layer = 4.0 * T * Tk * D
     st["vit_gemms"] = (L * gemm_layer, L * gemm_layer)
@@ -124,12 +126,12 @@ def flops_per_window(model_key: str) -> dict:
     else:
         st["dec_conv1"] = (conv_alg, 2.0 * Mp * D * 9 * D)
     st["dec_conv2"] = (conv_alg, 2.0 * Mp * D * 9 * D)
-    st["projection"] = (2.0 * g * g * D * E, 2.0 * Mp * 3 * D * E)
+    st["projection"] = (2.0 * g * g * D * E, 2.0 * Mp * seg * D * E)
     return st
 
 
-def flops_totals(model_key: str) -> dict:
-    st = flops_per_window(model_key)
+def flops_totals(model_key: str, split_precision: bool = False) -> dict:
+    st = flops_per_window(model_key, split_precision)
     alg = sum(a for a, _ in st.values())
     exe = sum(e for _, e in st.values())
     vit_alg = st["vit_gemms"][0] + st["attention"][0] + st["patch_embed"][0]
@@ -469,8 +471,9 @@ class Runner:
         gemm_launches = sum(v["launches"] for v in gemm.values())
         total_ms = sum(v["ms"] for v in prof.values())
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
-        ft = flops_totals(model_key)
-        st = flops_per_window(model_key)
+        split = self.args.operand_dtype == "bf16"
+        ft = flops_totals(model_key, split)
+        st = flops_per_window(model_key, split)
         # algorithmic share of the GEMM family: everything but the attention kernel's FLOPs
         alg_gemm = sum(a for k, (a, _) in st.items() if k != "attention") * windows_per_step * prof_steps
         exe_gemm = sum(e for k, (_, e) in st.items() if k != "attention") * windows_per_step * prof_steps
@@ -532,7 +535,7 @@ class Runner:
                "images_per_sec": None, "clocks": self.sampler.summary(win),
                "l2": f"ring of {n_ring} distinct input batches ({n_ring * B * 3 * WINDOW * WINDOW * 4 / 1e6:.0f} MB > 126 MB L2); "
                      "per-step weights + activations > L2"}
-        ft = flops_totals(spec["model"])
+        ft = flops_totals(spec["model"], (operand_dtype or self.args.operand_dtype) == "bf16")
         for regime in ("burst", "sustained"):
             pk = self.peaks[f"bf16_{regime}"]
             rec[f"tensor_frac_whole_step_executed_{regime}"] = (value / world) * ft["executed"] / 1e12 / pk
@@ -663,7 +666,7 @@ class Runner:
                               "bytes": 4 * n_images, "calls": 1},
                "counts_bit_exact_vs_1gpu": bit_exact, "clocks": self.sampler.summary(win),
                "l2": "each image touches > 1 GB of activations (>> 126 MB L2)"}
-        ft = flops_totals(spec["model"])
+        ft = flops_totals(spec["model"], self.args.operand_dtype == "bf16")
         for regime in ("burst", "sustained"):
             pk = self.peaks[f"bf16_{regime}"]
             rec[f"tensor_frac_whole_step_executed_{regime}"] = (value / world) * ft["executed"] / 1e12 / pk

@@ -72,7 +72,7 @@ SIGNATURES = {
                                _i, _i, _i, _i, _i, _i, _vp]),
     "clipebc_layernorm": (_i, [_fp, _fp, _fp, _i, _vp, _i, _i64, _i, _i, _i, _vp]),
     "clipebc_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
-    "clipebc_patchify": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "clipebc_patchify": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "clipebc_resample_to_padded": (_i, [_fp, _i, _i, _i, _i, _i, _i, _vp, _fp, _i, _vp]),
     "clipebc_fold_average": (_i, [_fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "clipebc_resize_bicubic_aa": (_i, [_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _cfp, _cfp, _vp]),

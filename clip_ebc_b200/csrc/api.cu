@@ -150,6 +150,12 @@ struct clipebc_model {
   clipebc_config cfg;       // normalised: patch / width / layers / embed_dim filled in
   int device = 0;           // the CUDA device the handle was created on: every buffer below lives there
   int kp_pad = 0;           // patch row length 3 * patch^2 rounded up to the GEMM's K granularity (64)
+  // Split precision (hi + lo operands, three K-segments [hi | lo | hi] x [Whi | Whi | Wlo]) of the two GEMMs whose rounding
+  // reaches the head directly: patch embedding and the 1x1 projection. On for bf16 operands (8-bit mantissa: a single
+  // segment costs 0.6-1.3e-2 on the logits and 0.1-0.3 % of the bin argmax at the projection alone); off for fp16 operands
+  // (11 bits: 0.7-1.5e-3 and >= 99.97 %, measured against the fp32 oracle stage by stage) -- there the split would be 2.4 of
+  // 48.8 GFLOP per window spent on bits the other twelve 16-bit roundings per block have already given up.
+  bool split_precision = false;
   std::map<std::string, RawTensor> raw;
   bool packed = false;
   // packed
@@ -276,12 +282,15 @@ GemmParams plain(int fp16, int out16_fp16, int M, int N, int K, void* out, int l
   return p;
 }
 
-// patch embedding as a split-precision GEMM: rows [hi | lo] (2 * kp) x W3 = [Whi | Whi | Wlo] (3 * kp), segments hi, lo,
-// hi; kp = 3 * patch^2 rounded up to 64 (768 for ViT-B/16, 3072 for ViT-B/32, 640 for ViT-L/14)
-GemmParams patch_embed_params(int fp16, int rows, int width, void* out, int kp) {
-  GemmParams p = gemm_params_plain(rows, width, 3 * kp);
-  p.n_seg = 3; p.seg_kblocks = kp / 64;
-  p.seg_col_start[0] = 0; p.seg_col_start[1] = kp; p.seg_col_start[2] = 0;
+// patch embedding: split precision (rows [hi | lo] (2 * kp) x W3 = [Whi | Whi | Wlo] (3 * kp), segments hi, lo, hi) or a
+// single segment (rows [hi] (kp) x the Whi columns of W3); kp = 3 * patch^2 rounded up to 64 (768 for ViT-B/16, 3072 for
+// ViT-B/32, 640 for ViT-L/14)
+GemmParams patch_embed_params(int fp16, bool split, int rows, int width, void* out, int kp) {
+  GemmParams p = gemm_params_plain(rows, width, (split ? 3 : 1) * kp);
+  if (split) {
+    p.n_seg = 3; p.seg_kblocks = kp / 64;
+    p.seg_col_start[0] = 0; p.seg_col_start[1] = kp; p.seg_col_start[2] = 0;
+  }
   p.out = out; p.ldo = width; p.bias = nullptr; p.ab_fp16 = fp16; p.out_fp16 = fp16;
   return p;
 }
@@ -363,7 +372,9 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
     CUDA_TRY(m->ws_Uf.reserve(static_cast<size_t>(Mp) * D * 4));
   }
   CUDA_TRY(m->ws_D1.reserve(static_cast<size_t>(Mp) * D * 2));
-  CUDA_TRY(m->ws_D2.reserve(static_cast<size_t>(Mp) * 2 * D * 2));
+  const bool split = m->split_precision;
+  const int d2_cols = (split ? 2 : 1) * D;  // conv2 output: hi | lo, or hi only
+  CUDA_TRY(m->ws_D2.reserve(static_cast<size_t>(Mp) * d2_cols * 2));
   const int kParts = 2 * (E / 256);  // head partials per cell: one per half of a 256-wide projection tile
   CUDA_TRY(m->ws_F.reserve(static_cast<size_t>(Mp) * kParts * (1 + c.num_bins) * 4));
 
@@ -440,25 +451,27 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
     K_TRY(gemm_dispatch(s, EPI_BIAS_RELU_MASK_BF16, Ub, Mp, D, D, m->w_c1.as<__nv_bfloat16>(), 9 * D, p1, 0));
   }
   GemmParams p2 = pc;
-  p2.out = D2; p2.ldo = 2 * D; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = D;
+  p2.out = D2; p2.ldo = d2_cols; p2.split_lo = split; p2.bias = m->b_c2.as<float>(); p2.resid = Uf; p2.ldr = D;
   if (coarse1) { p2.resid = Y; p2.mask_hp = Hp; p2.mask_wp = Wp; p2.up_hp = hp; p2.up_wp = wp; }
   set_launch_tag("dec_conv2");
   K_TRY(gemm_dispatch(s, coarse1 ? EPI_BIAS_UPSKIP_RELU_SPLIT : EPI_BIAS_RESID_RELU_SPLIT, D1, Mp, D, D,
                       m->w_c2.as<__nv_bfloat16>(), 9 * D, p2, 0));
 
-  // projection 1x1 in split precision, [hi | lo | hi] x [Whi | Whi | Wlo] (the A segments re-use the hi columns), fused
-  // with the head: the `embed` projected features of a cell are never written; the GEMM epilogue leaves ||f||^2 and the N
-  // bin dot products per half tile (kParts partials per row), ebc_head_finish does the rest
-  GemmParams pp = gemm_params_plain(Mp, E, 3 * D);
+  // projection 1x1 -- in split precision, [hi | lo | hi] x [Whi | Whi | Wlo] (the A segments re-use the hi columns), or one
+  // segment hi x Whi -- fused with the head: the `embed` projected features of a cell are never written; the GEMM epilogue
+  // leaves ||f||^2 and the N bin dot products per half tile (kParts partials per row), ebc_head_finish does the rest
+  GemmParams pp = gemm_params_plain(Mp, E, (split ? 3 : 1) * D);
   pp.ab_fp16 = fp16; pp.out_fp16 = fp16;
-  pp.n_seg = 3; pp.seg_kblocks = D / 64;
-  pp.seg_col_start[0] = 0; pp.seg_col_start[1] = D; pp.seg_col_start[2] = 0;
+  if (split) {
+    pp.n_seg = 3; pp.seg_kblocks = D / 64;
+    pp.seg_col_start[0] = 0; pp.seg_col_start[1] = D; pp.seg_col_start[2] = 0;
+  }
   float* F = m->ws_F.as<float>();
   pp.bias = raw_ptr(m, "projection.bias");
   pp.out = F; pp.ldo = kParts * (1 + c.num_bins);
   pp.head_tmat = m->tmat.as<float>(); pp.head_bins = c.num_bins;
   set_launch_tag("projection+head");
-  K_TRY(gemm_dispatch(s, EPI_BIAS_HEAD_PARTIAL, D2, Mp, 2 * D, 2 * D, m->w_p3.as<__nv_bfloat16>(), 3 * D, pp, 256));
+  K_TRY(gemm_dispatch(s, EPI_BIAS_HEAD_PARTIAL, D2, Mp, d2_cols, d2_cols, m->w_p3.as<__nv_bfloat16>(), 3 * D, pp, 256));
   set_launch_tag(nullptr);
   K_TRY(ebc_head_finish(s, F, kParts, raw_ptr(m, "anchor_points"), c.num_bins, nw, gh, gw, exp_out, logits_out));
   return CLIPEBC_OK;
@@ -498,7 +511,7 @@ int check_device(const clipebc_model* m) {
 // patch rows of a call: [rows, 2 * kp_pad] 16-bit; when 3 * patch^2 is not a multiple of 64 (ViT-L/14: 588 -> 640) the
 // pad columns must be zero, and since patchify never writes them they are cleared whenever the buffer is (re)allocated
 int reserve_patch_rows(clipebc_model* m, int64_t rows, cudaStream_t s) {
-  const size_t bytes = static_cast<size_t>(rows) * 2 * m->kp_pad * 2;
+  const size_t bytes = static_cast<size_t>(rows) * (m->split_precision ? 2 : 1) * m->kp_pad * 2;
   const void* before = m->ws_patch_rows.p;
   CUDA_TRY(m->ws_patch_rows.reserve(bytes));
   if (m->ws_patch_rows.p != before && m->kp_pad != 3 * m->cfg.patch * m->cfg.patch)
@@ -511,8 +524,10 @@ int reserve_patch_rows(clipebc_model* m, int64_t rows, cudaStream_t s) {
 int patch_embed(clipebc_model* m, cudaStream_t s, int64_t rows) {
   const int fp16 = m->cfg.operand_fp16 != 0, kp = m->kp_pad;
   set_launch_tag("patch_embed");
-  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, 2 * kp, 2 * kp, m->w_patch.as<__nv_bfloat16>(),
-                      3 * kp, patch_embed_params(fp16, static_cast<int>(rows), m->cfg.width, m->ws_patch_embed.p, kp), 0));
+  const int a_cols = (m->split_precision ? 2 : 1) * kp;
+  K_TRY(gemm_dispatch(s, EPI_F32, m->ws_patch_rows.as<__nv_bfloat16>(), rows, a_cols, a_cols, m->w_patch.as<__nv_bfloat16>(),
+                      3 * kp, patch_embed_params(fp16, m->split_precision, static_cast<int>(rows), m->cfg.width,
+                                                 m->ws_patch_embed.p, kp), 0));
   set_launch_tag(nullptr);
   return CLIPEBC_OK;
 }
@@ -609,6 +624,7 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   clipebc_model* m = new clipebc_model();
   m->cfg = c;
   m->kp_pad = (3 * c.patch * c.patch + 63) / 64 * 64;
+  m->split_precision = c.operand_fp16 == 0;
   m->layer.reset(new LayerPack[c.layers]);
   // the device current at creation owns the handle (-1 on a host without a CUDA device: such a handle can be configured
   // and inspected, every compute entry point then fails with CLIPEBC_ECUDA)
@@ -762,7 +778,7 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   const int64_t rows = static_cast<int64_t>(B) * npatch;
   const int fp16 = m->cfg.operand_fp16 != 0;
   if ((rc = reserve_patch_rows(m, rows, s))) return rc;
-  K_TRY(patchify(s, x_dev, B, h, w, 0, 0, hp, wp, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
+  K_TRY(patchify(s, x_dev, B, h, w, 0, 0, hp, wp, kPatch, m->kp_pad, m->split_precision, m->ws_patch_rows.p, fp16));
   if ((rc = patch_embed(m, s, rows))) return rc;
   // window b reads patch rows [b * npatch, (b+1) * npatch)
   std::vector<int> base(B);
@@ -854,8 +870,8 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
 
   const int fp16 = m->cfg.operand_fp16 != 0;
   if ((rc = reserve_patch_rows(m, rows, s))) return rc;
-  if (on_grid) K_TRY(patchify(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
-  else K_TRY(patchify_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, kPatch, m->kp_pad, m->ws_patch_rows.p, fp16));
+  if (on_grid) K_TRY(patchify(s, image_dev, 1, H, W, 0, 0, H / kPatch, W / kPatch, kPatch, m->kp_pad, m->split_precision, m->ws_patch_rows.p, fp16));
+  else K_TRY(patchify_windows(s, image_dev, H, W, d_orig, n_win, hp, wp, kPatch, m->kp_pad, m->split_precision, m->ws_patch_rows.p, fp16));
   if ((rc = patch_embed(m, s, rows))) return rc;
 
   CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
@@ -944,9 +960,9 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   if ((rc = reserve_patch_rows(m, total_rows, s))) return rc;
   for (int i = 0; i < n_images; ++i) {
     const Geom& g = gs[i];
-    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * 2 * m->kp_pad;
-    if (g.on_grid) K_TRY(patchify(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, kPatch, m->kp_pad, dst, fp16));
-    else K_TRY(patchify_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, kPatch, m->kp_pad, dst, fp16));
+    uint16_t* dst = m->ws_patch_rows.as<uint16_t>() + g.row_off * (m->split_precision ? 2 : 1) * m->kp_pad;
+    if (g.on_grid) K_TRY(patchify(s, images_dev[i], 1, g.H, g.W, 0, 0, g.H / kPatch, g.W / kPatch, kPatch, m->kp_pad, m->split_precision, dst, fp16));
+    else K_TRY(patchify_windows(s, images_dev[i], g.H, g.W, d_orig + 2 * g.win_off, g.n_win, hp, wp, kPatch, m->kp_pad, m->split_precision, dst, fp16));
   }
   if ((rc = patch_embed(m, s, total_rows))) return rc;
 
@@ -989,6 +1005,7 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
   }
   p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp; p.mask_lead = mask_lead != 0;
   p.ab_fp16 = ab_fp16 != 0; p.out_fp16 = out_fp16 != 0;
+  p.split_lo = 1;  // epilogue 6 as a test hook always writes hi | lo
   const char* e = gemm_dispatch(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
                                lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);
   if (e) return fail(std::strncmp(e, "gemm:", 5) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);
@@ -1015,9 +1032,9 @@ int clipebc_attention(const void* qkv, const void* const_kv, int n_const, int n_
 }
 
 int clipebc_patchify(const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch, int kp_pad,
-                     void* out, int fp16, void* stream) {
+                     int split, void* out, int fp16, void* stream) {
   if (!image || !out) return fail(CLIPEBC_EINVAL, "null argument");
-  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, patch, kp_pad, out, fp16 != 0));
+  K_TRY(patchify(static_cast<cudaStream_t>(stream), image, n_img, H, W, y0, x0, gh, gw, patch, kp_pad, split, out, fp16 != 0));
   return CLIPEBC_OK;
 }
 

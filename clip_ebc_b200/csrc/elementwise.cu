@@ -200,22 +200,24 @@ __global__ void __launch_bounds__(256, 2) layernorm_stream_kernel(const float* _
 // One thread per VEC horizontally adjacent pixels of a patch row (VEC = 4 for patch 16 / 32, 2 for the 14-pixel patches of
 // ViT-L/14); consecutive threads walk along an image row (coalesced reads), each writes VEC 16-bit values into its patch
 // row. P = patch size, KP = columns per half (>= 3 * P * P; the columns beyond 3 * P * P are zeroed once by the caller).
-// Rows are written as [hi(KP) | lo(KP)] with hi = round16(x), lo = round16(x - hi): the patch-embed GEMM multiplies
-// [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9 (the stem is 0.4 % of the FLOPs).
+// split = 1 (bf16 operands): rows are written as [hi(KP) | lo(KP)] with hi = round16(x), lo = round16(x - hi): the patch-embed
+// GEMM multiplies [hi | lo | hi] x [Whi | Whi | Wlo] and so sees the fp32 pixels to ~2^-17 instead of 2^-9. split = 0 (fp16
+// operands, 11-bit mantissa): hi only -- one rounding of the pixels, like every later activation of the path.
 template <int VEC>
-__device__ __forceinline__ void load_store_hi_lo(const float* src, uint16_t* dst, int kp, int fp16) {
+__device__ __forceinline__ void load_store_hi_lo(const float* src, uint16_t* dst, int kp, int split, int fp16) {
   if constexpr (VEC == 4) {
     float4 v;
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) v = *reinterpret_cast<const float4*>(src);
     else v = make_float4(src[0], src[1], src[2], src[3]);
     const float hx = round16(v.x, fp16), hy = round16(v.y, fp16), hz = round16(v.z, fp16), hw = round16(v.w, fp16);
     *reinterpret_cast<uint2*>(dst) = make_uint2(pack16x2(hx, hy, fp16), pack16x2(hz, hw, fp16));
-    *reinterpret_cast<uint2*>(dst + kp) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
+    if (split)
+      *reinterpret_cast<uint2*>(dst + kp) = make_uint2(pack16x2(v.x - hx, v.y - hy, fp16), pack16x2(v.z - hz, v.w - hw, fp16));
   } else {
     const float vx = src[0], vy = src[1];
     const float hx = round16(vx, fp16), hy = round16(vy, fp16);
     *reinterpret_cast<uint32_t*>(dst) = pack16x2(hx, hy, fp16);
-    *reinterpret_cast<uint32_t*>(dst + kp) = pack16x2(vx - hx, vy - hy, fp16);
+    if (split) *reinterpret_cast<uint32_t*>(dst + kp) = pack16x2(vx - hx, vy - hy, fp16);
   }
 }
 
@@ -224,7 +226,7 @@ __device__ __forceinline__ void load_store_hi_lo(const float* src, uint16_t* dst
 template <int VEC>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ image, int n_units, int H, int W, int y0,
                                                        int x0, const int* __restrict__ origins_yx, int gh, int gw, int P,
-                                                       int kp, uint16_t* __restrict__ out, int fp16) {
+                                                       int kp, int split, uint16_t* __restrict__ out, int fp16) {
   pdl_launch_dependents();
   pdl_wait();
   const int vpp = P / VEC;                                                 // vectors per patch row
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
     else
       src = image + ((static_cast<int64_t>(unit) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * VEC;
     const int64_t patch = (static_cast<int64_t>(unit) * gh + gy) * gw + gx;
-    load_store_hi_lo<VEC>(src, out + patch * 2 * kp + c * P * P + py * P + pxv * VEC, kp, fp16);
+    load_store_hi_lo<VEC>(src, out + patch * (1 + split) * kp + c * P * P + py * P + pxv * VEC, kp, split, fp16);
   }
 }
 
@@ -593,33 +595,34 @@ const char* layernorm_rows(cudaStream_t stream, int width, const float* in, cons
 
 namespace {
 const char* patchify_launch(cudaStream_t stream, const float* image, int n_units, int H, int W, int y0, int x0,
-                            const int* origins, int gh, int gw, int patch, int kp_pad, void* out, int fp16) {
+                            const int* origins, int gh, int gw, int patch, int kp_pad, int split, void* out, int fp16) {
+  split = split != 0;
   if (patch != 14 && patch != 16 && patch != 32) return "patchify: patch size must be 14, 16 or 32";
   if (kp_pad < 3 * patch * patch || kp_pad % 8 != 0) return "patchify: bad padded patch row length";
   const int vec = patch % 4 == 0 ? 4 : 2;
   const int64_t total = static_cast<int64_t>(n_units) * 3 * gh * patch * gw * (patch / vec);
-  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * vec * (4.0 + 4.0));
+  LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * vec * (4.0 + 2.0 * (1 + split)));
   const dim3 grid(grid_for(total, 256, device_num_sms() * 16));
   cudaError_t e = vec == 4 ? launch_pdl(patchify_kernel<4>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
-                                        gw, patch, kp_pad, static_cast<uint16_t*>(out), fp16)
+                                        gw, patch, kp_pad, split, static_cast<uint16_t*>(out), fp16)
                            : launch_pdl(patchify_kernel<2>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
-                                        gw, patch, kp_pad, static_cast<uint16_t*>(out), fp16);
+                                        gw, patch, kp_pad, split, static_cast<uint16_t*>(out), fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 }  // namespace
 
 const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                     int patch, int kp_pad, void* out, int fp16) {
+                     int patch, int kp_pad, int split, void* out, int fp16) {
   if (n_img <= 0 || gh <= 0 || gw <= 0) return "patchify: empty grid";
   if (y0 < 0 || x0 < 0 || y0 + gh * patch > H || x0 + gw * patch > W) return "patchify: grid exceeds image";
-  return patchify_launch(stream, image, n_img, H, W, y0, x0, nullptr, gh, gw, patch, kp_pad, out, fp16);
+  return patchify_launch(stream, image, n_img, H, W, y0, x0, nullptr, gh, gw, patch, kp_pad, split, out, fp16);
 }
 
 const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                             int n_win, int hp, int wp, int patch, int kp_pad, void* out, int fp16) {
+                             int n_win, int hp, int wp, int patch, int kp_pad, int split, void* out, int fp16) {
   if (n_win <= 0) return "patchify: no windows";
   if (origins_yx_dev == nullptr) return "patchify: window origins missing";
-  return patchify_launch(stream, image, n_win, H, W, 0, 0, origins_yx_dev, hp, wp, patch, kp_pad, out, fp16);
+  return patchify_launch(stream, image, n_win, H, W, 0, 0, origins_yx_dev, hp, wp, patch, kp_pad, split, out, fp16);
 }
 
 const char* assemble_tokens(cudaStream_t stream, int width, const float* patch_embed, const int* win_base_dev, int src_pitch,

@@ -189,8 +189,9 @@ __device__ __forceinline__ void epi_f32_chunk32(const GemmParams& p, uint8_t* st
         const float hz = round16(v.z, p.out_fp16), hw = round16(v.w, p.out_fp16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4;
         *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(hx, hy, p.out_fp16), pack16x2(hz, hw, p.out_fp16));
-        *reinterpret_cast<uint2*>(o + p.N) =
-            make_uint2(pack16x2(v.x - hx, v.y - hy, p.out_fp16), pack16x2(v.z - hz, v.w - hw, p.out_fp16));
+        if (p.split_lo)
+          *reinterpret_cast<uint2*>(o + p.N) =
+              make_uint2(pack16x2(v.x - hx, v.y - hy, p.out_fp16), pack16x2(v.z - hz, v.w - hw, p.out_fp16));
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldo + n + c4) = v;
       }

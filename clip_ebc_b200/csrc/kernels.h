@@ -16,7 +16,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_GELU_BF16 = 3,       // out bf16 = quickgelu(acc + bias)
   EPI_BIAS_RESID_F32 = 4,       // out f32 = acc + bias + resid   (out may alias resid)
   EPI_BIAS_RELU_MASK_BF16 = 5,  // out bf16 = border ? 0 : relu(acc + bias)          (decoder conv1 on the padded grid)
-  EPI_BIAS_RESID_RELU_SPLIT = 6,// t = relu(acc + bias + resid); out[:, n] = hi(t), out[:, N + n] = lo(t)  (bf16 pair)
+  EPI_BIAS_RESID_RELU_SPLIT = 6,// t = relu(acc + bias + resid); out[:, n] = hi(t) and, when split_lo, out[:, N + n] = lo(t)
   EPI_BIAS_HEAD_PARTIAL = 7,    // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
                                 // tiles) out[row][2 * n_blk + half][0] = sum f^2, [1 + b] = sum f * head_tmat[b][n]
                                 // -- the projection fused with the first half of the EBC head (ebc_head_finish)
@@ -45,6 +45,8 @@ struct GemmParams {
                                       // leading border of the next)
   int ab_fp16;                        // 16-bit format of A and W: 0 = bf16, 1 = fp16
   int out_fp16;                       // 16-bit format written by the *_BF16 / SPLIT epilogues: 0 = bf16, 1 = fp16
+  int split_lo;                       // *_SPLIT epilogues: 1 = also write lo(t) = t - hi(t) at column N + n (split precision for
+                                      // the GEMM behind it), 0 = hi only
   const float* head_tmat;             // EPI_BIAS_HEAD_PARTIAL: f32 [head_bins, N] (logit_scale * normalised text features)
   int head_bins;                      // 1..32
   int w_prefetch;                     // 1 (gemm_params_plain default): W does not depend on the previous kernel of the
@@ -134,15 +136,15 @@ const char* layernorm_rows(cudaStream_t stream, int width, const float* in, cons
                            int in_row_offset, void* out16_extra = nullptr, int fp16_extra = 0);
 
 // ------------------------------------------------------------------ stem ---------------------------------------
-// image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag) [n_img * gh * gw, 2 * KP] = [hi | lo] split of the
-// pixels, KP = kp_pad >= 3 * patch^2 (columns beyond 3 * patch^2 are zero: the GEMM needs K % 64 == 0, ViT-L/14 has
+// image f32 [n_img, 3, H, W] -> patch rows (16-bit, fp16 flag): split = 1: [n_img * gh * gw, 2 * KP] = [hi | lo] split
+// of the pixels (hi = round16(x), lo = round16(x - hi)); split = 0: [n_img * gh * gw, KP] = hi only. KP = kp_pad >= 3 * patch^2 (columns beyond 3 * patch^2 are zero: the GEMM needs K % 64 == 0, ViT-L/14 has
 // 3 * 14^2 = 588 -> 640), k = c * patch^2 + py * patch + px (= conv1.weight.view(width, 3 * patch^2)), on the grid whose
 // (0,0) patch starts at pixel (y0, x0) of each image (gh, gw patches). patch = 16 / 32 (ViT-B) or 14 (ViT-L/14).
 const char* patchify(cudaStream_t stream, const float* image, int n_img, int H, int W, int y0, int x0, int gh, int gw,
-                     int patch, int kp_pad, void* out, int fp16);
-// per-window patchify when window origins are not on the patch grid: out rows [n_win * hp * wp, 2 * KP]
+                     int patch, int kp_pad, int split, void* out, int fp16);
+// per-window patchify when window origins are not on the patch grid: out rows [n_win * hp * wp, (1 + split) * KP]
 const char* patchify_windows(cudaStream_t stream, const float* image, int H, int W, const int* origins_yx_dev,
-                             int n_win, int hp, int wp, int patch, int kp_pad, void* out, int fp16);
+                             int n_win, int hp, int wp, int patch, int kp_pad, int split, void* out, int fp16);
 
 // Assemble the residual stream X f32 [n_win * t_live, width]:
 //   row 0            : LN_pre(class_emb + pos[0])

@@ -109,17 +109,17 @@ def attention(qkv: torch.Tensor, n_win: int, t_live: int, const_kv: Optional[tor
 
 
 def patchify(image: torch.Tensor, y0: int = 0, x0: int = 0, gh: Optional[int] = None,
-             gw: Optional[int] = None, fp16: bool = False, patch: int = 16) -> torch.Tensor:
-    """-> [n*gh*gw, 2*KP], KP = 3*patch^2 rounded up to 64: columns [0, KP) = hi, [KP, 2 KP) = lo of the hi/lo split of
-    the pixels (pad columns zero)."""
+             gw: Optional[int] = None, fp16: bool = False, patch: int = 16, split: bool = True) -> torch.Tensor:
+    """-> [n*gh*gw, 2*KP] (split) or [n*gh*gw, KP], KP = 3*patch^2 rounded up to 64: columns [0, KP) = hi, [KP, 2 KP) = lo of
+    the hi/lo split of the pixels (pad columns zero)."""
     n, c, H, W = image.shape
     assert c == 3 and image.dtype == torch.float32
     gh = (H - y0) // patch if gh is None else gh
     gw = (W - x0) // patch if gw is None else gw
     kp = (3 * patch * patch + 63) // 64 * 64
-    out = torch.zeros((n * gh * gw, 2 * kp), dtype=_dt16(fp16), device=image.device)
-    _lib.check(_lib.load().clipebc_patchify(_ptr(image), n, H, W, y0, x0, gh, gw, int(patch), kp, _ptr(out), int(fp16),
-                                            _stream()), "patchify")
+    out = torch.zeros((n * gh * gw, (2 if split else 1) * kp), dtype=_dt16(fp16), device=image.device)
+    _lib.check(_lib.load().clipebc_patchify(_ptr(image), n, H, W, y0, x0, gh, gw, int(patch), kp, int(split), _ptr(out),
+                                            int(fp16), _stream()), "patchify")
     return out
 
 

@@ -50,7 +50,8 @@ typedef struct clipebc_config {
   int window_chunk; /* windows per internal pass (0 = library default)                                               */
   int operand_fp16; /* 16-bit tensor-core operand format: 1 = fp16 (11-bit mantissa; CLIP's released weights are fp16,
                        all operands are range-bounded and saturated), 0 = bf16. Accumulation, residual stream,
-                       LayerNorm statistics, softmax and the head are fp32 either way.                               */
+                       LayerNorm statistics, softmax and the head are fp32 either way. With bf16 the patch-embedding and
+                       projection GEMMs run in split precision (hi + lo operands, 3 K-segments), with fp16 in one.   */
   int patch;        /* ViT patch size = encoder reduction: 16 (also when 0), 32 or 14
                        -- _clip/image_encoder.py:141, models/clip/model.py:78                                        */
   int width;        /* transformer width = decoder channels: 768 (also when 0) or 1024                               */
@@ -147,10 +148,11 @@ int clipebc_layernorm(const float* in_dev, const float* gamma_dev, const float* 
  * t_live + n_const <= 256 and n_const % 8 == 0, streamed-K/V kernel otherwise. */
 int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
                       int heads, void* out_16_dev, int out_fp16, void* stream);
-/* out: [n_img*gh*gw, 2*kp_pad] = [hi | lo] split of the pixels in the 16-bit format; kp_pad >= 3 * patch^2 (a multiple of
- * 8; pad columns are not written), patch 14, 16 or 32 */
+/* out: split = 1: [n_img*gh*gw, 2*kp_pad] = [hi | lo] split of the pixels in the 16-bit format (what the path uses with bf16
+ * operands); split = 0: [n_img*gh*gw, kp_pad] = hi only (fp16 operands). kp_pad >= 3 * patch^2 (a multiple of 8; pad columns
+ * are not written), patch 14, 16 or 32 */
 int clipebc_patchify(const float* image_dev, int n_img, int H, int W, int y0, int x0, int gh, int gw, int patch,
-                     int kp_pad, void* out_16_dev, int fp16, void* stream);
+                     int kp_pad, int split, void* out_16_dev, int fp16, void* stream);
 /* Shared-border grid [n_win, gh+1, gw+1, width]: cell (y, x) at row y*(gw+1)+x, column gw and row gh are zero; the zero
  * column ending a line is the left border of the next line, the zero row ending a window the top border of the next.
  * U_16_dev may be NULL. */

@@ -288,6 +288,10 @@ def test_patchify_matches_unfold(ops, dt, patch):
     assert torch.equal(out[:, :, 1], (ref - hi).to(dt).float())
     # hi + lo carries the pixels to ~2 roundings of the 16-bit format
     assert (out[:, :, 0] + out[:, :, 1] - ref).abs().max().item() < 4 * ROUND16[dt] ** 2 * ref.abs().max().item()
+    # the single-precision form (fp16 operands): hi only, rows of kp columns
+    single = ops.patchify(img, fp16=dt == torch.float16, patch=patch, split=False).float()
+    assert single.shape == (2 * (H // patch) * (W // patch), kp)
+    assert torch.equal(single.view(2, -1, kp)[..., :k], hi)
 
 
 @pytest.mark.parametrize("g", [28, 14, 7])
