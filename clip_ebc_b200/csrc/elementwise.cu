@@ -115,19 +115,21 @@ __global__ void __launch_bounds__(256, D == 768 ? 4 : 3) layernorm_kernel(const 
 // shared-memory ring with bulk async copies (2 CTAs per SM: 144 KB in flight whatever the warps are doing), warp w
 // normalises row w of a block from shared memory, and gamma / beta live in registers for the whole kernel (they are
 // loaded before the dependency wait -- they do not depend on the previous kernel).
-constexpr int kLnRows = 8, kLnStages = 3;
-template <int D>
+constexpr int kLnRows = 8, kLnStages = 3, kLnCtasPerSm = 2;
+template <int D, int STAGES = kLnStages>
 struct LnStream {
-  static constexpr int kStageBytes = kLnRows * D * 4;                                 // 24 KB / 32 KB
-  static constexpr int kSmem = kLnStages * kStageBytes + 2 * kLnStages * 8 + 128;     // ring + barriers + alignment slack
+  static constexpr int kStageBytes = kLnRows * D * 4;                           // 24 KB / 32 KB
+  static constexpr int kSmem = STAGES * kStageBytes + 2 * STAGES * 8 + 128;     // ring + barriers + alignment slack
 };
 
-template <int D>
-__global__ void __launch_bounds__(256, 2) layernorm_stream_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+// STAGES x CTAS: ring depth per CTA and resident CTAs per SM (profiles/probes/ln_probe.cu sweeps them)
+template <int D, int STAGES = kLnStages, int CTAS = kLnCtasPerSm>
+__global__ void __launch_bounds__(256, CTAS) layernorm_stream_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, uint16_t* __restrict__ out,
                                                                 int64_t n_rows, int fp16) {
   constexpr int kVec = Row<D>::kVec;
-  constexpr int kStageBytes = LnStream<D>::kStageBytes;
+  constexpr int kStageBytes = LnStream<D, STAGES>::kStageBytes;
+  constexpr int kLnStages = STAGES;  // shadows the default: this instance's ring depth
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLnStages * kStageBytes);

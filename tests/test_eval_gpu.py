@@ -153,3 +153,27 @@ def test_cross_image_window_batching_is_bit_identical_to_per_image_calls():
             assert torch.equal(cnt[i:i + 1], c1.reshape(1))
         dens_cpu, cnt_cpu = sliding_window_predict_batch(model, [im.cpu() for im in images], 224, 112)
         assert all(d.device.type == "cpu" for d in dens_cpu) and torch.equal(cnt_cpu, cnt.cpu())
+
+
+def test_prefetched_host_images_give_the_same_counts_as_device_images():
+    """predict_counts copies pinned host images on a side stream while the previous image is computed (`_prefetch_to_device`):
+    the counts equal, bit for bit, those of the same images already resident on the device, in order, for images of
+    different sizes (including one large enough to take several internal passes)."""
+    from clip_ebc_b200 import get_model
+    from clip_ebc_b200.eval_loop import predict_counts
+
+    case = CASES[0]
+    sd, tf, bins, anchors, reduction, _ = case_inputs(case)
+    model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+                      prompt_type="word", num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda").eval()
+    from oracle import weights
+
+    sizes = [(448, 672), (1344, 1792), (224, 224), (672, 448), (1344, 1792), (448, 448)]
+    host = [weights.make_image((1, 3, h, w), seed=700 + i).pin_memory() for i, (h, w) in enumerate(sizes)]
+    dev = torch.device("cuda")
+    on_device = predict_counts(model, [im.cuda() for im in host], dev, True, 224, 112)
+    for _ in range(3):
+        assert predict_counts(model, host, dev, True, 224, 112) == on_device
+    assert predict_counts(model, (im[0] for im in host), dev, True, 224, 112) == on_device  # [3,H,W] items, a generator
