@@ -34,15 +34,16 @@ class ClipEbcConfig(C.Structure):
         ("layers", C.c_int),
         ("embed_dim", C.c_int),
         ("decoder_conv1_fine", C.c_int),
+        ("encoder", C.c_int),
     ]
 
 
 def make_config(input_size: int, reduction: int, num_vpt: int, deep_vpt: int, num_bins: int, window_chunk: int = 0,
                 operand_fp16: int = 1, patch: int = 16, width: int = 768, layers: int = 12, embed_dim: int = 512,
-                decoder_conv1_fine: int = 0) -> ClipEbcConfig:
+                decoder_conv1_fine: int = 0, encoder: int = 0) -> ClipEbcConfig:
     return ClipEbcConfig(C.sizeof(ClipEbcConfig), int(input_size), int(reduction), int(num_vpt), int(deep_vpt), int(num_bins),
                          int(window_chunk), int(operand_fp16), int(patch), int(width), int(layers), int(embed_dim),
-                         int(decoder_conv1_fine))
+                         int(decoder_conv1_fine), int(encoder))
 
 
 _vp, _i, _i64, _fp = C.c_void_p, C.c_int, C.c_int64, C.c_void_p  # float* passed as raw addresses

@@ -17,6 +17,7 @@
 
 #include "../../include/clipebc_b200.h"
 #include "kernels.h"
+#include "model_state.h"
 
 namespace cebc {
 
@@ -76,15 +77,10 @@ const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, co
   return attention_h64_long(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
 }
 
-namespace {
-
-thread_local std::string g_err;
-
-}  // namespace
+namespace { thread_local std::string g_err; }
 namespace { thread_local const cudaAccessPolicyWindow* g_l2_window_tls = nullptr; }
 const cudaAccessPolicyWindow* current_l2_window() { return g_l2_window_tls; }
 static void set_l2_window(const cudaAccessPolicyWindow* w) { g_l2_window_tls = w; }
-namespace {
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -94,104 +90,18 @@ int fail_cuda(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return CLIPEBC_ECUDA;
 }
-#define CUDA_TRY(expr)                                         \
-  do {                                                         \
-    cudaError_t _e = (expr);                                   \
-    if (_e != cudaSuccess) return fail_cuda(_e, #expr);        \
-  } while (0)
-// kernel launchers return nullptr or a message
-#define K_TRY(expr)                                                        \
-  do {                                                                     \
-    const char* _m = (expr);                                               \
-    if (_m != nullptr) return fail(CLIPEBC_ECUDA, std::string(_m));        \
-  } while (0)
-
-// Bumped by every (re)allocation or release of a device buffer of this library: host layers that cache captured CUDA
-// graphs of the library's launches key them on it (a graph holds the buffer addresses used at capture time -- replaying
-// it after a workspace has moved would write to freed memory).
 std::atomic<int64_t> g_config_epoch{0};
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DevBuf() { if (p) { cudaFree(p); g_config_epoch.fetch_add(1); } }
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  cudaError_t reserve(size_t n) {
-    if (n <= bytes) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    g_config_epoch.fetch_add(1);
-    return e;
-  }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
-
-struct RawTensor {
-  DevBuf buf;
-  std::vector<int64_t> shape;
-  int64_t numel = 0;
-};
-
-struct LayerPack {
-  DevBuf w_qkv, w_out, w_fc, w_proj;  // 16-bit, nn.Linear layout [N, K]
-  DevBuf const_kv;                    // bf16 [num_vpt, 3 * width] (deep VPT): in_proj(LN1_l(vpt_l)), input-independent
-  const float *b_qkv, *b_out, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-};
-
-}  // namespace
 }  // namespace cebc
 
 using namespace cebc;
 
-struct clipebc_model {
-  clipebc_config cfg;       // normalised: patch / width / layers / embed_dim filled in
-  int device = 0;           // the CUDA device the handle was created on: every buffer below lives there
-  int kp_pad = 0;           // patch row length 3 * patch^2 rounded up to the GEMM's K granularity (64)
-  // Split precision (hi + lo operands, three K-segments [hi | lo | hi] x [Whi | Whi | Wlo]) of the two GEMMs whose rounding
-  // reaches the head directly: patch embedding and the 1x1 projection. On for bf16 operands (8-bit mantissa: a single
-  // segment costs 0.6-1.3e-2 on the logits and 0.1-0.3 % of the bin argmax at the projection alone); off for fp16 operands
-  // (11 bits: 0.7-1.5e-3 and >= 99.97 %, measured against the fp32 oracle stage by stage) -- there the split would be 2.4 of
-  // 48.8 GFLOP per window spent on bits the other twelve 16-bit roundings per block have already given up.
-  bool split_precision = false;
-  std::map<std::string, RawTensor> raw;
-  bool packed = false;
-  // packed
-  std::unique_ptr<LayerPack[]> layer;  // [cfg.layers]
-  DevBuf w_patch;           // 16-bit [width, 3 * kp_pad] = hi | hi | lo
-  DevBuf w_c1z;             // 16-bit [9 * width, width]: conv1 with the tap on the output side (coarse-grid form)
-  DevBuf zero_bias;         // f32 [9 * width] zeros
-  DevBuf ws_Y16, ws_Z;      // coarse-grid conv1: 16-bit ln_post rows, per-tap products [n * hp * wp, 9 * width]
-  DevBuf w_c1, w_c2;        // 16-bit [width, 9 * width]
-  DevBuf b_c1, b_c2;        // f32 [width]
-  DevBuf w_p3;              // 16-bit [embed, 3 * width] = hi | hi | lo
-  DevBuf tmat;              // f32 [N, embed]
-  DevBuf pack_tmp_16;
-  std::map<int, DevBuf> pos_cache;  // key hp * 4096 + wp -> f32 [1 + hp*wp, width]; bounded (kMaxPosCache)
-  // workspace
-  DevBuf ws_patch_rows, ws_patch_embed, ws_X, ws_Xn, ws_QKV, ws_AO, ws_Hid, ws_Y, ws_Ub, ws_Uf, ws_D1, ws_D2, ws_F,
-      ws_preds;
-  // device-resident index tables (window -> patch-grid row, window origins, fold cell origins), cached per geometry so
-  // the steady state has no host->device upload and no host synchronisation; bounded (kMaxIdxCache)
-  std::map<std::string, DevBuf> idx_cache;
-};
+namespace cebc {
 
-namespace {
-
-constexpr size_t kMaxPosCache = 16, kMaxIdxCache = 64;
-
-// Tensor by its state_dict key, or nullptr: pack() has checked every key the path reads, so a miss can only be a tensor
-// the configuration does not need (never throws across the C ABI)
 const float* raw_ptr(clipebc_model* m, const std::string& name) {
   auto it = m->raw.find(name);
   return it == m->raw.end() ? nullptr : it->second.buf.as<float>();
 }
-
-// Every entry point that touches a handle: the handle's buffers live on the device it was created on, and the kernels'
-// per-device attributes are keyed on the current device, so the two must agree.
-int check_device(const clipebc_model* m);
 
 bool check_shape(clipebc_model* m, const std::string& name, std::initializer_list<int64_t> want, std::string* err) {
   auto it = m->raw.find(name);
@@ -206,6 +116,21 @@ bool check_shape(clipebc_model* m, const std::string& name, std::initializer_lis
     return false;
   }
   return true;
+}
+
+}  // namespace cebc
+
+namespace {
+
+constexpr size_t kMaxPosCache = 16, kMaxIdxCache = 64;
+
+// Every entry point that touches a handle: the handle's buffers live on the device it was created on, and the kernels'
+// per-device attributes are keyed on the current device, so the two must agree.
+int check_device(const clipebc_model* m);
+
+bool check_shape_ok(clipebc_model* m, const std::string& scalar_name) {
+  auto it = m->raw.find(scalar_name);
+  return it != m->raw.end() && it->second.numel == 1;
 }
 
 std::string blk(int l, const char* tail) {
@@ -489,6 +414,12 @@ int default_chunk(const clipebc_model* m, int hp, int wp) {
 }
 
 int check_window_geometry(clipebc_model* m, int h, int w) {
+  if (m->cfg.encoder == 1) {
+    if (h <= 0 || w <= 0 || h % 32 != 0 || w % 32 != 0)
+      return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of 32 for the CLIP-ResNet encoders");
+    if (h > 2048 || w > 2048) return fail(CLIPEBC_EINVAL, "window too large for the CLIP-ResNet path (max 2048 pixels a side)");
+    return CLIPEBC_OK;
+  }
   const int kPatch = m->cfg.patch;
   if (h <= 0 || w <= 0 || h % kPatch != 0 || w % kPatch != 0)
     return fail(CLIPEBC_EINVAL, "window height/width must be positive multiples of the patch size");
@@ -549,6 +480,35 @@ int cached_table(clipebc_model* m, const std::string& key, const std::vector<int
   return CLIPEBC_OK;
 }
 
+// sliding_window_predict with a CLIP-ResNet encoder: the windows are convolved independently (the reference slices a window
+// first and zero-pads it, so overlapping windows share no activations), chunk by chunk, then folded like the ViT windows
+int sliding_resnet(clipebc_model* m, cudaStream_t s, const float* image_dev, int H, int W, int wh, int ww, int sh, int sw,
+                   const std::vector<int>& ro, const std::vector<int>& co, float* density_out_dev, float* count_out_dev) {
+  const int r = m->cfg.reduction, nr = static_cast<int>(ro.size()), nc = static_cast<int>(co.size()), n_win = nr * nc;
+  const int gh = wh / r, gw = ww / r;
+  // index table: origins (y, x) per window | row cells | col cells
+  std::vector<int> tab(static_cast<size_t>(2) * n_win + nr + nc);
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j) { tab[2 * (i * nc + j)] = ro[i]; tab[2 * (i * nc + j) + 1] = co[j]; }
+  for (int i = 0; i < nr; ++i) tab[2 * n_win + i] = ro[i] / r;
+  for (int j = 0; j < nc; ++j) tab[2 * n_win + nr + j] = co[j] / r;
+  const std::string key = "rsw:" + std::to_string(H) + ":" + std::to_string(W) + ":" + std::to_string(wh) + ":" + std::to_string(ww) +
+                          ":" + std::to_string(sh) + ":" + std::to_string(sw);
+  const int* d_tab;
+  int rc;
+  if ((rc = cached_table(m, key, tab, s, &d_tab))) return rc;
+  CUDA_TRY(m->ws_preds.reserve(static_cast<size_t>(n_win) * gh * gw * 4));
+  float* preds = m->ws_preds.as<float>();
+  const int chunk = resnet_default_chunk(m, wh, ww);
+  for (int b0 = 0; b0 < n_win; b0 += chunk) {
+    const int nw = std::min(chunk, n_win - b0);
+    if ((rc = resnet_run_windows(m, s, image_dev, H, W, d_tab + 2 * b0, nw, wh, ww, preds + static_cast<int64_t>(b0) * gh * gw, nullptr)))
+      return rc;
+  }
+  K_TRY(fold_average(s, preds, d_tab + 2 * n_win, d_tab + 2 * n_win + nr, nr, nc, gh, gw, H / r, W / r, density_out_dev, count_out_dev));
+  return CLIPEBC_OK;
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -605,6 +565,11 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
                 "clipebc_config has " + std::to_string(sizeof(clipebc_config)) + " bytes (ABI v" +
                 std::to_string(CLIPEBC_ABI_VERSION) + "): the caller was built against another header");
   clipebc_config c = *cfg;
+  if (c.encoder != 0 && c.encoder != 1) return fail(CLIPEBC_EINVAL, "encoder must be 0 (ViT) or 1 (CLIP-ResNet)");
+  if (c.encoder == 1) {  // the ViT-only fields are ignored: normalise them so that the checks below pass
+    c.patch = 16; c.width = 768; c.layers = 12; c.input_size = 224; c.num_vpt = 0; c.deep_vpt = 0;
+    if (c.embed_dim == 0) c.embed_dim = 1024;
+  }
   if (c.patch == 0) c.patch = 16;
   if (c.width == 0) c.width = 768;
   if (c.layers == 0) c.layers = 12;
@@ -667,6 +632,15 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const clipebc_config& c = m->cfg;
   const int fp16 = c.operand_fp16 != 0;
+  if (c.encoder == 1) {
+    if ((rc = resnet_pack(m, s))) return rc;
+    if (!check_shape_ok(m, "logit_scale")) return fail(CLIPEBC_ESTATE, "pack: tensor 'logit_scale' missing or not a scalar");
+    CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * c.embed_dim * 4));
+    K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, c.embed_dim, m->tmat.as<float>()));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    m->packed = true;
+    return CLIPEBC_OK;
+  }
   const int D = c.width, hidden = 4 * D, E = c.embed_dim, nL = c.layers;
   const int kPatch = c.patch, kp = 3 * kPatch * kPatch;
   const int g0 = c.input_size / kPatch;
@@ -769,6 +743,18 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
   if ((rc = check_device(m))) return rc;
   if ((rc = check_window_geometry(m, h, w))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (m->cfg.encoder == 1) {
+    const int gh = h / m->cfg.reduction, gw = w / m->cfg.reduction;
+    const int chunk = resnet_default_chunk(m, h, w);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int nw = std::min(chunk, B - b0);
+      float* lo = logits_out_dev ? logits_out_dev + static_cast<int64_t>(b0) * m->cfg.num_bins * gh * gw : nullptr;
+      if ((rc = resnet_run_windows(m, s, x_dev + static_cast<int64_t>(b0) * 3 * h * w, h, w, nullptr, nw, h, w,
+                                   exp_out_dev + static_cast<int64_t>(b0) * gh * gw, lo)))
+        return rc;
+    }
+    return CLIPEBC_OK;
+  }
   const int kPatch = m->cfg.patch;
   const int hp = h / kPatch, wp = w / kPatch, npatch = hp * wp;
   const int gh = h / m->cfg.reduction, gw = w / m->cfg.reduction;
@@ -826,6 +812,7 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   std::vector<int> ro(nr), co(nc);
   clipebc_window_origins(H, W, wh, ww, sh, sw, &nr, &nc, ro.data(), co.data());
   const int n_win = nr * nc;
+  if (m->cfg.encoder == 1) return sliding_resnet(m, s, image_dev, H, W, wh, ww, sh, sw, ro, co, density_out_dev, count_out_dev);
   const int kPatch = m->cfg.patch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
   const int gh = wh / r, gw = ww / r;
@@ -897,6 +884,15 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
   if ((rc = check_device(m))) return rc;
   if ((rc = check_window_geometry(m, wh, ww))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (m->cfg.encoder == 1) {  // no activations are shared between windows: image by image
+    for (int i = 0; i < n_images; ++i) {
+      if (!images_dev[i] || !density_out_dev[i]) return fail(CLIPEBC_EINVAL, "null image or output pointer in the batch");
+      if ((rc = clipebc_sliding_window_predict(m, images_dev[i], heights[i], widths[i], wh, ww, sh, sw, density_out_dev[i],
+                                               counts_out_dev ? counts_out_dev + i : nullptr, stream_)))
+        return rc;
+    }
+    return CLIPEBC_OK;
+  }
   const int r = m->cfg.reduction;
   const int kPatch = m->cfg.patch;
   const int hp = wh / kPatch, wp = ww / kPatch, npatch = hp * wp;
@@ -1006,6 +1002,7 @@ int clipebc_gemm_bf16(int epi, const void* A, int64_t a_rows, int64_t a_cols, in
   p.out = out; p.ldo = ldo; p.bias = bias; p.resid = resid; p.ldr = ldr; p.mask_hp = mask_hp; p.mask_wp = mask_wp; p.mask_lead = mask_lead != 0;
   p.ab_fp16 = ab_fp16 != 0; p.out_fp16 = out_fp16 != 0;
   p.split_lo = 1;  // epilogue 6 as a test hook always writes hi | lo
+  if (epi == EPI_BIAS_RESID16_RELU_MASK_BF16) { p.resid16 = resid; p.resid = nullptr; }  // resid_dev is 16-bit for epilogue 9
   const char* e = gemm_dispatch(static_cast<cudaStream_t>(stream), epi, static_cast<const __nv_bfloat16*>(A), a_rows, a_cols,
                                lda, static_cast<const __nv_bfloat16*>(W), ldw, p, block_n);
   if (e) return fail(std::strncmp(e, "gemm:", 5) == 0 ? CLIPEBC_EINVAL : CLIPEBC_ECUDA, e);

@@ -57,7 +57,8 @@ __device__ __forceinline__ float quick_gelu2(float x) {
 
 template <int EPI>
 constexpr bool out_is_bf16() {
-  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16;
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RELU_MASK_BF16 ||
+         EPI == EPI_BIAS_RESID16_RELU_MASK_BF16;
 }
 template <int EPI>
 constexpr bool has_resid() {
@@ -75,7 +76,7 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
                                                  int n, const uint32_t (&r)[32], int tma_half = -1) {
   const int row = row0 + lane;
   bool border = false;
-  if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
+  if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16 || EPI == EPI_BIAS_RESID16_RELU_MASK_BF16) {
     const int rpi = p.mask_hp * p.mask_wp;
     const int q = row % rpi;
     const int py = q / p.mask_wp, px = q - py * p.mask_wp;
@@ -95,7 +96,21 @@ __device__ __forceinline__ void epi_bf16_chunk32(const GemmParams& p, uint8_t* s
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = quick_gelu2(v[k]);
     }
-    if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16) {
+    if constexpr (EPI == EPI_BIAS_RESID16_RELU_MASK_BF16) {
+      // identity branch: 8 values of this thread's row in the 16-bit output format
+      uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+      if (row < p.M && !border)
+        rv = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.resid16) + static_cast<size_t>(row) * p.ldr + n + 8 * j);
+      const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f;
+        if (p.out_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&ru[k]));
+        else f = make_float2(__uint_as_float(ru[k] << 16), __uint_as_float(ru[k] & 0xFFFF0000u));
+        v[2 * k] += f.x; v[2 * k + 1] += f.y;
+      }
+    }
+    if constexpr (EPI == EPI_BIAS_RELU_MASK_BF16 || EPI == EPI_BIAS_RESID16_RELU_MASK_BF16) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = border ? 0.0f : fmaxf(v[k], 0.0f);
     }
@@ -630,6 +645,8 @@ cudaError_t launch_epi2(cudaStream_t stream, int epi, const CUtensorMap& ta, con
     case EPI_BIAS_RELU_MASK_BF16: return launch_one2<BLOCK_N, EPI_BIAS_RELU_MASK_BF16>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_RESID_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_RESID_RELU_SPLIT>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_UPSKIP_RELU_SPLIT: return launch_one2<BLOCK_N, EPI_BIAS_UPSKIP_RELU_SPLIT>(stream, ta, tb, p, num_sms);
+    case EPI_BIAS_RESID16_RELU_MASK_BF16:
+      return launch_one2<BLOCK_N, EPI_BIAS_RESID16_RELU_MASK_BF16>(stream, ta, tb, p, num_sms);
     case EPI_BIAS_HEAD_PARTIAL:
       if constexpr (BLOCK_N == 256) return launch_one2<256, EPI_BIAS_HEAD_PARTIAL>(stream, ta, tb, p, num_sms);
       else return cudaErrorInvalidValue;
@@ -689,7 +706,11 @@ const char* gemm2_bf16_tn(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
     return "gemm: epilogue needs a residual";
   if (epi == EPI_BIAS_UPSKIP_RELU_SPLIT && (p.mask_hp < 2 || p.mask_wp < 2 || p.up_hp < 1 || p.up_wp < 1))
     return "gemm: upsampled-skip epilogue needs the grid (mask_hp, mask_wp) and the patch grid (up_hp, up_wp)";
-  if (epi == EPI_BIAS_RELU_MASK_BF16 && (p.mask_hp < 2 || p.mask_wp < 2)) return "gemm: mask grid missing";
+  if ((epi == EPI_BIAS_RELU_MASK_BF16 || epi == EPI_BIAS_RESID16_RELU_MASK_BF16) && (p.mask_hp < 2 || p.mask_wp < 2))
+    return "gemm: mask grid missing";
+  if (epi == EPI_BIAS_RESID16_RELU_MASK_BF16 &&
+      (p.resid16 == nullptr || (reinterpret_cast<uintptr_t>(p.resid16) & 15) || (p.ldr * 2) % 16 != 0))
+    return "gemm: 16-bit residual missing or not 16-byte aligned";
   if (epi == EPI_BIAS_HEAD_PARTIAL) {
     if (p.head_tmat == nullptr || p.head_bins < 1 || p.head_bins > 32) return "gemm: head epilogue needs the text matrix and 1..32 bins";
     if (p.N % 256 != 0) return "gemm: head epilogue needs N to be a multiple of 256";

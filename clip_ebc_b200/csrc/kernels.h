@@ -20,6 +20,8 @@ enum GemmEpilogue : int {
   EPI_BIAS_HEAD_PARTIAL = 7,    // f = acc + bias is never written: per row and per half tile (CTA-pair kernel, 256-wide
                                 // tiles) out[row][2 * n_blk + half][0] = sum f^2, [1 + b] = sum f * head_tmat[b][n]
                                 // -- the projection fused with the first half of the EBC head (ebc_head_finish)
+  EPI_BIAS_RESID16_RELU_MASK_BF16 = 9,  // out 16-bit = border ? 0 : relu(acc + bias + resid16[row, n]); resid16 is a 16-bit
+                                // [M, ldr] tensor in the output format (the identity branch of a ResNet bottleneck)
   EPI_BIAS_UPSKIP_RELU_SPLIT = 8  // EPI_BIAS_RESID_RELU_SPLIT whose residual is the bilinear upsample of the coarse map,
                                 // evaluated on the fly: resid = Y f32 [n_win * up_hp * up_wp, ldr] (ln_post rows), the row's
                                 // cell comes from the shared-border grid (mask_hp x mask_wp rows per window); border rows add 0.
@@ -37,6 +39,7 @@ struct GemmParams {
   int ldo;                            // elements
   const float* bias;                  // [N]
   const float* resid;                 // f32 [M, ldr]
+  const void* resid16;                // EPI_BIAS_RESID16_RELU_MASK_BF16: 16-bit [M, ldr]
   int ldr;
   int mask_hp, mask_wp;               // padded grid (rows per image = mask_hp * mask_wp), EPI_BIAS_RELU_MASK_BF16
   int up_hp, up_wp;                   // EPI_BIAS_UPSKIP_RELU_SPLIT: patch grid of the coarse map
@@ -194,6 +197,25 @@ const char* fold_conv3x3_bn_tapout(cudaStream_t stream, const float* W, const fl
 // [n_win, n_bins, gh, gw]  (model.py:200-212).
 const char* ebc_head_finish(cudaStream_t stream, const float* partial, int n_part, const float* anchors, int n_bins, int n_win,
                             int gh, int gw, float* exp_out, float* logits_out);
+
+// ------------------------------------------------------------------ CLIP-ResNet encoder path (resnet.cu) ---------
+// Stem conv1 (3 -> 32, 3x3, stride 2, pad 1) as im2col rows for the GEMM: 16-bit [n_units * (h/2+1) * (w/2+1), 64] on the
+// shared-border grid, k = c * 9 + ky * 3 + kx < 27, rest zero. Units: images of a batch [n, 3, H, W] (origins == nullptr,
+// h == H, w == W) or windows of one image [3, H, W] at origins_yx_dev (device, y then x per unit).
+const char* stem_im2col(cudaStream_t stream, const float* image, int n_units, int H, int W, const int* origins_yx_dev, int h,
+                        int w, void* out, int fp16);
+// 16-bit NHWC maps on shared-border grids: dst[.., dst_col + c] = S x S mean of src[.., src_col + c] (S = 1 copy, S = 2
+// nn.AvgPool2d(2)); dst grid (go_h + 1) x (go_w + 1) per unit, src grid (S go_h + 1) x (S go_w + 1); dst border = 0.
+const char* pool_copy(cudaStream_t stream, const void* src, int ld_src, int src_col, void* dst, int ld_dst, int dst_col, int C,
+                      int n_units, int go_h, int go_w, int S, int fp16);
+// bilinear resample (align_corners = False) of a 16-bit NHWC map [.., C] between shared-border grids gi -> go
+const char* resample16(cudaStream_t stream, const void* src, void* dst, int C, int n_units, int gi_h, int gi_w, int go_h, int go_w,
+                       int fp16);
+// BatchNorm (eval) folded into the conv before it, written as a K-major GEMM operand with padding / concatenation:
+// Wp[o * ldw + col_off + tap * i_pad + i] = W[o, i, tap] * s(o); bias[o] (+)= beta - mean * s(o), s = gamma / sqrt(var + eps)
+const char* fold_conv_bn_general(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* mean,
+                                 const float* var, float eps, int O, int I, int taps, int i_pad, void* Wp, int ldw, int col_off,
+                                 float* bias, int accumulate_bias, int fp16);
 
 // ------------------------------------------------------------------ fold ---------------------------------------
 // preds f32 [n_rows * n_cols, 1, gh, gw] -> density f32 [Ho, Wo]: average of overlapping windows, summed in ascending

@@ -38,8 +38,12 @@ resnet_backbones = ["resnet50", "resnet101", "resnet50x4", "resnet50x16", "resne
 vit_backbones = ["vit_b_16", "vit_b_32", "vit_l_14", "vit_l_14_336px"]
 
 # backbone -> (patch size = encoder reduction, width, layers, embed_dim); heads = width // 64 (_clip/model.py:50),
-# models/clip/model.py:16-24. The CLIP-ResNet backbones are not implemented.
+# models/clip/model.py:16-24
 _VIT_DIMS = {"vit_b_16": (16, 768, 12, 512), "vit_b_32": (32, 768, 12, 512), "vit_l_14": (14, 1024, 24, 768)}
+# CLIP-ResNet backbones of stem width 64: backbone -> (blocks per layer, embed_dim, decoder_cfg) -- the configs prepare.py
+# extracts from the OpenAI checkpoints (_clip/__init__.py:73-96) and models/clip/model.py:228-239. resnet50x4 / x16 / x64
+# (stem widths 80 / 96 / 128) are not implemented.
+_RESNET_DIMS = {"resnet50": ((3, 4, 6, 3), 1024, (2048,)), "resnet101": ((3, 4, 23, 3), 512, (2048, 1024))}
 
 
 class _Block(nn.Module):
@@ -79,6 +83,57 @@ class _ImageEncoder(nn.Module):
         self.clip_embed_dim = embed
 
 
+def _conv_bn(prefix_conv: str, prefix_bn: str, mod: nn.Module, cin: int, cout: int, k: int, stride: int = 1) -> None:
+    setattr(mod, prefix_conv, nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=False))
+    setattr(mod, prefix_bn, nn.BatchNorm2d(cout))
+
+
+class _ClipBottleneck(nn.Module):
+    """Parameter names of the CLIP Bottleneck (_clip/blocks.py:56-86). Never called."""
+
+    def __init__(self, inplanes: int, planes: int, stride: int) -> None:
+        super().__init__()
+        _conv_bn("conv1", "bn1", self, inplanes, planes, 1)
+        _conv_bn("conv2", "bn2", self, planes, planes, 3)
+        _conv_bn("conv3", "bn3", self, planes, planes * 4, 1)
+        self.downsample = None
+        if stride > 1 or inplanes != planes * 4:
+            self.downsample = nn.Sequential(OrderedDict([("-1", nn.AvgPool2d(stride)),
+                                                         ("0", nn.Conv2d(inplanes, planes * 4, 1, bias=False)),
+                                                         ("1", nn.BatchNorm2d(planes * 4))]))
+
+
+class _ModifiedResNet(nn.Module):
+    """Parameter names of ModifiedResNet(features_only=True) (_clip/image_encoder.py:33-58), stem width 64."""
+
+    def __init__(self, layers: Tuple[int, int, int, int], embed: int, reduction: int) -> None:
+        super().__init__()
+        _conv_bn("conv1", "bn1", self, 3, 32, 3, stride=2)
+        _conv_bn("conv2", "bn2", self, 32, 32, 3)
+        _conv_bn("conv3", "bn3", self, 32, 64, 3)
+        inplanes = 64
+        for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+            stride = 1 if li == 1 or (li == 4 and reduction <= 16) else 2
+            seq = [_ClipBottleneck(inplanes, planes, stride)]
+            inplanes = planes * 4
+            seq += [_ClipBottleneck(inplanes, planes, 1) for _ in range(1, blocks)]
+            setattr(self, f"layer{li}", nn.Sequential(*seq))
+        self.channels = inplanes
+        self.reduction = 16 if reduction <= 16 else 32
+        self.clip_embed_dim = embed
+
+
+class _DecoderBottleneck(nn.Module):
+    """Parameter names of models/utils.py Bottleneck (expansion 1): the decoder block of the ResNet backbones."""
+
+    def __init__(self, cin: int, cout: int) -> None:
+        super().__init__()
+        _conv_bn("conv1", "bn1", self, cin, cout, 1)
+        _conv_bn("conv2", "bn2", self, cout, cout, 3)
+        _conv_bn("conv3", "bn3", self, cout, cout, 1)
+        self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout)) if cin != cout else nn.Identity()
+
+
 class _BasicBlock(nn.Module):
     """Parameter names of BasicBlock(768, 768) (models/utils.py:254-288)."""
 
@@ -103,7 +158,8 @@ def _init_decoder(m: nn.Module) -> None:
 
 
 class CLIP_EBC(nn.Module):
-    """B200-native CLIP-EBC (ViT-B/16, ViT-B/32 or ViT-L/14 + VPT). Constructor arguments as in models/clip/model.py:31-45,
+    """B200-native CLIP-EBC (ViT-B/16, ViT-B/32, ViT-L/14 + VPT, or CLIP-ResNet-50 / -101). Constructor arguments as in
+    models/clip/model.py:31-45,
     plus: text_features (required, see the module docstring), window_chunk (windows per internal pass, 0 = default),
     operand_dtype ("fp16" | "bf16": the 16-bit tensor-core operand format) and decoder_conv1_fine (A/B switch of the
     decoder's conv1 form, see include/clipebc_b200.h)."""
@@ -130,21 +186,28 @@ class CLIP_EBC(nn.Module):
         super().__init__()
         assert backbone in resnet_backbones + vit_backbones, \
             f"Backbone should be in {resnet_backbones + vit_backbones}, got {backbone}"
-        if backbone not in _VIT_DIMS:
+        if backbone not in _VIT_DIMS and backbone not in _RESNET_DIMS:
             raise NotImplementedError(
-                f"clip_ebc_b200 implements the hot path for the ViT backbones {sorted(_VIT_DIMS)} only (got '{backbone}'); the "
-                "CLIP-ResNet backbones of the reference are outside the scope of this build (SURVEY.md section 8f).")
-        patch, width, layers, embed = _VIT_DIMS[backbone]
+                f"clip_ebc_b200 implements the hot path for {sorted(_VIT_DIMS) + sorted(_RESNET_DIMS)} (got '{backbone}'); the wider "
+                "CLIP-ResNets (resnet50x4 / x16 / x64) are not built (DESIGN.md section 8).")
+        self.is_resnet = backbone in _RESNET_DIMS
+        if self.is_resnet:
+            rn_layers, embed, rn_decoder = _RESNET_DIMS[backbone]
+            patch, width, layers = 0, 0, 0
+            assert reduction is not None, "Expected reduction to be an integer for the CLIP-ResNet backbones, got None."
+        else:
+            patch, width, layers, embed = _VIT_DIMS[backbone]
+            assert input_size is not None, "Expected input_size to be an integer, got None."
+            assert num_vpt is not None, "Expected num_vpt to be an integer, got None."
+            assert deep_vpt is not None, "Expected deep_vpt to be a boolean, got None."
+            assert vpt_drop is not None, "Expected vpt_drop to be a float, got None."
         self.patch, self.width, self.layers, self.embed_dim = patch, width, layers, embed
-        assert input_size is not None, "Expected input_size to be an integer, got None."
-        assert num_vpt is not None, "Expected num_vpt to be an integer, got None."
-        assert deep_vpt is not None, "Expected deep_vpt to be a boolean, got None."
-        assert vpt_drop is not None, "Expected vpt_drop to be a float, got None."
         assert prompt_type in ["number", "word"], f"Expected prompt_type to be 'number' or 'word', got {prompt_type}"
         if not freeze_text_encoder:
             raise NotImplementedError("freeze_text_encoder=False (training the text tower) is outside the inference hot path")
-        if decoder_cfg is not None and list(decoder_cfg) != [width]:
-            raise NotImplementedError(f"only the reference default decoder_cfg=[{width}] (one BasicBlock) is implemented")
+        default_cfg = list(rn_decoder) if self.is_resnet else [width]
+        if decoder_cfg is not None and list(decoder_cfg) != default_cfg:
+            raise NotImplementedError(f"only the reference default decoder_cfg={default_cfg} is implemented")
         assert bins is not None and anchor_points is not None and len(bins) == len(anchor_points)
         if text_features is None:
             # the reference computes this matrix here, in __init__, with its CLIP text tower (models/clip/model.py:97-129);
@@ -156,27 +219,40 @@ class CLIP_EBC(nn.Module):
                 "are outside the scope of clip_ebc_b200.")
 
         self.backbone = backbone
-        self.image_encoder = _ImageEncoder(int(input_size), patch, width, layers, embed)
-        self.image_encoder_depth = layers
-        for p in self.image_encoder.parameters():
-            p.requires_grad = False
-        self.num_vpt = int(num_vpt)
-        self.deep_vpt = bool(deep_vpt)
-        self.input_size = int(input_size)
-        val = math.sqrt(6.0 / float(3 * patch + width))  # model.py:70-75
-        for idx in range(layers if self.deep_vpt else 1):
-            p = nn.Parameter(torch.empty(self.num_vpt, width))
-            nn.init.uniform_(p, -val, val)
-            setattr(self, f"vpt_{idx}", p)
-        self.vpt_drop = float(vpt_drop)  # identity in eval mode; the inference path has no dropout
-
-        self.encoder_reduction = patch
-        self.reduction = self.encoder_reduction if reduction is None else int(reduction)
-        self.channels = width
+        if self.is_resnet:
+            # models/clip/model.py:50-52: ModifiedResNet(features_only=True, out_indices=(-1,), reduction=reduction)
+            self.image_encoder = _ModifiedResNet(rn_layers, embed, int(reduction))
+            self.input_size = 224 if input_size is None else int(input_size)
+            self.num_vpt, self.deep_vpt = 0, False
+            self.encoder_reduction = self.image_encoder.reduction
+            self.reduction = int(reduction)
+            blocks, cin = [], self.image_encoder.channels
+            for cout in rn_decoder:  # make_resnet_layers(Bottleneck, decoder_cfg, expansion=1), model.py:83-87
+                blocks.append(_DecoderBottleneck(cin, cout))
+                cin = cout
+            self.channels = cin
+            self.image_decoder = nn.Sequential(*blocks)
+        else:
+            self.image_encoder = _ImageEncoder(int(input_size), patch, width, layers, embed)
+            self.image_encoder_depth = layers
+            for p in self.image_encoder.parameters():
+                p.requires_grad = False
+            self.num_vpt = int(num_vpt)
+            self.deep_vpt = bool(deep_vpt)
+            self.input_size = int(input_size)
+            val = math.sqrt(6.0 / float(3 * patch + width))  # model.py:70-75
+            for idx in range(layers if self.deep_vpt else 1):
+                p = nn.Parameter(torch.empty(self.num_vpt, width))
+                nn.init.uniform_(p, -val, val)
+                setattr(self, f"vpt_{idx}", p)
+            self.vpt_drop = float(vpt_drop)  # identity in eval mode; the inference path has no dropout
+            self.encoder_reduction = patch
+            self.reduction = self.encoder_reduction if reduction is None else int(reduction)
+            self.channels = width
+            self.image_decoder = nn.Sequential(_BasicBlock(width))
         self.clip_embed_dim = embed
-        self.image_decoder = nn.Sequential(_BasicBlock(width))
         _init_decoder(self.image_decoder)
-        self.projection = nn.Conv2d(width, embed, kernel_size=1)
+        self.projection = nn.Conv2d(self.channels, embed, kernel_size=1)
         _init_decoder(self.projection)
 
         self.prompt_type = prompt_type
@@ -254,7 +330,7 @@ class CLIP_EBC(nn.Module):
             if self._handle is None:
                 cfg = _lib.make_config(self.input_size, self.reduction, self.num_vpt, int(self.deep_vpt), len(self.bins),
                                        self._window_chunk, int(self.operand_dtype == "fp16"), self.patch, self.width,
-                                       self.layers, self.embed_dim, int(self.decoder_conv1_fine))
+                                       self.layers, self.embed_dim, int(self.decoder_conv1_fine), int(self.is_resnet))
                 h = C.c_void_p()
                 _lib.check(lib.clipebc_model_create(C.byref(cfg), C.byref(h)), "model_create")
                 self._handle, self._handle_device = h, dev_index

@@ -13,6 +13,7 @@ from . import _lib
 
 EPI_F32, EPI_BIAS_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_RELU_MASK_BF16, \
     EPI_BIAS_RESID_RELU_SPLIT = range(7)
+EPI_BIAS_RESID16_RELU_MASK_BF16 = 9  # `resid` is a 16-bit tensor in the output format
 
 
 def _stream() -> int:

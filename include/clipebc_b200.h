@@ -34,7 +34,7 @@ extern "C" {
 
 typedef struct clipebc_model clipebc_model;
 
-/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16" | "vit_b_32" | "vit_l_14") -- models/clip/model.py:16-24,31-45,
+/* Hyper-parameters of CLIP_EBC(backbone="vit_b_16" | "vit_b_32" | "vit_l_14" | "resnet50" | "resnet101") -- models/clip/model.py:16-24,31-45,
  * _clip_ebc :220-270. The backbone is given by its dimensions:
  *     vit_b_16: patch 16, width 768,  layers 12, embed_dim 512      vit_b_32: patch 32, width 768, layers 12, embed_dim 512
  *     vit_l_14: patch 14, width 1024, layers 24, embed_dim 768      (heads = width / 64, hidden = 4 * width)
@@ -61,6 +61,12 @@ typedef struct clipebc_config {
                        grid is at least twice as fine (conv3x3(bilinear_up(Y)) = 9 per-tap channel contractions on the patch
                        grid + a bilinear gather; DESIGN.md section 2 rewrite 8); 1: always the implicit GEMM on the fine
                        grid. Same result to a few 16-bit roundings; per model, for A/B measurements.                  */
+  int encoder;      /* 0 (default): CLIP VisionTransformer + VPT, described by patch / width / layers above. 1: CLIP
+                       ModifiedResNet of width 64 (resnet50, resnet101 -- _clip/image_encoder.py:10-115) with the Bottleneck
+                       decoder of models/clip/model.py:228-239: its depth, channel counts and decoder blocks are read off the
+                       tensors loaded with clipebc_model_set_tensor (image_encoder.{conv1..3,bn1..3,layer{1..4}.{i}.*},
+                       image_decoder.{j}.*, projection.*); input_size / num_vpt / deep_vpt / patch / width / layers are
+                       ignored, embed_dim is the CLIP embedding (1024 / 512), windows must be multiples of 32 pixels.  */
 } clipebc_config;
 
 const char* clipebc_last_error(void);
@@ -128,7 +134,8 @@ int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_
 int clipebc_f32_to_16(const float* in_dev, void* out_16_dev, int64_t n, int fp16, void* stream);
 /* D[M,N] = A[M,K] W[N,K]^T on the CTA-pair tcgen05 kernel with a fused epilogue.
  * epi: 0 f32, 1 bias f32, 2 bias ->16, 3 bias+quickgelu ->16, 4 bias+resid f32, 5 bias+relu+border-mask ->16,
- *      6 bias+resid+relu hi/lo split ->16. ab_fp16: format of A and W; out_fp16: format of a 16-bit output.
+ *      6 bias+resid+relu hi/lo split ->16, 9 bias + 16-bit resid (resid_dev points to a 16-bit [M, ldr] tensor) + relu +
+ *      border-mask ->16. ab_fp16: format of A and W; out_fp16: format of a 16-bit output.
  *      n_seg K-segments of A with per-segment row shift / column start (implicit-GEMM 3x3 taps, split precision).
  *      mask_hp x mask_wp: rows per image of the zero-bordered grid of epi 5; mask_lead 1: first and last row/column are
  *      border, 0: only the last ones (shared-border grid, see clipebc_resample_to_padded). block_n: 0 (auto), 128, 192, 256.

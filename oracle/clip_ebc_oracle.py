@@ -112,18 +112,90 @@ def basic_block(x: Tensor, sd: Dict[str, Tensor], prefix: str = "image_decoder.0
     return F.relu(out + x)
 
 
+def is_resnet(sd: Dict[str, Tensor]) -> bool:
+    """CLIP ModifiedResNet image encoder (resnet50 / resnet101 ...) rather than a VisionTransformer?"""
+    return "image_encoder.layer1.0.conv1.weight" in sd
+
+
+def _bn(t: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
+    # nn.BatchNorm2d in eval mode: running statistics, eps 1e-5
+    return F.batch_norm(t, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], False, 0.0, 1e-5)
+
+
+def clip_bottleneck(x: Tensor, sd: Dict[str, Tensor], p: str, stride: int) -> Tensor:
+    """_clip/blocks.py:56-101 -- all convs have stride 1; an avgpool follows conv2 (and precedes the downsample conv) when
+    stride > 1."""
+    out = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"]), sd, p + "bn1"))
+    out = F.relu(_bn(F.conv2d(out, sd[p + "conv2.weight"], padding=1), sd, p + "bn2"))
+    if stride > 1:
+        out = F.avg_pool2d(out, stride)
+    out = _bn(F.conv2d(out, sd[p + "conv3.weight"]), sd, p + "bn3")
+    identity = x
+    if p + "downsample.0.weight" in sd:
+        identity = F.avg_pool2d(x, stride) if stride > 1 else x  # nn.AvgPool2d(1) is the identity
+        identity = _bn(F.conv2d(identity, sd[p + "downsample.0.weight"]), sd, p + "downsample.1")
+    return F.relu(out + identity)
+
+
+def resnet_encoder_reduction(reduction: int) -> int:
+    # _clip/image_encoder.py:50,68: layer4 keeps stride 1 when reduction <= 16
+    return 16 if reduction <= 16 else 32
+
+
+def forward_resnet(x: Tensor, sd: Dict[str, Tensor], reduction: int, taps: Optional[dict] = None) -> Tensor:
+    """_clip/image_encoder.py:77-115 (`ModifiedResNet._stem` / `forward`, features_only, out_indices=(-1,))."""
+    e = "image_encoder."
+    x = F.relu(_bn(F.conv2d(x, sd[e + "conv1.weight"], stride=2, padding=1), sd, e + "bn1"))
+    x = F.relu(_bn(F.conv2d(x, sd[e + "conv2.weight"], padding=1), sd, e + "bn2"))
+    x = F.relu(_bn(F.conv2d(x, sd[e + "conv3.weight"], padding=1), sd, e + "bn3"))
+    x = F.avg_pool2d(x, 2)
+    if taps is not None:
+        taps["stem"] = x.clone()
+    for layer in (1, 2, 3, 4):
+        first_stride = 1 if layer == 1 or (layer == 4 and reduction <= 16) else 2
+        i = 0
+        while f"{e}layer{layer}.{i}.conv1.weight" in sd:
+            x = clip_bottleneck(x, sd, f"{e}layer{layer}.{i}.", first_stride if i == 0 else 1)
+            i += 1
+        if taps is not None:
+            taps[f"layer{layer}"] = x.clone()
+    return x
+
+
+def decoder_bottleneck(x: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
+    """models/utils.py:334-390 (`Bottleneck`, expansion 1, stride 1) -- the decoder block of the ResNet backbones."""
+    out = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"]), sd, p + "bn1"))
+    out = F.relu(_bn(F.conv2d(out, sd[p + "conv2.weight"], padding=1), sd, p + "bn2"))
+    out = _bn(F.conv2d(out, sd[p + "conv3.weight"]), sd, p + "bn3")
+    identity = x
+    if p + "downsample.0.weight" in sd:
+        identity = _bn(F.conv2d(x, sd[p + "downsample.0.weight"]), sd, p + "downsample.1")
+    return F.relu(out + identity)
+
+
 def clip_ebc_forward(x: Tensor, sd: Dict[str, Tensor], text_features: Tensor, anchor_points: Sequence[float],
                      reduction: int, num_vpt: int = 32, deep_vpt: bool = True, input_size: int = 224,
                      taps: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
     """models/clip/model.py:191-217 (`CLIP_EBC.forward`, ViT branch). Returns (logits [B,N,g,g], exp [B,1,g,g])."""
-    PATCH = patch_size(sd)
     with torch.no_grad():
-        f = forward_vpt(x.float(), sd, num_vpt, deep_vpt, input_size, taps)
-        if taps is not None:
-            taps["ln_post"] = f.clone()
+        if is_resnet(sd):
+            PATCH = resnet_encoder_reduction(reduction)
+            f = forward_resnet(x.float(), sd, reduction, taps)  # :193
+        else:
+            PATCH = patch_size(sd)
+            f = forward_vpt(x.float(), sd, num_vpt, deep_vpt, input_size, taps)
+            if taps is not None:
+                taps["ln_post"] = f.clone()
         if reduction != PATCH:
             f = F.interpolate(f, scale_factor=PATCH / reduction, mode="bilinear")  # :195-196
-        f = basic_block(f, sd)  # :197
+        if is_resnet(sd):
+            j = 0
+            while f"image_decoder.{j}.conv1.weight" in sd:  # make_resnet_layers(Bottleneck, decoder_cfg), model.py:83-87,228-239
+                f = decoder_bottleneck(f, sd, f"image_decoder.{j}.")
+                j += 1
+        else:
+            f = basic_block(f, sd)  # :197
         if taps is not None:
             taps["decoder"] = f.clone()
         f = F.conv2d(f, sd["projection.weight"], sd["projection.bias"])  # :198

@@ -73,17 +73,39 @@ CASES += [
          variant="default", wseed=26, xseed=27, shape=(1, 3, 224, 448), window=224, stride=224, patch=14),
 ]
 
+# the CLIP-ResNet encoders behind the same boundary (_clip/image_encoder.py:10-115; Bottleneck decoder,
+# models/clip/model.py:228-239). resnet50 at reduction 8 (layer4 stride 1, x2 resample), reduction 32 (layer4 stride 2, no
+# resample); resnet101 at reduction 16 (two decoder blocks, the second with a downsample conv); overlapping sliding windows.
+CASES += [
+    dict(name="rn50_forward_r8", kind="forward", bins="r8_t4_nwpu", backbone="resnet50", variant="stress", wseed=40, xseed=41,
+         shape=(2, 3, 224, 224), num_vpt=0, deep_vpt=False),
+    dict(name="rn50_forward_r32", kind="forward", bins="r32_t19_qnrf", backbone="resnet50", variant="stress", wseed=42, xseed=43,
+         shape=(3, 3, 224, 224), num_vpt=0, deep_vpt=False),
+    dict(name="rn101_forward_r16", kind="forward", bins="r16_t8_qnrf", backbone="resnet101", variant="stress", wseed=44, xseed=45,
+         shape=(2, 3, 224, 224), num_vpt=0, deep_vpt=False),
+    dict(name="rn50_sliding_448x672_s112_r8", kind="sliding", bins="r8_t4_nwpu", backbone="resnet50", variant="stress", wseed=46,
+         xseed=47, shape=(1, 3, 448, 672), window=224, stride=112, num_vpt=0, deep_vpt=False),
+    dict(name="rn50_sliding_300x500_s200_r8_default", kind="sliding", bins="r8_t4_nwpu", backbone="resnet50", variant="default",
+         wseed=48, xseed=49, shape=(1, 3, 300, 500), window=224, stride=200, num_vpt=0, deep_vpt=False),
+]
+
 # cases pinned for the oracle only (no CUDA implementation yet): none
 ORACLE_ONLY_CASES = []
 
 
 def backbone_of(case: dict) -> str:
+    if "backbone" in case:
+        return case["backbone"]
     return {32: "vit_b_32", 14: "vit_l_14"}.get(case.get("patch", 16), "vit_b_16")
 
 
 def case_inputs(case: dict):
     """-> (state_dict, text_features, bins, anchors, reduction, x) regenerated from the case's seeds."""
     reduction, bins, anchors = weights.bins_and_anchors(case["bins"])
+    if case.get("backbone", "").startswith("resnet"):
+        sd = weights.make_resnet_state_dict(case["wseed"], case["backbone"], case["variant"])
+        tf = weights.make_text_features(len(bins), seed=100 + case["wseed"], embed=weights.RESNETS[case["backbone"]]["embed"])
+        return sd, tf, bins, anchors, reduction, weights.make_image(case["shape"], seed=case["xseed"])
     sd = weights.make_state_dict(case["wseed"], input_size=224, num_vpt=case["num_vpt"], deep_vpt=case["deep_vpt"],
                                  variant=case["variant"], patch=case.get("patch", 16))
     tf = weights.make_text_features(len(bins), seed=100 + case["wseed"], embed=768 if case.get("patch", 16) == 14 else 512)

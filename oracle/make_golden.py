@@ -31,7 +31,26 @@ def run_case(case: dict) -> dict:
                                              deep_vpt=case["deep_vpt"], input_size=224, backbone=backbone_of(case))
     _, ev = ref_loader.load_reference()
     out = {}
-    if case["kind"] == "forward":
+    resnet = backbone_of(case).startswith("resnet")
+    if case["kind"] == "forward" and resnet:
+        taps = {}
+        hooks = [
+            model.image_encoder.avgpool.register_forward_hook(lambda m, i, o: taps.__setitem__("stem", o.detach().clone())),
+            model.image_encoder.layer4.register_forward_hook(lambda m, i, o: taps.__setitem__("layer4", o.detach().clone())),
+            model.image_decoder.register_forward_hook(lambda m, i, o: taps.__setitem__("decoder", o.detach().clone())),
+        ]
+        model.training = True
+        with torch.no_grad():
+            logits, exp = model(x)
+        model.training = False
+        for h in hooks:
+            h.remove()
+        out["logits"] = logits.numpy()
+        out["exp"] = exp.numpy()
+        out["tap_stem"] = taps["stem"][0, :8, :4, :4].numpy()
+        out["tap_layer4"] = taps["layer4"][0, :16, :2, :2].numpy()
+        out["tap_decoder"] = taps["decoder"][0, :16, :2, :2].numpy()
+    elif case["kind"] == "forward":
         taps = {}
         hooks = [
             model.image_encoder.ln_pre.register_forward_hook(lambda m, i, o: taps.__setitem__("ln_pre", o.detach().clone())),

@@ -134,6 +134,74 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
+RESNETS = {"resnet50": dict(layers=(3, 4, 6, 3), embed=1024, decoder=(2048,)),
+           "resnet101": dict(layers=(3, 4, 23, 3), embed=512, decoder=(2048, 1024))}
+
+
+def make_resnet_state_dict(seed: int = 0, backbone: str = "resnet50", variant: str = "stress") -> Dict[str, torch.Tensor]:
+    """Reference-keyed fp32 state_dict of CLIP_EBC with a CLIP ModifiedResNet encoder (width 64) and its Bottleneck decoder
+    (models/clip/model.py:50-93,228-239; _clip/image_encoder.py:33-58; _clip/blocks.py:56-86; models/utils.py:334-371).
+    Conv weights: nn.Conv2d default (kaiming-uniform, a = sqrt 5 -> U(+-1/sqrt(fan_in))) in the encoder, kaiming-normal fan_out in
+    the decoder / projection (`_init_weights`). "stress" randomises every BatchNorm's affine parameters and running statistics
+    (with gains > 1 on the residual branches, so that they are not drowned by the identity path of 16 untrained blocks)."""
+    assert variant in ("default", "stress")
+    spec = RESNETS[backbone]
+    rng = np.random.default_rng(seed)
+    stress = variant == "stress"
+    sd: Dict[str, np.ndarray] = {}
+    sd["logit_scale"] = np.array(math.log(30.0) if stress else math.log(1 / 0.07), dtype=np.float32)
+
+    def conv(name, o, i, k, decoder=False):
+        if decoder:
+            sd[name] = _n(rng, (o, i, k, k), math.sqrt(2.0 / (o * k * k)))
+        else:
+            sd[name] = _u(rng, (o, i, k, k), 1.0 / math.sqrt(i * k * k))
+
+    def bn(prefix, c, gain=1.0):
+        if stress:
+            sd[prefix + ".weight"] = (rng.uniform(0.5, 1.5, size=(c,)) * gain).astype(np.float32)
+            sd[prefix + ".bias"] = _n(rng, (c,), 0.1)
+            sd[prefix + ".running_mean"] = _n(rng, (c,), 0.1)
+            sd[prefix + ".running_var"] = rng.uniform(0.5, 1.5, size=(c,)).astype(np.float32)
+        else:
+            sd[prefix + ".weight"] = np.ones((c,), np.float32)
+            sd[prefix + ".bias"] = np.zeros((c,), np.float32)
+            sd[prefix + ".running_mean"] = np.zeros((c,), np.float32)
+            sd[prefix + ".running_var"] = np.ones((c,), np.float32)
+        sd[prefix + ".num_batches_tracked"] = np.array(0, dtype=np.int64)
+
+    e = "image_encoder."
+    # gain of the residual branches' BatchNorms: large enough for the branches to matter next to the identity path, small enough
+    # for 16 (resnet50) / 33 (resnet101) untrained blocks not to leave the 16-bit range
+    g = (2.0 if sum(spec["layers"]) <= 16 else 1.3) if stress else 1.0
+    conv(e + "conv1.weight", 32, 3, 3); bn(e + "bn1", 32, g)
+    conv(e + "conv2.weight", 32, 32, 3); bn(e + "bn2", 32, g)
+    conv(e + "conv3.weight", 64, 32, 3); bn(e + "bn3", 64, g)
+    inplanes = 64
+    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), spec["layers"]), start=1):
+        for b in range(blocks):
+            p = f"{e}layer{li}.{b}."
+            stride = 2 if (b == 0 and li > 1) else 1   # tensor shapes do not depend on layer4's stride
+            conv(p + "conv1.weight", planes, inplanes, 1); bn(p + "bn1", planes, g)
+            conv(p + "conv2.weight", planes, planes, 3); bn(p + "bn2", planes, g)
+            conv(p + "conv3.weight", planes * 4, planes, 1); bn(p + "bn3", planes * 4, g)
+            if stride > 1 or inplanes != planes * 4:
+                conv(p + "downsample.0.weight", planes * 4, inplanes, 1); bn(p + "downsample.1", planes * 4)
+            inplanes = planes * 4
+    c_in = inplanes
+    for j, c_out in enumerate(spec["decoder"]):
+        p = f"image_decoder.{j}."
+        conv(p + "conv1.weight", c_out, c_in, 1, True); bn(p + "bn1", c_out)
+        conv(p + "conv2.weight", c_out, c_out, 3, True); bn(p + "bn2", c_out)
+        conv(p + "conv3.weight", c_out, c_out, 1, True); bn(p + "bn3", c_out)
+        if c_in != c_out:
+            conv(p + "downsample.0.weight", c_out, c_in, 1, True); bn(p + "downsample.1", c_out)
+        c_in = c_out
+    sd["projection.weight"] = _n(rng, (spec["embed"], c_in, 1, 1), math.sqrt(2.0 / spec["embed"]))
+    sd["projection.bias"] = _n(rng, (spec["embed"],), 0.1) if stress else np.zeros((spec["embed"],), np.float32)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) if v.ndim else torch.tensor(v) for k, v in sd.items()}
+
+
 def make_text_features(n_bins: int, seed: int = 100, embed: int = EMBED) -> torch.Tensor:
     """Stand-in for ``text_encoder(prompts)`` ([N, 512]); a constant input of the hot path (model.py:127-129)."""
     rng = np.random.default_rng(seed)

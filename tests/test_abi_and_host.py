@@ -144,7 +144,7 @@ def test_model_create_rejects_a_struct_of_another_abi(lib):
         assert raw(C.byref(cfg), C.byref(h)) == 1
     finally:
         raw.argtypes = old_argtypes
-    assert C.sizeof(_lib.ClipEbcConfig) == 52
+    assert C.sizeof(_lib.ClipEbcConfig) == 56
 
 
 def test_window_origins_bit_exact_randomised(lib):
@@ -173,8 +173,18 @@ def test_python_host_mirrors_reference_interface():
         get_model("clip_vit_b_99", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
     with pytest.raises(AssertionError, match="num_vpt"):
         get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
-    with pytest.raises(NotImplementedError):
-        get_model("clip_resnet50", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    with pytest.raises(NotImplementedError):  # stem width 80: not built
+        get_model("clip_resnet50x4", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
+    # CLIP-ResNet-50 / -101: the reference needs none of the ViT arguments (models/clip/model.py:50-52); same state_dict keys
+    for name, embed, n_keys in (("resnet50", 1024, 351), ("resnet101", 512, 681)):
+        rn = get_model("clip_" + name, input_size=224, reduction=8, bins=bins, anchor_points=anchors,
+                       text_features=weights.make_text_features(5, embed=embed))
+        sd_rn = weights.make_resnet_state_dict(0, name)
+        assert set(sd_rn) == set(rn.state_dict()) and len(sd_rn) == n_keys
+        rn.load_state_dict(sd_rn, strict=True)
+        assert rn.encoder_reduction == 16 and rn.reduction == 8 and rn.clip_embed_dim == embed
+    assert get_model("clip_resnet50", input_size=224, reduction=32, bins=bins, anchor_points=anchors,
+                     text_features=weights.make_text_features(5, embed=1024)).encoder_reduction == 32
     model = get_model("CLIP_ViT_B_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors, prompt_type="word",
                       num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=weights.make_text_features(5))
     assert model.reduction == 8 and model.bins == bins and tuple(model.anchor_points.shape) == (1, 5, 1, 1)

@@ -193,6 +193,25 @@ def test_gemm_remainder_rows_conv_segments(ops):
     assert _rel(out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), ref) < 1.5 * ROUND16[dt]
 
 
+@pytest.mark.parametrize("dt", DT16, ids=DT16_IDS)
+def test_gemm_resid16_relu_mask(ops, dt):
+    """Epilogue 9 (last 1x1 conv of a ResNet bottleneck without a downsample conv): relu(acc + bias + identity) on the interior
+    cells of a shared-border grid, zero on its border row / column; the identity is a 16-bit tensor."""
+    n, g, cin, cout = 3, 7, 128, 256
+    rows = n * (g + 1) * (g + 1)
+    a = _rand((rows, cin), 90).to(dt)
+    w = _rand((cout, cin), 91, 0.1).to(dt)
+    bias = _rand((cout,), 92)
+    ident = _rand((rows, cout), 93).to(dt)
+    out = ops.gemm(a, w, ops.EPI_BIAS_RESID16_RELU_MASK_BF16, bias=bias, resid=ident, mask_hw=(g + 1, g + 1), mask_lead=False)
+    ref = torch.relu(a.float() @ w.float().t() + bias + ident.float()).view(n, g + 1, g + 1, cout)
+    ref[:, g, :, :] = 0
+    ref[:, :, g, :] = 0
+    out = out.float().view(n, g + 1, g + 1, cout)
+    assert out[:, g].abs().max().item() == 0.0 and out[:, :, g].abs().max().item() == 0.0
+    assert _rel(out, ref) < 1.5 * ROUND16[dt]
+
+
 def test_gemm_rejects_bad_shapes(ops):
     a, w = _bf(_rand((64, 100), 1)), _bf(_rand((256, 100), 2))
     with pytest.raises(RuntimeError):

@@ -18,7 +18,17 @@ def test_oracle_matches_reference_fixture(case):
     torch.manual_seed(0)
     sd, tf, bins, anchors, reduction, x = case_inputs(case)
     gold = parity.load_golden(case["name"])
-    if case["kind"] == "forward":
+    if case["kind"] == "forward" and O.is_resnet(sd):
+        taps = {}
+        logits, exp = O.clip_ebc_forward(x, sd, tf, anchors, reduction, taps=taps)
+        scale = max(1.0, float(np.abs(gold["tap_decoder"]).max()))  # untrained 2048-channel maps reach O(100)
+        assert np.abs(logits.numpy() - gold["logits"]).max() < ATOL * scale
+        assert np.abs(exp.numpy() - gold["exp"]).max() < ATOL
+        assert np.abs(taps["stem"][0, :8, :4, :4].numpy() - gold["tap_stem"]).max() < ATOL
+        assert np.abs(taps["layer4"][0, :16, :2, :2].numpy() - gold["tap_layer4"]).max() < ATOL * scale
+        assert np.abs(taps["decoder"][0, :16, :2, :2].numpy() - gold["tap_decoder"]).max() < ATOL * scale
+        assert parity.argmax_agreement(logits.numpy(), gold["logits"]) >= 0.999
+    elif case["kind"] == "forward":
         taps = {}
         logits, exp = O.clip_ebc_forward(x, sd, tf, anchors, reduction, case["num_vpt"], case["deep_vpt"], 224, taps)
         assert np.abs(logits.numpy() - gold["logits"]).max() < ATOL

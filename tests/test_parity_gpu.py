@@ -35,7 +35,7 @@ def _coarse_conv1_applies(case):
     """Decoder conv1 has two forms (DESIGN.md section 2 rewrite 8); the coarse-grid one is the default wherever the decoder
     grid is at least twice as fine as the patch grid. Only there does decoder_conv1_fine=True select different kernels."""
     reduction = {"r8_t4_nwpu": 8, "r16_t8_qnrf": 16, "r32_t19_qnrf": 32}[case["bins"]]
-    return case.get("patch", 16) // reduction >= 2
+    return "backbone" not in case and case.get("patch", 16) // reduction >= 2
 
 
 PATH_FORMS = [(c, False) for c in CASES] + [(c, True) for c in CASES if _coarse_conv1_applies(c)]
