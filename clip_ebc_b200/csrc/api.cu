@@ -579,8 +579,10 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
     return fail(CLIPEBC_EINVAL, "patch must be 16 (ViT-B/16), 32 (ViT-B/32) or 14 (ViT-L/14)");
   if (c.width != 768 && c.width != 1024) return fail(CLIPEBC_EINVAL, "width must be 768 (ViT-B) or 1024 (ViT-L)");
   if (c.layers < 1 || c.layers > 48) return fail(CLIPEBC_EINVAL, "layers must be in 1..48");
-  if (c.embed_dim <= 0 || c.embed_dim % 256 != 0 || c.embed_dim > 1024)
+  if (c.encoder == 0 && (c.embed_dim <= 0 || c.embed_dim % 256 != 0 || c.embed_dim > 1024))
     return fail(CLIPEBC_EINVAL, "embed_dim must be 256, 512, 768 or 1024");
+  if (c.encoder == 1 && (c.embed_dim <= 0 || c.embed_dim % 8 != 0 || c.embed_dim > 2048))
+    return fail(CLIPEBC_EINVAL, "embed_dim must be a positive multiple of 8, at most 2048");
   if (c.input_size <= 0 || c.input_size % c.patch != 0) return fail(CLIPEBC_EINVAL, "input_size must be a multiple of the patch size");
   if (c.num_vpt < 0 || c.num_vpt > 64) return fail(CLIPEBC_EINVAL, "num_vpt out of range");
   if (c.num_bins < 1 || c.num_bins > 32) return fail(CLIPEBC_EINVAL, "num_bins must be in 1..32");
@@ -635,8 +637,10 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   if (c.encoder == 1) {
     if ((rc = resnet_pack(m, s))) return rc;
     if (!check_shape_ok(m, "logit_scale")) return fail(CLIPEBC_ESTATE, "pack: tensor 'logit_scale' missing or not a scalar");
-    CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * c.embed_dim * 4));
-    K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, c.embed_dim, m->tmat.as<float>()));
+    const int e_pad = m->resnet->e_pad;  // text matrix with zero columns up to the padded embedding (see resnet_pack)
+    CUDA_TRY(m->tmat.reserve(static_cast<size_t>(c.num_bins) * e_pad * 4));
+    CUDA_TRY(cudaMemsetAsync(m->tmat.p, 0, static_cast<size_t>(c.num_bins) * e_pad * 4, s));
+    K_TRY(pack_text(s, raw_ptr(m, "text_features"), raw_ptr(m, "logit_scale"), c.num_bins, c.embed_dim, m->tmat.as<float>(), e_pad));
     CUDA_TRY(cudaStreamSynchronize(s));
     m->packed = true;
     return CLIPEBC_OK;

@@ -535,7 +535,7 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int O, int I, i
 
 // F.normalize(text, p=2, dim=-1) (eps 1e-12) scaled by exp(logit_scale)  (model.py:204,207-208); one warp per bin
 __global__ void pack_text_kernel(const float* __restrict__ text, const float* __restrict__ logit_scale, int n, int d,
-                                 float* __restrict__ tmat) {
+                                 float* __restrict__ tmat, int ld_out) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -543,7 +543,7 @@ __global__ void pack_text_kernel(const float* __restrict__ text, const float* __
   for (int i = lane; i < d; i += 32) { const float v = text[static_cast<int64_t>(row) * d + i]; s += v * v; }
   s = warp_sum(s);
   const float scale = expf(logit_scale[0]) / fmaxf(sqrtf(s), 1e-12f);
-  for (int i = lane; i < d; i += 32) tmat[static_cast<int64_t>(row) * d + i] = text[static_cast<int64_t>(row) * d + i] * scale;
+  for (int i = lane; i < d; i += 32) tmat[static_cast<int64_t>(row) * ld_out + i] = text[static_cast<int64_t>(row) * d + i] * scale;
 }
 
 inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
@@ -738,10 +738,12 @@ const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, in
   return last_err();
 }
 
-const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat) {
+const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat, int ld_out) {
   if (n <= 0) return "pack_text: no bins";
+  if (ld_out == 0) ld_out = d;
+  if (ld_out < d) return "pack_text: output pitch below the row length";
   LaunchScope scope(stream, "pack");
-  pack_text_kernel<<<(n + 3) / 4, 128, 0, stream>>>(text, logit_scale, n, d, tmat);
+  pack_text_kernel<<<(n + 3) / 4, 128, 0, stream>>>(text, logit_scale, n, d, tmat, ld_out);
   return last_err();
 }
 

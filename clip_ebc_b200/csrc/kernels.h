@@ -245,7 +245,7 @@ const char* fold_conv3x3_bn(cudaStream_t stream, const float* W, const float* ga
                             const float* var, float eps, int O, int I, void* Wp, float* bias, int fp16);
 // W f32 [O, I] -> 16-bit [O, 3 * Ip] = [hi | hi | lo], every third zero-padded from I to Ip >= I columns
 const char* split_weight_hi_hi_lo(cudaStream_t stream, const float* W, int O, int I, int Ip, void* out, int fp16);
-// text f32 [n, d] -> tmat = exp(logit_scale) * text / max(||text||, 1e-12)
-const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat);
+// text f32 [n, d] -> tmat [n, ld_out] (ld_out = 0: d; columns beyond d are left untouched) = exp(logit_scale) * text / max(||text||, 1e-12)
+const char* pack_text(cudaStream_t stream, const float* text, const float* logit_scale, int n, int d, float* tmat, int ld_out = 0);
 
 }  // namespace cebc

@@ -82,8 +82,8 @@ struct RnBlock {
 struct ResNetPack {
   ConvPack stem1, stem2, stem3;
   std::vector<std::unique_ptr<RnBlock>> enc, dec;  // encoder blocks in execution order; decoder blocks
-  int enc_reduction = 16, c_feat = 0, c_dec = 0;
-  DevBuf w_proj;                                   // 16-bit [embed, c_dec]
+  int enc_reduction = 16, stem_width = 64, c_feat = 0, c_dec = 0, e_pad = 0;
+  DevBuf w_proj, b_proj;                           // 16-bit [e_pad, k64(c_dec)], f32 [e_pad]: embed_dim padded to 256 with zeros
   // workspaces of one pass (activations are 16-bit NHWC on shared-border grids)
   DevBuf col, s1, s2, s3, xa, xb, t1, t2, cc, up;
 };

@@ -157,9 +157,9 @@ __global__ void fold_conv_bn_general_kernel(const float* __restrict__ W, const f
     const int i = static_cast<int>(idx % I);
     const int tap = static_cast<int>((idx / I) % taps);
     const int o = static_cast<int>(idx / (static_cast<int64_t>(I) * taps));
-    const float sc = gamma[o] / sqrtf(var[o] + eps);
+    const float sc = gamma != nullptr ? gamma[o] / sqrtf(var[o] + eps) : 1.0f;  // gamma == nullptr: no BatchNorm, no bias
     Wp[static_cast<int64_t>(o) * ldw + col_off + tap * i_pad + i] = cvt16(W[(static_cast<int64_t>(o) * I + i) * taps + tap] * sc, fp16);
-    if (i == 0 && tap == 0) {
+    if (gamma != nullptr && i == 0 && tap == 0) {
       const float b = beta[o] - mean[o] * sc;
       bias[o] = accumulate_bias ? bias[o] + b : b;
     }

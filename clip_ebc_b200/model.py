@@ -40,10 +40,11 @@ vit_backbones = ["vit_b_16", "vit_b_32", "vit_l_14", "vit_l_14_336px"]
 # backbone -> (patch size = encoder reduction, width, layers, embed_dim); heads = width // 64 (_clip/model.py:50),
 # models/clip/model.py:16-24
 _VIT_DIMS = {"vit_b_16": (16, 768, 12, 512), "vit_b_32": (32, 768, 12, 512), "vit_l_14": (14, 1024, 24, 768)}
-# CLIP-ResNet backbones of stem width 64: backbone -> (blocks per layer, embed_dim, decoder_cfg) -- the configs prepare.py
-# extracts from the OpenAI checkpoints (_clip/__init__.py:73-96) and models/clip/model.py:228-239. resnet50x4 / x16 / x64
-# (stem widths 80 / 96 / 128) are not implemented.
-_RESNET_DIMS = {"resnet50": ((3, 4, 6, 3), 1024, (2048,)), "resnet101": ((3, 4, 23, 3), 512, (2048, 1024))}
+# CLIP-ResNet backbones: backbone -> (blocks per layer, stem width, embed_dim, decoder_cfg) -- the configs prepare.py extracts from
+# the OpenAI checkpoints (_clip/__init__.py:73-96) and models/clip/model.py:228-239
+_RESNET_DIMS = {"resnet50": ((3, 4, 6, 3), 64, 1024, (2048,)), "resnet101": ((3, 4, 23, 3), 64, 512, (2048, 1024)),
+                "resnet50x4": ((4, 6, 10, 6), 80, 640, (1280,)), "resnet50x16": ((6, 8, 18, 8), 96, 768, (1536,)),
+                "resnet50x64": ((3, 15, 36, 10), 128, 1024, (2048,))}
 
 
 class _Block(nn.Module):
@@ -104,15 +105,15 @@ class _ClipBottleneck(nn.Module):
 
 
 class _ModifiedResNet(nn.Module):
-    """Parameter names of ModifiedResNet(features_only=True) (_clip/image_encoder.py:33-58), stem width 64."""
+    """Parameter names of ModifiedResNet(features_only=True) (_clip/image_encoder.py:33-58)."""
 
-    def __init__(self, layers: Tuple[int, int, int, int], embed: int, reduction: int) -> None:
+    def __init__(self, layers: Tuple[int, int, int, int], width: int, embed: int, reduction: int) -> None:
         super().__init__()
-        _conv_bn("conv1", "bn1", self, 3, 32, 3, stride=2)
-        _conv_bn("conv2", "bn2", self, 32, 32, 3)
-        _conv_bn("conv3", "bn3", self, 32, 64, 3)
-        inplanes = 64
-        for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+        _conv_bn("conv1", "bn1", self, 3, width // 2, 3, stride=2)
+        _conv_bn("conv2", "bn2", self, width // 2, width // 2, 3)
+        _conv_bn("conv3", "bn3", self, width // 2, width, 3)
+        inplanes = width
+        for li, (planes, blocks) in enumerate(zip((width, 2 * width, 4 * width, 8 * width), layers), start=1):
             stride = 1 if li == 1 or (li == 4 and reduction <= 16) else 2
             seq = [_ClipBottleneck(inplanes, planes, stride)]
             inplanes = planes * 4
@@ -188,11 +189,10 @@ class CLIP_EBC(nn.Module):
             f"Backbone should be in {resnet_backbones + vit_backbones}, got {backbone}"
         if backbone not in _VIT_DIMS and backbone not in _RESNET_DIMS:
             raise NotImplementedError(
-                f"clip_ebc_b200 implements the hot path for {sorted(_VIT_DIMS) + sorted(_RESNET_DIMS)} (got '{backbone}'); the wider "
-                "CLIP-ResNets (resnet50x4 / x16 / x64) are not built (DESIGN.md section 8).")
+                f"clip_ebc_b200 implements the hot path for {sorted(_VIT_DIMS) + sorted(_RESNET_DIMS)} (got '{backbone}').")
         self.is_resnet = backbone in _RESNET_DIMS
         if self.is_resnet:
-            rn_layers, embed, rn_decoder = _RESNET_DIMS[backbone]
+            rn_layers, rn_width, embed, rn_decoder = _RESNET_DIMS[backbone]
             patch, width, layers = 0, 0, 0
             assert reduction is not None, "Expected reduction to be an integer for the CLIP-ResNet backbones, got None."
         else:
@@ -221,7 +221,7 @@ class CLIP_EBC(nn.Module):
         self.backbone = backbone
         if self.is_resnet:
             # models/clip/model.py:50-52: ModifiedResNet(features_only=True, out_indices=(-1,), reduction=reduction)
-            self.image_encoder = _ModifiedResNet(rn_layers, embed, int(reduction))
+            self.image_encoder = _ModifiedResNet(rn_layers, rn_width, embed, int(reduction))
             self.input_size = 224 if input_size is None else int(input_size)
             self.num_vpt, self.deep_vpt = 0, False
             self.encoder_reduction = self.image_encoder.reduction

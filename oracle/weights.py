@@ -134,8 +134,12 @@ def make_state_dict(seed: int = 0, input_size: int = 224, num_vpt: int = 32, dee
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
-RESNETS = {"resnet50": dict(layers=(3, 4, 6, 3), embed=1024, decoder=(2048,)),
-           "resnet101": dict(layers=(3, 4, 23, 3), embed=512, decoder=(2048, 1024))}
+# CLIP-ResNet image encoders (OpenAI checkpoints via prepare.py) and their decoder_cfg (models/clip/model.py:228-239)
+RESNETS = {"resnet50": dict(layers=(3, 4, 6, 3), width=64, embed=1024, decoder=(2048,)),
+           "resnet101": dict(layers=(3, 4, 23, 3), width=64, embed=512, decoder=(2048, 1024)),
+           "resnet50x4": dict(layers=(4, 6, 10, 6), width=80, embed=640, decoder=(1280,)),
+           "resnet50x16": dict(layers=(6, 8, 18, 8), width=96, embed=768, decoder=(1536,)),
+           "resnet50x64": dict(layers=(3, 15, 36, 10), width=128, embed=1024, decoder=(2048,))}
 
 
 def make_resnet_state_dict(seed: int = 0, backbone: str = "resnet50", variant: str = "stress") -> Dict[str, torch.Tensor]:
@@ -173,12 +177,14 @@ def make_resnet_state_dict(seed: int = 0, backbone: str = "resnet50", variant: s
     e = "image_encoder."
     # gain of the residual branches' BatchNorms: large enough for the branches to matter next to the identity path, small enough
     # for 16 (resnet50) / 33 (resnet101) untrained blocks not to leave the 16-bit range
-    g = (2.0 if sum(spec["layers"]) <= 16 else 1.3) if stress else 1.0
-    conv(e + "conv1.weight", 32, 3, 3); bn(e + "bn1", 32, g)
-    conv(e + "conv2.weight", 32, 32, 3); bn(e + "bn2", 32, g)
-    conv(e + "conv3.weight", 64, 32, 3); bn(e + "bn3", 64, g)
-    inplanes = 64
-    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), spec["layers"]), start=1):
+    nb = sum(spec["layers"])
+    g = (2.0 if nb <= 16 else 1.5 if nb <= 26 else 1.3 if nb <= 40 else 1.2) if stress else 1.0
+    w = spec["width"]
+    conv(e + "conv1.weight", w // 2, 3, 3); bn(e + "bn1", w // 2, g)
+    conv(e + "conv2.weight", w // 2, w // 2, 3); bn(e + "bn2", w // 2, g)
+    conv(e + "conv3.weight", w, w // 2, 3); bn(e + "bn3", w, g)
+    inplanes = w
+    for li, (planes, blocks) in enumerate(zip((w, 2 * w, 4 * w, 8 * w), spec["layers"]), start=1):
         for b in range(blocks):
             p = f"{e}layer{li}.{b}."
             stride = 2 if (b == 0 and li > 1) else 1   # tensor shapes do not depend on layer4's stride

@@ -173,10 +173,11 @@ def test_python_host_mirrors_reference_interface():
         get_model("clip_vit_b_99", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
     with pytest.raises(AssertionError, match="num_vpt"):
         get_model("clip_vit_b_16", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
-    with pytest.raises(NotImplementedError):  # stem width 80: not built
-        get_model("clip_resnet50x4", input_size=224, reduction=8, bins=bins, anchor_points=anchors)
-    # CLIP-ResNet-50 / -101: the reference needs none of the ViT arguments (models/clip/model.py:50-52); same state_dict keys
-    for name, embed, n_keys in (("resnet50", 1024, 351), ("resnet101", 512, 681)):
+    with pytest.raises(AssertionError):  # listed by the reference's vit_backbones but absent from its clip_names (models/__init__.py:21)
+        get_model("clip_vit_l_14_336px", input_size=336, reduction=8, bins=bins, anchor_points=anchors, num_vpt=32, vpt_drop=0.0,
+                  deep_vpt=True)
+    # the CLIP-ResNets: the reference needs none of the ViT arguments (models/clip/model.py:50-52); same state_dict keys
+    for name, embed, n_keys in (("resnet50", 1024, 351), ("resnet101", 512, 681), ("resnet50x4", 640, 537)):
         rn = get_model("clip_" + name, input_size=224, reduction=8, bins=bins, anchor_points=anchors,
                        text_features=weights.make_text_features(5, embed=embed))
         sd_rn = weights.make_resnet_state_dict(0, name)
