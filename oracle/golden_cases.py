@@ -89,7 +89,7 @@ CASES += [
          wseed=48, xseed=49, shape=(1, 3, 300, 500), window=224, stride=200, num_vpt=0, deep_vpt=False),
     # the wider CLIP-ResNets: stem widths 80 / 96 / 128 (channel counts that are not multiples of 64 -> zero-padded operands),
     # embed_dim 640 (padded to 768 for the head epilogue) / 768 / 1024
-    dict(name="rn50x4_forward_r8", kind="forward", bins="r8_t4_nwpu", backbone="resnet50x4", variant="stress", wseed=50, xseed=51,
+    dict(name="rn50x4_forward_r8", kind="forward", bins="r8_t4_nwpu", backbone="resnet50x4", variant="stress", wseed=59, xseed=51,
          shape=(2, 3, 224, 224), num_vpt=0, deep_vpt=False),
     dict(name="rn50x16_forward_r16", kind="forward", bins="r16_t8_qnrf", backbone="resnet50x16", variant="stress", wseed=52, xseed=53,
          shape=(1, 3, 224, 288), num_vpt=0, deep_vpt=False),
