@@ -133,9 +133,10 @@ int run_block(clipebc_model* m, cudaStream_t s, const RnBlock& b, int n, int gh,
 
 int resnet_default_chunk(const clipebc_model* m, int h, int w) {
   if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
-  // ~15 MB of 16-bit activations per 224 x 224 window (the three stem maps at 113 x 113 x 128 dominate)
+  // ~15 MB of 16-bit activations per 224 x 224 window (the three stem maps at 113 x 113 x 128 dominate): 96 windows per pass
+  // are 1.4 GB of workspace and give the GEMMs of layer3 / layer4 (15 x 15 grids) 85 row tiles for the 74 CTA pairs
   const int64_t px = static_cast<int64_t>(h) * w;
-  return static_cast<int>(std::max<int64_t>(1, 32 * 224 * 224 / px));
+  return static_cast<int>(std::max<int64_t>(1, 96 * 224 * 224 / px));
 }
 
 int resnet_pack(clipebc_model* m, cudaStream_t s) {

@@ -1,5 +1,7 @@
-"""Throughput of the three ViT backbones behind the same entry point: model(x) on windows of 224x224, >= 1 s timed per backbone
-(python profiles/backbones_bench.py)."""
+"""Throughput of every backbone behind the same entry point: model(x) on windows of 224x224, >= 1 s timed per backbone, plus the
+per-kernel breakdown of the CLIP-ResNet-50 path (python profiles/backbones_bench.py)."""
+import ctypes
+import json
 import os
 import sys
 
@@ -11,9 +13,17 @@ from oracle import weights  # noqa: E402
 
 dev = torch.device("cuda", 0)
 reduction, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
-for backbone, patch, B in (("clip_vit_b_32", 32, 256), ("clip_vit_b_16", 16, 256), ("clip_vit_l_14", 14, 96)):
-    sd = weights.make_state_dict(0, input_size=224, num_vpt=32, deep_vpt=True, variant="default", patch=patch)
-    tf = weights.make_text_features(len(bins), seed=100, embed=768 if patch == 14 else 512)
+from clip_ebc_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+for backbone, patch, B in (("clip_vit_b_32", 32, 256), ("clip_vit_b_16", 16, 256), ("clip_vit_l_14", 14, 96), ("clip_resnet50", 0, 96),
+                           ("clip_resnet101", 0, 96), ("clip_resnet50x4", 0, 96), ("clip_resnet50x16", 0, 96), ("clip_resnet50x64", 0, 96)):
+    if patch:
+        sd = weights.make_state_dict(0, input_size=224, num_vpt=32, deep_vpt=True, variant="default", patch=patch)
+        tf = weights.make_text_features(len(bins), seed=100, embed=768 if patch == 14 else 512)
+    else:
+        sd = weights.make_resnet_state_dict(0, backbone[5:], "stress")
+        tf = weights.make_text_features(len(bins), seed=100, embed=weights.RESNETS[backbone[5:]]["embed"])
     model = get_model(backbone, input_size=224, reduction=reduction, bins=bins, anchor_points=anchors, prompt_type="word",
                       num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
     model.load_state_dict(sd, strict=True)
@@ -32,5 +42,18 @@ for backbone, patch, B in (("clip_vit_b_32", 32, 256), ("clip_vit_b_16", 16, 256
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     print(f"{backbone}: {B} windows in {ms:.2f} ms -> {B / ms * 1e3:.0f} windows/s ({n} passes)")
+    if backbone == "clip_resnet50":
+        model.use_cuda_graphs = False
+        lib.clipebc_profile_enable(1)
+        for i in range(3):
+            model(xs[i % 2])
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.clipebc_profile_dump(buf, len(buf))
+        lib.clipebc_profile_enable(0)
+        prof = json.loads(buf.value.decode())
+        tot = sum(v["ms"] for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            tf_s = f"{v['flops'] / v['ms'] / 1e9:7.0f} TF/s" if v["flops"] else ""
+            print(f"    {k:28s} {v['ms'] / 3:8.3f} ms {100 * v['ms'] / tot:5.1f}%  x{v['launches'] / 3:5.1f} {tf_s}")
     del model, xs
     torch.cuda.empty_cache()
