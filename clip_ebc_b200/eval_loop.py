@@ -41,10 +41,14 @@ class _WindowBatcher:
     def add(self, image: Tensor) -> None:
         for b in range(image.shape[0]):
             im = image[b:b + 1]
-            self.pending.append(im)
             self.pending_windows += _n_windows(im.shape[-2], im.shape[-1], self.window_size, self.stride)
             if self.pending_windows >= self.target:
+                self.pending.append(im)
                 self.flush()
+            else:
+                # held until later images fill the pass: the caller's tensor may be a slot of the prefetch ring that is
+                # overwritten a few images from now, so a small image that waits is copied (large ones never wait)
+                self.pending.append(im.clone())
 
     def flush(self) -> None:
         if self.pending:
@@ -61,11 +65,19 @@ def _prefetch_to_device(items: Iterable, device: torch.device, image_of: Callabl
                         depth: int = 2) -> Iterator[Tuple[Tensor, object]]:
     """Yields (image on `device`, item) for every item, with the host->device copies of the next `depth` images already
     issued on a side stream: the copy of image i+1 (38 MB for 2048x1536, 151 MB for 4096x3072) runs while the caller's stream
-    computes image i, instead of in front of it on the same stream. Images already on the device pass through."""
+    computes image i, instead of in front of it on the same stream. The copies land in a ring of depth + 1 persistent device
+    buffers (grown to the largest image seen), so the steady state allocates nothing; a slot is overwritten only after the
+    work the caller enqueued on its previous image has completed. Images already on the device pass through.
+
+    The yielded tensor is valid until the generator is advanced again (the caller consumes one image per iteration)."""
     copy_stream = torch.cuda.Stream(device)
     compute = torch.cuda.current_stream(device)
+    n_slots = max(1, depth) + 1
+    slots: List[Optional[Tensor]] = [None] * n_slots
+    reusable: List[Optional[torch.cuda.Event]] = [None] * n_slots
     queue: collections.deque = collections.deque()
     it = iter(items)
+    state = {"next_slot": 0}
 
     def issue() -> None:
         try:
@@ -74,23 +86,37 @@ def _prefetch_to_device(items: Iterable, device: torch.device, image_of: Callabl
             return
         image = image_of(item)
         if image.device == device:
-            queue.append((image, None, item))
+            queue.append((image, None, item, None))
             return
+        slot = state["next_slot"]
+        state["next_slot"] = (slot + 1) % n_slots
+        n = image.numel()
         with torch.cuda.stream(copy_stream):
-            dev_image = image.to(device, non_blocking=True)
+            if reusable[slot] is not None:
+                copy_stream.wait_event(reusable[slot])
+            buf = slots[slot]
+            if buf is None or buf.numel() < n or buf.dtype != image.dtype:
+                buf = torch.empty(n, dtype=image.dtype, device=device)
+                buf.record_stream(compute)  # allocated under the copy stream, read (and outlived) by the compute stream
+                slots[slot] = buf
+            dev_image = buf[:n].view(image.shape)
+            dev_image.copy_(image, non_blocking=True)
             done = torch.cuda.Event()
             done.record(copy_stream)
-        queue.append((dev_image, done, item))  # `item` keeps the (pinned) host tensor alive until the copy has been consumed
+        queue.append((dev_image, done, item, slot))  # `item` keeps the (pinned) host tensor alive until the copy was consumed
 
     for _ in range(max(1, depth)):
         issue()
     while queue:
-        dev_image, done, item = queue.popleft()
+        dev_image, done, item, slot = queue.popleft()
         if done is not None:
             compute.wait_event(done)
-            dev_image.record_stream(compute)  # allocated on the copy stream, used (and later freed) under the compute stream
         issue()
         yield dev_image, item
+        if slot is not None:  # everything the caller does with this image has been enqueued by now
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            reusable[slot] = ev
 
 
 def _device_counts(model: CLIP_EBC, image: Tensor, sliding_window: bool, window_size, stride) -> Tensor:
