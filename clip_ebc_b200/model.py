@@ -273,6 +273,7 @@ class CLIP_EBC(nn.Module):
         self._packed_key = None
         self.use_cuda_graphs = True   # forward(): replay a captured CUDA graph per input shape (see _forward_graphed)
         self._graph_cache: dict = {}
+        self._capture_streams: dict = {}  # device index -> the side stream graphs of that device are captured on
         self._warned_train = False
 
     # ------------------------------------------------------------------ text features (constant input of the head)
@@ -434,7 +435,13 @@ class CLIP_EBC(nn.Module):
                 # thread_local: only THIS thread's CUDA calls are checked during the capture. The default ("global") makes
                 # an unrelated cudaMalloc / event query of any other thread -- a DataLoader's pin-memory thread, another
                 # model -- fail with "operation not permitted when stream is capturing" while we capture.
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                # an explicit capture stream ON THE MODEL'S DEVICE: torch's default capture stream is created once, on
+                # whichever device captured first, and a capture on a stream of another device records nothing
+                dev_index = x.device.index if x.device.index is not None else torch.cuda.current_device()
+                cap = self._capture_streams.get(dev_index)
+                if cap is None:
+                    cap = self._capture_streams[dev_index] = torch.cuda.Stream(x.device)
+                with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
                     outs = self._forward_eager(static_x)
             except Exception:
                 # a capture that cannot be completed (e.g. an allocation inside the library for a shape the eager call

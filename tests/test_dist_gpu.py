@@ -37,3 +37,58 @@ def test_sharded_counts_equal_single_gpu_counts_bit_for_bit(world, tmp_path):
     if keep:
         os.makedirs(keep, exist_ok=True)
         json.dump(rec, open(os.path.join(keep, f"dist_bit_exact_{world}gpu.json"), "w"), indent=1)
+
+
+def test_two_devices_in_one_process():
+    """One process, two GPUs (round-1 ADVICE): a native handle lives on the device it was created on; per-device kernel
+    attributes (dynamic shared memory, SM count, cluster occupancy, L2 carve-out) are kept per device. A model on cuda:1 next
+    to one on cuda:0 gives the same bits, `.to("cuda:1")` re-creates the handle there, and both keep working afterwards."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip(f"needs 2 GPUs, this box has {torch.cuda.device_count()}")
+    from clip_ebc_b200 import get_model, sliding_window_predict
+    from oracle import weights
+
+    reduction, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
+    sd = weights.make_state_dict(3, variant="stress")
+    tf = weights.make_text_features(len(bins), seed=103)
+
+    def build(dev):
+        m = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+                      prompt_type="word", num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
+        m.load_state_dict(sd, strict=True)
+        return m.to(dev).eval()
+
+    x = weights.make_image((5, 3, 224, 224), seed=800)
+    img = weights.make_image((1, 3, 448, 672), seed=801)
+    m0, m1 = build("cuda:0"), build("cuda:1")
+    y0 = m0(x.to("cuda:0"))
+    y1 = m1(x.to("cuda:1"))                      # first use of every kernel on the second device
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+    d0 = sliding_window_predict(m0, img, 224, 112)
+    d1 = sliding_window_predict(m1, img, 224, 112)
+    assert torch.equal(d0, d1)
+    x2 = weights.make_image((5, 3, 224, 224), seed=802)
+    m0.use_cuda_graphs = False
+    y2 = m0(x2.to("cuda:0")).cpu()
+    m0.use_cuda_graphs = True
+    assert not torch.equal(y2, y0.cpu())
+    for i in range(4):                           # interleaved calls with alternating inputs: graph capture / replay on both devices
+        xi, yi = (x, y0.cpu()) if i % 2 == 0 else (x2, y2)
+        assert torch.equal(m0(xi.to("cuda:0")).cpu(), yi)
+        assert torch.equal(m1(xi.to("cuda:1")).cpu(), yi)
+    assert any("graph" in e for e in m1._graph_cache.values()), "no graph was captured on the second device"
+    m0 = m0.to("cuda:1")                         # the handle is re-created on the new device, the old buffers are released
+    assert torch.equal(m0(x.to("cuda:1")).cpu(), y0.cpu())
+    with pytest.raises(RuntimeError):            # an input on another device than the model is refused, not dereferenced
+        m0(x.to("cuda:0"))
+    m0 = m0.to("cuda:0")
+    assert torch.equal(m0(x.to("cuda:0")).cpu(), y0.cpu())
+    # a CLIP-ResNet model on the second device as well
+    sd_rn = weights.make_resnet_state_dict(40, "resnet50", "stress")
+    tf_rn = weights.make_text_features(len(bins), seed=140, embed=1024)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        rn = get_model("clip_resnet50", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors, text_features=tf_rn)
+        rn.load_state_dict(sd_rn, strict=True)
+        outs.append(rn.to(dev).eval()(x[:2].to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
