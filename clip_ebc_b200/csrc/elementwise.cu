@@ -474,6 +474,150 @@ __global__ void __launch_bounds__(256) conv1_from_coarse_kernel(const uint16_t* 
   }
 }
 
+// The same gather for a decoder grid exactly twice the patch grid in height (reduction 8 on patch 16, reduction 16 on patch
+// 32: the benchmark shapes), with the horizontal and the vertical half of the bilinear weights applied one after the other:
+//   H[i, px, dy] = sum_dx sum_{j in {x0, x1}(px + dx)} wx * Z[i, j, tap(dy, dx)]                       (6 terms, coarse row i)
+//   out[py, px]  = bias + sum_dy ( wa * H[ia(py + dy), px, dy] + wb * H[ib(py + dy), px, dy] )        (6 terms)
+// At ratio 2 the fine row f reads the coarse rows floor((f - 1) / 2) and the one after it (clamped to the window) with
+// weights (1/4, 3/4) for even f and (3/4, 1/4) for odd f, so the pair of output rows (2k, 2k + 1) needs H of the coarse rows
+// k - 1, k, k + 1 only and every H row serves four output rows: a thread = (output column, 8 channels) walks down its column
+// with the three H rows in registers -- 9 shared-memory terms + 6 register terms per output value instead of 36
+// shared-memory terms, and the column geometry is computed once per thread instead of once per cell (the cell-per-thread
+// kernel above is issue-bound on exactly that: 151 M instructions per 64 windows). `rs` threads share a column (each a
+// range of coarse rows, recomputing one H row either side). Rows are staged per band of `nb` coarse rows (+ one either side).
+template <int D, bool FP16>
+__global__ void __launch_bounds__(256, 2) conv1_from_coarse_x2_kernel(const uint16_t* __restrict__ Z, const float* __restrict__ bias,
+                                                                      int n_win, int hp, int wp, int gw, int nb, int n_bands,
+                                                                      int rs, uint16_t* __restrict__ D1) {
+  constexpr int fp16 = FP16 ? 1 : 0;
+  constexpr int CS = 16, kSlices = D / CS, kG = CS / 8, kRowB = CS * 2, kPosB = 9 * kRowB;
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  pdl_launch_dependents();
+  const int gh = 2 * hp, Hp = gh + 1, Wp = gw + 1;
+  int b = blockIdx.x;
+  const int slice = b % kSlices; b /= kSlices;
+  const int band = b % n_bands;
+  const int win = b / n_bands;
+  const int kb_lo = band * nb, kb_hi = min(kb_lo + nb, hp);  // output row pairs [kb_lo, kb_hi)
+  const int i_lo = max(kb_lo - 1, 0), i_hi = min(kb_hi, hp - 1);
+  // ---- this thread's column: sources and weights of the three horizontal taps ----
+  const int per_seg = Wp * kG;
+  const int seg = threadIdx.x / per_seg, rem = threadIdx.x - seg * per_seg;
+  const int px = rem / kG, g = rem - px * kG;
+  const float inv_sx = static_cast<float>(wp) / static_cast<float>(gw);
+  int xo0[3], xo1[3];
+  float wl[3], wr[3];
+#pragma unroll
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = px + dx;
+    const bool ok = seg < rs && px < gw && xx >= 0 && xx < gw;  // zero padding applies to the FINE grid; the border column is zero
+    int x0, x1;
+    float lx;
+    bilinear_src(ok ? xx : 0, inv_sx, wp, x0, x1, lx);
+    xo0[dx + 1] = x0 * kPosB + (dx + 1) * kRowB + (g << 4);
+    xo1[dx + 1] = x1 * kPosB + (dx + 1) * kRowB + (g << 4);
+    wl[dx + 1] = ok ? 1.f - lx : 0.f;
+    wr[dx + 1] = ok ? lx : 0.f;
+  }
+  float2 bia[4];
+  {
+    const float* bp = bias + slice * CS + g * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+    bia[0] = make_float2(b0.x, b0.y); bia[1] = make_float2(b0.z, b0.w); bia[2] = make_float2(b1.x, b1.y); bia[3] = make_float2(b1.z, b1.w);
+  }
+  pdl_wait();
+  // ---- stage Z[i_lo..i_hi, all columns, all taps, slice] ----
+  {
+    const int64_t ldz = 9 * D;
+    const uint16_t* zw = Z + (static_cast<int64_t>(win) * hp + i_lo) * wp * ldz + slice * CS;
+    const int n_chunks = (i_hi - i_lo + 1) * wp * 9 * kG;
+    for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+      const int ch = i % kG, pt = i / kG;
+      const int tap = pt % 9, pos = pt / 9;
+      cp_async_16(smem_u32(c1_smem + pt * kRowB + (ch << 4)), zw + pos * ldz + tap * D + ch * 8, true);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+  const int nk = kb_hi - kb_lo, per = (nk + rs - 1) / rs;
+  const int k_lo = kb_lo + seg * per, k_hi = min(k_lo + per, kb_hi);
+  if (seg >= rs || px >= Wp || k_lo >= k_hi) return;
+  // H of one coarse row for the vertical taps [d_lo, d_hi]
+  auto hrow = [&](int i, float2 (&h)[3][4], int d_lo, int d_hi) {
+    const uint8_t* zr = c1_smem + (i - i_lo) * wp * kPosB;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      if (dy < d_lo || dy > d_hi) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[dy][q] = make_float2(0.f, 0.f);
+      const uint8_t* zt = zr + dy * 3 * kRowB;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint4 a = *reinterpret_cast<const uint4*>(zt + xo0[dx]);
+        const uint4 c = *reinterpret_cast<const uint4*>(zt + xo1[dx]);
+        fma8_16<FP16>(h[dy], a, wl[dx]);
+        fma8_16<FP16>(h[dy], c, wr[dx]);
+      }
+    }
+  };
+  auto axpy2 = [](float2 (&acc)[4], const float2 (&u)[4], float wu, const float2 (&v)[4], float wv) {
+    const float2 a2 = make_float2(wu, wu), b2 = make_float2(wv, wv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = __ffma2_rn(b2, v[q], __ffma2_rn(a2, u[q], acc[q]));
+  };
+  const bool border_col = px >= gw;
+  auto store_row = [&](int py, const float2 (&acc)[4]) {
+    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+    if (!border_col)
+      outv = make_uint4(pack16x2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f), fp16), pack16x2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f), fp16),
+                        pack16x2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f), fp16), pack16x2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f), fp16));
+    const int64_t r = (static_cast<int64_t>(win) * Hp + py) * Wp + px;
+    *reinterpret_cast<uint4*>(D1 + r * D + slice * CS + g * 8) = outv;
+  };
+  float2 Hm[3][4], Hc[3][4], Hn[3][4];
+  hrow(k_lo, Hc, 0, 2);
+  if (k_lo > 0) hrow(k_lo - 1, Hm, 0, 1);
+  else {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Hm[dy][q] = Hc[dy][q];
+  }
+  for (int k = k_lo; k < k_hi; ++k) {
+    if (k + 1 < hp) hrow(k + 1, Hn, k + 1 < k_hi ? 0 : 1, 2);
+    else {
+#pragma unroll
+      for (int dy = 1; dy < 3; ++dy)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Hn[dy][q] = Hc[dy][q];
+    }
+    float2 acc[4];
+    // fine row 2k: taps read the fine rows 2k - 1 (k-1: 3/4, k: 1/4), 2k (k-1: 1/4, k: 3/4), 2k + 1 (k: 3/4, k+1: 1/4)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = bia[q];
+    if (k > 0) axpy2(acc, Hm[0], 0.75f, Hc[0], 0.25f);
+    axpy2(acc, Hm[1], 0.25f, Hc[1], 0.75f);
+    axpy2(acc, Hc[2], 0.75f, Hn[2], 0.25f);
+    store_row(2 * k, acc);
+    // fine row 2k + 1: 2k (k-1: 1/4, k: 3/4), 2k + 1 (k: 3/4, k+1: 1/4), 2k + 2 (k: 1/4, k+1: 3/4)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = bia[q];
+    axpy2(acc, Hm[0], 0.25f, Hc[0], 0.75f);
+    axpy2(acc, Hc[1], 0.75f, Hn[1], 0.25f);
+    if (k + 1 < hp) axpy2(acc, Hc[2], 0.25f, Hn[2], 0.75f);
+    store_row(2 * k + 1, acc);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { Hm[dy][q] = Hc[dy][q]; Hc[dy][q] = Hn[dy][q]; }
+  }
+  if (k_hi == hp) {  // the zero border row below the window
+    const int64_t r = (static_cast<int64_t>(win) * Hp + gh) * Wp + px;
+    *reinterpret_cast<uint4*>(D1 + r * D + slice * CS + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------ pack-time ----------------------------------
 __global__ void f32_to_16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int64_t n, int fp16) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -667,11 +811,13 @@ const char* conv1_from_coarse_t(cudaStream_t stream, const void* Z, const float*
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr_done & (1ull << (dev & 63)))) {
-      unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+      unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
       cudaError_t ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 16, true>, 57344, &m0);
       if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 16, false>, 57344, &m1);
       if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 32, true>, kC1Smem, &m2);
       if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_kernel<D, 32, false>, kC1Smem, &m3);
+      if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_x2_kernel<D, true>, 57344, &m4);
+      if (ea == cudaSuccess) ea = ensure_dyn_smem(conv1_from_coarse_x2_kernel<D, false>, 57344, &m5);
       if (ea != cudaSuccess) return cudaGetErrorString(ea);
       attr_done |= 1ull << (dev & 63);
     }
@@ -680,7 +826,21 @@ const char* conv1_from_coarse_t(cudaStream_t stream, const void* Z, const float*
                     static_cast<double>(n_win) * hp * wp * 9 * D * 2.0 + static_cast<double>(n_win) * (gh + 1) * (gw + 1) * D * 2.0);
   cudaError_t e;
   const int whole = hp * wp * 9 * 16 * 2;  // the window's patch grid, all taps, 16 channels
-  if (whole <= 57344) {
+  constexpr int c1_rs = 2;  // threads per column (profiles/r02/conv1_x2_ab.txt: 1 -> 106 us, 2 -> 95, 3 / 4 -> 116 at 64 windows)
+  const int row_b = wp * 9 * 16 * 2;                  // one coarse row, all taps, 16 channels
+  const int nb_fit = 57344 / row_b - 2;               // band height that fits with a row either side
+  if (gh == 2 * hp && gw >= 2 * wp && (whole <= 57344 || nb_fit >= 2) && (gw + 1) * 2 <= 256) {
+    const int nb = whole <= 57344 ? hp : nb_fit;
+    const int n_bands = (hp + nb - 1) / nb;
+    int rs = std::max(1, std::min(c1_rs, std::min(nb, 256 / ((gw + 1) * 2))));
+    const int threads = ((gw + 1) * 2 * rs + 31) / 32 * 32;
+    const int smem = std::min(hp, nb + 2) * row_b;
+    const int64_t blocks = static_cast<int64_t>(n_win) * n_bands * (D / 16);
+    if (blocks > 0x7fffffff) return "conv1_from_coarse: grid too large";
+    e = launch_pdl(fp16 ? conv1_from_coarse_x2_kernel<D, true> : conv1_from_coarse_x2_kernel<D, false>,
+                   dim3(static_cast<unsigned>(blocks)), dim3(threads), static_cast<size_t>(smem), stream, 1,
+                   static_cast<const uint16_t*>(Z), bias, n_win, hp, wp, gw, nb, n_bands, rs, static_cast<uint16_t*>(D1));
+  } else if (whole <= 57344) {
     const int64_t blocks = static_cast<int64_t>(n_win) * (D / 16);
     e = launch_pdl(fp16 ? conv1_from_coarse_kernel<D, 16, true> : conv1_from_coarse_kernel<D, 16, false>,
                    dim3(static_cast<unsigned>(blocks)), dim3(256), static_cast<size_t>(whole), stream, 1,
