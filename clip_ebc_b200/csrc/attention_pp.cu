@@ -31,6 +31,17 @@ namespace cebc {
 
 namespace {
 
+#ifdef CLIPEBC_ATTN_TRACE
+// Build with `make EXTRA=-DCLIPEBC_ATTN_TRACE` for profiles/probes/attn_trace.py: clock64 time line of CTA 0, one slot per
+// (warp, tile of the warp's loop, event); plain stores, no atomics. Compiled out otherwise.
+__device__ long long g_tr[20 * 16 * 16];
+__device__ __forceinline__ void tr_rec(int ev, int k) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && k < 16) g_tr[((threadIdx.x >> 5) * 16 + k) * 16 + (ev & 15)] = clock64();
+}
+#define TR(ev, k) tr_rec(ev, k)
+#else
+#define TR(ev, k)
+#endif
 constexpr int kThreadsP = 384;
 constexpr int kQTileBytesP = 128 * 128;    // one 128-query tile
 constexpr int kQBytesP = 2 * kQTileBytesP; // 256 query rows x 64 dims, 16-bit
@@ -171,7 +182,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       uint8_t* sQ = smem + s * kStageBytesP;
       uint8_t* sK = sQ + kQBytesP;
       uint8_t* sV = sK + kKVBytesP;
+      TR(20, it);
       mbar_wait(&qk_empty[s], ph ^ 1);
+      TR(21, it);
       if (lane == 0) {
         mbar_arrive_expect_tx(&qk_full[s], kQBytesP + kKVBytesP);
         tma_load_2d(sQ, &tm_q, &qk_full[s], head * 64, row_base);
@@ -180,6 +193,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       __syncwarp();
       mbar_wait(&v_empty[s], ph ^ 1);
+      TR(22, it);
       if (lane == 0) {
         mbar_arrive_expect_tx(&v_full[s], kKVBytesP);
         if (n_const > 0) tma_load_2d(sV, &tm_const, &v_full[s], 2 * width + head * 64, 0);
@@ -213,8 +227,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t k_addr = stage_addr + kQBytesP;
       const uint32_t v_addr = k_addr + kKVBytesP;
       // S = Q_t K^T once Q / K have landed and the previous tile of this chain has been written out
+      TR(0, k);
       mbar_wait(&qk_full[s], ph);
+      TR(4, k);
       mbar_wait(&buf_free[b], (k & 1) ^ 1);
+      TR(1, k);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -229,6 +246,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // O = P V once the softmax group has written P
       mbar_wait(&v_full[s], ph);
       mbar_wait(&p_ready[b], k & 1);
+      TR(2, k);
       tc_fence_after();
       if (lane == 0) {
         for (int ks = 0; ks < k_steps; ++ks)
@@ -256,7 +274,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int row0 = t * 128 + q * 32;          // first row of this warp inside the window
       const bool active = row0 < t_live;          // warps whose 32 rows are all padding only keep the protocol going
       float row_sum = 0.f;
+      TR(10, k);
       mbar_wait(&s_full[b], k & 1);
+      TR(11, k);
       tc_fence_after();
       if (active) {
         // Single pass over S. Softmax is shift invariant, so the reference maximum only has to keep exp2 in range: the
@@ -283,6 +303,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         tmem_st_wait_p();
       }
+      TR(12, k);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[b]);
@@ -290,6 +311,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // O / rowsum -> 16-bit -> global, two halves of 32 dims through the warp's smem staging tile (thread = row holds
       // 64 B of its row; staged, one instruction writes 8 complete 64 B row segments)
       mbar_wait(&o_full[b], k & 1);
+      TR(13, k);
       tc_fence_after();
       if (active) {
         const float inv = 1.0f / row_sum;
@@ -303,6 +325,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&buf_free[b]);
+        TR(14, k);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t(&o)[32] = hh == 0 ? o0 : o1;
@@ -328,6 +351,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&buf_free[b]);
       }
+      TR(15, k);
     }
   }
 
@@ -397,5 +421,17 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
+
+#ifdef CLIPEBC_ATTN_TRACE
+extern "C" int clipebc_debug_attn_trace(long long* out, int cap) {
+  const int n = 20 * 16 * 16;
+  if (cap < n) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_tr, sizeof(long long) * n);
+  static long long zeros[20 * 16 * 16];
+  cudaMemcpyToSymbol(g_tr, zeros, sizeof(long long) * n);
+  return n;
+}
+#endif
 
 }  // namespace cebc
