@@ -723,6 +723,41 @@ class Runner:
         return rec
 
 
+def one_image_latency(R, spec):
+    """N > 1 only: the latency of ONE image on all ranks (clip_ebc_b200.dist.sliding_window_predict_sharded: windows sharded,
+    per-window maps all-gathered, every rank folds) next to the same image on rank 0 alone; strong scaling, bit-exact check."""
+    from clip_ebc_b200 import sliding_window_predict
+    from clip_ebc_b200.dist import sliding_window_predict_sharded
+    from oracle import weights
+
+    model = R.model(spec["model"])
+    H, Wd, stride = spec["H"], spec["W"], spec["stride"]
+    img = weights.make_image((1, 3, H, Wd), seed=4242).to(R.dev)  # the same image on every rank
+    sharded = lambda j: sliding_window_predict_sharded(model, img, WINDOW, stride, R.rank, R.world, return_count=True)[1]  # noqa: E731
+    single = lambda j: sliding_window_predict(model, img, WINDOW, stride, return_device=True, return_count=True)[1]  # noqa: E731
+    out = {"workload": f"{spec['config']}: one image on {R.world} GPUs", "scaling": "strong"}
+    d_s = sliding_window_predict_sharded(model, img, WINDOW, stride, R.rank, R.world)
+    d_1 = sliding_window_predict(model, img, WINDOW, stride, return_device=True)
+    same = torch.tensor([int(torch.equal(d_s.view(torch.int32), d_1.view(torch.int32)))], device=R.dev)
+    if R.world > 1:
+        R.dist.all_reduce(same, op=R.dist.ReduceOp.MIN)
+    out["density_bit_exact_vs_1gpu_on_every_rank"] = bool(same.item())
+    for name, step in (("sharded", sharded), ("one_gpu", single)):
+        for _ in range(2):
+            step(0)
+        n = 3
+        while True:
+            ms, _, _, _ = R.timed(step, n)
+            if ms >= 1000.0 or n >= 4096:
+                break
+            n = int(math.ceil(n * max(1.3, 1100.0 / max(ms, 1.0))))
+        out[f"{name}_ms_per_image"] = ms / n
+    out["speedup"] = out["one_gpu_ms_per_image"] / out["sharded_ms_per_image"]
+    out["collective"] = {"op": "all_gather_into_tensor (NCCL) of the per-window maps", "bytes": 4 * (WINDOW // model.reduction) ** 2 *
+                         (int(math.ceil((H - WINDOW) / stride) + 1) * int(math.ceil((Wd - WINDOW) / stride) + 1))}
+    return out
+
+
 def kernel_table(prof, prof_steps):
     return {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                 "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
@@ -771,6 +806,7 @@ def main():
         r16 = R.run_windows(HEADLINE, WORKLOADS[HEADLINE], K, W, operand_dtype="bf16", with_e2e=False, with_profile=False)
         bf16 = {k: r16[k] for k in ("value", "unit", "ms_per_step", "timed_region_s", "timed_passes")}
     clocks = R.sampler.summary()
+    latency = one_image_latency(R, WORKLOADS["qnrf112"]) if R.world > 1 and args.workload == "all" else None
     R.sampler.stop()
 
     head = results[head_name]
@@ -808,6 +844,7 @@ def main():
             "images_per_sec_e2e": results["sliding"].get("e2e", {}).get("images_per_sec") if "sliding" in results else None,
             "counts_bit_exact_vs_1gpu": {k: v["counts_bit_exact_vs_1gpu"] for k, v in results.items() if "counts_bit_exact_vs_1gpu" in v},
             "bf16_operands": bf16,
+            "one_image_latency": latency,
             "vit_forward": head.get("vit_forward"),
             "kernels": head.get("kernels"),
             "workloads": {k: {kk: vv for kk, vv in v.items() if kk != "kernels" or k != head_name} for k, v in results.items()},

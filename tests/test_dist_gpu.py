@@ -33,10 +33,34 @@ def test_sharded_counts_equal_single_gpu_counts_bit_for_bit(world, tmp_path):
     print(f"\n[{world} ranks] counts {rec['counts'][:4]} ... bit-exact on every rank: {rec['bit_exact_on_every_rank']}")
     assert rec["world"] == world and rec["finite"] and rec["bit_exact_on_every_rank"]
     assert rec["counts"] == rec["counts_1gpu"]
+    assert rec["balanced_partition_bit_exact"] and rec["one_image_window_sharded_bit_exact"]
+    print(f"one 672x896 image, stride 112 (35 windows): {rec['one_image_672x896_s112_ms']} ms")
     keep = os.environ.get("CLIPEBC_DIST_RECORD_DIR")  # gpurun sessions keep the record under profiles/
     if keep:
         os.makedirs(keep, exist_ok=True)
         json.dump(rec, open(os.path.join(keep, f"dist_bit_exact_{world}gpu.json"), "w"), indent=1)
+
+
+def test_window_sharded_path_on_one_rank_equals_sliding_window_predict():
+    """`dist.sliding_window_predict_sharded` with a world of one (no process group): window crops -> model(x) -> the fold
+    entry point gives the bits of the one-call sliding path, on grid-aligned and off-grid windows."""
+    from clip_ebc_b200 import get_model, sliding_window_predict
+    from clip_ebc_b200.dist import sliding_window_predict_sharded
+    from oracle import weights
+
+    reduction, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
+    tf = weights.make_text_features(len(bins), seed=103)
+    model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors,
+                      prompt_type="word", num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
+    model.load_state_dict(weights.make_state_dict(3, variant="stress"), strict=True)
+    model = model.to("cuda:0").eval()
+    for shape, stride in (((1, 3, 448, 672), 112), ((1, 3, 300, 500), 200), ((1, 3, 224, 224), 224)):
+        img = weights.make_image(shape, seed=91).to("cuda:0")
+        d1, c1 = sliding_window_predict(model, img, 224, stride, return_device=True, return_count=True)
+        d2, c2 = sliding_window_predict_sharded(model, img, 224, stride, 0, 1, return_count=True)
+        assert d1.shape == d2.shape
+        assert torch.equal(d1.view(torch.int32), d2.view(torch.int32)), shape
+        assert torch.equal(c1.view(torch.int32), c2.view(torch.int32)), shape
 
 
 def test_two_devices_in_one_process():
