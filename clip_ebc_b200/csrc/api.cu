@@ -558,7 +558,7 @@ int clipebc_profile_dump(char* buf, int cap) {
   return CLIPEBC_OK;
 }
 
-int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
+int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) try {
   if (!cfg || !out) return fail(CLIPEBC_EINVAL, "null argument");
   if (cfg->struct_size != sizeof(clipebc_config))
     return fail(CLIPEBC_EINVAL, "clipebc_config.struct_size is " + std::to_string(cfg->struct_size) + " but this library's "
@@ -598,6 +598,10 @@ int clipebc_model_create(const clipebc_config* cfg, clipebc_model** out) {
   if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); m->device = -1; }
   *out = m;
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
 void clipebc_model_destroy(clipebc_model* m) {
@@ -609,7 +613,7 @@ void clipebc_model_destroy(clipebc_model* m) {
   cudaGetLastError();
 }
 
-int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim) {
+int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* data, const int64_t* shape, int ndim) try {
   if (!m || !name || !data || ndim < 0 || (ndim > 0 && !shape)) return fail(CLIPEBC_EINVAL, "null argument");
   int rc;
   if ((rc = check_device(m))) return rc;
@@ -625,9 +629,13 @@ int clipebc_model_set_tensor(clipebc_model* m, const char* name, const float* da
   CUDA_TRY(cudaMemcpy(t.buf.p, data, static_cast<size_t>(numel) * 4, cudaMemcpyDefault));
   m->packed = false;
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
-int clipebc_model_pack(clipebc_model* m, void* stream_) {
+int clipebc_model_pack(clipebc_model* m, void* stream_) try {
   if (!m) return fail(CLIPEBC_EINVAL, "null model");
   int rc;
   if ((rc = check_device(m))) return rc;
@@ -736,10 +744,14 @@ int clipebc_model_pack(clipebc_model* m, void* stream_) {
   m->pos_cache.clear();
   m->packed = true;
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
 int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, int w, float* exp_out_dev,
-                            float* logits_out_dev, void* stream_) {
+                            float* logits_out_dev, void* stream_) try {
   if (!m || !x_dev || !exp_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
   if (B <= 0) return fail(CLIPEBC_EINVAL, "batch must be positive");
@@ -785,6 +797,10 @@ int clipebc_forward_windows(clipebc_model* m, const float* x_dev, int B, int h, 
       return rc;
   }
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
 int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_rows, int* n_cols, int* row_origins,
@@ -804,7 +820,7 @@ int clipebc_window_origins(int H, int W, int wh, int ww, int sh, int sw, int* n_
 }
 
 int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int H, int W, int wh, int ww, int sh,
-                                   int sw, float* density_out_dev, float* count_out_dev, void* stream_) {
+                                   int sw, float* density_out_dev, float* count_out_dev, void* stream_) try {
   if (!m || !image_dev || !density_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
   int rc, nr = 0, nc = 0;
@@ -875,12 +891,16 @@ int clipebc_sliding_window_predict(clipebc_model* m, const float* image_dev, int
   }
   K_TRY(fold_average(s, preds, d_rc, d_cc, nr, nc, gh, gw, H / r, W / r, density_out_dev, count_out_dev));
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
 
 int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const float* const* images_dev, const int* heights,
                                          const int* widths, int wh, int ww, int sh, int sw, float* const* density_out_dev,
-                                         float* counts_out_dev, void* stream_) {
+                                         float* counts_out_dev, void* stream_) try {
   if (!m || !images_dev || !heights || !widths || !density_out_dev) return fail(CLIPEBC_EINVAL, "null argument");
   if (n_images <= 0) return fail(CLIPEBC_EINVAL, "batch must contain at least one image");
   if (!m->packed) return fail(CLIPEBC_ESTATE, "model is not packed (call clipebc_model_pack after loading tensors)");
@@ -981,6 +1001,10 @@ int clipebc_sliding_window_predict_batch(clipebc_model* m, int n_images, const f
                        g.nc, gh, gw, g.H / r, g.W / r, density_out_dev[i], counts_out_dev ? counts_out_dev + i : nullptr));
   }
   return CLIPEBC_OK;
+} catch (const std::exception& e) {
+  return fail(CLIPEBC_ESTATE, std::string("C++ exception inside the library: ") + e.what());
+} catch (...) {
+  return fail(CLIPEBC_ESTATE, "unknown C++ exception inside the library");
 }
 
 // ------------------------------------------------------------------------------------------------ single kernels
