@@ -234,6 +234,7 @@ struct L2Window {
     constexpr int kMaxDev = 64;
     static std::mutex mu;
     static long long max_persist[kMaxDev];  // 0 = not queried yet, -1 = none
+    static long long max_window[kMaxDev];   // largest access-policy window of the device (a larger one fails the LAUNCH)
     static size_t limit_now[kMaxDev];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { cudaGetLastError(); return; }
@@ -242,7 +243,12 @@ struct L2Window {
       int v = 0;
       if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) { cudaGetLastError(); v = 0; }
       max_persist[dev] = v > 0 ? v : -1;
+      int w = 0;
+      if (cudaDeviceGetAttribute(&w, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess) { cudaGetLastError(); w = 0; }
+      max_window[dev] = w;
     }
+    if (max_window[dev] <= 0) return;
+    bytes = std::min(bytes, static_cast<size_t>(max_window[dev]));  // a buffer beyond the limit gets a window over its head
     size_t carve = std::min(bytes, static_cast<size_t>(env_mb > 0 ? env_mb : kL2PersistCapMB) << 20);
     carve = std::min(carve, static_cast<size_t>(std::max(0ll, max_persist[dev])));
     if (carve == 0) return;
@@ -402,15 +408,17 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
   return CLIPEBC_OK;
 }
 
-// windows per internal pass: 96 windows of 197 / 229 tokens (~148 x 128 rows) by default; windows with more tokens (or the
-// wider ViT-L/14 rows) get proportionally fewer per pass so that the workspaces stay the same size
+// windows per internal pass: 148 windows of 197 / 229 tokens by default (profiles/r02/chunk_sweep.txt: 96 / 128 / 148 / 192
+// windows per pass give 75.1 / 75.4 / 76.6 / 76.3 images/s on 2048x1536 at stride 112, 66.4 / 64.5 / 67.2 / 67.5 on 4096x3072 at
+// stride 224; an equalised split of an image's windows is not better); windows with more tokens (or the wider ViT-L/14 rows)
+// get proportionally fewer per pass so that the workspaces stay the same size
 int default_chunk(const clipebc_model* m, int hp, int wp) {
   if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
   const int64_t tokens = 1 + m->cfg.num_vpt + static_cast<int64_t>(hp) * wp;
   const int64_t wide = m->cfg.width > 768 ? 2 : 1;
-  if (tokens <= 128) return static_cast<int>(256 / wide);  // ViT-B/32 windows (82 tokens): as many GEMM rows as 96 x 197
-  if (tokens <= 256) return static_cast<int>(96 / wide);
-  return static_cast<int>(std::max<int64_t>(1, 96 * 229 / tokens / wide));
+  if (tokens <= 128) return static_cast<int>(256 / wide);  // ViT-B/32 windows (82 tokens)
+  if (tokens <= 256) return static_cast<int>(148 / wide);
+  return static_cast<int>(std::max<int64_t>(1, 148 * 229 / tokens / wide));
 }
 
 int check_window_geometry(clipebc_model* m, int h, int w) {

@@ -19,10 +19,10 @@ from torch import Tensor, nn
 from .eval_utils import calculate_errors, sliding_window_predict, sliding_window_predict_batch
 from .model import CLIP_EBC
 
-# Cross-image window batching: images are collected until their windows fill at least one internal pass (96 windows)
+# Cross-image window batching: images are collected until their windows fill at least one internal pass (148 windows)
 # and then go through ONE C-ABI call (clipebc_sliding_window_predict_batch). Images that fill a pass on their own
 # (NWPU / QNRF scale) are unaffected; small ones (a dozen windows each) no longer leave most SMs idle.
-BATCH_WINDOWS = 96
+BATCH_WINDOWS = 148
 
 
 def _n_windows(h: int, w: int, window, stride) -> int:

@@ -200,7 +200,7 @@ def test_batch256_shallow_vpt_reduction_16_32(bins_key, g):
     logits, exp = model(x.cuda())
     model.training = False
     assert tuple(exp.shape) == (256, 1, g, g) and tuple(logits.shape) == (256, len(bins), g, g)
-    idx = [0, 95, 96, 255]  # both sides of the internal 96-window chunk boundary
+    idx = [0, 147, 148, 255]  # both sides of the internal 148-window chunk boundary
     lo, eo = O.clip_ebc_forward(x[idx], sd, tf, anchors, reduction, 32, False)
     assert parity.density_max_rel(exp[idx].cpu().numpy(), eo.numpy()) <= parity.DENSITY_MAX_REL
     assert parity.count_rel(exp[idx].cpu().numpy(), eo.numpy()) <= parity.COUNT_REL
@@ -259,3 +259,26 @@ def test_errors_follow_the_reference_convention():
                           num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf)
     with pytest.raises(RuntimeError):
         cpu_model(x[:, :, :224, :224])  # no CPU fallback
+
+
+def test_large_explicit_window_chunk_runs_and_matches_default():
+    """A caller-chosen `window_chunk` whose residual stream exceeds the device's largest L2 access-policy window (128 MB: 234
+    windows of ViT-B/16 are 141 MB) used to fail every launch of the pass with 'invalid argument'; the window is clamped now.
+    Per-window results do not depend on the chunking."""
+    from clip_ebc_b200 import get_model, sliding_window_predict
+    from oracle import weights
+
+    reduction, bins, anchors = weights.bins_and_anchors("r8_t4_nwpu")
+    sd = weights.make_state_dict(3, variant="stress")
+    tf = weights.make_text_features(len(bins), seed=103)
+    img = weights.make_image((1, 3, 1536, 2048), seed=612).cuda()
+    outs = []
+    for chunk in (0, 234):
+        model = get_model("clip_vit_b_16", input_size=224, reduction=reduction, bins=bins, anchor_points=anchors, prompt_type="word",
+                          num_vpt=32, vpt_drop=0.0, deep_vpt=True, text_features=tf, window_chunk=chunk)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        outs.append(sliding_window_predict(model, img, 224, 112, return_device=True))
+        del model
+    assert torch.isfinite(outs[1]).all()
+    assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32))
