@@ -67,13 +67,15 @@ const char* gemm_dispatch(cudaStream_t stream, int epi, const __nv_bfloat16* A, 
   return gemm2_bf16_tn(stream, epi, A, a_rows, a_cols, lda, W, ldw, p, block_n);
 }
 
-// tcgen05 / TMEM kernel for windows of at most 256 keys whose constant-key count is a multiple of 8 (every stock
-// configuration of ViT-B/16 and ViT-B/32); the streamed-K/V kernel takes everything else (ViT-L/14: 289 keys per 224 window,
-// windows larger than 224 x 224, odd prompt counts)
+// tcgen05 / TMEM kernels: windows of at most 256 keys whose constant-key count is a multiple of 8 (every stock configuration
+// of ViT-B/16 and ViT-B/32) take the one-block kernel, windows of 257..320 keys (ViT-L/14: 289 keys per 224 window) the
+// two-block one; the streamed-K/V kernel takes everything else (windows larger than 224 x 224, odd prompt counts)
 const char* attention_dispatch(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                                int n_win, int t_live, int heads, void* out, int out_fp16) {
   if (t_live + n_const <= 256 && n_const % 8 == 0)
     return attention_h64_pp(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
+  if (attention_h64_ppl_takes(n_const, t_live))
+    return attention_h64_ppl(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
   return attention_h64_long(stream, qkv, const_kv, n_const, n_win, t_live, heads, out, out_fp16);
 }
 

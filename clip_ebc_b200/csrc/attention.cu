@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_h64_long_kernel(const 
         ldmatrix_x4(qa[ks], sQ + sw_off(q0 + (m & 1) * 8 + (lane & 7), 2 * ks + (m >> 1)));
       }
     }
+    // A warp whose 16 queries all lie beyond the sequence only takes part in the loads and barriers: 257 tokens (ViT-L/14)
+    // are 4 chunks of 64 and one chunk with a single query, i.e. one busy warp in the fifth CTA.
+    if (qbase + q0 >= Tq) continue;
     const uint32_t sK = sKV + (kb & 1) * 16384, sV = sK + 8192;
     const int k0 = kb << 6;
     float s[8][4];

@@ -24,6 +24,8 @@
 //   warps 4-7     softmax + output of chain 0, warps 8-11 of chain 1 (thread = query row = TMEM lane)
 // TMEM buffer of a tile: S fp32 [0,256)  ->  P packed bf16 [0,128) | O fp32 [128,192)
 // Scores and probabilities never leave the SM: HBM traffic is Q, K, V in and O out.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,6 +45,7 @@ __device__ __forceinline__ void tr_rec(int ev, int k) {
 #define TR(ev, k)
 #endif
 constexpr int kThreadsP = 384;
+constexpr int kPolyP = 0;  // share 1/kPolyP of the softmax exponentials on the FMA pipe; 0 = none (measured: no gain)
 constexpr int kQTileBytesP = 128 * 128;    // one 128-query tile
 constexpr int kQBytesP = 2 * kQTileBytesP; // 256 query rows x 64 dims, 16-bit
 constexpr int kKVBytesP = 256 * 128;       // 256 key rows x 64 dims, 16-bit
@@ -92,16 +95,36 @@ __device__ __forceinline__ float ex2f_p(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe instead of the special-function pipe (4 lanes / clk and sub-partition, the busiest pipe of this
+// kernel): x = n + f with n = floor(x) read off the low mantissa bits of x + 1.5 * 2^23 (rounded down), 2^f by a degree-3
+// minimax polynomial on [0, 1) (relative error 8.8e-5, 40x below the bf16 rounding P gets next), 2^n added into the
+// exponent field. x in [-126, 120] keeps 127 + n a valid exponent.
+__device__ __forceinline__ float ex2_poly_p(float x) {
+  x = fmaxf(x, -126.f);
+  float xr;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.f));
+  const float f = x - (xr - 12582912.f);
+  const float p = fmaf(fmaf(fmaf(0.077119089663028717f, f, 0.227564394474029541f), f, 0.695146143436431885f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+// Element e of a chunk goes to the polynomial when POLY > 0 and e % POLY == POLY - 1 (POLY = 4: every fourth exponential).
+template <int POLY>
+__device__ __forceinline__ float ex2_sel_p(float x, int e) {
+  if (POLY > 0 && (e % (POLY > 0 ? POLY : 1)) == POLY - 1) return ex2_poly_p(x);
+  return ex2f_p(x);
+}
+
 // p_j = exp2(min(s_j * scale - m_scaled, 120)) for the `lim` real keys of a 32-key chunk (0 beyond), fp32 row sum,
 // P as packed bf16 pairs into TMEM over S columns that have already been consumed.
+template <int POLY>
 __device__ __forceinline__ void chunk_exp_store_p(const uint32_t (&v)[32], int lim, float scale, float m_scaled,
                                                   float& row_sum, uint32_t p_taddr) {
   uint32_t pk[16];
   if (lim >= 32) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float p0 = ex2f_p(fminf(__uint_as_float(v[2 * j]) * scale - m_scaled, 120.f));
-      const float p1 = ex2f_p(fminf(__uint_as_float(v[2 * j + 1]) * scale - m_scaled, 120.f));
+      const float p0 = ex2_sel_p<POLY>(fminf(__uint_as_float(v[2 * j]) * scale - m_scaled, 120.f), 2 * j);
+      const float p1 = ex2_sel_p<POLY>(fminf(__uint_as_float(v[2 * j + 1]) * scale - m_scaled, 120.f), 2 * j + 1);
       row_sum += p0 + p1;
       pk[j] = pack_bf16x2(p0, p1);
     }
@@ -119,6 +142,7 @@ __device__ __forceinline__ void chunk_exp_store_p(const uint32_t (&v)[32], int l
   tmem_st_x16_p(p_taddr, pk);
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(kThreadsP, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items, int heads,
@@ -293,11 +317,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll 1
         for (int c = 0; c < n_chunks; c += 2) {
           if (c + 1 < n_chunks) tmem_ld_32x32b_x32(row_base_t + (c + 1) * 32, vb);
-          chunk_exp_store_p(va, Tk - c * 32, kScale, m_scaled, row_sum, row_base_t + c * 16);
+          chunk_exp_store_p<POLY>(va, Tk - c * 32, kScale, m_scaled, row_sum, row_base_t + c * 16);
           tmem_ld_wait();
           if (c + 1 < n_chunks) {
             if (c + 2 < n_chunks) tmem_ld_32x32b_x32(row_base_t + (c + 2) * 32, va);
-            chunk_exp_store_p(vb, Tk - (c + 1) * 32, kScale, m_scaled, row_sum, row_base_t + (c + 1) * 16);
+            chunk_exp_store_p<POLY>(vb, Tk - (c + 1) * 32, kScale, m_scaled, row_sum, row_base_t + (c + 1) * 16);
             tmem_ld_wait();
           }
         }
@@ -396,7 +420,24 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
   if (t_live + n_const > 256) return "attention: sequence longer than 256 keys is not supported by the tcgen05 kernel";
   if (n_const % 8 != 0) return "attention(pp): constant key count must be a multiple of 8";
   static unsigned long long attr_done = 0;
-  cudaError_t ea = ensure_dyn_smem(attention_pp_kernel, kSmemP, &attr_done);
+#ifdef CLIPEBC_ATTN_POLY_AB
+  // A/B build only (make EXTRA=-DCLIPEBC_ATTN_POLY_AB): CLIPEBC_ATTN_POLY = 0 | 2 | 3 | 4 picks the share of exponentials
+  // evaluated on the FMA pipe. The shipped library has the one instantiation below.
+  static unsigned long long attr_done_ab[4] = {0, 0, 0, 0};
+  static const int poly_env = [] { const char* e = getenv("CLIPEBC_ATTN_POLY"); return e ? atoi(e) : kPolyP; }();
+  auto kern = attention_pp_kernel<kPolyP>;
+  unsigned long long* mask = &attr_done;
+  if (poly_env != kPolyP) {
+    if (poly_env == 0) { kern = attention_pp_kernel<0>; mask = &attr_done_ab[0]; }
+    else if (poly_env == 2) { kern = attention_pp_kernel<2>; mask = &attr_done_ab[1]; }
+    else if (poly_env == 3) { kern = attention_pp_kernel<3>; mask = &attr_done_ab[2]; }
+    else if (poly_env == 4) { kern = attention_pp_kernel<4>; mask = &attr_done_ab[3]; }
+  }
+#else
+  auto kern = attention_pp_kernel<kPolyP>;
+  unsigned long long* mask = &attr_done;
+#endif
+  cudaError_t ea = ensure_dyn_smem(kern, kSmemP, mask);
   if (ea != cudaSuccess) return cudaGetErrorString(ea);
   const int64_t rows = static_cast<int64_t>(n_win) * t_live;
   const int ld = 3 * 64 * heads;
@@ -414,7 +455,7 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
   {
     const double tk = t_live + n_const;
     LaunchScope scope(stream, "attention", 4.0 * n_items * t_live * tk * 64.0, 2.0 * n_win * t_live * 4.0 * 64.0 * heads);
-    cudaError_t le = launch_pdl(attention_pp_kernel, dim3(grid), dim3(kThreadsP), kSmemP, stream, 1, tq, tkv, tc, n_const,
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kThreadsP), kSmemP, stream, 1, tq, tkv, tc, n_const,
                                 t_live, n_items, heads, static_cast<uint16_t*>(out), out_fp16);
     if (le != cudaSuccess) return cudaGetErrorString(le);
   }

@@ -224,33 +224,32 @@ __device__ __forceinline__ void load_store_hi_lo(const float* src, uint16_t* dst
 }
 
 // origins_yx == nullptr: n_units images [3, H, W], patch grid gh x gw starting at pixel (y0, x0) of every image;
-// else: n_units windows of ONE image, window u has its (0, 0) patch at pixel origins_yx[2u], origins_yx[2u + 1]
-template <int VEC>
+// else: n_units windows of ONE image, window u has its (0, 0) patch at pixel origins_yx[2u], origins_yx[2u + 1].
+// Grid: x = 64-vector segments of a pixel row of the grid, y = groups of 4 pixel rows, z = (unit, channel) planes -- the
+// position of a thread needs no run-time division (P is a template constant; the first version decoded a flat 64-bit index with
+// four 64-bit divisions: 231 instructions per thread, issue-bound at a quarter of the HBM rate).
+template <int VEC, int P>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ image, int n_units, int H, int W, int y0,
-                                                       int x0, const int* __restrict__ origins_yx, int gh, int gw, int P,
-                                                       int kp, int split, uint16_t* __restrict__ out, int fp16) {
+                                                       int x0, const int* __restrict__ origins_yx, int gh, int gw, int kp,
+                                                       int split, uint16_t* __restrict__ out, int fp16) {
   pdl_launch_dependents();
   pdl_wait();
-  const int vpp = P / VEC;                                                 // vectors per patch row
-  const int64_t vec_per_row = static_cast<int64_t>(gw) * vpp;
-  const int64_t per_unit = static_cast<int64_t>(3) * gh * P * vec_per_row;
-  const int64_t total = per_unit * n_units;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int64_t t = idx;
-    const int qx = static_cast<int>(t % vec_per_row); t /= vec_per_row;
-    const int yy = static_cast<int>(t % (gh * P)); t /= (gh * P);
-    const int c = static_cast<int>(t % 3);
-    const int unit = static_cast<int>(t / 3);
-    const int gx = qx / vpp, pxv = qx - gx * vpp;
-    const int gy = yy / P, py = yy - gy * P;
+  constexpr int vpp = P / VEC;  // vectors per patch row
+  const int qx = blockIdx.x * 64 + threadIdx.x;
+  const int yy = blockIdx.y * 4 + threadIdx.y;
+  if (qx >= gw * vpp || yy >= gh * P) return;
+  const int gx = qx / vpp, pxv = qx - gx * vpp;
+  const int gy = yy / P, py = yy - gy * P;
+  const int row_stride = (1 + split) * kp;
+  for (int z = blockIdx.z; z < 3 * n_units; z += gridDim.z) {
+    const int unit = z / 3, c = z - 3 * unit;
     const float* src;
     if (origins_yx != nullptr)
       src = image + (static_cast<int64_t>(c) * H + (origins_yx[2 * unit] + yy)) * W + origins_yx[2 * unit + 1] + qx * VEC;
     else
-      src = image + ((static_cast<int64_t>(unit) * 3 + c) * H + (y0 + yy)) * W + x0 + qx * VEC;
+      src = image + (static_cast<int64_t>(z) * H + (y0 + yy)) * W + x0 + qx * VEC;
     const int64_t patch = (static_cast<int64_t>(unit) * gh + gy) * gw + gx;
-    load_store_hi_lo<VEC>(src, out + patch * (1 + split) * kp + c * P * P + py * P + pxv * VEC, kp, split, fp16);
+    load_store_hi_lo<VEC>(src, out + patch * row_stride + c * P * P + py * P + pxv * VEC, kp, split, fp16);
   }
 }
 
@@ -748,11 +747,14 @@ const char* patchify_launch(cudaStream_t stream, const float* image, int n_units
   const int vec = patch % 4 == 0 ? 4 : 2;
   const int64_t total = static_cast<int64_t>(n_units) * 3 * gh * patch * gw * (patch / vec);
   LaunchScope scope(stream, "patchify", 0.0, static_cast<double>(total) * vec * (4.0 + 2.0 * (1 + split)));
-  const dim3 grid(grid_for(total, 256, device_num_sms() * 16));
-  cudaError_t e = vec == 4 ? launch_pdl(patchify_kernel<4>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
-                                        gw, patch, kp_pad, split, static_cast<uint16_t*>(out), fp16)
-                           : launch_pdl(patchify_kernel<2>, grid, dim3(256), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh,
-                                        gw, patch, kp_pad, split, static_cast<uint16_t*>(out), fp16);
+  const int64_t planes = static_cast<int64_t>(n_units) * 3;
+  const dim3 grid((gw * (patch / vec) + 63) / 64, (gh * patch + 3) / 4, static_cast<unsigned>(planes < 65535 ? planes : 65535));
+  if (grid.y > 65535u) return "patchify: patch grid too tall";
+  auto go = [&](auto kern) {
+    return launch_pdl(kern, grid, dim3(64, 4), 0, stream, 1, image, n_units, H, W, y0, x0, origins, gh, gw, kp_pad, split,
+                      static_cast<uint16_t*>(out), fp16);
+  };
+  cudaError_t e = patch == 16 ? go(patchify_kernel<4, 16>) : patch == 32 ? go(patchify_kernel<4, 32>) : go(patchify_kernel<2, 14>);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
 }  // namespace

@@ -169,6 +169,11 @@ const char* assemble_tokens(cudaStream_t stream, int width, const float* patch_e
 // t_live + n_const <= 256 and n_const % 8 == 0.
 const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
                              int n_win, int t_live, int heads, void* out, int out_fp16);
+// attention_h64_ppl (attention_ppl.cu): the two-chain tcgen05 kernel with the keys of a tile taken in two blocks (256 + up to
+// 64) inside the chain's TMEM buffer: 257..320 keys (ViT-L/14 at 224 x 224: 257 + 32), n_const % 16 == 0, t_live <= 384.
+bool attention_h64_ppl_takes(int n_const, int t_live);
+const char* attention_h64_ppl(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,
+                              int n_win, int t_live, int heads, void* out, int out_fp16);
 // attention_h64_long (attention.cu): any sequence length and any n_const -- 64-query chunks, K / V streamed in 64-key
 // blocks, online softmax, mma.sync. Windows with more than 256 tokens (ViT-L/14 224-windows: 289; 448 x 448 windows).
 const char* attention_h64_long(cudaStream_t stream, const __nv_bfloat16* qkv, const __nv_bfloat16* const_kv, int n_const,

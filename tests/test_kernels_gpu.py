@@ -266,17 +266,47 @@ def test_attention(ops, n_win, t_live, n_const, out_fp16, heads):
 
 
 @pytest.mark.parametrize("n_win,t_live,n_const,heads", [(2, 401, 32, 12), (1, 785, 32, 12), (2, 817, 0, 12), (3, 257, 0, 12),
-                                                        (1, 300, 7, 12), (3, 257, 32, 16), (2, 289, 0, 16)])
+                                                        (1, 300, 7, 12), (3, 257, 32, 16), (2, 289, 0, 16), (1, 288, 32, 12),
+                                                        (3, 300, 16, 12), (2, 225, 32, 12), (1, 320, 0, 12), (40, 257, 32, 16),
+                                                        (1, 300, 24, 12), (7, 193, 64, 12), (5, 321, 0, 12), (3, 264, 32, 16),
+                                                        (2, 136, 128, 12)])
 def test_attention_beyond_256_tokens(ops, n_win, t_live, n_const, heads):
-    """Windows with more than 256 keys (ViT-B/16 320 x 320: 401 live + 32 prompt keys; 448 x 448: 785 + 32; shallow VPT: all
-    817 live; ViT-L/14 224 x 224: 257 + 32 deep, 289 shallow) go through the streamed-K/V kernel (64-query chunks, 64-key
-    blocks, online softmax)."""
+    """Windows with more than 256 keys. 257..320 keys with a constant-key count that is a multiple of 16 (ViT-L/14 224 x 224:
+    257 + 32 deep, 289 shallow; the 320-key maximum; 1 and 64 keys in the second block; two and three query tiles; enough
+    windows for the K / V stages and the query ring to wrap; 1 and 8 query rows in the last tile) take the two-block tcgen05 kernel (attention_ppl.cu); everything
+    else (ViT-B/16 320 x 320: 401 live + 32 prompt keys; 448 x 448: 785 + 32; 817 live; 321 keys; prompt counts 7 and 24) the
+    streamed-K/V kernel (64-query chunks, 64-key blocks, online softmax)."""
     qkv = _bf(_rand((n_win * t_live, 3 * 64 * heads), 34, 1.5))
     ckv = _bf(_rand((n_const, 3 * 64 * heads), 35, 1.5)) if n_const else None
     out = ops.attention(qkv, n_win, t_live, ckv, out_fp16=True, heads=heads).float().view(n_win, t_live, heads, 64)
     ref = _attention_ref(qkv, ckv, n_win, t_live, n_const, heads)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()  # P rounded to bf16, 16-bit output
+
+
+def test_attention_two_block_kernel_is_deterministic_and_batch_invariant(ops):
+    """The two-block kernel gives a window the same bits whatever batch it is part of (work is dealt per CTA in tile ranges
+    that depend on the batch) and from call to call: the cross-image batching of the evaluation loop relies on it."""
+    heads, t_live, n_const = 16, 257, 32
+    qkv = _bf(_rand((24 * t_live, 3 * 64 * heads), 36, 1.5))
+    ckv = _bf(_rand((n_const, 3 * 64 * heads), 37, 1.5))
+    full = ops.attention(qkv, 24, t_live, ckv, out_fp16=True, heads=heads).view(24, t_live, heads * 64)
+    again = ops.attention(qkv, 24, t_live, ckv, out_fp16=True, heads=heads).view(24, t_live, heads * 64)
+    assert torch.equal(full, again)
+    for w0, n in ((0, 1), (5, 3), (17, 7)):
+        part = ops.attention(qkv[w0 * t_live:(w0 + n) * t_live].contiguous(), n, t_live, ckv, out_fp16=True, heads=heads)
+        assert torch.equal(part.view(n, t_live, heads * 64), full[w0:w0 + n])
+
+
+def test_attention_two_block_kernel_large_scores(ops):
+    """Peaky softmax over 289 keys: the reference maximum of the first block also scales the second one."""
+    n_win, t_live, n_const, heads = 2, 257, 32, 16
+    qkv = _bf(_rand((n_win * t_live, 3 * 64 * heads), 38, 3.0))
+    ckv = _bf(_rand((n_const, 3 * 64 * heads), 39, 3.0))
+    out = ops.attention(qkv, n_win, t_live, ckv, heads=heads).float().view(n_win, t_live, heads, 64)
+    ref = _attention_ref(qkv, ckv, n_win, t_live, n_const, heads)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
 def test_attention_large_scores(ops):
