@@ -412,15 +412,21 @@ int run_windows(clipebc_model* m, cudaStream_t s, const int* win_base_dev, int s
 
 // windows per internal pass: 148 windows of 197 / 229 tokens by default (profiles/r02/chunk_sweep.txt: 96 / 128 / 148 / 192
 // windows per pass give 75.1 / 75.4 / 76.6 / 76.3 images/s on 2048x1536 at stride 112, 66.4 / 64.5 / 67.2 / 67.5 on 4096x3072 at
-// stride 224; an equalised split of an image's windows is not better); windows with more tokens (or the wider ViT-L/14 rows)
-// get proportionally fewer per pass so that the workspaces stay the same size
+// stride 224; an equalised split of an image's windows is not better); windows with more tokens get proportionally fewer per
+// pass so that the workspaces stay the same size
 int default_chunk(const clipebc_model* m, int hp, int wp) {
   if (m->cfg.window_chunk > 0) return m->cfg.window_chunk;
   const int64_t tokens = 1 + m->cfg.num_vpt + static_cast<int64_t>(hp) * wp;
-  const int64_t wide = m->cfg.width > 768 ? 2 : 1;
-  if (tokens <= 128) return static_cast<int>(256 / wide);  // ViT-B/32 windows (82 tokens)
-  if (tokens <= 256) return static_cast<int>(148 / wide);
-  return static_cast<int>(std::max<int64_t>(1, 148 * 229 / tokens / wide));
+  if (m->cfg.width > 768) {
+    // ViT-L/14: as many windows as fill one 256-row tile per CTA pair (74 row tiles), so that every GEMM of a pass runs whole
+    // rounds whatever its N: 73 windows of 257 live rows (65 of 289 with shallow VPT). profiles/r02/l14_chunk_sweep.txt: 292
+    // windows at 48 / 58 / 64 / 73 / 96 / 146 per pass -> 4538 / 4480 / 4627 / 4776 / 4589 / 4680 windows/s
+    const int64_t live = m->cfg.deep_vpt ? 1 + static_cast<int64_t>(hp) * wp : tokens;
+    return static_cast<int>(std::max<int64_t>(1, static_cast<int64_t>(device_num_sms() / 2) * 256 / live));
+  }
+  if (tokens <= 128) return 256;  // ViT-B/32 windows (82 tokens)
+  if (tokens <= 256) return 148;
+  return static_cast<int>(std::max<int64_t>(1, 148 * 229 / tokens));
 }
 
 int check_window_geometry(clipebc_model* m, int h, int w) {
