@@ -25,14 +25,15 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   pdl_launch_dependents();
   pdl_wait();
   const int gh = h / 2, gw = w / 2, Hp = gh + 1, Wp = gw + 1;
-  const int64_t total = static_cast<int64_t>(n_units) * Hp * Wp * 8;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g8 = static_cast<int>(idx & 7);
-    const int64_t row = idx >> 3;
-    const int unit = static_cast<int>(row / (Hp * Wp));
-    const int q = static_cast<int>(row - static_cast<int64_t>(unit) * Hp * Wp);
-    const int y = q / Wp, x = q - y * Wp;
+  // grid: y = unit, x = (cell, 8-column group) of the unit -- a thread's position is two 32-bit divisions (the flat 64-bit index
+  // of the first version cost two 64-bit ones per thread: these kernels are issue-bound, not bandwidth-bound)
+  const unsigned per_unit = static_cast<unsigned>(Hp) * Wp * 8;
+  for (int unit = blockIdx.y; unit < n_units; unit += gridDim.y)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_unit; i += gridDim.x * blockDim.x) {
+    const int g8 = static_cast<int>(i & 7);
+    const int q = static_cast<int>(i >> 3);
+    const int64_t row = static_cast<int64_t>(unit) * Hp * Wp + q;
+    const int y = static_cast<int>(static_cast<unsigned>(q) / static_cast<unsigned>(Wp)), x = q - y * Wp;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -66,15 +67,14 @@ __global__ void __launch_bounds__(256) pool_copy_kernel(const uint16_t* __restri
   pdl_wait();
   const int Ho = go_h + 1, Wo = go_w + 1, Wi = S * go_w + 1, Hi = S * go_h + 1;
   const int groups = C >> 3;
-  const int64_t total = static_cast<int64_t>(n_units) * Ho * Wo * groups;
   const float inv = 1.0f / static_cast<float>(S * S);
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
-    const int64_t row = idx / groups;
-    const int unit = static_cast<int>(row / (Ho * Wo));
-    const int q = static_cast<int>(row - static_cast<int64_t>(unit) * Ho * Wo);
-    const int y = q / Wo, x = q - y * Wo;
+  const unsigned per_unit = static_cast<unsigned>(Ho) * Wo * groups;  // grid: y = unit, x = (cell, channel group) of the unit
+  for (int unit = blockIdx.y; unit < n_units; unit += gridDim.y)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_unit; i += gridDim.x * blockDim.x) {
+    const int q = static_cast<int>(i / static_cast<unsigned>(groups));
+    const int g = static_cast<int>(i) - q * groups;
+    const int64_t row = static_cast<int64_t>(unit) * Ho * Wo + q;
+    const int y = static_cast<int>(static_cast<unsigned>(q) / static_cast<unsigned>(Wo)), x = q - y * Wo;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (y < go_h && x < go_w) {
       const uint16_t* s0 = src + (static_cast<int64_t>(unit) * Hi * Wi) * ld_src + src_col + g * 8;
@@ -109,14 +109,13 @@ __global__ void __launch_bounds__(256) resample16_kernel(const uint16_t* __restr
   const int Ho = go_h + 1, Wo = go_w + 1, Hi = gi_h + 1, Wi = gi_w + 1;
   const int groups = C >> 3;
   const float inv_sy = static_cast<float>(gi_h) / static_cast<float>(go_h), inv_sx = static_cast<float>(gi_w) / static_cast<float>(go_w);
-  const int64_t total = static_cast<int64_t>(n_units) * Ho * Wo * groups;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
-    const int64_t row = idx / groups;
-    const int unit = static_cast<int>(row / (Ho * Wo));
-    const int q = static_cast<int>(row - static_cast<int64_t>(unit) * Ho * Wo);
-    const int y = q / Wo, x = q - y * Wo;
+  const unsigned per_unit = static_cast<unsigned>(Ho) * Wo * groups;  // grid: y = unit, x = (cell, channel group) of the unit
+  for (int unit = blockIdx.y; unit < n_units; unit += gridDim.y)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_unit; i += gridDim.x * blockDim.x) {
+    const int q = static_cast<int>(i / static_cast<unsigned>(groups));
+    const int g = static_cast<int>(i) - q * groups;
+    const int64_t row = static_cast<int64_t>(unit) * Ho * Wo + q;
+    const int y = static_cast<int>(static_cast<unsigned>(q) / static_cast<unsigned>(Wo)), x = q - y * Wo;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (y < go_h && x < go_w) {
       int y0, y1, x0, x1;
@@ -179,12 +178,22 @@ inline const char* last_err() {
 
 }  // namespace
 
+// grid of the (unit, flat index inside the unit) kernels: y = units (grid-strided beyond 65535), x = enough 256-thread blocks to
+// cover a unit, capped so that the whole grid stays near 16 blocks per SM
+dim3 grid_units(int n_units, int64_t per_unit) {
+  const int64_t need = (per_unit + 255) / 256;
+  const int gy = n_units < 65535 ? n_units : 65535;
+  int64_t gx = (static_cast<int64_t>(device_num_sms()) * 16 + gy - 1) / gy;
+  gx = gx < 1 ? 1 : (gx > need ? need : gx);
+  return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+}
+
 const char* stem_im2col(cudaStream_t stream, const float* image, int n_units, int H, int W, const int* origins_yx_dev, int h,
                         int w, void* out, int fp16) {
   if (n_units <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return "stem_im2col: bad geometry";
   const int64_t rows = static_cast<int64_t>(n_units) * (h / 2 + 1) * (w / 2 + 1);
   LaunchScope scope(stream, "stem_im2col", 0.0, static_cast<double>(n_units) * 3 * h * w * 4.0 + static_cast<double>(rows) * 128.0);
-  cudaError_t e = launch_pdl(stem_im2col_kernel, dim3(grid_1d(rows * 8, device_num_sms() * 16)), dim3(256), 0, stream, 1, image,
+  cudaError_t e = launch_pdl(stem_im2col_kernel, grid_units(n_units, static_cast<int64_t>(h / 2 + 1) * (w / 2 + 1) * 8), dim3(256), 0, stream, 1, image,
                              n_units, H, W, origins_yx_dev, h, w, static_cast<uint16_t*>(out), fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
@@ -195,7 +204,7 @@ const char* pool_copy(cudaStream_t stream, const void* src, int ld_src, int src_
   if ((ld_src & 7) || (ld_dst & 7) || (src_col & 7) || (dst_col & 7)) return "pool_copy: pitches / offsets must be multiples of 8";
   const int64_t items = static_cast<int64_t>(n_units) * (go_h + 1) * (go_w + 1) * (C / 8);
   LaunchScope scope(stream, S == 1 ? "copy" : "avgpool", 0.0, static_cast<double>(items) * 16.0 * (1 + S * S));
-  cudaError_t e = launch_pdl(pool_copy_kernel, dim3(grid_1d(items, device_num_sms() * 16)), dim3(256), 0, stream, 1,
+  cudaError_t e = launch_pdl(pool_copy_kernel, grid_units(n_units, items / n_units), dim3(256), 0, stream, 1,
                              static_cast<const uint16_t*>(src), ld_src, src_col, static_cast<uint16_t*>(dst), ld_dst, dst_col, C,
                              n_units, go_h, go_w, S, fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
@@ -206,7 +215,7 @@ const char* resample16(cudaStream_t stream, const void* src, void* dst, int C, i
   if (n_units <= 0 || C <= 0 || (C & 7)) return "resample16: bad arguments";
   const int64_t items = static_cast<int64_t>(n_units) * (go_h + 1) * (go_w + 1) * (C / 8);
   LaunchScope scope(stream, "resample", 0.0, static_cast<double>(items) * 16.0 * 2);
-  cudaError_t e = launch_pdl(resample16_kernel, dim3(grid_1d(items, device_num_sms() * 16)), dim3(256), 0, stream, 1,
+  cudaError_t e = launch_pdl(resample16_kernel, grid_units(n_units, items / n_units), dim3(256), 0, stream, 1,
                              static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), C, n_units, gi_h, gi_w, go_h, go_w, fp16);
   return e != cudaSuccess ? cudaGetErrorString(e) : last_err();
 }
