@@ -151,8 +151,9 @@ int clipebc_layernorm(const float* in_dev, const float* gamma_dev, const float* 
                       int out_kind, int64_t n_rows_out, int rows_out_per_group, int rows_in_per_group,
                       int in_row_offset, void* stream);
 /* softmax(q k^T / 8) v per (window, head): qkv bf16 [n_win * t_live, 3 * 64 * heads], const_kv bf16 [n_const, 3 * 64 * heads]
- * extra keys / values of every window (deep-VPT prompts), out 16-bit [n_win * t_live, 64 * heads]. tcgen05 kernel when
- * t_live + n_const <= 256 and n_const % 8 == 0, streamed-K/V kernel otherwise. */
+ * extra keys / values of every window (deep-VPT prompts), out 16-bit [n_win * t_live, 64 * heads]. tcgen05 kernels when
+ * t_live + n_const <= 256 and n_const % 8 == 0, or 257..320 keys with n_const % 16 == 0 (ViT-L/14); streamed-K/V kernel
+ * otherwise. */
 int clipebc_attention(const void* qkv_bf16_dev, const void* const_kv_bf16_dev, int n_const, int n_win, int t_live,
                       int heads, void* out_16_dev, int out_fp16, void* stream);
 /* out: split = 1: [n_img*gh*gw, 2*kp_pad] = [hi | lo] split of the pixels in the 16-bit format (what the path uses with bf16
