@@ -22,7 +22,8 @@
 //                 place as MN-major B)
 //   warp 2        TMEM allocator (512 columns: one 256-column buffer per chain)
 //   warps 4-7     softmax + output of chain 0, warps 8-11 of chain 1 (thread = query row = TMEM lane)
-// TMEM buffer of a tile: S fp32 [0,256)  ->  P packed bf16 [0,128) | O fp32 [128,192)
+// TMEM buffer of a tile: S fp32 [0,256)  ->  P packed bf16 [0,128) | O fp32 [128,192); in the shipped two-block form (SPLIT = 1, see
+// the kernel): P of keys [0,128) at [0,64) | O [64,128) | P of keys [128,256) at [128,192)
 // Scores and probabilities never leave the SM: HBM traffic is Q, K, V in and O out.
 #include <cstdlib>
 
@@ -45,6 +46,7 @@ __device__ __forceinline__ void tr_rec(int ev, int k) {
 #define TR(ev, k)
 #endif
 constexpr int kThreadsP = 384;
+constexpr int kSplitP = 1;  // 1: keys of a tile in two blocks of 128, P_A V_A under the second half of the softmax (0: one block)
 constexpr int kPolyP = 0;  // share 1/kPolyP of the softmax exponentials on the FMA pipe; 0 = none (measured: no gain)
 constexpr int kQTileBytesP = 128 * 128;    // one 128-query tile
 constexpr int kQBytesP = 2 * kQTileBytesP; // 256 query rows x 64 dims, 16-bit
@@ -142,7 +144,10 @@ __device__ __forceinline__ void chunk_exp_store_p(const uint32_t (&v)[32], int l
   tmem_st_x16_p(p_taddr, pk);
 }
 
-template <int POLY>
+// SPLIT = 1: the keys of a tile are taken in two blocks of 128 (attention_ppl.cu does the same for 256 + 64): the softmax group
+// announces P of keys [0, 128) half way, the MMA warp runs O = P_A V_A under the second half of the softmax, and only the k-steps
+// of keys [128, Tk) are left behind it. TMEM buffer of a tile: S fp32 [0,256) -> P_A bf16 [0,64) | O fp32 [64,128) | P_B [128,192).
+template <int POLY, int SPLIT>
 __global__ void __launch_bounds__(kThreadsP, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const __grid_constant__ CUtensorMap tm_const, int n_const, int t_live, int n_items, int heads,
@@ -160,7 +165,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* p_ready = bars + 10;   // [2 chains] softmax group (4 warps) -> MMA
   uint64_t* o_full = bars + 12;    // [2 chains] MMA (commit) -> softmax group
   uint64_t* buf_free = bars + 14;  // [2 chains] softmax group (4 warps) -> MMA
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* pb_ready = bars + 16;  // [2 chains] SPLIT: softmax group -> MMA, P of keys [128, Tk) written
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tk = n_const + t_live;
@@ -185,6 +191,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1);
       mbar_init(&qk_empty[i], 2); mbar_init(&v_empty[i], 2);  // two commits per item (see the MMA issuers)
       mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&buf_free[i], 4);
+      mbar_init(&pb_ready[i], 4);
     }
     fence_mbar_init();
   }
@@ -235,7 +242,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     // De-phase the chains: left alone they start together and stay in lockstep (both softmax groups fight for the MUFU
     // pipe, then both wait for the tensor pipe). Chain 1 therefore starts when chain 0 has finished its first softmax;
     // from then on one chain's softmax runs while the other is in its P.V / output / next-S phase.
-    if (b == 1 && total_tiles > 1) mbar_wait(&p_ready[0], 0);
+    if (b == 1 && total_tiles > 1) mbar_wait(SPLIT ? &pb_ready[0] : &p_ready[0], 0);
+    constexpr uint32_t o_col = SPLIT ? 64 : 128;
     int k = 0;
     for (int u = b; u < total_tiles; u += 2, ++k) {
       const int g = g0 + u;
@@ -272,9 +280,19 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_wait(&p_ready[b], k & 1);
       TR(2, k);
       tc_fence_after();
+      if (SPLIT) {
+        const int ks_a = k_steps < 8 ? k_steps : 8;
+        if (lane == 0)
+          for (int ks = 0; ks < ks_a; ++ks)
+            umma_bf16_ts_p(buf + o_col, buf + ks * 8, desc_sw128_mn_p(v_addr + ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
+        __syncwarp();
+        mbar_wait(&pb_ready[b], k & 1);
+        tc_fence_after();
+      }
       if (lane == 0) {
-        for (int ks = 0; ks < k_steps; ++ks)
-          umma_bf16_ts_p(buf + 128, buf + ks * 8, desc_sw128_mn_p(v_addr + ks * 2048), idesc_o, ks != 0 ? 1u : 0u);
+        for (int ks = SPLIT ? 8 : 0; ks < k_steps; ++ks)
+          umma_bf16_ts_p(buf + o_col, buf + (SPLIT ? 64 : 0) + ks * 8, desc_sw128_mn_p(v_addr + ks * 2048), idesc_o,
+                         (SPLIT || ks != 0) ? 1u : 0u);
         umma_commit(&o_full[b]);
         umma_commit(&v_empty[s]);
         if (sole) umma_commit(&v_empty[s]);
@@ -298,6 +316,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int row0 = t * 128 + q * 32;          // first row of this warp inside the window
       const bool active = row0 < t_live;          // warps whose 32 rows are all padding only keep the protocol going
       float row_sum = 0.f;
+      bool pa_done = false;
       TR(10, k);
       mbar_wait(&s_full[b], k & 1);
       TR(11, k);
@@ -314,15 +333,25 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int j = 0; j < 32; ++j)
           if (j < lim0) mx = fmaxf(mx, __uint_as_float(va[j]));
         const float m_scaled = mx * kScale;
+        // P of chunk c: packed pairs over consumed S columns -- [16c, 16c + 16), or from column 128 on for keys >= 128 (SPLIT)
+        const uint32_t p_hi = SPLIT ? 64 : 0;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; c += 2) {
           if (c + 1 < n_chunks) tmem_ld_32x32b_x32(row_base_t + (c + 1) * 32, vb);
-          chunk_exp_store_p<POLY>(va, Tk - c * 32, kScale, m_scaled, row_sum, row_base_t + c * 16);
+          chunk_exp_store_p<POLY>(va, Tk - c * 32, kScale, m_scaled, row_sum, row_base_t + (c >= 4 ? p_hi : 0) + c * 16);
           tmem_ld_wait();
           if (c + 1 < n_chunks) {
             if (c + 2 < n_chunks) tmem_ld_32x32b_x32(row_base_t + (c + 2) * 32, va);
-            chunk_exp_store_p<POLY>(vb, Tk - (c + 1) * 32, kScale, m_scaled, row_sum, row_base_t + (c + 1) * 16);
+            chunk_exp_store_p<POLY>(vb, Tk - (c + 1) * 32, kScale, m_scaled, row_sum,
+                                    row_base_t + (c >= 4 ? p_hi : 0) + (c + 1) * 16);
             tmem_ld_wait();
+          }
+          if (SPLIT && c == 2) {  // keys [0, 128) are done: let the MMA warp start O = P_A V_A
+            tmem_st_wait_p();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[b]);
+            pa_done = true;
           }
         }
         tmem_st_wait_p();
@@ -330,7 +359,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       TR(12, k);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[b]);
+      if (lane == 0) {
+        if (!SPLIT || !pa_done) mbar_arrive(&p_ready[b]);
+        if (SPLIT) mbar_arrive(&pb_ready[b]);
+      }
 
       // O / rowsum -> 16-bit -> global, two halves of 32 dims through the warp's smem staging tile (thread = row holds
       // 64 B of its row; staged, one instruction writes 8 complete 64 B row segments)
@@ -342,8 +374,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int sw = (lane >> 1) & 3;
         const int slot = lane & 3, rsub = lane >> 2;
         uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(row_base_t + 128, o0);
-        tmem_ld_32x32b_x32(row_base_t + 160, o1);
+        tmem_ld_32x32b_x32(row_base_t + (SPLIT ? 64 : 128), o0);
+        tmem_ld_32x32b_x32(row_base_t + (SPLIT ? 96 : 160), o1);
         tmem_ld_wait();
         // O is in registers: hand the TMEM buffer back before the stores so the next S of this chain can start
         tc_fence_before();
@@ -425,16 +457,20 @@ const char* attention_h64_pp(cudaStream_t stream, const __nv_bfloat16* qkv, cons
   // evaluated on the FMA pipe. The shipped library has the one instantiation below.
   static unsigned long long attr_done_ab[4] = {0, 0, 0, 0};
   static const int poly_env = [] { const char* e = getenv("CLIPEBC_ATTN_POLY"); return e ? atoi(e) : kPolyP; }();
-  auto kern = attention_pp_kernel<kPolyP>;
+  static unsigned long long attr_done_split = 0;
+  static const int split_env = [] { const char* e = getenv("CLIPEBC_ATTN_SPLIT"); return e ? atoi(e) : kSplitP; }();
+  auto kern = attention_pp_kernel<kPolyP, kSplitP>;
   unsigned long long* mask = &attr_done;
-  if (poly_env != kPolyP) {
-    if (poly_env == 0) { kern = attention_pp_kernel<0>; mask = &attr_done_ab[0]; }
-    else if (poly_env == 2) { kern = attention_pp_kernel<2>; mask = &attr_done_ab[1]; }
-    else if (poly_env == 3) { kern = attention_pp_kernel<3>; mask = &attr_done_ab[2]; }
-    else if (poly_env == 4) { kern = attention_pp_kernel<4>; mask = &attr_done_ab[3]; }
+  if (split_env != kSplitP) {
+    kern = attention_pp_kernel<kPolyP, 1 - kSplitP>; mask = &attr_done_split;
+  } else if (poly_env != kPolyP) {
+    if (poly_env == 0) { kern = attention_pp_kernel<0, kSplitP>; mask = &attr_done_ab[0]; }
+    else if (poly_env == 2) { kern = attention_pp_kernel<2, kSplitP>; mask = &attr_done_ab[1]; }
+    else if (poly_env == 3) { kern = attention_pp_kernel<3, kSplitP>; mask = &attr_done_ab[2]; }
+    else if (poly_env == 4) { kern = attention_pp_kernel<4, kSplitP>; mask = &attr_done_ab[3]; }
   }
 #else
-  auto kern = attention_pp_kernel<kPolyP>;
+  auto kern = attention_pp_kernel<kPolyP, kSplitP>;
   unsigned long long* mask = &attr_done;
 #endif
   cudaError_t ea = ensure_dyn_smem(kern, kSmemP, mask);
